@@ -1,0 +1,287 @@
+/*
+ * libmreserve_b200 -- flat C ABI of the B200-native MERLOT Reserve encoder + contrastive hot path.
+ *
+ * The reference (rowanz/merlot_reserve) is pure Python/JAX/Flax and has no FFI of its own; the
+ * boundary it exposes is the Flax module call (mreserve/modeling.py) whose arithmetic XLA emits.
+ * Each entry below replaces the XLA-lowered op group of one reference call site (cited per entry)
+ * and is what a jax.ffi custom call for that site would bind.
+ *
+ * Conventions (every entry):
+ *   - `stream` is a cudaStream_t passed as void*.  The library only ENQUEUES work on it; it never
+ *     synchronises, never allocates device memory and keeps no mutable global state.
+ *   - `in` / `out` are arrays of DEVICE pointers (entries may be NULL where marked optional).
+ *   - `workspace` is caller-allocated device scratch of at least <entry>_workspace_bytes(desc).
+ *   - return value: MR_OK (0) or a negative MrStatus.  CUDA launch errors are returned as
+ *     MR_ERR_CUDA_BASE - cudaError_t.
+ *   - all matrices are row-major; "bf16" is __nv_bfloat16; row strides are in ELEMENTS.
+ */
+#ifndef MRESERVE_B200_H_
+#define MRESERVE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* mr_stream_t;
+
+typedef enum MrStatus {
+  MR_OK = 0,
+  MR_ERR_BAD_SHAPE = -1,
+  MR_ERR_MISALIGNED = -2,
+  MR_ERR_UNSUPPORTED_ARCH = -3,
+  MR_ERR_NULL_POINTER = -4,
+  MR_ERR_WORKSPACE = -5,
+  MR_ERR_DRIVER = -6,
+  MR_ERR_CUDA_BASE = -1000
+} MrStatus;
+
+/* Library / device probe.  Returns MR_OK when device `device` is compute capability 10.x. */
+int32_t mr_check_device(int32_t device);
+/* ABI version: bumped when any struct below changes. */
+int32_t mr_abi_version(void);
+/* Human readable text for a status code (static storage). */
+const char* mr_status_string(int32_t status);
+/* Number of kernels this library has launched since load (per process, all threads). */
+int64_t mr_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * mr_gemm_epilogue: D = epilogue(A . W^T)      [tcgen05 tensor cores, TMEM accumulators, TMA]
+ *
+ * Replaces every flax nn.Dense / nn.DenseGeneral / nn.Conv(k=s=2) on the path:
+ *   patch embed modeling.py:402, audio embed :453, qkv :228 (+ apply_rotary :116-144 and the
+ *   1/sqrt(d) query scale of flax dot_product_attention_weights), attn_proj :235 (+ residual
+ *   :275), MLP intermediate + my_gelu :252-254,:240, MLP out :255 (+ residual :279), cls_proj
+ *   :371, head :631, attention-pool q/k/v/out :424,:468.
+ *
+ *   in[0]  A        bf16 [M, lda]      activations (K-major)
+ *   in[1]  W        bf16 [N, K]        weight, TRANSPOSED flax kernel (flax stores [K, N])
+ *   in[2]  bias     f32  [N]           optional (MR_EPI_BIAS)
+ *   in[3]  residual bf16 [rows, ldd]   optional (MR_EPI_RESIDUAL), indexed like the output
+ *   in[4]  rot      f32  [rot_rows,32] optional (MR_EPI_ROTARY_QKV) per-position scale table
+ *   out[0] D        bf16 or f32 [rows, ldd]
+ *
+ * Epilogue order: acc -> +bias -> rotary/q-scale -> gelu -> +residual -> cast.
+ * Output row of input row r:  seq_in == 0 ? r : (r / seq_in) * seq_out + (r % seq_in) + row_off
+ * (used to drop the patch-embed result into rows 1.. of the [B, 1+hw, H] token buffer).
+ * MR_EPI_ROTARY_QKV: N == 3*hidden; for columns c < 2*hidden with (c % 64) < 32 the value is
+ * multiplied by rot[(r % rot_rows) * 32 + (c % 64)]; columns c < hidden are then multiplied by
+ * q_scale.
+ * Constraints: K % 8 == 0, lda % 8 == 0, N % 8 == 0, ldd % 8 == 0, all pointers 16-byte aligned.
+ * ------------------------------------------------------------------------------------------ */
+enum {
+  MR_EPI_BIAS = 1,
+  MR_EPI_GELU = 2,       /* x * sigmoid(1.702 x)  (modeling.py:240) */
+  MR_EPI_RESIDUAL = 4,
+  MR_EPI_ROTARY_QKV = 8,
+  MR_EPI_OUT_F32 = 16
+};
+
+enum { MR_GEMM_ALGO_TCGEN05 = 0, MR_GEMM_ALGO_SIMT_DEBUG = 1 };
+
+typedef struct MrGemmDesc {
+  int32_t M, N, K;
+  int32_t lda;
+  int32_t ldd;
+  int32_t epilogue; /* bit-or of MR_EPI_* */
+  int32_t seq_in, seq_out, row_off;
+  int32_t rot_rows;
+  int32_t hidden;
+  int32_t algo;     /* MR_GEMM_ALGO_* ; SIMT_DEBUG is a slow CUDA-core kernel kept for bisecting */
+  float q_scale;
+  int32_t num_sms;  /* 0 = use every SM of the current device */
+} MrGemmDesc;
+
+int32_t mr_gemm_epilogue(mr_stream_t stream, const MrGemmDesc* d, const void* const* in, void* const* out,
+                         void* workspace, size_t workspace_bytes);
+size_t mr_gemm_epilogue_workspace_bytes(const MrGemmDesc* d);
+
+/* ------------------------------------------------------------------------------------------
+ * mr_attention_fwd: softmax(q k^T + mask) v per (sequence, head), flash style, never
+ * materialising [T, T].  Replaces apply_attention modeling.py:188-200 (after the rotary/q-scale
+ * already folded into the qkv GEMM epilogue) and the mask construction of :343-358 / :743-756.
+ *
+ *   in[0]  qkv    bf16 [B*T, 3*H]   columns: q heads | k heads | v heads, 64 per head
+ *   in[1]  valid  u8   [B*T]        optional; 0 = padding position (modeling.py:726)
+ *   in[2]  group  i32  [B*T]        optional video_src id per position (modeling.py:746-756)
+ *   out[0] ctx    bf16 [B*T, H]
+ * Mask(q,k) = valid[q] & valid[k] & (group[q] == group[k]).  A query row whose mask is all
+ * false sees a constant -1e10 bias in the reference, i.e. attends UNIFORMLY to all T keys; that
+ * behaviour is reproduced (it matters for padding rows returned by embed_video :842).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct MrAttentionDesc {
+  int32_t B, T, H; /* H = hidden = 64 * heads */
+} MrAttentionDesc;
+
+int32_t mr_attention_fwd(mr_stream_t stream, const MrAttentionDesc* d, const void* const* in, void* const* out,
+                         void* workspace, size_t workspace_bytes);
+size_t mr_attention_fwd_workspace_bytes(const MrAttentionDesc* d);
+
+/* ------------------------------------------------------------------------------------------
+ * mr_layernorm_fwd: flax LayerNorm(eps) (modeling.py:272,277,360,366): fp32 statistics,
+ * var = E[x^2] - E[x]^2, y = (x - mean) * rsqrt(var + eps) * gamma + beta.
+ *   in[0] x bf16 [rows_in, ldx]; in[1] gamma f32 [H]; in[2] beta f32 [H]; out[0] y bf16 [rows, H]
+ * Row map: output row r reads input row  seq_out == 0 ? r : (r / seq_out) * seq_in + (r % seq_out) + row_off
+ * (used to normalise only the first L rows of every joint sequence / only the CLS row).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct MrLayerNormDesc {
+  int32_t rows; /* output rows */
+  int32_t H;
+  int32_t ldx;
+  int32_t seq_in, seq_out, row_off;
+  float eps;
+} MrLayerNormDesc;
+
+int32_t mr_layernorm_fwd(mr_stream_t stream, const MrLayerNormDesc* d, const void* const* in, void* const* out,
+                         void* workspace, size_t workspace_bytes);
+
+/* ------------------------------------------------------------------------------------------
+ * mr_cast_pad: f32 [rows, cols] -> bf16 [rows, ld_out] (zero padded columns).  Stages the
+ * fp32 pixel patches (modeling.py:402 casts to module dtype) and the [B,30,130] audio patches
+ * (:453; K=130 is padded to a TMA-legal pitch).
+ *   in[0] x f32 [rows, cols]; out[0] y bf16 [rows, ld_out]
+ * ------------------------------------------------------------------------------------------ */
+typedef struct MrCastDesc {
+  int64_t rows;
+  int32_t cols;
+  int32_t ld_out;
+} MrCastDesc;
+int32_t mr_cast_pad(mr_stream_t stream, const MrCastDesc* d, const void* const* in, void* const* out,
+                    void* workspace, size_t workspace_bytes);
+
+/* ------------------------------------------------------------------------------------------
+ * mr_fill_cls: writes the CLS parameter into row 0 of every sequence of x [B, T, H]
+ * (modeling.py:316-320).   in[0] cls f32 [H]; out[0] x bf16 [B*T, H]
+ * ------------------------------------------------------------------------------------------ */
+typedef struct MrFillClsDesc {
+  int32_t B, T, H;
+} MrFillClsDesc;
+int32_t mr_fill_cls(mr_stream_t stream, const MrFillClsDesc* d, const void* const* in, void* const* out,
+                    void* workspace, size_t workspace_bytes);
+
+/* ------------------------------------------------------------------------------------------
+ * Attention pooling (flax MultiHeadDotProductAttention with a single mean query per window;
+ * modeling.py:413-429 vision 2x2 windows, :464-475 audio windows of 5).
+ *
+ * mr_window_mean: q_in[w] = mean over the window's tokens of x.
+ *   in[0] x bf16 [B, T, H] (row 0 = CLS, skipped);  out[0] q_in bf16 [B*n_win, H]
+ * mr_window_attention: ctx[w] = softmax_j(q[w].k[w,j] / 8) v[w,j], per head.
+ *   in[0] q bf16 [B*n_win, H]; in[1] kv bf16 [B*T, 2H] (k | v, computed on every token row);
+ *   out[0] ctx bf16 [B*n_win, H]
+ * Window w of sequence b covers token rows 1 + idx(w, j):
+ *   mode 0 (1-D, audio):  idx = w * win + j
+ *   mode 1 (2-D, vision): w = (y, x) on the (grid_h/2, grid_w/2) grid, j = (dy, dx):
+ *                         idx = (2y + dy) * grid_w + 2x + dx          (reshape/swapaxes :419-421)
+ * ------------------------------------------------------------------------------------------ */
+typedef struct MrWindowDesc {
+  int32_t B, T, H;
+  int32_t mode;
+  int32_t win;            /* tokens per window (4 for 2x2, 5 for audio) */
+  int32_t n_win;          /* windows per sequence */
+  int32_t grid_h, grid_w; /* mode 1 only */
+} MrWindowDesc;
+int32_t mr_window_mean(mr_stream_t stream, const MrWindowDesc* d, const void* const* in, void* const* out,
+                       void* workspace, size_t workspace_bytes);
+int32_t mr_window_attention(mr_stream_t stream, const MrWindowDesc* d, const void* const* in, void* const* out,
+                            void* workspace, size_t workspace_bytes);
+
+/* ------------------------------------------------------------------------------------------
+ * mr_embed_assemble: builds the joint-encoder input (prepare_multimodal_inputs,
+ * modeling.py:651-758, incl. TokenEmbedder :507-538 and the audio splice :685-695).
+ *   in[0] tokens   i32  [B, L]
+ *   in[1] seg_idx  i32  [B, L]     token_segment_idx (already // 3 where the caller does that); optional
+ *   in[2] aud_ptr  i32  [B, L]     audio_pointers; optional (no audio splice when NULL)
+ *   in[3] emb      bf16 [vocab, H] token embedding table
+ *   in[4] audio    bf16 [B, n_aud, 6, H] audio_spans; optional
+ *   in[5] vision   bf16 [B, n_vis, H]    vision_input; optional
+ *   in[6] tok_emb  bf16 [B, L, H]        optional pre-computed token_embs (replaces the lookup)
+ *   out[0] x     bf16 [B, T (+1 if cls_offset), H]   T = max(L + n_vis, pad_len)
+ *   out[1] rot   f32  [B, T, 32]  rotary scale table (construct_rotary_sinusoids + apply_rotary,
+ *                                 :81-144, 4 coordinate axes x 4 frequencies)
+ *   out[2] valid u8   [B, T]
+ * ------------------------------------------------------------------------------------------ */
+typedef struct MrAssembleDesc {
+  int32_t B, L, H;
+  int32_t n_aud;          /* audio spans per sequence (0 = none) */
+  int32_t n_vis;          /* vision rows per sequence (0 = none) */
+  int32_t pool_h, pool_w; /* pooled vision grid (output_grid / vit_pooling_ratio) */
+  int32_t T;              /* total rows per sequence incl. right padding */
+  int32_t vocab;
+  int32_t audio_token_length; /* 6 */
+  int32_t cls_offset;     /* 1: leave row 0 of every sequence free for a CLS token (span encoder,
+                             modeling.py:311-326); the output then has T + 1 rows per sequence,
+                             valid[b, 0] = 1 and rot[b, 0] is the zero-coordinate row */
+} MrAssembleDesc;
+int32_t mr_embed_assemble(mr_stream_t stream, const MrAssembleDesc* d, const void* const* in, void* const* out,
+                          void* workspace, size_t workspace_bytes);
+
+/* ------------------------------------------------------------------------------------------
+ * mr_rotary_table: scale table for coordinates given explicitly (vision / audio / span encoders,
+ * whose coordinates are trace-time constants in the reference: modeling.py:405,457,498).
+ *   in[0] coords f32 [rows, ndims]  (ndims in {1, 2, 4});  out[0] rot f32 [rows, 32]
+ * ------------------------------------------------------------------------------------------ */
+typedef struct MrRotaryDesc {
+  int32_t rows;
+  int32_t ndims;
+} MrRotaryDesc;
+int32_t mr_rotary_table(mr_stream_t stream, const MrRotaryDesc* d, const void* const* in, void* const* out,
+                        void* workspace, size_t workspace_bytes);
+
+/* ------------------------------------------------------------------------------------------
+ * mr_unit_normalize: y = x / sqrt(sum(x^2) + 1e-5) * scale in fp32 (modeling.py:570-578; the
+ * optional scale is exp(log_scale/2) of pretrain_model.py:251-253).
+ *   in[0] x f32 or bf16 [rows, H]; out[0] y f32 or bf16 [rows, H]
+ * ------------------------------------------------------------------------------------------ */
+typedef struct MrNormalizeDesc {
+  int32_t rows, H;
+  int32_t in_f32, out_f32;
+  float scale;
+} MrNormalizeDesc;
+int32_t mr_unit_normalize(mr_stream_t stream, const MrNormalizeDesc* d, const void* const* in, void* const* out,
+                          void* workspace, size_t workspace_bytes);
+
+/* ------------------------------------------------------------------------------------------
+ * mr_segment_pool: one_hot_pool (modeling.py:541-567) as a gather/segment-sum.
+ *   in[0] do_pool u8  [B, L]; in[1] idx i32 [B, L]; in[2] v bf16 or f32 [B, L, H]
+ *   out[0] pooled f32 [B, S, H] (zero where no position points at the segment)
+ *   out[1] count  f32 [B, S]    (idx_oh.sum(1))
+ * ------------------------------------------------------------------------------------------ */
+typedef struct MrSegmentPoolDesc {
+  int32_t B, L, H, S;
+  int32_t v_f32;
+} MrSegmentPoolDesc;
+int32_t mr_segment_pool(mr_stream_t stream, const MrSegmentPoolDesc* d, const void* const* in, void* const* out,
+                        void* workspace, size_t workspace_bytes);
+
+/* ------------------------------------------------------------------------------------------
+ * mr_contrastive_lse_fwd: one direction of loss_fn_given_preds (pretrain_model.py:276,293-295):
+ *   numer[i] = sum_h x[i,h] * y[i,h]            (the positive logit)
+ *   lse[i]   = logsumexp_j( x[i] . y_all[j] )   in fp32, [n, n_all] never materialised
+ *   in[0] x bf16 [n, H]; in[1] y_all bf16 [n_all, H] (rank-major all-gather of y);
+ *   in[2] y_pos bf16 [n, H] (this rank's positives)
+ *   out[0] lse f32 [n]; out[1] numer f32 [n]
+ * ------------------------------------------------------------------------------------------ */
+typedef struct MrContrastiveDesc {
+  int32_t n, n_all, H;
+} MrContrastiveDesc;
+int32_t mr_contrastive_lse_fwd(mr_stream_t stream, const MrContrastiveDesc* d, const void* const* in,
+                               void* const* out, void* workspace, size_t workspace_bytes);
+size_t mr_contrastive_lse_fwd_workspace_bytes(const MrContrastiveDesc* d);
+
+/* ------------------------------------------------------------------------------------------
+ * mr_row_dot: logits[r] = x[r] . w  (finetune `proj` head H -> 1, no bias;
+ * finetune/vcr/qa_qar_joint_finetune.py:163-170), with an optional row gather.
+ *   in[0] x bf16 [rows_in, H]; in[1] w f32 [H]; in[2] row_idx i32 [rows] optional; out[0] f32 [rows]
+ * ------------------------------------------------------------------------------------------ */
+typedef struct MrRowDotDesc {
+  int32_t rows, H;
+} MrRowDotDesc;
+int32_t mr_row_dot(mr_stream_t stream, const MrRowDotDesc* d, const void* const* in, void* const* out,
+                   void* workspace, size_t workspace_bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MRESERVE_B200_H_ */

@@ -1,0 +1,306 @@
+"""ctypes binding of libmreserve_b200.so (include/mreserve_b200.h).
+
+torch is used here only as the owner of device memory and of the CUDA stream: every wrapper passes raw
+device pointers + the current stream handle through the C ABI.  There is NO fallback: if the shared
+library is missing or the device is not a B200 the import / first call fails loudly.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+from typing import Optional, Sequence
+
+import torch
+
+_LIB_PATH = Path(__file__).resolve().parent / "lib" / "libmreserve_b200.so"
+
+EPI_BIAS, EPI_GELU, EPI_RESIDUAL, EPI_ROTARY_QKV, EPI_OUT_F32 = 1, 2, 4, 8, 16
+ALGO_TCGEN05, ALGO_SIMT_DEBUG = 0, 1
+
+
+class MrError(RuntimeError):
+    pass
+
+
+class GemmDesc(C.Structure):
+    _fields_ = [("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32), ("lda", C.c_int32), ("ldd", C.c_int32),
+                ("epilogue", C.c_int32), ("seq_in", C.c_int32), ("seq_out", C.c_int32), ("row_off", C.c_int32),
+                ("rot_rows", C.c_int32), ("hidden", C.c_int32), ("algo", C.c_int32), ("q_scale", C.c_float),
+                ("num_sms", C.c_int32)]
+
+
+class AttentionDesc(C.Structure):
+    _fields_ = [("B", C.c_int32), ("T", C.c_int32), ("H", C.c_int32)]
+
+
+class LayerNormDesc(C.Structure):
+    _fields_ = [("rows", C.c_int32), ("H", C.c_int32), ("ldx", C.c_int32), ("seq_in", C.c_int32),
+                ("seq_out", C.c_int32), ("row_off", C.c_int32), ("eps", C.c_float)]
+
+
+class CastDesc(C.Structure):
+    _fields_ = [("rows", C.c_int64), ("cols", C.c_int32), ("ld_out", C.c_int32)]
+
+
+class FillClsDesc(C.Structure):
+    _fields_ = [("B", C.c_int32), ("T", C.c_int32), ("H", C.c_int32)]
+
+
+class WindowDesc(C.Structure):
+    _fields_ = [("B", C.c_int32), ("T", C.c_int32), ("H", C.c_int32), ("mode", C.c_int32), ("win", C.c_int32),
+                ("n_win", C.c_int32), ("grid_h", C.c_int32), ("grid_w", C.c_int32)]
+
+
+class AssembleDesc(C.Structure):
+    _fields_ = [("B", C.c_int32), ("L", C.c_int32), ("H", C.c_int32), ("n_aud", C.c_int32), ("n_vis", C.c_int32),
+                ("pool_h", C.c_int32), ("pool_w", C.c_int32), ("T", C.c_int32), ("vocab", C.c_int32),
+                ("audio_token_length", C.c_int32), ("cls_offset", C.c_int32)]
+
+
+class RotaryDesc(C.Structure):
+    _fields_ = [("rows", C.c_int32), ("ndims", C.c_int32)]
+
+
+class NormalizeDesc(C.Structure):
+    _fields_ = [("rows", C.c_int32), ("H", C.c_int32), ("in_f32", C.c_int32), ("out_f32", C.c_int32),
+                ("scale", C.c_float)]
+
+
+class SegmentPoolDesc(C.Structure):
+    _fields_ = [("B", C.c_int32), ("L", C.c_int32), ("H", C.c_int32), ("S", C.c_int32), ("v_f32", C.c_int32)]
+
+
+class ContrastiveDesc(C.Structure):
+    _fields_ = [("n", C.c_int32), ("n_all", C.c_int32), ("H", C.c_int32)]
+
+
+class RowDotDesc(C.Structure):
+    _fields_ = [("rows", C.c_int32), ("H", C.c_int32)]
+
+
+# every compute entry point has the same signature
+ENTRY_POINTS = {
+    "mr_gemm_epilogue": GemmDesc,
+    "mr_attention_fwd": AttentionDesc,
+    "mr_layernorm_fwd": LayerNormDesc,
+    "mr_cast_pad": CastDesc,
+    "mr_fill_cls": FillClsDesc,
+    "mr_window_mean": WindowDesc,
+    "mr_window_attention": WindowDesc,
+    "mr_embed_assemble": AssembleDesc,
+    "mr_rotary_table": RotaryDesc,
+    "mr_unit_normalize": NormalizeDesc,
+    "mr_segment_pool": SegmentPoolDesc,
+    "mr_contrastive_lse_fwd": ContrastiveDesc,
+    "mr_row_dot": RowDotDesc,
+}
+WORKSPACE_FNS = {
+    "mr_gemm_epilogue_workspace_bytes": GemmDesc,
+    "mr_attention_fwd_workspace_bytes": AttentionDesc,
+    "mr_contrastive_lse_fwd_workspace_bytes": ContrastiveDesc,
+}
+MISC_FNS = ["mr_check_device", "mr_abi_version", "mr_status_string", "mr_launch_count"]
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Loads the shared library (once).  Raises MrError when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not _LIB_PATH.exists():
+        raise MrError(f"{_LIB_PATH} is missing: build it with `python -m merlot_reserve_b200.build` "
+                      f"(there is no CPU or PyTorch fallback for this path)")
+    lib = C.CDLL(str(_LIB_PATH))
+    for name, desc in ENTRY_POINTS.items():
+        fn = getattr(lib, name)
+        fn.restype = C.c_int32
+        fn.argtypes = [C.c_void_p, C.POINTER(desc), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p, C.c_size_t]
+    for name, desc in WORKSPACE_FNS.items():
+        fn = getattr(lib, name)
+        fn.restype = C.c_size_t
+        fn.argtypes = [C.POINTER(desc)]
+    lib.mr_check_device.restype = C.c_int32
+    lib.mr_check_device.argtypes = [C.c_int32]
+    lib.mr_abi_version.restype = C.c_int32
+    lib.mr_status_string.restype = C.c_char_p
+    lib.mr_status_string.argtypes = [C.c_int32]
+    lib.mr_launch_count.restype = C.c_int64
+    _lib = lib
+    return lib
+
+
+def launch_count() -> int:
+    return int(load().mr_launch_count())
+
+
+def require_b200(device: int = 0) -> None:
+    if not torch.cuda.is_available():
+        raise MrError("no CUDA device: the MERLOT Reserve B200 path has no CPU fallback")
+    st = load().mr_check_device(device)
+    if st != 0:
+        raise MrError(f"device {device}: {load().mr_status_string(st).decode()}")
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise MrError("expected a CUDA tensor")
+    if not t.is_contiguous():
+        raise MrError("expected a contiguous tensor")
+    return t.data_ptr()
+
+
+def _call(name: str, desc, ins: Sequence[Optional[torch.Tensor]], outs: Sequence[Optional[torch.Tensor]],
+          workspace: Optional[torch.Tensor] = None) -> None:
+    lib = load()
+    in_arr = (C.c_void_p * len(ins))(*[_ptr(t) for t in ins])
+    out_arr = (C.c_void_p * len(outs))(*[_ptr(t) for t in outs])
+    stream = torch.cuda.current_stream().cuda_stream
+    ws_ptr = _ptr(workspace)
+    ws_bytes = workspace.numel() * workspace.element_size() if workspace is not None else 0
+    st = getattr(lib, name)(C.c_void_p(stream), C.byref(desc), in_arr, out_arr, C.c_void_p(ws_ptr), ws_bytes)
+    if st != 0:
+        raise MrError(f"{name} failed ({st}): {lib.mr_status_string(st).decode()}")
+
+
+# ------------------------------------------------------------------------------------------------
+# typed wrappers
+# ------------------------------------------------------------------------------------------------
+def gemm(a: torch.Tensor, w: torch.Tensor, *, bias=None, residual=None, rot=None, out=None, gelu=False,
+         out_f32=False, hidden=0, q_scale=1.0, seq_in=0, seq_out=0, row_off=0, out_rows=None, M=None, lda=None,
+         algo=ALGO_TCGEN05) -> torch.Tensor:
+    """D = epilogue(A @ W^T).  a: bf16 [M, K] (or strided rows via M / lda), w: bf16 [N, K]."""
+    assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16
+    N, K = w.shape
+    if M is None:
+        M = a.shape[0]
+    if lda is None:
+        lda = a.shape[-1]
+    rows = out_rows if out_rows is not None else M
+    if out is None:
+        out = torch.empty((rows, N), dtype=torch.float32 if out_f32 else torch.bfloat16, device=a.device)
+    epi = 0
+    if bias is not None:
+        epi |= EPI_BIAS
+    if gelu:
+        epi |= EPI_GELU
+    if residual is not None:
+        epi |= EPI_RESIDUAL
+    if rot is not None:
+        epi |= EPI_ROTARY_QKV
+    if out.dtype == torch.float32:
+        epi |= EPI_OUT_F32
+    d = GemmDesc(M=M, N=N, K=K, lda=lda, ldd=out.shape[-1], epilogue=epi, seq_in=seq_in, seq_out=seq_out,
+                 row_off=row_off, rot_rows=(rot.shape[0] if rot is not None else 0), hidden=hidden, algo=algo,
+                 q_scale=q_scale, num_sms=0)
+    _call("mr_gemm_epilogue", d, [a, w, bias, residual, rot], [out])
+    return out
+
+
+def attention(qkv: torch.Tensor, B: int, T: int, H: int, valid=None, group=None, out=None) -> torch.Tensor:
+    if out is None:
+        out = torch.empty((B * T, H), dtype=torch.bfloat16, device=qkv.device)
+    _call("mr_attention_fwd", AttentionDesc(B=B, T=T, H=H), [qkv, valid, group], [out])
+    return out
+
+
+def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, rows=None, H=None, ldx=None, seq_in=0,
+              seq_out=0, row_off=0, eps=1e-5, out=None) -> torch.Tensor:
+    H = H or x.shape[-1]
+    rows = rows if rows is not None else x.numel() // H
+    ldx = ldx or H
+    if out is None:
+        out = torch.empty((rows, H), dtype=torch.bfloat16, device=x.device)
+    d = LayerNormDesc(rows=rows, H=H, ldx=ldx, seq_in=seq_in, seq_out=seq_out, row_off=row_off, eps=eps)
+    _call("mr_layernorm_fwd", d, [x, gamma, beta], [out])
+    return out
+
+
+def cast_pad(x: torch.Tensor, rows: int, cols: int, ld_out: int, out=None) -> torch.Tensor:
+    assert x.dtype == torch.float32
+    if out is None:
+        out = torch.empty((rows, ld_out), dtype=torch.bfloat16, device=x.device)
+    _call("mr_cast_pad", CastDesc(rows=rows, cols=cols, ld_out=ld_out), [x], [out])
+    return out
+
+
+def fill_cls(x: torch.Tensor, cls: torch.Tensor, B: int, T: int, H: int) -> None:
+    _call("mr_fill_cls", FillClsDesc(B=B, T=T, H=H), [cls], [x])
+
+
+def _window_desc(B, T, H, mode, win, n_win, grid_h=0, grid_w=0):
+    return WindowDesc(B=B, T=T, H=H, mode=mode, win=win, n_win=n_win, grid_h=grid_h, grid_w=grid_w)
+
+
+def window_mean(x, B, T, H, mode, win, n_win, grid_h=0, grid_w=0) -> torch.Tensor:
+    out = torch.empty((B * n_win, H), dtype=torch.bfloat16, device=x.device)
+    _call("mr_window_mean", _window_desc(B, T, H, mode, win, n_win, grid_h, grid_w), [x], [out])
+    return out
+
+
+def window_attention(q, kv, B, T, H, mode, win, n_win, grid_h=0, grid_w=0) -> torch.Tensor:
+    out = torch.empty((B * n_win, H), dtype=torch.bfloat16, device=q.device)
+    _call("mr_window_attention", _window_desc(B, T, H, mode, win, n_win, grid_h, grid_w), [q, kv], [out])
+    return out
+
+
+def embed_assemble(tokens, emb, *, H, seg_idx=None, aud_ptr=None, audio=None, vision=None, tok_emb=None, n_aud=0,
+                   n_vis=0, pool_h=0, pool_w=0, T=None, audio_token_length=6, cls_offset=0):
+    B, L = tokens.shape
+    T = T if T is not None else L + n_vis
+    dev = tokens.device
+    rows = B * (T + cls_offset)
+    x = torch.empty((rows, H), dtype=torch.bfloat16, device=dev)
+    rot = torch.empty((rows, 32), dtype=torch.float32, device=dev)
+    valid = torch.empty((rows,), dtype=torch.uint8, device=dev)
+    d = AssembleDesc(B=B, L=L, H=H, n_aud=n_aud, n_vis=n_vis, pool_h=pool_h, pool_w=pool_w, T=T,
+                     vocab=(emb.shape[0] if emb is not None else 1), audio_token_length=audio_token_length,
+                     cls_offset=cls_offset)
+    _call("mr_embed_assemble", d, [tokens, seg_idx, aud_ptr, emb, audio, vision, tok_emb], [x, rot, valid])
+    return x, rot, valid
+
+
+def rotary_table(coords: torch.Tensor) -> torch.Tensor:
+    rows, nd = coords.shape
+    out = torch.empty((rows, 32), dtype=torch.float32, device=coords.device)
+    _call("mr_rotary_table", RotaryDesc(rows=rows, ndims=nd), [coords], [out])
+    return out
+
+
+def unit_normalize(x: torch.Tensor, scale: float = 1.0, out_f32: bool = True) -> torch.Tensor:
+    rows, H = x.shape
+    out = torch.empty((rows, H), dtype=torch.float32 if out_f32 else torch.bfloat16, device=x.device)
+    d = NormalizeDesc(rows=rows, H=H, in_f32=int(x.dtype == torch.float32), out_f32=int(out_f32), scale=scale)
+    _call("mr_unit_normalize", d, [x], [out])
+    return out
+
+
+def segment_pool(do_pool: torch.Tensor, idx: torch.Tensor, v: torch.Tensor, S: int):
+    B, L, H = v.shape
+    pooled = torch.empty((B, S, H), dtype=torch.float32, device=v.device)
+    count = torch.empty((B, S), dtype=torch.float32, device=v.device)
+    d = SegmentPoolDesc(B=B, L=L, H=H, S=S, v_f32=int(v.dtype == torch.float32))
+    _call("mr_segment_pool", d, [do_pool, idx, v], [pooled, count])
+    return pooled, count
+
+
+def contrastive_lse(x: torch.Tensor, y_all: torch.Tensor, y_pos: torch.Tensor):
+    n, H = x.shape
+    d = ContrastiveDesc(n=n, n_all=y_all.shape[0], H=H)
+    nbytes = load().mr_contrastive_lse_fwd_workspace_bytes(C.byref(d))
+    ws = torch.empty((max(nbytes, 16),), dtype=torch.uint8, device=x.device)
+    lse = torch.empty((n,), dtype=torch.float32, device=x.device)
+    numer = torch.empty((n,), dtype=torch.float32, device=x.device)
+    _call("mr_contrastive_lse_fwd", d, [x, y_all, y_pos], [lse, numer], ws)
+    return lse, numer
+
+
+def row_dot(x: torch.Tensor, w: torch.Tensor, row_idx=None, rows=None) -> torch.Tensor:
+    H = x.shape[-1]
+    rows = rows if rows is not None else (row_idx.numel() if row_idx is not None else x.shape[0])
+    out = torch.empty((rows,), dtype=torch.float32, device=x.device)
+    _call("mr_row_dot", RowDotDesc(rows=rows, H=H), [x, w, row_idx], [out])
+    return out

@@ -1,0 +1,50 @@
+// Library-level entry points: device probe, status strings, launch accounting.
+#include "common.cuh"
+
+namespace mr {
+
+std::atomic<int64_t> g_launches{0};
+
+int device_sm_count() {
+  // cached per device; cudaGetDevice is cheap and keeps the library free of global mutable state
+  // beyond this read-only cache
+  static int cache[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 0;
+  if (cache[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+    cache[dev] = n;
+  }
+  return cache[dev];
+}
+
+}  // namespace mr
+
+extern "C" int32_t mr_abi_version(void) { return 1; }
+
+extern "C" int64_t mr_launch_count(void) { return mr::g_launches.load(std::memory_order_relaxed); }
+
+extern "C" int32_t mr_check_device(int32_t device) {
+  int major = 0, minor = 0;
+  cudaError_t e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device);
+  if (e != cudaSuccess) return mr::cuda_status(e);
+  e = cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, device);
+  if (e != cudaSuccess) return mr::cuda_status(e);
+  return major == 10 ? MR_OK : MR_ERR_UNSUPPORTED_ARCH;
+}
+
+extern "C" const char* mr_status_string(int32_t status) {
+  switch (status) {
+    case MR_OK: return "ok";
+    case MR_ERR_BAD_SHAPE: return "bad shape or unsupported argument combination";
+    case MR_ERR_MISALIGNED: return "pointer not 16-byte aligned";
+    case MR_ERR_UNSUPPORTED_ARCH: return "device is not sm_100 (B200)";
+    case MR_ERR_NULL_POINTER: return "required pointer is NULL";
+    case MR_ERR_WORKSPACE: return "workspace too small";
+    case MR_ERR_DRIVER: return "CUDA driver call failed (tensor map encode)";
+    default: break;
+  }
+  if (status <= MR_ERR_CUDA_BASE) return cudaGetErrorString(static_cast<cudaError_t>(MR_ERR_CUDA_BASE - status));
+  return "unknown status";
+}

@@ -1,0 +1,40 @@
+// Shared host-side plumbing for libmreserve_b200: status codes, launch accounting, argument checks.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+
+#include "../../include/mreserve_b200.h"
+
+namespace mr {
+
+using bf16 = __nv_bfloat16;
+
+extern std::atomic<int64_t> g_launches;
+
+inline int32_t cuda_status(cudaError_t e) {
+  return e == cudaSuccess ? MR_OK : (MR_ERR_CUDA_BASE - static_cast<int32_t>(e));
+}
+
+// Call right after a <<<>>> / cudaLaunchKernelEx: counts the launch and converts launch errors.
+inline int32_t after_launch() {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return cuda_status(cudaGetLastError());
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+int device_sm_count();
+
+}  // namespace mr
+
+#define MR_REQUIRE(cond, code) \
+  do {                         \
+    if (!(cond)) return (code); \
+  } while (0)

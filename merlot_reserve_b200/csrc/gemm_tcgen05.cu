@@ -1,0 +1,479 @@
+// mr_gemm_epilogue: D = epilogue(A . W^T) on the sm_100a tensor cores.
+//
+// Persistent, warp-specialised kernel (one CTA per SM):
+//   warp 0      TMA producer   : cp.async.bulk.tensor (128B swizzle) of A[128 x 64] and W[BN x 64] tiles
+//                                into a kStages-deep shared-memory ring, signalled through mbarriers
+//   warp 1      MMA issuer     : one thread issues tcgen05.mma (128 x BN x 16, bf16 -> fp32) with the
+//                                accumulator in TMEM; tcgen05.commit releases ring slots / publishes tiles
+//   warp 2      TMEM allocator
+//   warps 4..11 epilogue       : tcgen05.ld the accumulator (double buffered in TMEM, so the epilogue of
+//                                tile i overlaps the main loop of tile i+1), apply
+//                                bias / rotary scale / sigmoid-GELU / residual, cast and store.
+//
+// The arithmetic this replaces is flax Dense/DenseGeneral (+ the elementwise ops around it) at the
+// reference call sites listed in include/mreserve_b200.h.
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace mr {
+
+namespace {
+
+constexpr int kBM = 128;
+constexpr int kBK = 64;  // 64 bf16 = 128 bytes = one swizzle-128B row
+constexpr int kUmmaK = 16;
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = 128 + kEpiWarps * 32;
+
+struct GemmParams {
+  int M, N, K;
+  int ldd;
+  int bias_on, out_f32;
+  int seq_in, seq_out, row_off;
+  int rot_rows, hidden;
+  float q_scale;
+  const float* bias;
+  const bf16* residual;
+  const float* rot;
+  void* D;
+  int num_n_tiles, num_tiles, num_k_blocks;
+};
+
+template <int BN>
+struct Cfg {
+  static constexpr int kStages = BN == 256 ? 4 : 6;
+  static constexpr int kABytes = kBM * kBK * 2;
+  static constexpr int kBBytes = BN * kBK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kTmemCols = 2 * BN;  // two accumulator stages
+  static constexpr int kBarBytes = 256;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 1024;  // +1024: manual alignment
+};
+
+__device__ __forceinline__ float gelu_sigmoid(float x) {
+  // x * sigmoid(1.702 x) = x / (1 + exp(-1.702 x)); exp via ex2.approx, reciprocal via rcp.approx.
+  float e = exp2f(-1.702f * 1.4426950408889634f * x);
+  return __fdividef(x, 1.0f + e);
+}
+
+__device__ __forceinline__ int map_row(int r, int seq_in, int seq_out, int row_off) {
+  return seq_in == 0 ? r : (r / seq_in) * seq_out + (r % seq_in) + row_off;
+}
+
+template <int BN, bool kGelu, bool kResidual, bool kRotary>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                    const GemmParams p) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes);
+  uint64_t* empty_bar = full_bar + C::kStages;
+  uint64_t* tmem_full_bar = empty_bar + C::kStages;
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp_idx = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp_idx == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+  }
+  if (warp_idx == 1 && lane == 0) {
+    for (int s = 0; s < C::kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full_bar[a], 1);
+      mbar_init(&tmem_empty_bar[a], kEpiWarps);
+    }
+    fence_mbar_init();
+  }
+  if (warp_idx == 2) {
+    tmem_alloc(tmem_slot, C::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp_idx == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const int m_blk = tile / p.num_n_tiles;
+        const int n_blk = tile % p.num_n_tiles;
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * C::kStageBytes;
+          uint8_t* sb = sa + C::kABytes;
+          mbar_arrive_expect_tx(&full_bar[stage], C::kStageBytes);
+          // activations are streamed once per N-sweep; weights are re-read by every M block
+          tma_load_2d(&tmap_a, &full_bar[stage], sa, kb * kBK, m_blk * kBM, kEvictNormal);
+          tma_load_2d(&tmap_b, &full_bar[stage], sb, kb * kBK, n_blk * BN, kEvictLast);
+          if (++stage == C::kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp_idx == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16_f32(kBM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * C::kStageBytes);
+          const uint32_t sb = sa + C::kABytes;
+          const uint64_t adesc = umma_desc_k_sw128(sa);
+          const uint64_t bdesc = umma_desc_k_sw128(sb);
+#pragma unroll
+          for (int k = 0; k < kBK / kUmmaK; ++k) {
+            // advancing 16 bf16 = 32 bytes along K inside the 128-byte swizzle row: +2 in 16-byte units
+            umma_bf16_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the ring slot once these MMAs have read it
+          if (++stage == C::kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tmem_full_bar[acc]);  // accumulator complete
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else if (warp_idx >= 4) {
+    // ===================== epilogue =====================
+    const int ew = warp_idx - 4;
+    const int quarter = warp_idx & 3;          // TMEM lane quarter this warp may access
+    const int col_half = ew >> 2;              // which half of the BN columns this warp owns
+    constexpr int kChunks = BN / 64;           // 32-column chunks per warp
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const int m_blk = tile / p.num_n_tiles;
+      const int n_blk = tile % p.num_n_tiles;
+      const int r = m_blk * kBM + quarter * 32 + lane;
+      const bool row_ok = r < p.M;
+      const int out_row = map_row(r, p.seq_in, p.seq_out, p.row_off);
+      const int col_base = n_blk * BN + col_half * (BN / 2);
+
+      // Issue the global loads this row needs BEFORE waiting for the accumulator.
+      uint4 res[kResidual ? kChunks : 1][4];
+      if constexpr (kResidual) {
+#pragma unroll
+        for (int c = 0; c < kChunks; ++c) {
+          const int col0 = col_base + c * 32;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) res[c][j] = make_uint4(0, 0, 0, 0);
+          if (row_ok && col0 + 32 <= p.N) {
+            const uint4* src = reinterpret_cast<const uint4*>(p.residual + static_cast<size_t>(out_row) * p.ldd + col0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) res[c][j] = __ldg(src + j);
+          }
+        }
+      }
+      float rot[kRotary ? 32 : 1];
+      if constexpr (kRotary) {
+        const float4* src = reinterpret_cast<const float4*>(p.rot + static_cast<size_t>(row_ok ? (r % p.rot_rows) : 0) * 32);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float4 t = __ldg(src + j);
+          rot[4 * j + 0] = t.x;
+          rot[4 * j + 1] = t.y;
+          rot[4 * j + 2] = t.z;
+          rot[4 * j + 3] = t.w;
+        }
+      }
+
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tc_fence_after();
+
+#pragma unroll
+      for (int c = 0; c < kChunks; ++c) {
+        uint32_t v[32];
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
+                               static_cast<uint32_t>(acc * BN + col_half * (BN / 2) + c * 32);
+        tmem_ld_32x32(taddr, v);
+        tmem_ld_wait();
+        if (c == kChunks - 1) {
+          // all TMEM reads of this accumulator stage are done: hand it back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+        }
+        const int col0 = col_base + c * 32;
+        if (!row_ok || col0 >= p.N) continue;
+
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+        const bool full_chunk = col0 + 32 <= p.N;
+        if (p.bias_on) {
+          if (full_chunk) {
+            const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float4 t = __ldg(b4 + j);
+              f[4 * j + 0] += t.x;
+              f[4 * j + 1] += t.y;
+              f[4 * j + 2] += t.z;
+              f[4 * j + 3] += t.w;
+            }
+          } else {
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N) f[j] += __ldg(p.bias + col0 + j);
+          }
+        }
+        if constexpr (kRotary) {
+          // columns: [q heads | k heads | v heads]; first 32 dims of every q/k head are scaled
+          if (col0 < 2 * p.hidden && (col0 & 63) == 0) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] *= rot[j];
+          }
+          if (col0 < p.hidden) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] *= p.q_scale;
+          }
+        }
+        if constexpr (kGelu) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = gelu_sigmoid(f[j]);
+        }
+        if constexpr (kResidual) {
+          if (full_chunk) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint32_t w[4] = {res[c][j].x, res[c][j].y, res[c][j].z, res[c][j].w};
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                f[8 * j + 2 * q + 0] += bf16_lo(w[q]);
+                f[8 * j + 2 * q + 1] += bf16_hi(w[q]);
+              }
+            }
+          } else {
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N)
+                f[j] += __bfloat162float(p.residual[static_cast<size_t>(out_row) * p.ldd + col0 + j]);
+          }
+        }
+        if (p.out_f32) {
+          float* dst = reinterpret_cast<float*>(p.D) + static_cast<size_t>(out_row) * p.ldd + col0;
+          if (full_chunk) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              reinterpret_cast<float4*>(dst)[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+          } else {
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N) dst[j] = f[j];
+          }
+        } else {
+          bf16* dst = reinterpret_cast<bf16*>(p.D) + static_cast<size_t>(out_row) * p.ldd + col0;
+          if (full_chunk) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 o;
+              o.x = pack_bf16(f[8 * j + 0], f[8 * j + 1]);
+              o.y = pack_bf16(f[8 * j + 2], f[8 * j + 3]);
+              o.z = pack_bf16(f[8 * j + 4], f[8 * j + 5]);
+              o.w = pack_bf16(f[8 * j + 6], f[8 * j + 7]);
+              reinterpret_cast<uint4*>(dst)[j] = o;
+            }
+          } else {
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N) dst[j] = __float2bfloat16(f[j]);
+          }
+        }
+      }
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp_idx == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Slow CUDA-core kernel with the same epilogue contract, kept ONLY to bisect the tensor-core
+// path in tests (MR_GEMM_ALGO_SIMT_DEBUG).  One thread per output element.
+// ------------------------------------------------------------------------------------------
+__global__ void gemm_simt_debug_kernel(const bf16* __restrict__ A, int lda, const bf16* __restrict__ W,
+                                       GemmParams p, int gelu, int residual, int rotary) {
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<int64_t>(p.M) * p.N) return;
+  const int r = static_cast<int>(idx / p.N);
+  const int c = static_cast<int>(idx % p.N);
+  float acc = 0.f;
+  const bf16* a = A + static_cast<size_t>(r) * lda;
+  const bf16* w = W + static_cast<size_t>(c) * p.K;
+  for (int k = 0; k < p.K; ++k) acc += __bfloat162float(a[k]) * __bfloat162float(w[k]);
+  if (p.bias_on) acc += p.bias[c];
+  if (rotary) {
+    if (c < 2 * p.hidden && (c & 63) < 32) acc *= p.rot[static_cast<size_t>(r % p.rot_rows) * 32 + (c & 63)];
+    if (c < p.hidden) acc *= p.q_scale;
+  }
+  if (gelu) acc = acc / (1.0f + expf(-1.702f * acc));
+  const int out_row = map_row(r, p.seq_in, p.seq_out, p.row_off);
+  const size_t o = static_cast<size_t>(out_row) * p.ldd + c;
+  if (residual) acc += __bfloat162float(p.residual[o]);
+  if (p.out_f32)
+    reinterpret_cast<float*>(p.D)[o] = acc;
+  else
+    reinterpret_cast<bf16*>(p.D)[o] = __float2bfloat16(acc);
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = []() -> EncodeTiledFn {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess) return nullptr;
+    if (q != cudaDriverEntryPointSuccess) return nullptr;
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+
+// 2-D bf16 tensor [rows, cols] with row pitch `ld` elements; box = [box_rows, 64 cols], 128B swizzle.
+bool make_tmap_2d(CUtensorMap* m, const void* base, int rows, int cols, int ld, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return false;
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(kBK), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+template <int BN, bool G, bool R, bool Q>
+int32_t launch_one(cudaStream_t stream, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int grid) {
+  auto kern = gemm_tcgen05_kernel<BN, G, R, Q>;
+  static bool attr_set = false;  // benign race: the attribute is idempotent
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::kSmemBytes);
+    if (e != cudaSuccess) return cuda_status(e);
+    attr_set = true;
+  }
+  kern<<<grid, kThreads, Cfg<BN>::kSmemBytes, stream>>>(ta, tb, p);
+  return after_launch();
+}
+
+template <int BN>
+int32_t launch_bn(cudaStream_t stream, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int grid,
+                  bool gelu, bool residual, bool rotary) {
+  if (rotary && !gelu && !residual) return launch_one<BN, false, false, true>(stream, ta, tb, p, grid);
+  if (gelu && !residual && !rotary) return launch_one<BN, true, false, false>(stream, ta, tb, p, grid);
+  if (residual && !gelu && !rotary) return launch_one<BN, false, true, false>(stream, ta, tb, p, grid);
+  if (!gelu && !residual && !rotary) return launch_one<BN, false, false, false>(stream, ta, tb, p, grid);
+  if (gelu && residual && !rotary) return launch_one<BN, true, true, false>(stream, ta, tb, p, grid);
+  return MR_ERR_BAD_SHAPE;  // rotary never combines with gelu/residual on this path
+}
+
+}  // namespace
+
+}  // namespace mr
+
+extern "C" size_t mr_gemm_epilogue_workspace_bytes(const MrGemmDesc*) { return 0; }
+
+extern "C" int32_t mr_gemm_epilogue(mr_stream_t stream_, const MrGemmDesc* d, const void* const* in,
+                                    void* const* out, void*, size_t) {
+  using namespace mr;
+  MR_REQUIRE(d && in && out, MR_ERR_NULL_POINTER);
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const bf16* A = static_cast<const bf16*>(in[0]);
+  const bf16* W = static_cast<const bf16*>(in[1]);
+  MR_REQUIRE(A && W && out[0], MR_ERR_NULL_POINTER);
+  MR_REQUIRE(d->M >= 0 && d->N > 0 && d->K > 0, MR_ERR_BAD_SHAPE);
+  if (d->M == 0) return MR_OK;
+  MR_REQUIRE(d->K % 8 == 0 && d->lda % 8 == 0 && d->lda >= d->K, MR_ERR_BAD_SHAPE);
+  MR_REQUIRE(d->N % 8 == 0 && d->ldd % 8 == 0 && d->ldd >= d->N, MR_ERR_BAD_SHAPE);
+  MR_REQUIRE(aligned16(A) && aligned16(W) && aligned16(out[0]), MR_ERR_MISALIGNED);
+  const bool bias = d->epilogue & MR_EPI_BIAS, gelu = d->epilogue & MR_EPI_GELU;
+  const bool residual = d->epilogue & MR_EPI_RESIDUAL, rotary = d->epilogue & MR_EPI_ROTARY_QKV;
+  if (bias) MR_REQUIRE(in[2] && aligned16(in[2]), in[2] ? MR_ERR_MISALIGNED : MR_ERR_NULL_POINTER);
+  if (residual) MR_REQUIRE(in[3] && aligned16(in[3]), in[3] ? MR_ERR_MISALIGNED : MR_ERR_NULL_POINTER);
+  if (rotary) {
+    MR_REQUIRE(in[4] && aligned16(in[4]), in[4] ? MR_ERR_MISALIGNED : MR_ERR_NULL_POINTER);
+    MR_REQUIRE(d->rot_rows > 0 && d->hidden > 0 && d->hidden % 64 == 0 && d->N == 3 * d->hidden, MR_ERR_BAD_SHAPE);
+  }
+  if (d->seq_in != 0) MR_REQUIRE(d->seq_in > 0 && d->seq_out >= d->seq_in + d->row_off && d->row_off >= 0, MR_ERR_BAD_SHAPE);
+
+  GemmParams p{};
+  p.M = d->M;
+  p.N = d->N;
+  p.K = d->K;
+  p.ldd = d->ldd;
+  p.bias_on = bias;
+  p.out_f32 = (d->epilogue & MR_EPI_OUT_F32) ? 1 : 0;
+  p.seq_in = d->seq_in;
+  p.seq_out = d->seq_out;
+  p.row_off = d->row_off;
+  p.rot_rows = d->rot_rows > 0 ? d->rot_rows : 1;
+  p.hidden = d->hidden;
+  p.q_scale = d->q_scale;
+  p.bias = static_cast<const float*>(in[2]);
+  p.residual = static_cast<const bf16*>(in[3]);
+  p.rot = static_cast<const float*>(in[4]);
+  p.D = out[0];
+
+  if (d->algo == MR_GEMM_ALGO_SIMT_DEBUG) {
+    const int64_t total = static_cast<int64_t>(d->M) * d->N;
+    const int threads = 256;
+    gemm_simt_debug_kernel<<<static_cast<unsigned>(ceil_div64(total, threads)), threads, 0, stream>>>(
+        A, d->lda, W, p, gelu, residual, rotary);
+    return after_launch();
+  }
+  MR_REQUIRE(d->algo == MR_GEMM_ALGO_TCGEN05, MR_ERR_BAD_SHAPE);
+
+  // Tile width: 256 columns normally; 128 when that leaves SMs idle on a single wave.
+  int sms = d->num_sms > 0 ? d->num_sms : device_sm_count();
+  MR_REQUIRE(sms > 0, MR_ERR_UNSUPPORTED_ARCH);
+  const int m_tiles = ceil_div(d->M, kBM);
+  int bn = 256;
+  if (d->N % 256 != 0 || static_cast<int64_t>(m_tiles) * ceil_div(d->N, 256) < sms) bn = 128;
+  p.num_n_tiles = ceil_div(d->N, bn);
+  p.num_tiles = m_tiles * p.num_n_tiles;
+  p.num_k_blocks = ceil_div(d->K, kBK);
+  const int grid = p.num_tiles < sms ? p.num_tiles : sms;
+
+  CUtensorMap ta, tb;
+  MR_REQUIRE(make_tmap_2d(&ta, A, d->M, d->K, d->lda, kBM), MR_ERR_DRIVER);
+  MR_REQUIRE(make_tmap_2d(&tb, W, d->N, d->K, d->K, bn), MR_ERR_DRIVER);
+  if (bn == 256) return launch_bn<256>(stream, ta, tb, p, grid, gelu, residual, rotary);
+  return launch_bn<128>(stream, ta, tb, p, grid, gelu, residual, rotary);
+}

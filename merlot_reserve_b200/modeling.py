@@ -1,0 +1,610 @@
+"""B200-native drop-in for the encoder + contrastive path of `mreserve/modeling.py`.
+
+Same public surface as the reference module: `MerlotReserve.from_config(config)`, the zero-shot methods
+(`embed_video`, `batch_embed_video`, `embed_text_spans_only`, `embed_audio_only`, `get_imgseq_only`,
+`get_audioseq_only`, `embed_singleimg_with_multiimg_prompt`, `embed_preencoded_noaudio`,
+`embed_preencoded_audio`, `prepare_multimodal_inputs`), the flax-style `model.apply({'params': p}, *args,
+method=model.<name>)` call, and `PretrainedMerlotReserve` (`encoder`, `params`, `model`, attribute access
+returning the method bound to the params, `get_label_space`).  Three names required by the project brief
+that the reference snapshot lacks are defined per SURVEY.md §8(b): `get_imgs_enc`, `get_audio_enc`,
+`embed_singleimg_with_multiple_text`.
+
+Parameters are the reference's flax pytree (nested dicts of fp32 arrays, names per SURVEY.md §8b); they
+are packed once per tree into bf16 GEMM-ready device buffers.  All arithmetic runs in hand-written
+sm_100a kernels behind the C ABI of `include/mreserve_b200.h`; torch only owns memory and streams.
+Inputs may be numpy arrays (results come back as numpy) or torch tensors (results are CUDA tensors).
+"""
+from __future__ import annotations
+
+import math
+from copy import deepcopy
+from dataclasses import dataclass
+from functools import partial
+from typing import Any, Dict, Optional
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+PADDING, START, END, MASK, MASKAUDIO, AUDIOSPAN, LTOVPOOL = 0, 1, 2, 3, 4, 5, 6
+_AUDIO_K_PAD = 192  # 2 * 65 = 130 input features, zero padded to a multiple of the 64-wide K block
+
+
+# ------------------------------------------------------------------------------------------------
+# host-side coordinate helpers (trace-time constants in the reference: modeling.py:21-50)
+# ------------------------------------------------------------------------------------------------
+def get_rotary_coordinates(seq_len: int, center_origin: bool = True) -> np.ndarray:
+    if not center_origin:
+        return 1.0 + np.arange(seq_len, dtype=np.float32)
+    half = seq_len // 2
+    return np.concatenate([np.arange(half, dtype=np.float32) - float(half),
+                           1.0 + np.arange(seq_len - half, dtype=np.float32)], 0)
+
+
+def get_rotary_coordinates_2d(h: int, w: int) -> np.ndarray:
+    scale = np.float32(1.0 / (max(h, w) + 1.0))
+    hc = scale * get_rotary_coordinates(h)
+    wc = scale * get_rotary_coordinates(w)
+    return np.stack(np.meshgrid(hc, wc, indexing="ij"), -1).reshape(h * w, 2).astype(np.float32)
+
+
+def _dev(x, dtype=None, device="cuda"):
+    """numpy / torch (any device) -> contiguous CUDA tensor."""
+    if isinstance(x, torch.Tensor):
+        t = x
+    else:
+        t = torch.from_numpy(np.ascontiguousarray(x))
+    if dtype is not None and t.dtype != dtype:
+        t = t.to(dtype)
+    if not t.is_cuda:
+        t = t.to(device, non_blocking=True)
+    return t.contiguous()
+
+
+def _is_np(*xs) -> bool:
+    return all(not isinstance(x, torch.Tensor) for x in xs)
+
+
+def _ret(t: torch.Tensor, as_numpy: bool):
+    return t.cpu().numpy() if as_numpy else t
+
+
+# ------------------------------------------------------------------------------------------------
+# weight packing: flax tree (fp32, [in, out] kernels) -> device, bf16, [out, in] (K-major) kernels
+# ------------------------------------------------------------------------------------------------
+def _w(kernel, in_features: int, k_pad: Optional[int] = None) -> torch.Tensor:
+    k = torch.as_tensor(np.asarray(kernel), dtype=torch.float32).reshape(in_features, -1)
+    wt = k.t().contiguous()
+    if k_pad is not None and k_pad > in_features:
+        wt = torch.nn.functional.pad(wt, (0, k_pad - in_features))
+    return wt.to(torch.bfloat16).cuda().contiguous()
+
+
+def _f(x) -> torch.Tensor:
+    return torch.as_tensor(np.asarray(x), dtype=torch.float32).reshape(-1).cuda().contiguous()
+
+
+class _PackedEncoder:
+    def __init__(self, p: Dict, H: int, num_layers: int, add_cls: bool):
+        self.H, self.num_layers, self.add_cls = H, num_layers, add_cls
+        self.pre_ln = (_f(p["pre_ln"]["scale"]), _f(p["pre_ln"]["bias"]))
+        self.final_ln = (_f(p["final_ln"]["scale"]), _f(p["final_ln"]["bias"]))
+        if add_cls:
+            self.cls = _f(p["cls"])
+            self.cls_proj = (_w(p["cls_proj"]["kernel"], H), _f(p["cls_proj"]["bias"]))
+        self.layers = []
+        for i in range(num_layers):
+            lp = p[f"layer_{i:02d}"]
+            a, m = lp["attention_layer"], lp["mlp_layer"]
+            self.layers.append(dict(
+                ln1=(_f(lp["pre_attn_ln"]["scale"]), _f(lp["pre_attn_ln"]["bias"])),
+                wqkv=_w(a["qkv"]["kernel"], H), bqkv=_f(a["qkv"]["bias"]),
+                wo=_w(a["attn_proj"]["kernel"], H),
+                ln2=(_f(lp["pre_mlp_ln"]["scale"]), _f(lp["pre_mlp_ln"]["bias"])),
+                w1=_w(m["intermediate"]["kernel"], H), b1=_f(m["intermediate"]["bias"]),
+                w2=_w(m["out"]["kernel"], 4 * H),
+            ))
+
+
+class _PackedPool:
+    def __init__(self, p: Dict, H: int):
+        self.wq, self.bq = _w(p["query"]["kernel"], H), _f(p["query"]["bias"])
+        self.wkv = torch.cat([_w(p["key"]["kernel"], H), _w(p["value"]["kernel"], H)], 0).contiguous()
+        self.bkv = torch.cat([_f(p["key"]["bias"]), _f(p["value"]["bias"])], 0).contiguous()
+        self.wo, self.bo = _w(p["out"]["kernel"], H), _f(p["out"]["bias"])
+
+
+class _Packed:
+    """Device-resident weights of one parameter tree."""
+
+    def __init__(self, params: Dict, cfg: Dict):
+        H = cfg["hidden_size"]
+        self.H = H
+        if "vision_encoder" in params:
+            v = params["vision_encoder"]
+            self.vis_emb = (_w(v["embedding"]["kernel"], (cfg["vit_patch_size"] ** 2) * 3), _f(v["embedding"]["bias"]))
+            self.vis = _PackedEncoder(v["transformer"], H, cfg["vit_num_layers"], True)
+            self.vis_pool = _PackedPool(v["seq_attnpool"], H)
+        if "audio_encoder" in params:
+            a = params["audio_encoder"]
+            kin = cfg["audio_patch_size"] * 65
+            self.aud_emb = (_w(a["embedding"]["kernel"], kin, _AUDIO_K_PAD), _f(a["embedding"]["bias"]))
+            self.aud = _PackedEncoder(a["transformer"], H, cfg["audio_num_layers"], True)
+            self.aud_pool = _PackedPool(a["seq_attnpool"], H)
+        if "span_encoder" in params:
+            self.span = _PackedEncoder(params["span_encoder"]["transformer"], H, cfg["span_num_layers"], True)
+        self.joint = _PackedEncoder(params["joint_transformer"], H, cfg["joint_num_layers"], False)
+        self.tok_emb = torch.as_tensor(np.asarray(params["token_encoder"]["Embed_0"]["embedding"]),
+                                       dtype=torch.float32).to(torch.bfloat16).cuda().contiguous()
+        if "head" in params:
+            self.head = (_w(params["head"]["kernel"], H), _f(params["head"]["bias"]))
+        if "proj" in params:  # finetune heads (finetune/vcr/qa_qar_joint_finetune.py:147)
+            self.proj = _f(params["proj"]["kernel"])
+        self.contrastive_scales = np.asarray(params.get("contrastive_scales", np.zeros(3)), dtype=np.float32)
+
+
+# ------------------------------------------------------------------------------------------------
+# the model
+# ------------------------------------------------------------------------------------------------
+class MerlotReserve:
+    """Mirror of `mreserve.modeling.MerlotReserve` (modeling.py:581-931) on B200 kernels."""
+
+    def __init__(self, config: Dict):
+        self.config = config
+        for k, v in config.items():  # the reference setattr()s every model key (modeling.py:591-592)
+            if not hasattr(type(self), k):
+                setattr(self, k, v)
+        self.use_bfloat16 = True  # the kernels compute in bf16 with fp32 accumulation
+        self.output_grid_h, self.output_grid_w = config["output_grid"]
+        self.size_per_head = config.get("size_per_head", 64)
+        if self.size_per_head != 64 or config["hidden_size"] % 64:
+            raise ValueError("the B200 kernels require size_per_head == 64")
+        self.hidden_size = config["hidden_size"]
+        self.audio_pooling_ratio = config["audio_seq_length"] // (config["audio_token_length"] * config["audio_patch_size"])
+        self._packed_cache: Dict[int, _Packed] = {}
+        self._bound: Optional[_Packed] = None
+        self._tables: Dict[Any, torch.Tensor] = {}
+
+    @classmethod
+    def from_config(cls, config, **kwargs):
+        """modeling.py:584-588."""
+        my = deepcopy(config)
+        my["model"]["data"] = my.get("data", {})
+        return cls(config=my["model"], **kwargs)
+
+    # --- flax-style entry: model.apply({'params': p}, *args, method=model.embed_video) ---
+    def apply(self, variables: Dict, *args, method=None, **kwargs):
+        params = variables["params"] if "params" in variables else variables
+        self.bind(params)
+        fn = method if method is not None else self.__call__
+        if isinstance(fn, str):
+            fn = getattr(self, fn)
+        return fn(*args, **kwargs)
+
+    def bind(self, params: Dict) -> "MerlotReserve":
+        """Packs (once per tree) and selects the parameters used by subsequent method calls."""
+        L.require_b200(torch.cuda.current_device() if torch.cuda.is_available() else 0)
+        key = id(params)
+        if key not in self._packed_cache:
+            self._packed_cache[key] = _Packed(params, self.config)
+            self._packed_cache[key]._keepalive = params
+        self._bound = self._packed_cache[key]
+        return self
+
+    def init_params(self, seed: int = 0, weight_scale: float = 1.0) -> Dict:
+        """Random-init parameters of this architecture (the reference's `init_from_dummy_batch`,
+        modeling.py:636-649, needs JAX PRNG; the distribution here follows SURVEY.md §8d)."""
+        from .synthetic import synthetic_params
+        return synthetic_params({"model": self.config, "data": self.config.get("data", {})}, seed, weight_scale)
+
+    @property
+    def _p(self) -> _Packed:
+        if self._bound is None:
+            raise L.MrError("no parameters bound: call model.apply({'params': p}, ...) or model.bind(p)")
+        return self._bound
+
+    # --------------------------------------------------------------------------------------------
+    # static rotary scale tables (vision / audio / span), built once on the device
+    # --------------------------------------------------------------------------------------------
+    def _table(self, kind: str) -> torch.Tensor:
+        key = (kind, self.output_grid_h, self.output_grid_w)
+        if key not in self._tables:
+            if kind == "vision":
+                c = get_rotary_coordinates_2d(self.output_grid_h, self.output_grid_w)
+            elif kind == "audio":
+                n = self.config["audio_seq_length"] // self.config["audio_patch_size"]
+                c = (get_rotary_coordinates(n) / np.float32(n))[:, None]
+            elif kind == "span":
+                n = self.config["text_span_length"]
+                c = (get_rotary_coordinates(n, center_origin=False) / np.float32(16.0))[:, None]
+            else:
+                raise KeyError(kind)
+            c = np.concatenate([np.zeros((1, c.shape[1]), np.float32), c.astype(np.float32)], 0)  # CLS row
+            self._tables[key] = L.rotary_table(_dev(c, torch.float32))
+        return self._tables[key]
+
+    # --------------------------------------------------------------------------------------------
+    # transformer encoder: modeling.py:283-376 on the residual stream x [B*T, H] (bf16)
+    # --------------------------------------------------------------------------------------------
+    def _encoder(self, x: torch.Tensor, enc: _PackedEncoder, B: int, T: int, rot: torch.Tensor,
+                 valid: Optional[torch.Tensor] = None, group: Optional[torch.Tensor] = None) -> torch.Tensor:
+        H, M = enc.H, B * T
+        dev = x.device
+        x = L.layernorm(x, *enc.pre_ln)
+        h = torch.empty((M, H), dtype=torch.bfloat16, device=dev)
+        qkv = torch.empty((M, 3 * H), dtype=torch.bfloat16, device=dev)
+        ctx = torch.empty((M, H), dtype=torch.bfloat16, device=dev)
+        u = torch.empty((M, 4 * H), dtype=torch.bfloat16, device=dev)
+        for lw in enc.layers:
+            L.layernorm(x, *lw["ln1"], out=h)
+            L.gemm(h, lw["wqkv"], bias=lw["bqkv"], rot=rot, hidden=H, q_scale=0.125, out=qkv)
+            L.attention(qkv, B, T, H, valid=valid, group=group, out=ctx)
+            L.gemm(ctx, lw["wo"], residual=x, out=x)
+            L.layernorm(x, *lw["ln2"], out=h)
+            L.gemm(h, lw["w1"], bias=lw["b1"], gelu=True, out=u)
+            L.gemm(u, lw["w2"], residual=x, out=x)
+        return x  # before final_ln
+
+    def _pool(self, xf: torch.Tensor, pool: _PackedPool, B: int, T: int, mode: int, win: int, n_win: int,
+              gh: int = 0, gw: int = 0) -> torch.Tensor:
+        """Attention pool (flax MultiHeadDotProductAttention with one mean query per window)."""
+        H = self.hidden_size
+        q_in = L.window_mean(xf, B, T, H, mode, win, n_win, gh, gw)
+        q = L.gemm(q_in, pool.wq, bias=pool.bq)
+        kv = L.gemm(xf, pool.wkv, bias=pool.bkv)
+        ctx = L.window_attention(q, kv, B, T, H, mode, win, n_win, gh, gw)
+        return L.gemm(ctx, pool.wo, bias=pool.bo)
+
+    def _cls_out(self, xf: torch.Tensor, enc: _PackedEncoder, B: int, T: int, out_f32=False) -> torch.Tensor:
+        """cls_proj on row 0 of every sequence (modeling.py:370-372): strided A operand, no gather."""
+        return L.gemm(xf, enc.cls_proj[0], bias=enc.cls_proj[1], M=B, lda=T * enc.H, out_f32=out_f32)
+
+    # --- VisionTransformer.__call__ (modeling.py:391-430) ---
+    def _vision(self, images: torch.Tensor, want_cls: bool = False) -> Dict[str, torch.Tensor]:
+        p, H = self._p, self.hidden_size
+        gh, gw, r = self.output_grid_h, self.output_grid_w, self.config["vit_pooling_ratio"]
+        B, hw, pp3 = images.shape
+        if hw != gh * gw or pp3 != (self.config["vit_patch_size"] ** 2) * 3:
+            raise ValueError(f"images must be [*, {gh * gw}, {(self.config['vit_patch_size'] ** 2) * 3}], got {tuple(images.shape)}")
+        if r != 2:
+            raise ValueError("vit_pooling_ratio must be 2")
+        T = hw + 1
+        a = L.cast_pad(images.reshape(B * hw, pp3), B * hw, pp3, pp3)
+        x = torch.empty((B * T, H), dtype=torch.bfloat16, device=images.device)
+        L.gemm(a, p.vis_emb[0], bias=p.vis_emb[1], out=x, seq_in=hw, seq_out=T, row_off=1)
+        L.fill_cls(x, p.vis.cls, B, T, H)
+        x = self._encoder(x, p.vis, B, T, self._table("vision"))
+        xf = L.layernorm(x, *p.vis.final_ln)
+        out = {"seq_attnpool": self._pool(xf, p.vis_pool, B, T, 1, 4, (gh // 2) * (gw // 2), gh, gw)
+               .view(B, (gh // 2) * (gw // 2), H), "_xf": xf}
+        if want_cls:
+            out["cls"] = self._cls_out(xf, p.vis, B, T)
+        return out
+
+    # --- AudioTransformer.__call__ (modeling.py:443-476) ---
+    def _audio(self, audio: torch.Tensor, want_cls: bool = False) -> Dict[str, torch.Tensor]:
+        p, H = self._p, self.hidden_size
+        B, raw_len, nm = audio.shape
+        ps = self.config["audio_patch_size"]
+        if nm != 65 or raw_len % ps:
+            raise ValueError(f"audio_clips must be [*, L, 65] with L % {ps} == 0")
+        n = raw_len // ps
+        T = n + 1
+        a = L.cast_pad(audio.reshape(B * n, ps * nm), B * n, ps * nm, _AUDIO_K_PAD)
+        x = torch.empty((B * T, H), dtype=torch.bfloat16, device=audio.device)
+        L.gemm(a, p.aud_emb[0], bias=p.aud_emb[1], out=x, seq_in=n, seq_out=T, row_off=1)
+        L.fill_cls(x, p.aud.cls, B, T, H)
+        x = self._encoder(x, p.aud, B, T, self._table("audio"))
+        xf = L.layernorm(x, *p.aud.final_ln)
+        r = self.audio_pooling_ratio
+        out = {"seq_attnpool": self._pool(xf, p.aud_pool, B, T, 0, r, n // r).view(B, n // r, H)}
+        if want_cls:
+            out["cls"] = self._cls_out(xf, p.aud, B, T)
+        return out
+
+    # --- SpanTransformer.__call__ (modeling.py:488-504) on token ids ---
+    def _span(self, text_spans: torch.Tensor, out_f32: bool = True) -> torch.Tensor:
+        p, H = self._p, self.hidden_size
+        B, n = text_spans.shape
+        if n != self.config["text_span_length"]:
+            raise ValueError(f"text_spans must be [B, {self.config['text_span_length']}]")
+        T = n + 1
+        x, _, valid = L.embed_assemble(text_spans, p.tok_emb, H=H, cls_offset=1)
+        L.fill_cls(x, p.span.cls, B, T, H)
+        x = self._encoder(x, p.span, B, T, self._table("span"), valid=valid)
+        cls_ln = L.layernorm(x, *p.span.final_ln, rows=B, seq_in=T, seq_out=1, row_off=0)
+        return L.gemm(cls_ln, p.span.cls_proj[0], bias=p.span.cls_proj[1], out_f32=out_f32)
+
+    # --- joint encoder on assembled inputs ---
+    def _joint(self, x, rot, valid, B: int, T: int, n_keep: int, group=None) -> torch.Tensor:
+        """joint_transformer + final_ln restricted to the first n_keep rows of every sequence -> [B*n_keep, H]."""
+        p = self._p
+        x = self._encoder(x, p.joint, B, T, rot, valid=valid, group=group)
+        return L.layernorm(x, *p.joint.final_ln, rows=B * n_keep, seq_in=T, seq_out=n_keep, row_off=0)
+
+    def _joint_embed(self, tokens, seg_idx, *, vision=None, audio=None, aud_ptr=None) -> torch.Tensor:
+        """prepare_multimodal_inputs -> joint_transformer -> head -> unit_normalize: [B, L, H] fp32
+        (the tail of every embed_* method, modeling.py:834-843)."""
+        p, H = self._p, self.hidden_size
+        B, Ltok = tokens.shape
+        hp, wp = self.output_grid_h // 2, self.output_grid_w // 2
+        n_vis = 0 if vision is None else vision.shape[1]
+        n_aud = 0 if audio is None else audio.shape[1]
+        T = Ltok + n_vis
+        x, rot, valid = L.embed_assemble(tokens, p.tok_emb, H=H, seg_idx=seg_idx, aud_ptr=aud_ptr, audio=audio,
+                                         vision=vision, n_aud=n_aud, n_vis=n_vis, pool_h=hp, pool_w=wp, T=T,
+                                         audio_token_length=self.config["audio_token_length"])
+        kept = self._joint(x, rot, valid, B, T, Ltok)
+        proj = L.gemm(kept, p.head[0], bias=p.head[1], out_f32=True)
+        return L.unit_normalize(proj).view(B, Ltok, H)
+
+    # --------------------------------------------------------------------------------------------
+    # public zero-shot API (modeling.py:651-931)
+    # --------------------------------------------------------------------------------------------
+    def prepare_multimodal_inputs(self, tokens, token_segment_idx=None, token_embs=None, vision_input=None,
+                                  audio_spans=None, audio_pointers=None, padding_len=None, video_src_idx=None):
+        """modeling.py:651-758.  Returns x [B, T, H] (bf16), and -- instead of the reference's O(T^2)
+        boolean `attention_mask` and raw `rotary_coords` -- the equivalent compact forms the kernels
+        consume: `rotary_scale` [B, T, 32], `is_valid` [B, T] and `video_src` [B, T] (or None)."""
+        as_np = _is_np(tokens)
+        p, H = self._p, self.hidden_size
+        tok = _dev(tokens, torch.int32)
+        B, Ltok = tok.shape
+        seg = None if token_segment_idx is None else _dev(token_segment_idx, torch.int32)
+        vis = None if vision_input is None else _dev(vision_input, torch.bfloat16)
+        aud = None if audio_spans is None else _dev(audio_spans, torch.bfloat16)
+        ptr = None if audio_pointers is None else _dev(audio_pointers, torch.int32)
+        emb = None if token_embs is None else _dev(token_embs, torch.bfloat16)
+        if aud is None or ptr is None:
+            aud, ptr = None, None
+        n_vis = 0 if vis is None else vis.shape[1]
+        T = Ltok + n_vis
+        if padding_len is not None:
+            if padding_len < T:
+                raise ValueError("padding_len smaller than the assembled sequence")
+            T = padding_len
+        x, rot, valid = L.embed_assemble(tok, p.tok_emb, H=H, seg_idx=seg, aud_ptr=ptr, audio=aud, vision=vis,
+                                         tok_emb=emb, n_aud=0 if aud is None else aud.shape[1], n_vis=n_vis,
+                                         pool_h=self.output_grid_h // 2, pool_w=self.output_grid_w // 2, T=T,
+                                         audio_token_length=self.config["audio_token_length"])
+        video_src = None
+        if video_src_idx is not None and seg is not None:
+            vsi = _dev(video_src_idx, torch.int64)
+            parts = [torch.gather(vsi, 1, seg.long())]
+            if n_vis:
+                per = (self.output_grid_h // 2) * (self.output_grid_w // 2)
+                vseg = torch.arange(n_vis // per, device=tok.device).repeat_interleave(per)[None].expand(B, -1)
+                parts.append(torch.gather(vsi, 1, vseg))
+            if T > Ltok + n_vis:
+                parts.append(torch.full((B, T - Ltok - n_vis), -1, dtype=torch.int64, device=tok.device))
+            video_src = torch.cat(parts, 1).to(torch.int32).contiguous()
+        out = {"x": x.view(B, T, H), "rotary_scale": rot.view(B, T, 32), "is_valid": valid.view(B, T),
+               "video_src": video_src}
+        return {k: (_ret(v, True) if (as_np and v is not None and k != "x") else v) for k, v in out.items()}
+
+    def embed_text_spans_only(self, text_spans):
+        """modeling.py:767-774: [B, 15] token ids -> [B, H] unit vectors."""
+        as_np = _is_np(text_spans)
+        cls = self._span(_dev(text_spans, torch.int32))
+        return _ret(L.unit_normalize(cls), as_np)
+
+    def embed_audio_only(self, audio_clips):
+        """modeling.py:776-785."""
+        as_np = _is_np(audio_clips)
+        a = _dev(audio_clips, torch.float32)
+        lead = a.shape[:-2]
+        cls = self._audio(a.reshape(-1, self.config["audio_seq_length"], 65), want_cls=True)["cls"]
+        return _ret(L.unit_normalize(cls).view(*lead, self.hidden_size), as_np)
+
+    def get_imgseq_only(self, imgs):
+        """modeling.py:787-795."""
+        as_np = _is_np(imgs)
+        x = _dev(imgs, torch.float32)
+        lead, n, pp3 = x.shape[:-2], x.shape[-2], x.shape[-1]
+        enc = self._vision(x.reshape(-1, n, pp3))["seq_attnpool"]
+        return _ret(enc.reshape(*lead, n // 4, self.hidden_size), as_np)
+
+    get_imgs_enc = get_imgseq_only  # BASELINE.json name
+
+    def get_audioseq_only(self, audio_clips):
+        """modeling.py:797-803."""
+        as_np = _is_np(audio_clips)
+        a = _dev(audio_clips, torch.float32)
+        return _ret(self._audio(a.reshape(-1, self.config["audio_seq_length"], 65))["seq_attnpool"], as_np)
+
+    def get_audio_enc(self, audio_clips):
+        """BASELINE.json name: get_audioseq_only with the leading dims kept -> [*, 6, H]."""
+        as_np = _is_np(audio_clips)
+        a = _dev(audio_clips, torch.float32)
+        lead = a.shape[:-2]
+        enc = self._audio(a.reshape(-1, self.config["audio_seq_length"], 65))["seq_attnpool"]
+        return _ret(enc.reshape(*lead, self.config["audio_token_length"], self.hidden_size), as_np)
+
+    def batch_embed_video(self, images, audio_clips, tokens, subseg_idxs):
+        """modeling.py:845-846 (vmap of embed_video): images [B, nseg, hw, 768], audio_clips
+        [B, 3 nseg, 60, 65], tokens / subseg_idxs [B, L] -> [B, L, H] fp32 unit vectors."""
+        as_np = _is_np(images, audio_clips, tokens, subseg_idxs)
+        img = _dev(images, torch.float32)
+        aud = _dev(audio_clips, torch.float32)
+        tok = _dev(tokens, torch.int32)
+        sub = _dev(subseg_idxs, torch.int32)
+        B, nseg, hw, pp3 = img.shape
+        if pp3 != 768:
+            raise ValueError("images must be pre-patchified to 768 features (modeling.py:817)")
+        if aud.shape != (B, 3 * nseg, self.config["audio_seq_length"], 65):
+            raise ValueError(f"audio_clips must be [B, {3 * nseg}, {self.config['audio_seq_length']}, 65] "
+                             f"(modeling.py:819-822), got {tuple(aud.shape)}")
+        if tok.shape != sub.shape or tok.dim() != 2 or tok.shape[0] != B:
+            raise ValueError("tokens and subseg_idxs must both be [B, L] (modeling.py:824-826)")
+        H = self.hidden_size
+        imgs_enc = self._vision(img.reshape(B * nseg, hw, pp3))["seq_attnpool"].reshape(B, nseg * hw // 4, H)
+        audio_enc = self._audio(aud.reshape(B * 3 * nseg, aud.shape[2], 65))["seq_attnpool"]
+        audio_enc = audio_enc.reshape(B, 3 * nseg, self.config["audio_token_length"], H)
+        seg = torch.div(sub, 3, rounding_mode="floor").to(torch.int32)
+        out = self._joint_embed(tok, seg, vision=imgs_enc, audio=audio_enc, aud_ptr=sub)
+        return _ret(out, as_np)
+
+    def embed_video(self, images, audio_clips, tokens, subseg_idxs):
+        """modeling.py:806-843: one clip -> [L, H]."""
+        as_np = _is_np(images, audio_clips, tokens, subseg_idxs)
+        out = self.batch_embed_video(_dev(images)[None], _dev(audio_clips)[None], _dev(tokens)[None],
+                                     _dev(subseg_idxs)[None])
+        return _ret(out[0], as_np)
+
+    def embed_preencoded_noaudio(self, images_enc, tokens, subseg_idxs):
+        """modeling.py:880-904."""
+        as_np = _is_np(images_enc, tokens, subseg_idxs)
+        enc = _dev(images_enc, torch.bfloat16).reshape(1, -1, self.hidden_size)
+        tok, sub = _dev(tokens, torch.int32)[None], _dev(subseg_idxs, torch.int32)[None]
+        seg = torch.div(sub, 3, rounding_mode="floor").to(torch.int32)
+        return _ret(self._joint_embed(tok, seg, vision=enc)[0], as_np)
+
+    def embed_preencoded_audio(self, images_enc, audio_enc, tokens, subseg_idxs, audio_pointers):
+        """modeling.py:906-931."""
+        as_np = _is_np(images_enc, audio_enc, tokens, subseg_idxs, audio_pointers)
+        enc = _dev(images_enc, torch.bfloat16).reshape(1, -1, self.hidden_size)
+        aud = _dev(audio_enc, torch.bfloat16)[None]
+        tok, sub = _dev(tokens, torch.int32)[None], _dev(subseg_idxs, torch.int32)[None]
+        ptr = _dev(audio_pointers, torch.int32)[None]
+        seg = torch.div(sub, 3, rounding_mode="floor").to(torch.int32)
+        return _ret(self._joint_embed(tok, seg, vision=enc, audio=aud, aud_ptr=ptr)[0], as_np)
+
+    def embed_singleimg_with_multiimg_prompt(self, images_prompt, images, tokens, subseg_idxs):
+        """modeling.py:848-878."""
+        as_np = _is_np(images_prompt, images, tokens, subseg_idxs)
+        prompt = _dev(images_prompt, torch.bfloat16)
+        img = _dev(images, torch.float32)
+        if prompt.shape[0] + img.shape[0] > 8:
+            raise ValueError("at most 8 segments (modeling.py:860)")
+        enc = torch.cat([prompt, self._vision(img)["seq_attnpool"]], 0)
+        tok, sub = _dev(tokens, torch.int32), _dev(subseg_idxs, torch.int32)
+        return _ret(self.embed_preencoded_noaudio(enc, tok, sub), as_np)
+
+    def embed_singleimg_with_multiple_text(self, images, tokens, subseg_idxs):
+        """BASELINE.json name: images [ns, hw, 768] encoded ONCE, tokens / subseg_idxs
+        [n_cand, L]; every candidate runs the joint tail of modeling.py:869-878 -> [n_cand, L, H]."""
+        as_np = _is_np(images, tokens, subseg_idxs)
+        img = _dev(images, torch.float32)
+        tok, sub = _dev(tokens, torch.int32), _dev(subseg_idxs, torch.int32)
+        n_cand = tok.shape[0]
+        enc = self._vision(img)["seq_attnpool"].reshape(1, -1, self.hidden_size)
+        enc = enc.expand(n_cand, -1, -1).contiguous()
+        seg = torch.div(sub, 3, rounding_mode="floor").to(torch.int32)
+        return _ret(self._joint_embed(tok, seg, vision=enc), as_np)
+
+    def score_multiple_choice(self, images, tokens, proj_kernel=None):
+        """VCR-style multiple choice forward (MerlotReserveVCR.__call__,
+        finetune/vcr/qa_qar_joint_finetune.py:150-170): images [B, hw, 768], tokens [B, n_cand, L]
+        (each candidate contains a MASK) -> logits [B, n_cand] fp32."""
+        as_np = _is_np(images, tokens)
+        p, H = self._p, self.hidden_size
+        img = _dev(images, torch.float32)
+        tok = _dev(tokens, torch.int32)
+        B, n_cand, Ltok = tok.shape
+        proj = p.proj if proj_kernel is None else _f(proj_kernel)
+        enc = self._vision(img)["seq_attnpool"]
+        n_vis = enc.shape[1]
+        enc = enc.repeat_interleave(n_cand, dim=0).contiguous()
+        flat = tok.reshape(B * n_cand, Ltok).contiguous()
+        seg = torch.zeros_like(flat)
+        T = Ltok + n_vis
+        x, rot, valid = L.embed_assemble(flat, p.tok_emb, H=H, seg_idx=seg, vision=enc, n_vis=n_vis,
+                                         pool_h=self.output_grid_h // 2, pool_w=self.output_grid_w // 2, T=T)
+        kept = self._joint(x, rot, valid, B * n_cand, T, Ltok)
+        pool_idx = (flat == MASK).int().argmax(1).to(torch.int32)
+        rows = (torch.arange(B * n_cand, device=flat.device, dtype=torch.int32) * Ltok + pool_idx).contiguous()
+        return _ret(L.row_dot(kept, proj, rows).view(B, n_cand), as_np)
+
+    def __call__(self, batch):
+        raise NotImplementedError()  # modeling.py:760-761
+
+
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class PretrainedMerlotReserve:
+    """Mirror of modeling.py:933-1032.  `from_pretrained` reads a checkpoint that is ALREADY in the
+    cache directory (this environment has no network; the download branch of the reference,
+    modeling.py:974-989, is out of scope)."""
+    encoder: Any
+    params: Dict
+    model: MerlotReserve
+    _method_cache: Dict = None
+
+    @classmethod
+    def from_params(cls, config: Dict, params: Dict, encoder=None):
+        model = MerlotReserve.from_config(config)
+        model.bind(params)
+        return cls(model=model, params=params, encoder=encoder)
+
+    @classmethod
+    def from_pretrained(cls, model_name, image_grid_size=(18, 32), cache_dir=None):
+        import os
+        from .synthetic import load_config
+        if model_name not in ("base", "large"):
+            raise ValueError("Must provide a model that is `base' or `large'")
+        if tuple(image_grid_size) not in [(18, 32), (12, 20), (24, 24)]:
+            raise ValueError("Invalid grid size {}".format(image_grid_size))
+        suffix = "" if tuple(image_grid_size) == (12, 20) else "_resadapt"
+        cache_dir = cache_dir or os.path.join(os.path.expanduser("~"), ".cache", "merlotreserve")
+        path = os.path.join(cache_dir, model_name + suffix)
+        if not os.path.exists(path):
+            raise FileNotFoundError(f"{path} not found; place the reference checkpoint there (no network here)")
+        from .checkpoint import load_checkpoint
+        params = load_checkpoint(path)["params"]
+        config = load_config(model_name, tuple(image_grid_size))
+        return cls.from_params(config, params, encoder=_maybe_encoder())
+
+    def __getattr__(self, name):
+        """modeling.py:1005-1022: any model method, bound to the params (the reference jit-wraps it)."""
+        if name.startswith("_"):
+            raise AttributeError(name)
+        if self._method_cache is None:
+            self._method_cache = {}
+        if name in self._method_cache:
+            return self._method_cache[name]
+        if callable(getattr(self.model, name, None)):
+            fn = partial(self.model.apply, {"params": self.params}, method=getattr(self.model, name))
+            self._method_cache[name] = fn
+            return fn
+        raise ValueError(f"Unknown attribute {name}")
+
+    def get_label_space(self, options):
+        """modeling.py:1024-1032: tokenise, pad to 15, span-encode."""
+        if self.encoder is None:
+            raise L.MrError("no tokenizer attached (pass encoder=...)")
+        self.encoder.enable_padding(pad_token="<|PAD|>", length=15)
+        ids = np.array([x.ids[:15] for x in self.encoder.encode_batch(options)], dtype=np.int32)
+        self.encoder.no_padding()
+        return self.embed_text_spans_only(ids)
+
+
+def _maybe_encoder():
+    try:
+        from .lowercase_encoder import get_encoder
+        return get_encoder()
+    except Exception:
+        return None
+
+
+def unit_normalize(x):
+    """modeling.py:570-578 on a [rows, H] tensor / array."""
+    as_np = _is_np(x)
+    t = _dev(x)
+    if t.dtype not in (torch.float32, torch.bfloat16):
+        t = t.float()
+    return _ret(L.unit_normalize(t.reshape(-1, t.shape[-1])).view(*t.shape), as_np)
+
+
+def one_hot_pool(do_pool, idx, v, num_segments, real_bsize=None):
+    """modeling.py:541-567 as a segment gather; returns {'x': [b, S, H] fp32, 'count': [b, S]}."""
+    as_np = _is_np(do_pool, idx, v)
+    dp = _dev(do_pool).to(torch.uint8)
+    ix = _dev(idx, torch.int32)
+    vv = _dev(v)
+    B, Ls, H = vv.shape
+    if real_bsize is not None:
+        l2 = (Ls * B) // real_bsize
+        dp, ix, vv = dp.reshape(real_bsize, l2), ix.reshape(real_bsize, l2), vv.reshape(real_bsize, l2, H)
+    pooled, count = L.segment_pool(dp.contiguous(), ix.contiguous(), vv.contiguous(), num_segments)
+    return {"x": _ret(pooled, as_np), "count": _ret(count, as_np)}

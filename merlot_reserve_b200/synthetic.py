@@ -1,0 +1,191 @@
+"""Deterministic synthetic weights and inputs (numpy only) -- SURVEY.md §8(d).
+
+No dataset or checkpoint can be fetched in the build environment, so tests and benchmarks run on
+random-init weights of the named architecture and synthetic clips of the reference's shapes.
+
+* weights (seed 0): Dense kernels follow the reference's `kernel_init` (mreserve/modeling.py:147-186:
+  truncated normal(+-2) * min(18 / fan_in, 0.02) / sqrt(2), with its fan_in rule for 3-D kernels);
+  attention-pool projections use lecun-normal (flax default); biases / LayerNorm parameters / cls are
+  deliberately NON-trivial (N(0, 0.02), scale 1 + N(0, 0.02)) so that no bias or scale path can be
+  dropped silently; embedding N(0, 0.02); contrastive_scales = log(20).
+* clip (seeds 1..3): images U[0,1) [nseg, h*w, 768]; audio |N(0,1)|*1.5 with column 64 == 1.0
+  (playback speed, mreserve/preprocess.py:141-144); tokens / subseg_idxs laid out like
+  `preprocess_video` (mreserve/preprocess.py:497-540): segment 0 is text ending with MASK, the other
+  segments are 18 x AUDIOSPAN with subseg = 3 i + k // 6, truncated / padded to 160 with (0, -1).
+"""
+from __future__ import annotations
+
+import copy
+import math
+from pathlib import Path
+from typing import Dict, Tuple
+
+import numpy as np
+import yaml
+
+MASK, AUDIOSPAN = 3, 5
+VOCAB = 32768
+_CFG_DIR = Path(__file__).resolve().parent / "configs"
+
+
+def load_config(name: str = "base", output_grid: Tuple[int, int] | None = None, **model_overrides) -> Dict:
+    with open(_CFG_DIR / f"{name}.yaml") as f:
+        cfg = yaml.safe_load(f)
+    if output_grid is not None:
+        cfg["model"]["output_grid"] = list(output_grid)
+    cfg["model"].update(model_overrides)
+    return cfg
+
+
+def tiny_config(hidden_size=128, layers=2, output_grid=(4, 6), span_layers=2) -> Dict:
+    """A small geometry with the same structure, for tests the CPU oracle finishes in seconds."""
+    cfg = load_config("base", output_grid)
+    cfg["model"].update(hidden_size=hidden_size, joint_num_layers=layers, audio_num_layers=layers,
+                        vit_num_layers=layers, span_num_layers=span_layers)
+    return cfg
+
+
+def _trunc_normal(rng, shape):
+    x = rng.standard_normal(shape, dtype=np.float32)
+    bad = np.abs(x) > 2.0
+    while bad.any():
+        x[bad] = rng.standard_normal(int(bad.sum()), dtype=np.float32)
+        bad = np.abs(x) > 2.0
+    return x
+
+
+def _kernel_init(rng, shape, scale=1.0):
+    if len(shape) == 2:
+        fan_in = shape[0]
+    else:  # (H, heads, dh) or (heads, dh, H): modeling.py:173-180
+        fan_in = shape[0]
+        if shape[0] < shape[2]:
+            fan_in *= shape[1]
+    std = min(18.0 / fan_in, 0.02) / math.sqrt(2.0)
+    return (_trunc_normal(rng, shape) * np.float32(std * scale)).astype(np.float32)
+
+
+def _lecun(rng, shape, fan_in, scale=1.0):
+    return (_trunc_normal(rng, shape) * np.float32(scale * math.sqrt(1.0 / fan_in) / 0.87962566)).astype(np.float32)
+
+
+def _small(rng, shape):
+    return (rng.standard_normal(shape, dtype=np.float32) * np.float32(0.02)).astype(np.float32)
+
+
+def _ln(rng, H):
+    return {"scale": (1.0 + _small(rng, (H,))).astype(np.float32), "bias": _small(rng, (H,))}
+
+
+def _encoder_params(rng, H, num_layers, add_cls, scale):
+    nh = H // 64
+    p = {"pre_ln": _ln(rng, H), "final_ln": _ln(rng, H)}
+    if add_cls:
+        p["cls"] = _small(rng, (H,))
+        p["cls_proj"] = {"kernel": _kernel_init(rng, (H, H), scale), "bias": _small(rng, (H,))}
+    for i in range(num_layers):
+        p[f"layer_{i:02d}"] = {
+            "pre_attn_ln": _ln(rng, H),
+            "attention_layer": {
+                "qkv": {"kernel": _kernel_init(rng, (H, 3 * nh, 64), scale), "bias": _small(rng, (3 * nh, 64))},
+                "attn_proj": {"kernel": _kernel_init(rng, (nh, 64, H), scale)},
+            },
+            "pre_mlp_ln": _ln(rng, H),
+            "mlp_layer": {
+                "intermediate": {"kernel": _kernel_init(rng, (H, 4 * H), scale), "bias": _small(rng, (4 * H,))},
+                "out": {"kernel": _kernel_init(rng, (4 * H, H), scale)},
+            },
+        }
+    return p
+
+
+def _pool_params(rng, H, scale):
+    nh = H // 64
+    p = {k: {"kernel": _lecun(rng, (H, nh, 64), H, scale), "bias": _small(rng, (nh, 64))}
+         for k in ("query", "key", "value")}
+    p["out"] = {"kernel": _lecun(rng, (nh, 64, H), H, scale), "bias": _small(rng, (H,))}
+    return p
+
+
+def synthetic_params(config: Dict, seed: int = 0, weight_scale: float = 1.0) -> Dict:
+    """Parameter tree with the reference's flax names.  `weight_scale` multiplies every
+    projection kernel; tests use > 1 so that attention is far from uniform."""
+    m = config["model"]
+    H = m["hidden_size"]
+    rng = np.random.default_rng(seed)
+    pp3 = (m["vit_patch_size"] ** 2) * 3
+    s = weight_scale
+    return {
+        "vision_encoder": {
+            "embedding": {"kernel": _kernel_init(rng, (pp3, H), s), "bias": _small(rng, (H,))},
+            "transformer": _encoder_params(rng, H, m["vit_num_layers"], True, s),
+            "seq_attnpool": _pool_params(rng, H, s),
+        },
+        "audio_encoder": {
+            "embedding": {"kernel": _kernel_init(rng, (m["audio_patch_size"], 65, H), s), "bias": _small(rng, (H,))},
+            "transformer": _encoder_params(rng, H, m["audio_num_layers"], True, s),
+            "seq_attnpool": _pool_params(rng, H, s),
+        },
+        "span_encoder": {"transformer": _encoder_params(rng, H, m["span_num_layers"], True, s)},
+        "joint_transformer": _encoder_params(rng, H, m["joint_num_layers"], False, s),
+        "token_encoder": {"Embed_0": {"embedding": _small(rng, (VOCAB, H))}},
+        "head": {"kernel": _kernel_init(rng, (H, H), s), "bias": _small(rng, (H,))},
+        "contrastive_scales": np.full((3,), math.log(20.0), dtype=np.float32),
+    }
+
+
+def synthetic_clip(config: Dict, nseg: int = 16, seed: int = 1, token_length: int = 160, text_len: int = 12) -> Dict:
+    """One clip in the layout `MerlotReserve.embed_video` takes (modeling.py:806-826)."""
+    m = config["model"]
+    gh, gw = m["output_grid"]
+    images = np.random.default_rng(1000003 * seed + 1).random((nseg, gh * gw, 768), dtype=np.float32)
+    audio = np.abs(np.random.default_rng(1000003 * seed + 2).standard_normal(
+        (3 * nseg, m["audio_seq_length"], 65), dtype=np.float32)) * np.float32(1.5)
+    audio[..., 64] = 1.0
+    rng = np.random.default_rng(1000003 * seed + 3)
+    toks = list(rng.integers(10, VOCAB, size=text_len - 1)) + [MASK]
+    sub = [0] * text_len
+    for i in range(1, nseg):
+        toks += [AUDIOSPAN] * 18
+        sub += (3 * i + np.arange(18) // 6).tolist()
+    toks, sub = toks[:token_length], sub[:token_length]
+    while len(toks) < token_length:
+        toks.append(0)
+        sub.append(-1)
+    return {"images": images, "audio_clips": audio.astype(np.float32),
+            "tokens": np.asarray(toks, dtype=np.int32), "subseg_idxs": np.asarray(sub, dtype=np.int32)}
+
+
+def synthetic_batch(config: Dict, batch: int, nseg: int = 16, seed: int = 1, **kw) -> Dict:
+    clips = [synthetic_clip(config, nseg, seed + i, **kw) for i in range(batch)]
+    return {k: np.stack([c[k] for c in clips], 0) for k in clips[0]}
+
+
+def synthetic_spans(n: int, seed: int = 7, length: int = 15) -> np.ndarray:
+    """Tokenised label-space options padded to 15 (PretrainedMerlotReserve.get_label_space, modeling.py:1024)."""
+    rng = np.random.default_rng(seed)
+    out = np.zeros((n, length), dtype=np.int32)
+    for i in range(n):
+        k = int(rng.integers(1, length + 1))
+        out[i, :k] = rng.integers(10, VOCAB, size=k)
+    return out
+
+
+def count_params(tree) -> int:
+    if isinstance(tree, dict):
+        return sum(count_params(v) for v in tree.values())
+    return int(np.asarray(tree).size)
+
+
+def round_tree_bf16(tree):
+    """Round every leaf to the nearest bf16 value (kept as fp32) -- lets a test isolate kernel error
+    from weight-quantisation error."""
+    import torch
+
+    if isinstance(tree, dict):
+        return {k: round_tree_bf16(v) for k, v in tree.items()}
+    return torch.from_numpy(np.asarray(tree)).to(torch.bfloat16).to(torch.float32).numpy()
+
+
+def clone_tree(tree):
+    return copy.deepcopy(tree)

@@ -1,0 +1,522 @@
+"""CPU oracle for the MERLOT Reserve encoder + contrastive hot path.  TEST INFRASTRUCTURE ONLY.
+
+This file restates, in plain torch fp32 on the CPU, the arithmetic that the reference
+(`/root/reference/mreserve/modeling.py`, `pretrain/pretrain_model.py`) asks XLA to perform through
+flax.linen.  It is the checker for the CUDA path: only `tests/`, `__graft_entry__.smoke()` and the
+`cpu_baseline` / `--impl reference` legs of `bench.py` may import it.  The product package
+(`merlot_reserve_b200/`) never does.
+
+PARITY UNPINNED: the reference ships no tests or golden vectors, and JAX/Flax cannot be installed in
+this environment (no wheels, no network), so this restatement could not be checked against outputs of
+the reference itself.  It follows the reference source line by line (citations below) plus the
+documented semantics of flax 0.3.4 (`nn.Dense`, `nn.DenseGeneral`, `nn.LayerNorm`, `nn.Conv`,
+`nn.Embed`, `nn.MultiHeadDotProductAttention`, `dot_product_attention_weights`), which live outside
+the reference tree.  `tools/run_reference_jax.py` regenerates the golden vectors with the real
+reference on any machine that has jax + flax, so the oracle can be audited externally.
+
+Parameters use the reference's flax pytree (nested dicts, fp32 leaves) so that a real checkpoint maps
+one to one:  vision_encoder/{embedding, transformer/{cls, pre_ln, layer_XX/..., final_ln, cls_proj},
+seq_attnpool/{query,key,value,out}}, audio_encoder/..., span_encoder/transformer/...,
+joint_transformer/..., token_encoder/Embed_0/embedding, head/{kernel,bias}, contrastive_scales.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+# special token ids -- mreserve/lowercase_encoder.py:9-16
+PADDING, START, END, MASK, MASKAUDIO, AUDIOSPAN, LTOVPOOL = 0, 1, 2, 3, 4, 5, 6
+
+
+def _t(x, dtype=torch.float32):
+    if isinstance(x, torch.Tensor):
+        return x.to(dtype)
+    return torch.as_tensor(np.asarray(x)).to(dtype)
+
+
+# ------------------------------------------------------------------------------------------------
+# coordinates and the "rotary" scale (modeling.py:21-144)
+# ------------------------------------------------------------------------------------------------
+def rotary_coordinates(seq_len: int, center_origin: bool = True) -> torch.Tensor:
+    """modeling.py:21-35.  Centred: [-L//2 .. -1, 1 .. L - L//2] (zero is skipped); else 1..L."""
+    if not center_origin:
+        return 1.0 + torch.arange(seq_len, dtype=torch.float32)
+    half = seq_len // 2
+    neg = torch.arange(half, dtype=torch.float32) - float(half)
+    pos = 1.0 + torch.arange(seq_len - half, dtype=torch.float32)
+    return torch.cat([neg, pos], 0)
+
+
+def rotary_coordinates_2d(h: int, w: int) -> torch.Tensor:
+    """modeling.py:38-50: row-major [h*w, 2] = (h_coord, w_coord) / (max(h, w) + 1)."""
+    scale = 1.0 / (max(h, w) + 1.0)
+    hc = scale * rotary_coordinates(h)
+    wc = scale * rotary_coordinates(w)
+    hh, ww = torch.meshgrid(hc, wc, indexing="ij")
+    return torch.stack([hh, ww], -1).reshape(h * w, 2)
+
+
+def multimodal_coords(B, L, h=None, w=None, segment_idx=None, token_idx=None, max_segment=16.0, max_token=1024):
+    """modeling.py:53-78: stack (h, w, segment / 16, token / 1024)."""
+    z = torch.zeros(B, L, dtype=torch.float32)
+    hv = z if h is None else h
+    wv = z if w is None else w
+    sv = z if segment_idx is None else segment_idx / max_segment
+    tv = z if token_idx is None else token_idx / max_token
+    return torch.stack([hv, wv, sv, tv], -1)
+
+
+def rotary_sinusoids(coords: torch.Tensor, rotary_hsize: int = 32, max_freq: float = 10.0) -> torch.Tensor:
+    """modeling.py:81-113.  coords [..., L, n] -> [..., 2 (cos, sin), L, rotary_hsize]."""
+    *batch, L, n = coords.shape
+    assert rotary_hsize % (2 * n) == 0
+    d = rotary_hsize // (2 * n)
+    freqs = torch.logspace(0.0, math.log2(max_freq / 2.0), d, base=2.0, dtype=torch.float32)
+    rad = coords[..., None] * freqs * math.pi          # [..., L, n, d]
+    rad = rad.reshape(*batch, L, n * d)
+    sinus = torch.stack([torch.cos(rad), torch.sin(rad)], -3)
+    return torch.repeat_interleave(sinus, 2, dim=-1)
+
+
+def apply_rotary(qk: torch.Tensor, sinusoids: torch.Tensor) -> torch.Tensor:
+    """modeling.py:116-144, INCLUDING its quirk: plane 0 (cos) is used where a sine is expected and
+    plane 1 (sin) where a cosine is, and the "rotated" vector is [-x0, x1, -x2, x3, ...].
+    qk [..., L, heads, dh]; sinusoids [..., 2, L, r]."""
+    r = sinusoids.shape[-1]
+    first = sinusoids[..., 0, :, None, :]    # the reference calls this `sin`; it holds cos(theta)
+    second = sinusoids[..., 1, :, None, :]   # the reference calls this `cos`; it holds sin(theta)
+    while first.dim() < qk.dim():
+        first, second = first[None], second[None]
+    head = qk[..., :r]
+    flipped = torch.stack([-head[..., ::2], head[..., 1::2]], -1).reshape(head.shape)
+    head = head * second + flipped * first
+    return torch.cat([head, qk[..., r:]], -1)
+
+
+def rotary_scale_table(coords: torch.Tensor) -> torch.Tensor:
+    """Closed form of apply_rotary∘rotary_sinusoids: out[2i] = x[2i](sin-cos), out[2i+1] = x[2i+1](sin+cos).
+    Used by tests to show the CUDA table is the same function."""
+    s = rotary_sinusoids(coords)                      # [..., 2, L, 32]
+    cos, sin = s[..., 0, :, :], s[..., 1, :, :]
+    tab = torch.empty_like(cos)
+    tab[..., 0::2] = (sin - cos)[..., 0::2]
+    tab[..., 1::2] = (sin + cos)[..., 1::2]
+    return tab
+
+
+# ------------------------------------------------------------------------------------------------
+# flax.linen layers restated (flax 0.3.4 semantics; library not in the reference tree)
+# ------------------------------------------------------------------------------------------------
+def dense(x, p):
+    """nn.Dense / nn.DenseGeneral with the kernel flattened to [in, out]."""
+    k = _t(p["kernel"])
+    y = x @ k
+    if "bias" in p:
+        y = y + _t(p["bias"]).reshape(-1)
+    return y
+
+
+def layer_norm(x, p, eps=1e-5):
+    """flax LayerNorm: fp32 stats, var = E[x^2] - E[x]^2, (x - mean) * (rsqrt(var + eps) * scale) + bias."""
+    x = x.float()
+    mean = x.mean(-1, keepdim=True)
+    mean2 = (x * x).mean(-1, keepdim=True)
+    var = mean2 - mean * mean
+    mul = torch.rsqrt(var + eps) * _t(p["scale"])
+    return (x - mean) * mul + _t(p["bias"])
+
+
+def my_gelu(x):
+    """modeling.py:240."""
+    return x * torch.sigmoid(1.702 * x)
+
+
+def attention(qkv, sinusoids, bias):
+    """modeling.py:188-200 + flax dot_product_attention_weights.  qkv [B, T, 3nh, dh]."""
+    nh = qkv.shape[-2] // 3
+    qk, v = qkv[..., : 2 * nh, :], qkv[..., 2 * nh:, :]
+    if sinusoids is not None:
+        qk = apply_rotary(qk, sinusoids)
+    q, k = qk[..., :nh, :], qk[..., nh:, :]
+    q = q / math.sqrt(q.shape[-1])
+    w = torch.einsum("bqhd,bkhd->bhqk", q, k)
+    if bias is not None:
+        w = w + bias
+    w = torch.softmax(w, -1)
+    return torch.einsum("bhqk,bkhd->bqhd", w, v)
+
+
+def transformer_layer(x, p, sinusoids, bias):
+    """modeling.py:259-280 (pre-LN residual block), AttentionLayer :205-237, MLPBlock :244-256."""
+    B, T, H = x.shape
+    nh = H // 64
+    h = layer_norm(x, p["pre_attn_ln"])
+    ap = p["attention_layer"]
+    qkv_k = _t(ap["qkv"]["kernel"]).reshape(H, 3 * H)
+    qkv = h @ qkv_k + _t(ap["qkv"]["bias"]).reshape(3 * H)
+    ctx = attention(qkv.reshape(B, T, 3 * nh, 64), sinusoids, bias).reshape(B, T, H)
+    x = x + ctx @ _t(ap["attn_proj"]["kernel"]).reshape(H, H)
+    h2 = layer_norm(x, p["pre_mlp_ln"])
+    mp = p["mlp_layer"]
+    u = my_gelu(h2 @ _t(mp["intermediate"]["kernel"]) + _t(mp["intermediate"]["bias"]))
+    x = x + u @ _t(mp["out"]["kernel"])
+    return x
+
+
+def transformer_encoder(x, p, num_layers, *, rotary_coords=None, attention_mask=None, is_valid=None,
+                        add_cls_token=False, return_layers=False):
+    """modeling.py:283-376."""
+    B, T, H = x.shape
+    if add_cls_token:
+        assert attention_mask is None
+        cls = _t(p["cls"]).reshape(1, 1, H).expand(B, 1, H)
+        x = torch.cat([cls, x], 1)
+        T += 1
+        if is_valid is not None:
+            is_valid = torch.cat([torch.ones(B, 1, dtype=torch.bool), is_valid], 1)
+        if rotary_coords is not None:
+            rotary_coords = torch.cat([torch.zeros_like(rotary_coords[..., :1, :]), rotary_coords], -2)
+    sinusoids = None
+    if rotary_coords is not None:
+        assert rotary_coords.shape[-2] == T
+        sinusoids = rotary_sinusoids(rotary_coords)
+    else:
+        x = x + _t(p["pe"])[None]
+    if is_valid is not None:
+        assert attention_mask is None
+        attention_mask = is_valid[:, :, None] & is_valid[:, None, :]
+    bias = None
+    if attention_mask is not None:
+        m = attention_mask[:, None, :, :]
+        bias = torch.where(m, torch.zeros((), dtype=torch.float32), torch.full((), -1e10, dtype=torch.float32))
+    x = layer_norm(x, p["pre_ln"])
+    layers = []
+    for i in range(num_layers):
+        x = transformer_layer(x, p[f"layer_{i:02d}"], sinusoids, bias)
+        if return_layers:
+            layers.append(x)
+    xf = layer_norm(x, p["final_ln"])
+    out = {}
+    if add_cls_token:
+        out["cls"] = dense(xf[:, 0], p["cls_proj"])
+        out["seq"] = xf[:, 1:]
+    else:
+        out["seq"] = xf
+    if return_layers:
+        out["layers"] = layers
+    return out
+
+
+def mha_pool(q_in, kv_in, p):
+    """flax MultiHeadDotProductAttention with inputs_q [N, 1, H], inputs_kv [N, W, H]
+    (modeling.py:424-426, :468-472): q/k/v DenseGeneral(+bias) -> attention -> out DenseGeneral(+bias)."""
+    N, W, H = kv_in.shape
+    nh = H // 64
+
+    def proj(x, pp):
+        return (x @ _t(pp["kernel"]).reshape(H, H) + _t(pp["bias"]).reshape(H)).reshape(*x.shape[:-1], nh, 64)
+
+    q = proj(q_in, p["query"]) / math.sqrt(64)
+    k = proj(kv_in, p["key"])
+    v = proj(kv_in, p["value"])
+    w = torch.softmax(torch.einsum("nqhd,nkhd->nhqk", q, k), -1)
+    ctx = torch.einsum("nhqk,nkhd->nqhd", w, v).reshape(N, q_in.shape[1], H)
+    return ctx @ _t(p["out"]["kernel"]).reshape(H, H) + _t(p["out"]["bias"])
+
+
+# ------------------------------------------------------------------------------------------------
+# the model (modeling.py:379-931)
+# ------------------------------------------------------------------------------------------------
+class OracleMerlotReserve:
+    """fp32 CPU restatement of `MerlotReserve` (modeling.py:581-931).  `config` is the reference's
+    YAML dict (`pretrain/configs/*.yaml`); `params` the flax param tree."""
+
+    def __init__(self, config: Dict, params: Dict):
+        m = dict(config["model"])
+        self.data = dict(config.get("data", {}))
+        self.cfg = m
+        self.params = params
+        self.hidden_size = m["hidden_size"]
+        self.output_grid_h, self.output_grid_w = m["output_grid"]
+        self.vit_pooling_ratio = m["vit_pooling_ratio"]
+        self.audio_seq_length = m["audio_seq_length"]
+        self.audio_token_length = m["audio_token_length"]
+        self.audio_patch_size = m["audio_patch_size"]
+        # modeling.py:611-612
+        self.audio_pooling_ratio = self.audio_seq_length // (self.audio_token_length * self.audio_patch_size)
+
+    # --- encoders ---
+    def vision_encoder(self, x):
+        """VisionTransformer.__call__ modeling.py:391-430.  x [B, hw, 768]."""
+        p = self.params["vision_encoder"]
+        H, gh, gw, r = self.hidden_size, self.output_grid_h, self.output_grid_w, self.vit_pooling_ratio
+        B, hw, pp3 = x.shape
+        assert hw == gh * gw and pp3 == (self.cfg["vit_patch_size"] ** 2) * 3
+        x = dense(_t(x), p["embedding"])
+        coords = rotary_coordinates_2d(gh, gw)
+        t_out = transformer_encoder(x, p["transformer"], self.cfg["vit_num_layers"], rotary_coords=coords,
+                                    add_cls_token=True)
+        h2, w2 = gh // r, gw // r
+        seq = t_out["seq"].reshape(B * h2, r, w2, r, H).transpose(1, 2).reshape(B * h2 * w2, r * r, H)
+        pooled = mha_pool(seq.mean(1, keepdim=True), seq, p["seq_attnpool"])
+        t_out["seq_attnpool"] = pooled.reshape(B, h2 * w2, H)
+        return t_out
+
+    def audio_encoder(self, x):
+        """AudioTransformer.__call__ modeling.py:443-476.  x [B, 60, 65]."""
+        p = self.params["audio_encoder"]
+        H, ps = self.hidden_size, self.audio_patch_size
+        x = _t(x)
+        B, raw_len, nm = x.shape
+        assert nm == 65 and raw_len % ps == 0
+        L = raw_len // ps
+        # nn.Conv(kernel [ps], stride [ps], SAME): no padding when raw_len % ps == 0 -> reshape-GEMM
+        k = _t(p["embedding"]["kernel"]).reshape(ps * nm, H)
+        x = x.reshape(B, L, ps * nm) @ k + _t(p["embedding"]["bias"])
+        coords = rotary_coordinates(L)[:, None] / L
+        t_out = transformer_encoder(x, p["transformer"], self.cfg["audio_num_layers"], rotary_coords=coords,
+                                    add_cls_token=True)
+        r = self.audio_pooling_ratio
+        assert L % r == 0
+        seq = t_out["seq"].reshape(-1, r, H)
+        pooled = mha_pool(seq.mean(1, keepdim=True), seq, p["seq_attnpool"])
+        t_out["seq_attnpool"] = pooled.reshape(B, L // r, H)
+        return t_out
+
+    def span_encoder(self, x, x_isvalid):
+        """SpanTransformer.__call__ modeling.py:488-504."""
+        L = x.shape[1]
+        assert L < 16
+        coords = rotary_coordinates(L, center_origin=False)[:, None] / 16
+        t_out = transformer_encoder(x, self.params["span_encoder"]["transformer"], self.cfg["span_num_layers"],
+                                    rotary_coords=coords, is_valid=x_isvalid, add_cls_token=True)
+        return t_out["cls"]
+
+    def token_encoder(self, tokens):
+        """TokenEmbedder modeling.py:507-538 (one nn.Embed lookup)."""
+        emb = _t(self.params["token_encoder"]["Embed_0"]["embedding"])
+        return emb[torch.as_tensor(np.asarray(tokens)).long()]
+
+    def joint_transformer(self, x, rotary_coords, attention_mask, return_layers=False):
+        return transformer_encoder(x, self.params["joint_transformer"], self.cfg["joint_num_layers"],
+                                   rotary_coords=rotary_coords, attention_mask=attention_mask,
+                                   return_layers=return_layers)
+
+    def joint_proj(self, x):
+        return dense(x, self.params["head"])
+
+    # --- joint input assembly (modeling.py:651-758) ---
+    def prepare_multimodal_inputs(self, tokens, token_segment_idx=None, token_embs=None, vision_input=None,
+                                  audio_spans=None, audio_pointers=None, padding_len=None, video_src_idx=None):
+        tokens = torch.as_tensor(np.asarray(tokens)).long()
+        B, L = tokens.shape
+        H = self.hidden_size
+        if token_embs is None:
+            token_embs = self.token_encoder(tokens)
+        if audio_spans is not None and audio_pointers is not None:
+            audio_pointers = torch.as_tensor(np.asarray(audio_pointers)).long()
+            assert audio_spans.shape[0] == B and audio_spans.shape[2] == self.audio_token_length
+            is_audio = tokens == AUDIOSPAN
+            ptr = audio_pointers.clamp(min=0)
+            subpos = (torch.cumsum(is_audio.int(), -1) - 1).clamp(min=0) % self.audio_token_length
+            audio_embs = audio_spans[torch.arange(B)[:, None], ptr, subpos]
+            token_embs = torch.where(is_audio[..., None], audio_embs, token_embs)
+        token_idx = (1.0 + torch.arange(L, dtype=torch.float32))[None].expand(B, L)
+        seg = None
+        if token_segment_idx is not None:
+            token_segment_idx = torch.as_tensor(np.asarray(token_segment_idx)).long()
+            seg = token_segment_idx.float()
+        coords = multimodal_coords(B, L, segment_idx=seg, token_idx=token_idx)
+        vis_len, vis_seg = 0, None
+        if vision_input is not None:
+            hp = self.output_grid_h // self.vit_pooling_ratio
+            wp = self.output_grid_w // self.vit_pooling_ratio
+            pool_coords = rotary_coordinates_2d(hp, wp)
+            vis_len = vision_input.shape[1]
+            nseg = vis_len // (hp * wp)
+            img_coords = pool_coords.repeat(nseg, 1)[None].expand(B, -1, -1)
+            vis_seg = torch.arange(nseg).repeat_interleave(hp * wp)[None].expand(B, -1)
+            img_mm = multimodal_coords(B, vis_len, h=img_coords[..., 0], w=img_coords[..., 1],
+                                       segment_idx=vis_seg.float())
+            coords = torch.cat([coords, img_mm], 1)
+            token_embs = torch.cat([token_embs, vision_input], 1)
+        is_valid = tokens != PADDING
+        if vis_len > 0:
+            is_valid = torch.cat([is_valid, torch.ones(B, vis_len, dtype=torch.bool)], 1)
+        extra = 0
+        if padding_len is not None:
+            extra = padding_len - is_valid.shape[1]
+            assert extra >= 0
+            if extra > 0:
+                is_valid = torch.cat([is_valid, torch.zeros(B, extra, dtype=torch.bool)], 1)
+                coords = torch.cat([coords, torch.zeros(B, extra, 4)], 1)
+                token_embs = torch.cat([token_embs, torch.zeros(B, extra, H)], 1)
+        mask = is_valid[:, None, :] & is_valid[:, :, None]
+        video_src = None
+        if video_src_idx is not None and token_segment_idx is not None:
+            video_src_idx = torch.as_tensor(np.asarray(video_src_idx)).long()
+            rows = torch.arange(B)[:, None]
+            parts = [video_src_idx[rows, token_segment_idx]]
+            if vis_seg is not None:
+                parts.append(video_src_idx[rows, vis_seg])
+            if extra > 0:
+                parts.append(torch.full((B, extra), -1, dtype=torch.long))
+            video_src = torch.cat(parts, -1)
+            mask = mask & (video_src[:, None, :] == video_src[:, :, None])
+        return {"x": token_embs, "rotary_coords": coords, "attention_mask": mask,
+                "is_valid": is_valid, "video_src": video_src}
+
+    # --- zero-shot API (modeling.py:767-931) ---
+    def embed_text_spans_only(self, text_spans):
+        text_spans = torch.as_tensor(np.asarray(text_spans)).long()
+        return unit_normalize(self.span_encoder(self.token_encoder(text_spans), text_spans != PADDING))
+
+    def embed_audio_only(self, audio_clips):
+        a = _t(audio_clips)
+        lead = a.shape[:-2]
+        cls = self.audio_encoder(a.reshape(-1, self.audio_seq_length, 65))["cls"]
+        return unit_normalize(cls).reshape(*lead, self.hidden_size)
+
+    def get_imgseq_only(self, imgs):
+        x = _t(imgs)
+        lead, n, pp3 = x.shape[:-2], x.shape[-2], x.shape[-1]
+        enc = self.vision_encoder(x.reshape(-1, n, pp3))["seq_attnpool"]
+        return enc.reshape(*lead, n // 4, self.hidden_size)
+
+    def get_audioseq_only(self, audio_clips):
+        return self.audio_encoder(_t(audio_clips).reshape(-1, self.audio_seq_length, 65))["seq_attnpool"]
+
+    def _joint_tail(self, mm, token_length):
+        enc = self.joint_transformer(mm["x"], mm["rotary_coords"], mm["attention_mask"])["seq"]
+        return unit_normalize(self.joint_proj(enc[0, :token_length]))
+
+    def embed_video(self, images, audio_clips, tokens, subseg_idxs):
+        """modeling.py:806-843."""
+        images, audio_clips = _t(images), _t(audio_clips)
+        tokens = torch.as_tensor(np.asarray(tokens)).long()
+        subseg = torch.as_tensor(np.asarray(subseg_idxs)).long()
+        nseg, npatch, pp3 = images.shape
+        assert pp3 == 768
+        assert audio_clips.shape == (3 * nseg, self.audio_seq_length, 65)
+        (L,) = tokens.shape
+        assert subseg.shape == (L,)
+        imgs_enc = self.vision_encoder(images)["seq_attnpool"].reshape(nseg * npatch // 4, self.hidden_size)
+        audio_enc = self.audio_encoder(audio_clips)["seq_attnpool"]
+        mm = self.prepare_multimodal_inputs(
+            tokens=tokens[None], token_segment_idx=torch.div(subseg[None], 3, rounding_mode="floor"),
+            vision_input=imgs_enc[None], audio_pointers=subseg[None], audio_spans=audio_enc[None])
+        return self._joint_tail(mm, L)
+
+    def batch_embed_video(self, images, audio_clips, tokens, subseg_idxs):
+        return torch.stack([self.embed_video(i, a, t, s)
+                            for i, a, t, s in zip(images, audio_clips, tokens, subseg_idxs)], 0)
+
+    def embed_singleimg_with_multiimg_prompt(self, images_prompt, images, tokens, subseg_idxs):
+        """modeling.py:848-878."""
+        images_prompt, images = _t(images_prompt), _t(images)
+        ns0, (ns1, npatch, _) = images_prompt.shape[0], images.shape
+        assert ns0 + ns1 <= 8
+        enc = torch.cat([images_prompt, self.vision_encoder(images)["seq_attnpool"]], 0)
+        return self.embed_preencoded_noaudio(enc, tokens, subseg_idxs)
+
+    def embed_preencoded_noaudio(self, images_enc, tokens, subseg_idxs):
+        """modeling.py:880-904."""
+        images_enc = _t(images_enc).reshape(-1, self.hidden_size)
+        tokens = torch.as_tensor(np.asarray(tokens)).long()
+        subseg = torch.as_tensor(np.asarray(subseg_idxs)).long()
+        mm = self.prepare_multimodal_inputs(
+            tokens=tokens[None], token_segment_idx=torch.div(subseg[None], 3, rounding_mode="floor"),
+            vision_input=images_enc[None])
+        return self._joint_tail(mm, tokens.shape[0])
+
+    def embed_preencoded_audio(self, images_enc, audio_enc, tokens, subseg_idxs, audio_pointers):
+        """modeling.py:906-931."""
+        images_enc = _t(images_enc).reshape(-1, self.hidden_size)
+        tokens = torch.as_tensor(np.asarray(tokens)).long()
+        subseg = torch.as_tensor(np.asarray(subseg_idxs)).long()
+        ptrs = torch.as_tensor(np.asarray(audio_pointers)).long()
+        mm = self.prepare_multimodal_inputs(
+            tokens=tokens[None], token_segment_idx=torch.div(subseg[None], 3, rounding_mode="floor"),
+            vision_input=images_enc[None], audio_pointers=ptrs[None], audio_spans=_t(audio_enc)[None])
+        return self._joint_tail(mm, tokens.shape[0])
+
+    # --- names required by BASELINE.json north_star ---
+    def get_imgs_enc(self, images):
+        x = _t(images)
+        lead, n, pp3 = x.shape[:-2], x.shape[-2], x.shape[-1]
+        enc = self.vision_encoder(x.reshape(-1, n, pp3))["seq_attnpool"]
+        return enc.reshape(*lead, n // (self.vit_pooling_ratio ** 2), self.hidden_size)
+
+    def get_audio_enc(self, audio_clips):
+        a = _t(audio_clips)
+        lead = a.shape[:-2]
+        enc = self.audio_encoder(a.reshape(-1, self.audio_seq_length, 65))["seq_attnpool"]
+        return enc.reshape(*lead, self.audio_token_length, self.hidden_size)
+
+    def embed_singleimg_with_multiple_text(self, images, tokens, subseg_idxs):
+        """Vision encoded once, broadcast to every candidate, then the joint tail per candidate
+        (pattern of finetune/vcr/qa_qar_joint_finetune.py:155-163 + modeling.py:869-878)."""
+        images = _t(images)
+        tokens = torch.as_tensor(np.asarray(tokens)).long()
+        subseg = torch.as_tensor(np.asarray(subseg_idxs)).long()
+        n_cand, L = tokens.shape
+        enc = self.vision_encoder(images)["seq_attnpool"].reshape(1, -1, self.hidden_size)
+        mm = self.prepare_multimodal_inputs(
+            tokens=tokens, token_segment_idx=torch.div(subseg, 3, rounding_mode="floor"),
+            vision_input=enc.expand(n_cand, -1, -1))
+        seq = self.joint_transformer(mm["x"], mm["rotary_coords"], mm["attention_mask"])["seq"]
+        return unit_normalize(self.joint_proj(seq[:, :L]))
+
+    def score_multiple_choice(self, images, tokens, proj_kernel):
+        """MerlotReserveVCR.__call__ (finetune/vcr/qa_qar_joint_finetune.py:150-170):
+        images [B, hw, 768], tokens [B, n_cand, L] -> logits [B, n_cand]."""
+        images = _t(images)
+        tokens = torch.as_tensor(np.asarray(tokens)).long()
+        B, n_cand, L = tokens.shape
+        enc = self.vision_encoder(images)["seq_attnpool"]
+        enc = enc.repeat_interleave(n_cand, dim=0)
+        flat = tokens.reshape(B * n_cand, L)
+        mm = self.prepare_multimodal_inputs(tokens=flat, token_segment_idx=torch.zeros_like(flat), vision_input=enc)
+        seq = self.joint_transformer(mm["x"], mm["rotary_coords"], mm["attention_mask"])["seq"][:, :L]
+        pool_idx = (flat == MASK).int().argmax(1)
+        pooled = seq[torch.arange(B * n_cand), pool_idx]
+        return (pooled @ _t(proj_kernel).reshape(-1, 1)).reshape(B, n_cand)
+
+
+def unit_normalize(x):
+    """modeling.py:570-578."""
+    x = x.float()
+    return x / torch.sqrt((x * x).sum(-1, keepdim=True) + 1e-5)
+
+
+def one_hot_pool(do_pool, idx, v, num_segments, real_bsize=None):
+    """modeling.py:541-567 (einsum against a one-hot; index -1 -> all-zero row)."""
+    B, L, H = v.shape
+    if real_bsize is not None:
+        l2 = (L * B) // real_bsize
+        do_pool, idx, v = do_pool.reshape(real_bsize, l2), idx.reshape(real_bsize, l2), v.reshape(real_bsize, l2, H)
+    ptr = torch.where(do_pool, idx, torch.full_like(idx, -1))
+    oh = (ptr[..., None] == torch.arange(num_segments)).float()
+    return {"x": torch.einsum("bls,blh->bsh", oh, v.float()), "idx_oh": oh}
+
+
+def contrastive_loss(preds: Dict[str, Dict[str, torch.Tensor]], gather=None):
+    """loss_fn_given_preds (pretrain/pretrain_model.py:262-303).  `gather(y)` stands for
+    jax.lax.all_gather(y, 'batch').reshape(-1, H); identity when there is one replica."""
+    gather = gather or (lambda y: y)
+    info = {}
+    for name, d in preds.items():
+        x, y = d["x"].float(), d["y"].float()
+        numer = (x * y).sum(-1)
+        info[name] = torch.zeros(())
+        for a, b in ("xy", "yx"):
+            xa, yb = d[a].float(), d[b].float()
+            if f"{b}_extra" in d:
+                yb = torch.cat([yb, d[f"{b}_extra"].float()], 0)
+            logits = xa @ gather(yb).T
+            lse = torch.logsumexp(logits, -1)
+            info[name] = info[name] + (lse - numer).mean() / 2.0
+    return sum(info.values()), info

@@ -1,0 +1,288 @@
+"""Per-entry-point parity of the C ABI (include/mreserve_b200.h) against plain torch fp32 restatements
+of the same op, on seeded inputs.  Tolerances: inputs are exact bf16 values, accumulation is fp32, so the
+only error allowed is the final bf16 rounding (rel 2^-8) plus accumulation-order noise."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _bf(x):
+    return x.to(torch.bfloat16)
+
+
+def _close(got, ref, atol, rtol, what=""):
+    got, ref = got.float(), ref.float()
+    err = (got - ref).abs()
+    tol = atol + rtol * ref.abs()
+    bad = err > tol
+    assert not bad.any(), (f"{what}: {int(bad.sum())}/{bad.numel()} mismatches, max abs err {err.max().item():.4g} "
+                           f"at {np.unravel_index(int(err.argmax()), tuple(err.shape))}, ref there "
+                           f"{ref.flatten()[int(err.argmax())].item():.4g}")
+
+
+GEMM_SHAPES = [
+    (128, 256, 64), (128, 256, 768), (256, 768, 768), (1000, 768, 768), (3856, 2304, 768), (241, 3072, 768),
+    (300, 768, 3072), (77, 1024, 1024), (129, 1536, 192), (513, 4096, 1024), (64, 128, 128), (5, 8, 64),
+    (200, 264, 72),
+]
+
+
+@pytest.mark.parametrize("algo", [0, 1])
+@pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
+def test_gemm_plain(cuda, lib, M, N, K, algo):
+    if algo == 1 and M * N * K > 3e9:
+        pytest.skip("debug kernel too slow")
+    g = torch.Generator(device="cpu").manual_seed(M * 7 + N * 3 + K)
+    a = _bf(torch.randn(M, K, generator=g)).to(cuda)
+    w = _bf(torch.randn(N, K, generator=g) * 0.05).to(cuda)
+    ref = a.float() @ w.float().t()
+    out = lib.gemm(a, w, algo=algo)
+    _close(out, ref, 2e-2, 1e-2, f"gemm {M}x{N}x{K} algo{algo}")
+    out32 = lib.gemm(a, w, out_f32=True, algo=algo)
+    _close(out32, ref, 2e-3, 1e-3, f"gemm f32 {M}x{N}x{K} algo{algo}")
+
+
+@pytest.mark.parametrize("M,N,K", [(1000, 3072, 768), (260, 4096, 1024), (130, 256, 64)])
+def test_gemm_bias_gelu(cuda, lib, M, N, K):
+    g = torch.Generator().manual_seed(1)
+    a = _bf(torch.randn(M, K, generator=g)).to(cuda)
+    w = _bf(torch.randn(N, K, generator=g) * 0.05).to(cuda)
+    b = torch.randn(N, generator=g).to(cuda)
+    pre = a.float() @ w.float().t() + b
+    _close(lib.gemm(a, w, bias=b), pre, 2e-2, 1e-2, "bias")
+    _close(lib.gemm(a, w, bias=b, gelu=True), pre * torch.sigmoid(1.702 * pre), 2e-2, 1e-2, "gelu")
+
+
+@pytest.mark.parametrize("M,N,K", [(1000, 768, 3072), (300, 1024, 1024), (128, 256, 64)])
+def test_gemm_residual_inplace(cuda, lib, M, N, K):
+    g = torch.Generator().manual_seed(2)
+    a = _bf(torch.randn(M, K, generator=g)).to(cuda)
+    w = _bf(torch.randn(N, K, generator=g) * 0.05).to(cuda)
+    x = _bf(torch.randn(M, N, generator=g)).to(cuda)
+    ref = x.float() + a.float() @ w.float().t()
+    out = lib.gemm(a, w, residual=x)
+    _close(out, ref, 3e-2, 1e-2, "residual")
+    x2 = x.clone()
+    lib.gemm(a, w, residual=x2, out=x2)  # in place, as the encoder uses it
+    assert torch.equal(x2, out)
+
+
+@pytest.mark.parametrize("H,T,B", [(768, 241, 5), (1024, 31, 9), (128, 16, 7)])
+def test_gemm_rotary_qkv(cuda, lib, H, T, B):
+    g = torch.Generator().manual_seed(3)
+    M = B * T
+    a = _bf(torch.randn(M, H, generator=g)).to(cuda)
+    w = _bf(torch.randn(3 * H, H, generator=g) * 0.05).to(cuda)
+    b = torch.randn(3 * H, generator=g).to(cuda)
+    rot = torch.randn(T, 32, generator=g).to(cuda)
+    pre = (a.float() @ w.float().t() + b).view(B, T, 3, H // 64, 64).clone()
+    pre[:, :, :2, :, :32] *= rot.view(1, T, 1, 1, 32)
+    pre[:, :, 0] *= 0.125
+    out = lib.gemm(a, w, bias=b, rot=rot, hidden=H, q_scale=0.125)
+    _close(out, pre.view(M, 3 * H), 3e-2, 1e-2, "rotary qkv")
+    # per-row table (joint encoder): rot_rows == M
+    rot2 = torch.randn(M, 32, generator=g).to(cuda)
+    pre2 = (a.float() @ w.float().t() + b).view(M, 3, H // 64, 64).clone()
+    pre2[:, :2, :, :32] *= rot2.view(M, 1, 1, 32)
+    pre2[:, 0] *= 0.125
+    out2 = lib.gemm(a, w, bias=b, rot=rot2, hidden=H, q_scale=0.125)
+    _close(out2, pre2.view(M, 3 * H), 3e-2, 1e-2, "rotary qkv per-row")
+
+
+def test_gemm_row_map_and_strided_a(cuda, lib):
+    g = torch.Generator().manual_seed(4)
+    B, hw, K, N = 6, 24, 768, 256
+    a = _bf(torch.randn(B * hw, K, generator=g)).to(cuda)
+    w = _bf(torch.randn(N, K, generator=g) * 0.05).to(cuda)
+    b = torch.randn(N, generator=g).to(cuda)
+    out = torch.full((B * (hw + 1), N), 7.0, dtype=torch.bfloat16, device=cuda)
+    lib.gemm(a, w, bias=b, out=out, seq_in=hw, seq_out=hw + 1, row_off=1)
+    ref = (a.float() @ w.float().t() + b).view(B, hw, N)
+    o = out.view(B, hw + 1, N)
+    _close(o[:, 1:], ref, 2e-2, 1e-2, "row map")
+    assert (o[:, 0] == 7.0).all(), "CLS rows must be untouched"
+    # strided A: row 0 of every [T, K] block
+    T = 5
+    big = _bf(torch.randn(B * T, K, generator=g)).to(cuda)
+    out2 = lib.gemm(big, w, bias=b, M=B, lda=T * K)
+    _close(out2, big.view(B, T, K)[:, 0].float() @ w.float().t() + b, 2e-2, 1e-2, "strided A")
+
+
+def test_gemm_large_throughput_shape(cuda, lib):
+    """Many tiles per CTA (persistent loop, both TMEM accumulator stages, ring wrap-around)."""
+    g = torch.Generator().manual_seed(5)
+    M, N, K = 148 * 128 * 3 + 77, 768, 768
+    a = _bf(torch.randn(M, K, generator=g)).to(cuda)
+    w = _bf(torch.randn(N, K, generator=g) * 0.05).to(cuda)
+    out = lib.gemm(a, w)
+    ref = (a.float() @ w.float().t())
+    _close(out, ref, 2e-2, 1e-2, "large gemm")
+
+
+def _attn_ref(qkv, B, T, H, valid=None, group=None):
+    nh = H // 64
+    q, k, v = qkv.float().view(B, T, 3, nh, 64).unbind(2)
+    s = torch.einsum("bqhd,bkhd->bhqk", q, k)
+    if valid is not None or group is not None:
+        m = torch.ones(B, T, T, dtype=torch.bool, device=qkv.device)
+        if valid is not None:
+            vb = valid.view(B, T).bool()
+            m &= vb[:, :, None] & vb[:, None, :]
+        if group is not None:
+            gg = group.view(B, T)
+            m &= gg[:, :, None] == gg[:, None, :]
+        s = s + torch.where(m, 0.0, -1e10)[:, None]
+    p = torch.softmax(s, -1)
+    return torch.einsum("bhqk,bkhd->bqhd", p, v).reshape(B * T, H)
+
+
+@pytest.mark.parametrize("B,T,H", [(3, 241, 768), (5, 31, 768), (7, 16, 128), (2, 577, 1024), (1, 1120, 768),
+                                   (2, 64, 128), (2, 65, 128), (1, 640, 256)])
+def test_attention_unmasked(cuda, lib, B, T, H):
+    g = torch.Generator().manual_seed(T)
+    qkv = _bf(torch.randn(B * T, 3 * H, generator=g)).to(cuda)
+    qkv.view(B * T, 3, H)[:, 0] *= 0.35  # keep the softmax away from one-hot
+    out = lib.attention(qkv, B, T, H)
+    _close(out, _attn_ref(qkv, B, T, H), 2e-2, 2e-2, f"attention T={T}")
+
+
+@pytest.mark.parametrize("B,T,H", [(4, 16, 128), (3, 200, 128), (2, 640, 256)])
+def test_attention_masked(cuda, lib, B, T, H):
+    g = torch.Generator().manual_seed(T + 1)
+    qkv = _bf(torch.randn(B * T, 3 * H, generator=g)).to(cuda)
+    qkv.view(B * T, 3, H)[:, 0] *= 0.35
+    valid = (torch.rand(B, T, generator=g) > 0.3).to(torch.uint8)
+    valid[:, 0] = 1
+    valid[0, T // 2:] = 0  # a long padded tail, whole key blocks masked
+    group = torch.randint(0, 3, (B, T), generator=g).to(torch.int32)
+    valid, group = valid.to(cuda).contiguous(), group.to(cuda).contiguous()
+    _close(lib.attention(qkv, B, T, H, valid=valid.view(-1)), _attn_ref(qkv, B, T, H, valid), 2e-2, 2e-2, "valid")
+    _close(lib.attention(qkv, B, T, H, valid=valid.view(-1), group=group.view(-1)),
+           _attn_ref(qkv, B, T, H, valid, group), 2e-2, 2e-2, "valid+group")
+
+
+@pytest.mark.parametrize("rows,H", [(1000, 768), (333, 1024), (50, 128)])
+def test_layernorm(cuda, lib, rows, H):
+    g = torch.Generator().manual_seed(6)
+    x = _bf(torch.randn(rows, H, generator=g) * 3 + 0.5).to(cuda)
+    gm = (1 + 0.1 * torch.randn(H, generator=g)).to(cuda)
+    bt = (0.1 * torch.randn(H, generator=g)).to(cuda)
+    xf = x.float()
+    mean = xf.mean(-1, keepdim=True)
+    var = (xf * xf).mean(-1, keepdim=True) - mean * mean
+    ref = (xf - mean) * (torch.rsqrt(var + 1e-5) * gm) + bt
+    _close(lib.layernorm(x, gm, bt), ref, 2e-2, 1e-2, "layernorm")
+    # row map: first 3 rows of every block of 10
+    nb = rows // 10
+    sub = lib.layernorm(x, gm, bt, rows=nb * 3, seq_in=10, seq_out=3)
+    _close(sub, ref[: nb * 10].view(nb, 10, H)[:, :3].reshape(nb * 3, H), 2e-2, 1e-2, "layernorm rowmap")
+
+
+def test_cast_pad_fill_cls(cuda, lib):
+    g = torch.Generator().manual_seed(7)
+    x = torch.rand(90, 130, generator=g).to(cuda)
+    y = lib.cast_pad(x, 90, 130, 192)
+    assert torch.equal(y[:, :130], x.to(torch.bfloat16)) and (y[:, 130:] == 0).all()
+    x2 = torch.rand(77, 768, generator=g).to(cuda)
+    assert torch.equal(lib.cast_pad(x2, 77, 768, 768), x2.to(torch.bfloat16))
+    buf = torch.zeros(4 * 5, 128, dtype=torch.bfloat16, device=cuda)
+    cls = torch.randn(128, generator=g).to(cuda)
+    lib.fill_cls(buf, cls, 4, 5, 128)
+    assert torch.equal(buf.view(4, 5, 128)[:, 0], cls.to(torch.bfloat16)[None].expand(4, -1))
+    assert (buf.view(4, 5, 128)[:, 1:] == 0).all()
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_window_pool(cuda, lib, mode):
+    g = torch.Generator().manual_seed(8)
+    H, B = 128, 3
+    if mode == 0:
+        win, n_win, gh, gw = 5, 6, 0, 0
+        T = 31
+        idx = torch.arange(30).view(6, 5)
+    else:
+        gh, gw = 4, 6
+        win, n_win, T = 4, 6, 25
+        idx = torch.arange(24).view(2, 2, 3, 2).permute(0, 2, 1, 3).reshape(6, 4)
+    x = _bf(torch.randn(B * T, H, generator=g)).to(cuda)
+    xs = x.view(B, T, H)[:, 1:].float()
+    windows = xs[:, idx.to(cuda)]                       # [B, n_win, win, H]
+    _close(lib.window_mean(x, B, T, H, mode, win, n_win, gh, gw), windows.mean(2).reshape(B * n_win, H),
+           1e-2, 1e-2, "window mean")
+    q = _bf(torch.randn(B * n_win, H, generator=g)).to(cuda)
+    kv = _bf(torch.randn(B * T, 2 * H, generator=g)).to(cuda)
+    kvw = kv.view(B, T, 2 * H)[:, 1:].float()[:, idx.to(cuda)]   # [B, n_win, win, 2H]
+    k, v = kvw[..., :H].reshape(B, n_win, win, H // 64, 64), kvw[..., H:].reshape(B, n_win, win, H // 64, 64)
+    s = torch.einsum("bnhd,bnwhd->bnhw", q.float().view(B, n_win, H // 64, 64) / 8, k)
+    ref = torch.einsum("bnhw,bnwhd->bnhd", torch.softmax(s, -1), v).reshape(B * n_win, H)
+    _close(lib.window_attention(q, kv, B, T, H, mode, win, n_win, gh, gw), ref, 2e-2, 2e-2, "window attention")
+
+
+def test_unit_normalize_segment_pool_rowdot(cuda, lib):
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(37, 768, generator=g).to(cuda)
+    ref = x / torch.sqrt((x * x).sum(-1, keepdim=True) + 1e-5)
+    _close(lib.unit_normalize(x), ref, 1e-6, 1e-5, "unit_normalize f32")
+    _close(lib.unit_normalize(_bf(x), scale=2.0), 2 * _bf(x).float() / torch.sqrt((_bf(x).float() ** 2).sum(-1, keepdim=True) + 1e-5),
+           1e-6, 1e-5, "unit_normalize bf16 in")
+    B, L, H, S = 3, 50, 128, 7
+    v = torch.randn(B, L, H, generator=g).to(cuda)
+    do_pool = (torch.rand(B, L, generator=g) > 0.6).to(torch.uint8).to(cuda)
+    idx = torch.randint(0, S + 2, (B, L), generator=g).to(torch.int32).to(cuda)   # some out of range
+    pooled, count = lib.segment_pool(do_pool, idx, v, S)
+    oh = ((idx[..., None] == torch.arange(S, device=cuda)) & do_pool.bool()[..., None]).float()
+    _close(pooled, torch.einsum("bls,blh->bsh", oh, v), 1e-5, 1e-5, "segment pool")
+    assert torch.equal(count, oh.sum(1))
+    w = torch.randn(H, generator=g).to(cuda)
+    xb = _bf(v.view(B * L, H))
+    rows = torch.tensor([3, 0, 77, 149], dtype=torch.int32, device=cuda)
+    _close(lib.row_dot(xb, w, rows), xb.float()[rows.long()] @ w, 1e-4, 1e-4, "row dot")
+
+
+def test_contrastive_lse(cuda, lib):
+    g = torch.Generator().manual_seed(10)
+    n, n_all, H = 96, 384, 768
+    x = _bf(torch.nn.functional.normalize(torch.randn(n, H, generator=g), dim=-1) * 4.4).to(cuda)
+    y = _bf(torch.nn.functional.normalize(torch.randn(n_all, H, generator=g), dim=-1) * 4.4).to(cuda)
+    lse, numer = lib.contrastive_lse(x, y, y[:n].contiguous())
+    logits = x.float() @ y.float().t()
+    _close(lse, torch.logsumexp(logits, -1), 1e-3, 1e-4, "lse")
+    _close(numer, (x.float() * y[:n].float()).sum(-1), 1e-3, 1e-4, "numer")
+
+
+def test_rotary_table_and_assemble(cuda, lib):
+    import sys
+    from oracle import reserve_oracle as O
+    g = torch.Generator().manual_seed(11)
+    for nd in (1, 2, 4):
+        c = (torch.rand(40, nd, generator=g) * 2 - 1)
+        _close(lib.rotary_table(c.to(cuda).contiguous()), O.rotary_scale_table(c).to(cuda), 2e-5, 1e-5, f"rotary table nd={nd}")
+    # joint assembly against the oracle's prepare_multimodal_inputs
+    from merlot_reserve_b200.synthetic import tiny_config, synthetic_params, synthetic_clip
+    cfg = tiny_config()
+    H = cfg["model"]["hidden_size"]
+    params = synthetic_params(cfg)
+    orc = O.OracleMerlotReserve(cfg, params)
+    clip = synthetic_clip(cfg, nseg=4)
+    tokens = torch.from_numpy(clip["tokens"])[None]
+    sub = torch.from_numpy(clip["subseg_idxs"])[None]
+    vis = torch.randn(1, 4 * 6, H, generator=g)
+    aud = torch.randn(1, 12, 6, H, generator=g)
+    mm = orc.prepare_multimodal_inputs(tokens, token_segment_idx=torch.div(sub, 3, rounding_mode="floor"),
+                                       vision_input=_bf(vis).float(), audio_spans=_bf(aud).float(),
+                                       audio_pointers=sub, padding_len=200)
+    emb = _bf(torch.from_numpy(params["token_encoder"]["Embed_0"]["embedding"])).to(cuda)
+    x, rot, valid = lib.embed_assemble(tokens.int().to(cuda), emb, H=H,
+                                       seg_idx=torch.div(sub, 3, rounding_mode="floor").int().to(cuda),
+                                       aud_ptr=sub.int().to(cuda), audio=_bf(aud).to(cuda), vision=_bf(vis).to(cuda),
+                                       n_aud=12, n_vis=24, pool_h=2, pool_w=3, T=200)
+    ref_x = mm["x"][0].clone()
+    tok_rows = (tokens[0] != 5)
+    ref_x[:160][tok_rows] = _bf(ref_x[:160][tok_rows]).float()      # embedding table is bf16 on the device
+    _close(x, ref_x.to(cuda), 1e-6, 1e-6, "assembled x")
+    _close(rot, O.rotary_scale_table(mm["rotary_coords"][0]).to(cuda), 3e-5, 1e-5, "assembled rot")
+    assert torch.equal(valid.cpu().bool(), mm["is_valid"][0])

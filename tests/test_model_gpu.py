@@ -1,0 +1,143 @@
+"""End-to-end parity of the reference-facing API (merlot_reserve_b200.modeling) against the CPU oracle on
+identical random-init weights and synthetic inputs.  Tolerances (BASELINE.json north_star): embedding
+cosine >= 0.999 per row; identical argmax on multiple-choice scoring wherever the oracle's top-2 margin
+exceeds the stated logit tolerance."""
+import numpy as np
+import pytest
+import torch
+
+from merlot_reserve_b200 import MerlotReserve, PretrainedMerlotReserve
+from merlot_reserve_b200.synthetic import (synthetic_batch, synthetic_clip, synthetic_params, synthetic_spans,
+                                           tiny_config, load_config)
+from oracle.reserve_oracle import OracleMerlotReserve, MASK
+
+pytestmark = pytest.mark.gpu
+COS_MIN = 0.999
+
+
+def _cos(a, b):
+    a = torch.as_tensor(np.asarray(a)).float().reshape(-1, np.asarray(a).shape[-1])
+    b = torch.as_tensor(np.asarray(b)).float().reshape(-1, np.asarray(b).shape[-1])
+    return torch.nn.functional.cosine_similarity(a, b, dim=-1)
+
+
+@pytest.fixture(scope="module", params=[1.0, 4.0], ids=["init_scale", "scale4"])
+def setup(request, cuda):
+    cfg = tiny_config()
+    params = synthetic_params(cfg, seed=0, weight_scale=request.param)
+    model = MerlotReserve.from_config(cfg)
+    return cfg, params, model, OracleMerlotReserve(cfg, params)
+
+
+def test_vision_audio_span_encoders(setup):
+    cfg, params, model, orc = setup
+    clip = synthetic_clip(cfg, nseg=3)
+    got = model.apply({"params": params}, clip["images"], method=model.get_imgseq_only)
+    assert _cos(got, orc.get_imgseq_only(clip["images"])).min() >= COS_MIN
+    got = model.apply({"params": params}, clip["audio_clips"], method=model.get_audioseq_only)
+    assert _cos(got, orc.get_audioseq_only(clip["audio_clips"])).min() >= COS_MIN
+    got = model.apply({"params": params}, clip["audio_clips"], method=model.embed_audio_only)
+    assert _cos(got, orc.embed_audio_only(clip["audio_clips"])).min() >= COS_MIN
+    spans = synthetic_spans(21)
+    got = model.apply({"params": params}, spans, method=model.embed_text_spans_only)
+    ref = orc.embed_text_spans_only(spans)
+    assert _cos(got, ref).min() >= COS_MIN
+    assert np.allclose(np.linalg.norm(got, axis=-1), 1.0, atol=1e-3)
+
+
+@pytest.mark.parametrize("nseg", [2, 8])
+def test_embed_video(setup, nseg):
+    cfg, params, model, orc = setup
+    clip = synthetic_clip(cfg, nseg=nseg, seed=5)
+    got = model.apply({"params": params}, **clip, method=model.embed_video)
+    ref = orc.embed_video(**clip)
+    assert got.shape == tuple(ref.shape) == (160, cfg["model"]["hidden_size"])
+    cos = _cos(got, ref)
+    # every row, including the padding rows whose queries are fully masked (uniform attention)
+    assert cos.min() >= COS_MIN, f"min cosine {cos.min():.5f} at row {int(cos.argmin())}"
+
+
+def test_batch_embed_video_matches_single(setup):
+    cfg, params, model, orc = setup
+    batch = synthetic_batch(cfg, 3, nseg=4, seed=11)
+    got = model.apply({"params": params}, **batch, method=model.batch_embed_video)
+    for i in range(3):
+        one = model.apply({"params": params}, *[batch[k][i] for k in ("images", "audio_clips", "tokens", "subseg_idxs")],
+                          method=model.embed_video)
+        assert _cos(got[i], one).min() >= 0.99999
+        ref = orc.embed_video(*[batch[k][i] for k in ("images", "audio_clips", "tokens", "subseg_idxs")])
+        assert _cos(got[i], ref).min() >= COS_MIN
+
+
+def test_preencoded_and_prompt_paths(setup):
+    cfg, params, model, orc = setup
+    clip = synthetic_clip(cfg, nseg=4, seed=3)
+    enc_ref = orc.get_imgseq_only(clip["images"])
+    aud_ref = orc.get_audioseq_only(clip["audio_clips"])
+    a = model.apply({"params": params}, enc_ref.numpy(), clip["tokens"], clip["subseg_idxs"],
+                    method=model.embed_preencoded_noaudio)
+    assert _cos(a, orc.embed_preencoded_noaudio(enc_ref, clip["tokens"], clip["subseg_idxs"])).min() >= COS_MIN
+    b = model.apply({"params": params}, enc_ref.numpy(), aud_ref.numpy(), clip["tokens"], clip["subseg_idxs"],
+                    clip["subseg_idxs"], method=model.embed_preencoded_audio)
+    assert _cos(b, orc.embed_preencoded_audio(enc_ref, aud_ref, clip["tokens"], clip["subseg_idxs"],
+                                              clip["subseg_idxs"])).min() >= COS_MIN
+    c = model.apply({"params": params}, enc_ref[:2].numpy(), clip["images"][2:], clip["tokens"], clip["subseg_idxs"],
+                    method=model.embed_singleimg_with_multiimg_prompt)
+    assert _cos(c, orc.embed_singleimg_with_multiimg_prompt(enc_ref[:2], clip["images"][2:], clip["tokens"],
+                                                            clip["subseg_idxs"])).min() >= COS_MIN
+
+
+def test_multiple_text_and_mc_scoring(setup):
+    cfg, params, model, orc = setup
+    rng = np.random.default_rng(0)
+    clip = synthetic_clip(cfg, nseg=1, seed=2)
+    n_cand, Ltok = 4, 32
+    toks = rng.integers(10, 32768, size=(n_cand, Ltok)).astype(np.int32)
+    toks[:, -1] = MASK
+    toks[1, 20:] = 0
+    toks[1, 19] = MASK
+    sub = np.zeros_like(toks)
+    got = model.apply({"params": params}, clip["images"], toks, sub, method=model.embed_singleimg_with_multiple_text)
+    ref = orc.embed_singleimg_with_multiple_text(clip["images"], toks, sub)
+    assert _cos(got, ref).min() >= COS_MIN
+    # VCR-style scoring: logits within tolerance, same argmax where the margin is larger than the tolerance
+    B = 6
+    imgs = rng.random((B, clip["images"].shape[1], 768), dtype=np.float32)
+    tokens = rng.integers(10, 32768, size=(B, n_cand, Ltok)).astype(np.int32)
+    tokens[:, :, -1] = MASK
+    proj = (rng.standard_normal(cfg["model"]["hidden_size"]) * 0.3).astype(np.float32)
+    got = model.apply({"params": params}, imgs, tokens, proj, method=model.score_multiple_choice)
+    ref = orc.score_multiple_choice(imgs, tokens, proj).numpy()
+    tol = 0.05 + 0.02 * np.abs(ref)
+    assert (np.abs(got - ref) <= tol).all(), np.abs(got - ref).max()
+    srt = np.sort(ref, -1)
+    confident = (srt[:, -1] - srt[:, -2]) > 2 * tol.max()
+    assert (got.argmax(-1)[confident] == ref.argmax(-1)[confident]).all()
+
+
+def test_zero_shot_scoring_argmax(setup):
+    """demo/demo_video.py:33-47: MASK rows of embed_video against the span label space, x100."""
+    cfg, params, model, orc = setup
+    clip = synthetic_clip(cfg, nseg=4, seed=9)
+    spans = synthetic_spans(40, seed=1)
+    pm = PretrainedMerlotReserve.from_params(cfg, params)
+    h = pm.embed_video(**clip)[clip["tokens"] == MASK]
+    logits = 100.0 * h @ pm.embed_text_spans_only(spans).T
+    h_ref = orc.embed_video(**clip)[torch.from_numpy(clip["tokens"] == MASK)]
+    ref = (100.0 * h_ref @ orc.embed_text_spans_only(spans).T).numpy()
+    assert np.abs(logits - ref).max() <= 0.5          # logits live in [-100, 100]
+    srt = np.sort(ref, -1)
+    if (srt[:, -1] - srt[:, -2] > 1.0).all():
+        assert (logits.argmax(-1) == ref.argmax(-1)).all()
+
+
+def test_input_validation(setup):
+    cfg, params, model, orc = setup
+    model.bind(params)
+    clip = synthetic_clip(cfg, nseg=2)
+    with pytest.raises(ValueError):
+        model.embed_video(clip["images"][..., :700], clip["audio_clips"], clip["tokens"], clip["subseg_idxs"])
+    with pytest.raises(ValueError):
+        model.embed_video(clip["images"], clip["audio_clips"][:5], clip["tokens"], clip["subseg_idxs"])
+    with pytest.raises(ValueError):
+        model.embed_video(clip["images"], clip["audio_clips"], clip["tokens"], clip["subseg_idxs"][:10])

@@ -1,0 +1,318 @@
+#!/usr/bin/env python
+"""Benchmark of the MERLOT Reserve encoder hot path on B200 (BASELINE.json metric: segments/sec).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config base|large] [--clips B]
+
+One "step" = one pass of `MerlotReserve.batch_embed_video` (vision + audio + joint encoders + head +
+unit_normalize) over B synthetic clips of 16 segments; a segment = one 192x320 frame (12x20 patches) plus
+its 3 audio sub-segments.  N=1 runs BASELINE.json configs[1] (Reserve-Base, 64 clips, bf16).  N>1 (launched
+by torchrun, one rank per GPU) runs independent replicas on disjoint clips -- the path shards by clip with
+no data-path collective ("weak" scaling); the only communication is the timing barrier / max.
+
+JSON line keys: see the task contract.  `value` is timed with inputs resident in HBM, `e2e` through the
+same public call with pinned HOST buffers (H2D of the inputs and D2H of the [B,160,H] result inside the
+timed region).  `roofline` describes the dominant kernel class (the tcgen05 GEMM), timed live with CUDA
+events around every launch of a separate instrumented step sequence.  `cpu_baseline` / `--impl reference`
+time the CPU oracle (torch fp32 restatement of the reference -- the reference's own JAX path cannot be
+installed in this environment) on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+NSEG = 16
+METRIC, UNIT = "segments/sec", "segments/s"
+
+
+def flops_per_clip(cfg, nseg=NSEG, L=160):
+    """Algorithmic FLOPs of embed_video per clip: 24 T H^2 + 4 T^2 H per layer, plus
+    patch / audio embeds, the two attention pools and the head."""
+    m = cfg["model"]
+    H = m["hidden_size"]
+    gh, gw = m["output_grid"]
+    hw = gh * gw
+
+    def enc(T, layers):
+        return layers * (24 * T * H * H + 4 * T * T * H)
+
+    vis = nseg * (enc(hw + 1, m["vit_num_layers"]) + 2 * hw * 768 * H + 2 * hw * H * H * 2 + 2 * (hw // 4) * H * H * 2)
+    aud = 3 * nseg * (enc(31, m["audio_num_layers"]) + 2 * 30 * 130 * H + 2 * 30 * H * H * 2 + 2 * 6 * H * H * 2)
+    joint = enc(L + nseg * hw // 4, m["joint_num_layers"]) + 2 * L * H * H
+    return float(vis + aud + joint)
+
+
+class ClockSampler:
+    """Samples nvidia-smi SM clocks / throttle reasons while the timed region runs."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx = max(mx, float(parts[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def load_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return {"tflops_burst": d["bf16_tflops"], "tflops_sustained": d["bf16_tflops_sustained"],
+                "hbm_gbs": d["hbm_gbs"], "source": "measured"}
+    return {"tflops_burst": 1590.0, "tflops_sustained": 1400.0, "hbm_gbs": 6650.0, "source": "fallback"}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU oracle arm
+# ------------------------------------------------------------------------------------------------
+def cpu_oracle_segments_per_s(cfg, params, steps: int, warmup: int, nseg_sample: int):
+    """Times the CPU oracle's embed_video on ONE clip of `nseg_sample` segments per step."""
+    from merlot_reserve_b200.synthetic import synthetic_clip
+    from oracle.reserve_oracle import OracleMerlotReserve
+    torch.set_num_threads(os.cpu_count() or 1)
+    orc = OracleMerlotReserve(cfg, params)
+    clip = synthetic_clip(cfg, nseg=nseg_sample, seed=1)
+    with torch.no_grad():
+        for _ in range(warmup):
+            orc.embed_video(**clip)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            orc.embed_video(**clip)
+        dt = (time.perf_counter() - t0) / steps
+    return nseg_sample / dt, dt, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from merlot_reserve_b200.synthetic import load_config, synthetic_params
+    cfg = load_config(args.config)
+    params = synthetic_params(cfg, seed=0)
+    steps, warmup = min(args.steps, 5), min(args.warmup, 1)
+    val, dt, cores = cpu_oracle_segments_per_s(cfg, params, steps, warmup, NSEG)
+    sample = (f"CPU oracle (torch fp32 restatement of the reference; jax/flax not installable here): "
+              f"embed_video on 1 clip x {NSEG} segments per step, {steps} steps")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"reserve-{args.config} embed_video (vision+audio+joint), 16-segment clips, 12x20 patches, L=160",
+                   "clips_per_step": 1},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# B200 arm
+# ------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch.distributed as dist
+    from merlot_reserve_b200 import MerlotReserve, _lib
+    from merlot_reserve_b200.synthetic import load_config, synthetic_batch, synthetic_params
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    _lib.require_b200(local)
+
+    cfg = load_config(args.config)
+    H = cfg["model"]["hidden_size"]
+    B = args.clips
+    params = synthetic_params(cfg, seed=0)
+    model = MerlotReserve.from_config(cfg).bind(params)
+    batch = synthetic_batch(cfg, B, nseg=NSEG, seed=1 + 1000 * rank)      # disjoint clips per rank
+    host = {k: torch.from_numpy(v).pin_memory() for k, v in batch.items()}
+    resident = {k: v.to(dev) for k, v in host.items()}
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        return model.batch_embed_video(**resident)
+
+    out_host = torch.empty((B, 160, H), dtype=torch.float32).pin_memory()
+
+    def step_e2e():
+        out = model.batch_embed_video(**host)             # H2D of every input happens inside the call
+        out_host.copy_(out, non_blocking=True)            # D2H of the step's result
+        torch.cuda.current_stream().synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    launches0 = _lib.launch_count()
+    with ClockSampler(local) as clk:
+        total_ms = timed(step_resident, args.steps)
+    launches = _lib.launch_count() - launches0
+    ms_step = total_ms / args.steps
+    value = world * B * NSEG / (ms_step * 1e-3)
+
+    for _ in range(2):
+        step_e2e()
+    e2e_ms = timed(step_e2e, args.steps) / args.steps
+    e2e_value = world * B * NSEG / (e2e_ms * 1e-3)
+    h2d = sum(v.numel() * v.element_size() for v in host.values())
+    d2h = out_host.numel() * out_host.element_size()
+
+    # per-kernel-class timing: CUDA events around every launch of instrumented steps
+    peaks = load_peaks()
+    _lib.PROFILE = []
+    for _ in range(2):
+        step_resident()
+    torch.cuda.synchronize()
+    agg = {}
+    for name, (tag, fl, by), a, b in _lib.PROFILE:
+        d = agg.setdefault(tag, {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "launches": 0})
+        d["ms"] += a.elapsed_time(b)
+        d["flops"] += fl
+        d["bytes"] += by
+        d["launches"] += 1
+    _lib.PROFILE = None
+    prof_ms = sum(d["ms"] for d in agg.values())
+    kernels = {t: {"share": d["ms"] / prof_ms, "ms_per_step": d["ms"] / 2, "launches_per_step": d["launches"] // 2,
+                   "tflops": (d["flops"] / d["ms"] / 1e9) if d["flops"] else None,
+                   "gbs": (d["bytes"] / d["ms"] / 1e6) if (d["bytes"] and not d["flops"]) else None}
+               for t, d in sorted(agg.items(), key=lambda kv: -kv[1]["ms"])}
+    gemm = {"ms": 0.0, "flops": 0.0, "launches": 0}
+    for t, d in agg.items():
+        if t.startswith("gemm"):
+            for k in gemm:
+                gemm[k] += d[k]
+    achieved = gemm["flops"] / gemm["ms"] / 1e9
+    peak = peaks["tflops_sustained"]
+    roofline = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (all epilogue variants)", "achieved": achieved,
+                "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                "peak_source": f"{peaks['source']} sustained bf16 (kernel timed inside a long step)",
+                "avg_launch_ms": gemm["ms"] / gemm["launches"], "flops_per_launch": gemm["flops"] / gemm["launches"],
+                "share_of_step": gemm["ms"] / prof_ms, "traffic": None}
+    whole = flops_per_clip(cfg) * B / (ms_step * 1e-3) / 1e12
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        val, dt, cores = cpu_oracle_segments_per_s(cfg, params, steps=2, warmup=1, nseg_sample=NSEG)
+        cpu = {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"CPU oracle (torch fp32 port of the reference arithmetic; jax not installable): "
+                         f"1 clip x {NSEG} segments, 2 timed passes, {dt:.2f} s each"}
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"reserve-{args.config} zero-shot embed_video (vision+audio+joint encoders, head, "
+                                   f"unit_normalize), {B} clips x 16 segments (12x20 patches) + 48 audio "
+                                   f"sub-segments, L=160, per GPU",
+                       "clips_per_gpu": B, "segments_per_step_per_gpu": B * NSEG, "parallelism": f"replicas x{world}",
+                       "l2": "inputs (fp32 patches, 755 MB at 64 clips) and activations exceed the 126 MB L2"},
+            "clocks": clk.summary(),
+            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches),
+            "roofline": roofline,
+            "whole_step_tflops": whole, "whole_step_frac_of_sustained_peak": whole / peak,
+            "kernels": kernels,
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="base", choices=["base", "large"])
+    ap.add_argument("--clips", type=int, default=64)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        with torch.no_grad():
+            run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

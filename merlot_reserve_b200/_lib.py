@@ -161,9 +161,39 @@ def _call(name: str, desc, ins: Sequence[Optional[torch.Tensor]], outs: Sequence
     stream = torch.cuda.current_stream().cuda_stream
     ws_ptr = _ptr(workspace)
     ws_bytes = workspace.numel() * workspace.element_size() if workspace is not None else 0
+    prof = PROFILE
+    if prof is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     st = getattr(lib, name)(C.c_void_p(stream), C.byref(desc), in_arr, out_arr, C.c_void_p(ws_ptr), ws_bytes)
+    if prof is not None:
+        e1.record()
+        prof.append((name, _work(name, desc), e0, e1))
     if st != 0:
         raise MrError(f"{name} failed ({st}): {lib.mr_status_string(st).decode()}")
+
+
+# Optional per-launch timing (bench.py): set PROFILE = [] to collect (entry, (tag, flops, bytes), ev0, ev1)
+# for every call; CUDA events are recorded on the launching stream around the enqueue.
+PROFILE = None
+
+
+def _work(name: str, d):
+    """Algorithmic work of one call: (kernel tag, FLOPs, bytes) -- SURVEY.md §8(d) definitions."""
+    if name == "mr_gemm_epilogue":
+        tag = "gemm"
+        if d.epilogue & EPI_ROTARY_QKV:
+            tag = "gemm_qkv_rotary"
+        elif d.epilogue & EPI_GELU:
+            tag = "gemm_bias_gelu"
+        elif d.epilogue & EPI_RESIDUAL:
+            tag = "gemm_residual"
+        return (tag, 2.0 * d.M * d.N * d.K, 2.0 * (d.M * d.K + d.N * d.K + d.M * d.N))
+    if name == "mr_attention_fwd":
+        return ("attention", 4.0 * d.B * d.T * d.T * d.H, 8.0 * d.B * d.T * d.H)
+    if name == "mr_layernorm_fwd":
+        return ("layernorm", 0.0, 4.0 * d.rows * d.H)
+    return (name[3:], 0.0, 0.0)
 
 
 # ------------------------------------------------------------------------------------------------

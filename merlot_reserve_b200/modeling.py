@@ -67,7 +67,11 @@ def _is_np(*xs) -> bool:
 
 
 def _ret(t: torch.Tensor, as_numpy: bool):
-    return t.cpu().numpy() if as_numpy else t
+    if not as_numpy:
+        return t
+    if t.dtype == torch.bfloat16:  # numpy has no bf16: hand back fp32 (exact)
+        t = t.float()
+    return t.cpu().numpy()
 
 
 # ------------------------------------------------------------------------------------------------

@@ -111,8 +111,12 @@ size_t mr_gemm_epilogue_workspace_bytes(const MrGemmDesc* d);
  * false sees a constant -1e10 bias in the reference, i.e. attends UNIFORMLY to all T keys; that
  * behaviour is reproduced (it matters for padding rows returned by embed_video :842).
  * ------------------------------------------------------------------------------------------ */
+enum { MR_ATTN_ALGO_AUTO = 0, MR_ATTN_ALGO_MMA_SYNC = 1, MR_ATTN_ALGO_TCGEN05 = 2 };
+
 typedef struct MrAttentionDesc {
   int32_t B, T, H; /* H = hidden = 64 * heads */
+  int32_t algo;    /* AUTO: tcgen05/TMEM kernel (128-query tiles) when T > 64, else the small-sequence
+                      mma.sync kernel (64-query tiles; audio T=31, span T=16) */
 } MrAttentionDesc;
 
 int32_t mr_attention_fwd(mr_stream_t stream, const MrAttentionDesc* d, const void* const* in, void* const* out,

@@ -30,7 +30,7 @@ class GemmDesc(C.Structure):
 
 
 class AttentionDesc(C.Structure):
-    _fields_ = [("B", C.c_int32), ("T", C.c_int32), ("H", C.c_int32)]
+    _fields_ = [("B", C.c_int32), ("T", C.c_int32), ("H", C.c_int32), ("algo", C.c_int32)]
 
 
 class LayerNormDesc(C.Structure):
@@ -230,10 +230,13 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias=None, residual=None, rot=None
     return out
 
 
-def attention(qkv: torch.Tensor, B: int, T: int, H: int, valid=None, group=None, out=None) -> torch.Tensor:
+ATTN_AUTO, ATTN_MMA_SYNC, ATTN_TCGEN05 = 0, 1, 2
+
+
+def attention(qkv: torch.Tensor, B: int, T: int, H: int, valid=None, group=None, out=None, algo=ATTN_AUTO) -> torch.Tensor:
     if out is None:
         out = torch.empty((B * T, H), dtype=torch.bfloat16, device=qkv.device)
-    _call("mr_attention_fwd", AttentionDesc(B=B, T=T, H=H), [qkv, valid, group], [out])
+    _call("mr_attention_fwd", AttentionDesc(B=B, T=T, H=H, algo=algo), [qkv, valid, group], [out])
     return out
 
 

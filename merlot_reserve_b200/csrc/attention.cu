@@ -244,6 +244,11 @@ attention_fwd_kernel(const bf16* __restrict__ qkv, const uint8_t* __restrict__ v
 }  // namespace
 }  // namespace mr
 
+namespace mr {
+int32_t launch_attention_tc(cudaStream_t stream, const bf16* qkv, const uint8_t* valid, const int32_t* group,
+                            bf16* out, int B, int T, int H);
+}
+
 extern "C" size_t mr_attention_fwd_workspace_bytes(const MrAttentionDesc*) { return 0; }
 
 extern "C" int32_t mr_attention_fwd(mr_stream_t stream_, const MrAttentionDesc* d, const void* const* in,
@@ -253,6 +258,12 @@ extern "C" int32_t mr_attention_fwd(mr_stream_t stream_, const MrAttentionDesc* 
   MR_REQUIRE(d->B >= 0 && d->T > 0 && d->H > 0 && d->H % 64 == 0, MR_ERR_BAD_SHAPE);
   MR_REQUIRE(aligned16(in[0]) && aligned16(out[0]), MR_ERR_MISALIGNED);
   if (d->B == 0) return MR_OK;
+  MR_REQUIRE(d->algo >= MR_ATTN_ALGO_AUTO && d->algo <= MR_ATTN_ALGO_TCGEN05, MR_ERR_BAD_SHAPE);
+  if (d->algo == MR_ATTN_ALGO_TCGEN05 || (d->algo == MR_ATTN_ALGO_AUTO && d->T > 64)) {
+    return launch_attention_tc(static_cast<cudaStream_t>(stream_), static_cast<const bf16*>(in[0]),
+                               static_cast<const uint8_t*>(in[1]), static_cast<const int32_t*>(in[2]),
+                               static_cast<bf16*>(out[0]), d->B, d->T, d->H);
+  }
   const int nh = d->H / 64;
   const int nqb = ceil_div(d->T, kBlockM);
   const int64_t blocks = static_cast<int64_t>(d->B) * nh * nqb;

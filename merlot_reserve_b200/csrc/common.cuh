@@ -32,6 +32,10 @@ inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 int device_sm_count();
 
+// 2-D bf16 tensor map over [rows, cols] with row pitch `ld` elements, box [box_rows, box_cols],
+// 128-byte swizzle (box_cols * 2 bytes must be 128), zero fill out of bounds.
+bool make_tmap_2d(CUtensorMap* m, const void* base, int64_t rows, int cols, int64_t ld, int box_rows, int box_cols);
+
 }  // namespace mr
 
 #define MR_REQUIRE(cond, code) \

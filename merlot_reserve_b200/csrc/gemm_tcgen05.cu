@@ -351,35 +351,6 @@ __global__ void gemm_simt_debug_kernel(const bf16* __restrict__ A, int lda, cons
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
-using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn get_encode_fn() {
-  static EncodeTiledFn fn = []() -> EncodeTiledFn {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess) return nullptr;
-    if (q != cudaDriverEntryPointSuccess) return nullptr;
-    return reinterpret_cast<EncodeTiledFn>(p);
-  }();
-  return fn;
-}
-
-// 2-D bf16 tensor [rows, cols] with row pitch `ld` elements; box = [box_rows, 64 cols], 128B swizzle.
-bool make_tmap_2d(CUtensorMap* m, const void* base, int rows, int cols, int ld, int box_rows) {
-  EncodeTiledFn fn = get_encode_fn();
-  if (!fn) return false;
-  cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
-  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
-  cuuint32_t box[2] = {static_cast<cuuint32_t>(kBK), static_cast<cuuint32_t>(box_rows)};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS;
-}
-
 template <int BN, bool G, bool R, bool Q>
 int32_t launch_one(cudaStream_t stream, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int grid) {
   auto kern = gemm_tcgen05_kernel<BN, G, R, Q>;
@@ -472,8 +443,8 @@ extern "C" int32_t mr_gemm_epilogue(mr_stream_t stream_, const MrGemmDesc* d, co
   const int grid = p.num_tiles < sms ? p.num_tiles : sms;
 
   CUtensorMap ta, tb;
-  MR_REQUIRE(make_tmap_2d(&ta, A, d->M, d->K, d->lda, kBM), MR_ERR_DRIVER);
-  MR_REQUIRE(make_tmap_2d(&tb, W, d->N, d->K, d->K, bn), MR_ERR_DRIVER);
+  MR_REQUIRE(make_tmap_2d(&ta, A, d->M, d->K, d->lda, kBM, kBK), MR_ERR_DRIVER);
+  MR_REQUIRE(make_tmap_2d(&tb, W, d->N, d->K, d->K, bn, kBK), MR_ERR_DRIVER);
   if (bn == 256) return launch_bn<256>(stream, ta, tb, p, grid, gelu, residual, rotary);
   return launch_bn<128>(stream, ta, tb, p, grid, gelu, residual, rotary);
 }

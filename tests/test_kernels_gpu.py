@@ -142,16 +142,32 @@ def _attn_ref(qkv, B, T, H, valid=None, group=None):
 
 @pytest.mark.parametrize("B,T,H", [(3, 241, 768), (5, 31, 768), (7, 16, 128), (2, 577, 1024), (1, 1120, 768),
                                    (2, 64, 128), (2, 65, 128), (1, 640, 256)])
-def test_attention_unmasked(cuda, lib, B, T, H):
+@pytest.mark.parametrize("algo", [1, 2], ids=["mma_sync", "tcgen05"])
+def test_attention_unmasked(cuda, lib, B, T, H, algo):
     g = torch.Generator().manual_seed(T)
     qkv = _bf(torch.randn(B * T, 3 * H, generator=g)).to(cuda)
     qkv.view(B * T, 3, H)[:, 0] *= 0.35  # keep the softmax away from one-hot
-    out = lib.attention(qkv, B, T, H)
+    out = lib.attention(qkv, B, T, H, algo=algo)
     _close(out, _attn_ref(qkv, B, T, H), 2e-2, 2e-2, f"attention T={T}")
 
 
+def test_attention_lazy_rescale(cuda, lib):
+    """Scores that grow block after block force the tcgen05 kernel through its O-correction path."""
+    B, T, H = 2, 640, 128
+    g = torch.Generator().manual_seed(0)
+    qkv = _bf(torch.randn(B * T, 3 * H, generator=g)).to(cuda)
+    v3 = qkv.view(B, T, 3, H)
+    v3[:, :, 0] = _bf(torch.ones(B, T, H) * 0.25).to(cuda)
+    ramp = torch.linspace(-1.0, 1.0, T).view(1, T, 1).expand(B, T, H)       # later keys score much higher
+    v3[:, :, 1] = _bf(ramp * 1.5 + 0.05 * torch.randn(B, T, H, generator=g)).to(cuda)
+    ref = _attn_ref(qkv, B, T, H)
+    for algo in (1, 2):
+        _close(lib.attention(qkv, B, T, H, algo=algo), ref, 2e-2, 2e-2, f"lazy rescale algo {algo}")
+
+
 @pytest.mark.parametrize("B,T,H", [(4, 16, 128), (3, 200, 128), (2, 640, 256)])
-def test_attention_masked(cuda, lib, B, T, H):
+@pytest.mark.parametrize("algo", [1, 2], ids=["mma_sync", "tcgen05"])
+def test_attention_masked(cuda, lib, B, T, H, algo):
     g = torch.Generator().manual_seed(T + 1)
     qkv = _bf(torch.randn(B * T, 3 * H, generator=g)).to(cuda)
     qkv.view(B * T, 3, H)[:, 0] *= 0.35
@@ -160,8 +176,8 @@ def test_attention_masked(cuda, lib, B, T, H):
     valid[0, T // 2:] = 0  # a long padded tail, whole key blocks masked
     group = torch.randint(0, 3, (B, T), generator=g).to(torch.int32)
     valid, group = valid.to(cuda).contiguous(), group.to(cuda).contiguous()
-    _close(lib.attention(qkv, B, T, H, valid=valid.view(-1)), _attn_ref(qkv, B, T, H, valid), 2e-2, 2e-2, "valid")
-    _close(lib.attention(qkv, B, T, H, valid=valid.view(-1), group=group.view(-1)),
+    _close(lib.attention(qkv, B, T, H, valid=valid.view(-1), algo=algo), _attn_ref(qkv, B, T, H, valid), 2e-2, 2e-2, "valid")
+    _close(lib.attention(qkv, B, T, H, valid=valid.view(-1), group=group.view(-1), algo=algo),
            _attn_ref(qkv, B, T, H, valid, group), 2e-2, 2e-2, "valid+group")
 
 

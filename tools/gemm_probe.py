@@ -30,6 +30,8 @@ def main():
     H = int(sys.argv[1]) if len(sys.argv) > 1 else 768
     res = []
     shapes = [("vision", 246784), ("audio", 95232), ("joint", 71680), ("1clip-vision", 3856)]
+    if "--attn-only" in sys.argv:
+        shapes = []
     for name, M in shapes:
         a = torch.randn(M, H, device=dev).to(torch.bfloat16)
         a4 = torch.randn(M, 4 * H, device=dev).to(torch.bfloat16)
@@ -62,10 +64,11 @@ def main():
                          "large-joint16": (16, 2464)}.items():
         qkv = torch.randn(B * T, 3 * H, device=dev).to(torch.bfloat16)
         out = torch.empty(B * T, H, device=dev, dtype=torch.bfloat16)
-        ms = timeit(lambda: L.attention(qkv, B, T, H, out=out))
         fl = 4.0 * B * T * T * H
-        res.append(dict(kernel="attention", rows=name, B=B, T=T, ms=ms, tflops=fl / ms / 1e9))
-        print(json.dumps(res[-1]), flush=True)
+        for algo in (1, 2):
+            ms = timeit(lambda: L.attention(qkv, B, T, H, out=out, algo=algo))
+            res.append(dict(kernel="attention", algo=algo, rows=name, B=B, T=T, ms=ms, tflops=fl / ms / 1e9))
+            print(json.dumps(res[-1]), flush=True)
     Path("gpurun_out").mkdir(exist_ok=True)
     Path(f"gpurun_out/probe_H{H}.json").write_text(json.dumps(res, indent=1))
 

@@ -10,6 +10,15 @@
 //                                tile i overlaps the main loop of tile i+1), apply
 //                                bias / rotary scale / sigmoid-GELU / residual, cast and store.
 //
+// Two epilogue data paths:
+//   kDirect = false (bf16 output, no row remap -- every GEMM of the transformer layers): each epilogue warp
+//     owns a 32-row x 64-column box staged in shared memory with the 128-byte TMA swizzle.  The residual
+//     box is TMA-loaded into it while the MMAs of the tile are still running, the fused result is written
+//     over it in place and leaves with one TMA store.  A thread owns one accumulator ROW (that is how
+//     TMEM lanes map to threads), so direct global accesses would touch 32 different 128-byte lines per
+//     warp instruction; ncu showed exactly that as the limiter of the K=768 GEMMs (profiles/ncu_gemm_r01b.md).
+//   kDirect = true (fp32 output or row-remapped output): per-thread 16-byte global accesses (rare, small).
+//
 // The arithmetic this replaces is flax Dense/DenseGeneral (+ the elementwise ops around it) at the
 // reference call sites listed in include/mreserve_b200.h.
 #include "common.cuh"
@@ -39,6 +48,8 @@ struct GemmParams {
   int num_n_tiles, num_tiles, num_k_blocks;
 };
 
+constexpr int kBoxBytes = 32 * 128;  // one epilogue staging box: 32 rows x 64 bf16, 128B swizzle
+
 template <int BN>
 struct Cfg {
   static constexpr int kStages = BN == 256 ? 4 : 6;
@@ -46,33 +57,41 @@ struct Cfg {
   static constexpr int kBBytes = BN * kBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTmemCols = 2 * BN;  // two accumulator stages
+  static constexpr int kOutBytes = kEpiWarps * kBoxBytes;
   static constexpr int kBarBytes = 256;
-  static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 1024;  // +1024: manual alignment
+  static constexpr int kSmemBytes = kStages * kStageBytes + kOutBytes + kBarBytes + 1024;  // +1024: manual alignment
+  static_assert(kSmemBytes <= 232448, "exceeds the 227 KB dynamic shared memory limit");
 };
 
 __device__ __forceinline__ float gelu_sigmoid(float x) {
-  // x * sigmoid(1.702 x) = x / (1 + exp(-1.702 x)); exp via ex2.approx, reciprocal via rcp.approx.
-  float e = exp2f(-1.702f * 1.4426950408889634f * x);
-  return __fdividef(x, 1.0f + e);
+  // x * sigmoid(1.702 x) = 0.5 x (1 + tanh(0.851 x)): ONE SFU op (tanh.approx, rel. error 2^-11, far below
+  // the bf16 rounding of the result) instead of ex2 + rcp -- the SFU was the second limiter of this epilogue.
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.851f * x));
+  const float h = 0.5f * x;
+  return fmaf(h, t, h);
 }
 
 __device__ __forceinline__ int map_row(int r, int seq_in, int seq_out, int row_off) {
   return seq_in == 0 ? r : (r / seq_in) * seq_out + (r % seq_in) + row_off;
 }
 
-template <int BN, bool kGelu, bool kResidual, bool kRotary>
+template <int BN, bool kGelu, bool kResidual, bool kRotary, bool kDirect>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                    const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res,
                     const GemmParams p) {
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes + C::kOutBytes);
   uint64_t* empty_bar = full_bar + C::kStages;
   uint64_t* tmem_full_bar = empty_bar + C::kStages;
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  uint64_t* res_bar = tmem_empty_bar + 2;  // [kEpiWarps]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + kEpiWarps);
+  uint8_t* smem_out = smem + C::kStages * C::kStageBytes;
 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -80,6 +99,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   if (warp_idx == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
+    if constexpr (!kDirect) {
+      tma_prefetch_desc(&tmap_out);
+      if constexpr (kResidual) tma_prefetch_desc(&tmap_res);
+    }
   }
   if (warp_idx == 1 && lane == 0) {
     for (int s = 0; s < C::kStages; ++s) {
@@ -90,6 +113,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       mbar_init(&tmem_full_bar[a], 1);
       mbar_init(&tmem_empty_bar[a], kEpiWarps);
     }
+    for (int w = 0; w < kEpiWarps; ++w) mbar_init(&res_bar[w], 1);
     fence_mbar_init();
   }
   if (warp_idx == 2) {
@@ -101,12 +125,21 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // Static schedule over tiles in m-major order.  Default: round-robin (tile = cta, cta + grid, ...), so the
+  // CTAs that share an A row block run at the same time and a long-K A block is fetched from HBM once.
+  // Rotary (QKV) GEMMs: every CTA owns a CONTIGUOUS range instead, so consecutive tiles of a CTA share the row
+  // block and the per-row rotary scales stay in registers (K = hidden there: 148 live A blocks fit the L2).
+  const int tiles_per_cta = (p.num_tiles + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+  const int tile_step = kRotary ? 1 : static_cast<int>(gridDim.x);
+  const int tile_begin = kRotary ? static_cast<int>(blockIdx.x) * tiles_per_cta : static_cast<int>(blockIdx.x);
+  const int tile_end = kRotary ? min(tile_begin + tiles_per_cta, p.num_tiles) : p.num_tiles;
+
   if (warp_idx == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
         const int m_blk = tile / p.num_n_tiles;
         const int n_blk = tile % p.num_n_tiles;
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
@@ -132,7 +165,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
         mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
@@ -169,7 +202,157 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     constexpr int kChunks = BN / 64;           // 32-column chunks per warp
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    if constexpr (!kDirect) {
+      // ---------- staged path: TMEM -> registers -> swizzled smem box -> TMA store ----------
+      constexpr int kBoxes = BN / 128;         // 64-column boxes per warp
+      uint8_t* sbuf = smem_out + ew * kBoxBytes;
+      uint8_t* my_row = sbuf + lane * 128;     // this thread's 128-byte row of the box
+      const int sw = lane & 7;                 // 128B swizzle: 16-byte chunk j lives at chunk (j ^ (row & 7))
+      uint64_t* rbar = &res_bar[ew];
+      uint32_t res_phase = 0;
+      float rot[kRotary ? 32 : 1];
+      int rot_m = -1;
+      for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
+        const int m_blk = tile / p.num_n_tiles;
+        const int n_blk = tile % p.num_n_tiles;
+        const int row0 = m_blk * kBM + quarter * 32;
+        const int r = row0 + lane;
+        const int col_base = n_blk * BN + col_half * (BN / 2);
+
+        // Work that does not depend on the accumulator goes first: residual box 0 and the rotary row.
+        if (lane == 0) {
+          tma_store_wait_read<0>();            // the previous tile's store has finished reading the box
+          if constexpr (kResidual) {
+            if (col_base < p.N) {
+              mbar_arrive_expect_tx(rbar, kBoxBytes);
+              tma_load_2d(&tmap_res, rbar, sbuf, col_base, row0, kEvictFirst);
+            }
+          }
+        }
+        __syncwarp();
+        if constexpr (kRotary) {
+          if (m_blk != rot_m) {                // same row block as the previous tile: keep the registers
+            rot_m = m_blk;
+            const float4* src = reinterpret_cast<const float4*>(p.rot + static_cast<size_t>(r < p.M ? (r % p.rot_rows) : 0) * 32);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float4 t = __ldg(src + j);
+              rot[4 * j + 0] = t.x;
+              rot[4 * j + 1] = t.y;
+              rot[4 * j + 2] = t.z;
+              rot[4 * j + 3] = t.w;
+            }
+          }
+        }
+
+        mbar_wait(&tmem_full_bar[acc], acc_phase);
+        tc_fence_after();
+
+#pragma unroll
+        for (int box = 0; box < kBoxes; ++box) {
+          const int col0 = col_base + 64 * box;
+          const bool box_ok = col0 < p.N;      // warp-uniform
+          if (box > 0) {
+            if (lane == 0) {
+              tma_store_wait_read<0>();
+              if constexpr (kResidual) {
+                if (box_ok) {
+                  mbar_arrive_expect_tx(rbar, kBoxBytes);
+                  tma_load_2d(&tmap_res, rbar, sbuf, col0, row0, kEvictFirst);
+                }
+              }
+            }
+            __syncwarp();
+          }
+          uint32_t v[64];
+          {
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
+                                   static_cast<uint32_t>(acc * BN + col_half * (BN / 2) + box * 64);
+            uint32_t lo[32], hi[32];
+            tmem_ld_32x32(taddr, lo);
+            tmem_ld_32x32(taddr + 32, hi);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              v[j] = lo[j];
+              v[32 + j] = hi[j];
+            }
+          }
+          if (box == kBoxes - 1) {
+            // all TMEM reads of this accumulator stage are done: hand it back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+          }
+          if (!box_ok) continue;
+          if constexpr (kResidual) {
+            mbar_wait(rbar, res_phase);
+            res_phase ^= 1;
+          }
+          const bool full_box = col0 + 64 <= p.N;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float f[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) f[q] = __uint_as_float(v[8 * j + q]);
+            const int c = col0 + 8 * j;
+            if (p.bias_on) {
+              if (full_box) {
+                const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + c));
+                const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + c + 4));
+                f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+                f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+              } else {
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                  if (c + q < p.N) f[q] += __ldg(p.bias + c + q);
+              }
+            }
+            if constexpr (kRotary) {
+              // a box is exactly one head: [q heads | k heads | v heads]; first 32 dims of q/k heads are scaled
+              if (j < 4 && col0 < 2 * p.hidden) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) f[q] *= rot[8 * j + q];
+              }
+              if (col0 < p.hidden) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) f[q] *= p.q_scale;
+              }
+            }
+            if constexpr (kGelu) {
+#pragma unroll
+              for (int q = 0; q < 8; ++q) f[q] = gelu_sigmoid(f[q]);
+            }
+            uint4* cell = reinterpret_cast<uint4*>(my_row + ((j ^ sw) << 4));
+            if constexpr (kResidual) {
+              const uint4 rr = *cell;
+              f[0] += bf16_lo(rr.x); f[1] += bf16_hi(rr.x);
+              f[2] += bf16_lo(rr.y); f[3] += bf16_hi(rr.y);
+              f[4] += bf16_lo(rr.z); f[5] += bf16_hi(rr.z);
+              f[6] += bf16_lo(rr.w); f[7] += bf16_hi(rr.w);
+            }
+            uint4 o;
+            o.x = pack_bf16(f[0], f[1]);
+            o.y = pack_bf16(f[2], f[3]);
+            o.z = pack_bf16(f[4], f[5]);
+            o.w = pack_bf16(f[6], f[7]);
+            *cell = o;
+          }
+          fence_proxy_async_smem();            // generic-proxy smem writes -> visible to the TMA (async proxy)
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tmap_out, sbuf, col0, row0);   // rows >= M and columns >= N are clipped by the tensor map
+            tma_store_commit();
+          }
+        }
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+      if (lane == 0) tma_store_wait<0>();      // all bulk stores complete before the CTA retires its smem
+    } else
+    for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
       const int m_blk = tile / p.num_n_tiles;
       const int n_blk = tile % p.num_n_tiles;
       const int r = m_blk * kBM + quarter * 32 + lane;
@@ -351,27 +534,31 @@ __global__ void gemm_simt_debug_kernel(const bf16* __restrict__ A, int lda, cons
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
-template <int BN, bool G, bool R, bool Q>
-int32_t launch_one(cudaStream_t stream, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int grid) {
-  auto kern = gemm_tcgen05_kernel<BN, G, R, Q>;
+struct Maps {
+  CUtensorMap a, b, out, res;
+};
+
+template <int BN, bool G, bool R, bool Q, bool D>
+int32_t launch_one(cudaStream_t stream, const Maps& m, const GemmParams& p, int grid) {
+  auto kern = gemm_tcgen05_kernel<BN, G, R, Q, D>;
   static bool attr_set = false;  // benign race: the attribute is idempotent
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::kSmemBytes);
     if (e != cudaSuccess) return cuda_status(e);
     attr_set = true;
   }
-  kern<<<grid, kThreads, Cfg<BN>::kSmemBytes, stream>>>(ta, tb, p);
+  kern<<<grid, kThreads, Cfg<BN>::kSmemBytes, stream>>>(m.a, m.b, m.out, m.res, p);
   return after_launch();
 }
 
-template <int BN>
-int32_t launch_bn(cudaStream_t stream, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int grid,
-                  bool gelu, bool residual, bool rotary) {
-  if (rotary && !gelu && !residual) return launch_one<BN, false, false, true>(stream, ta, tb, p, grid);
-  if (gelu && !residual && !rotary) return launch_one<BN, true, false, false>(stream, ta, tb, p, grid);
-  if (residual && !gelu && !rotary) return launch_one<BN, false, true, false>(stream, ta, tb, p, grid);
-  if (!gelu && !residual && !rotary) return launch_one<BN, false, false, false>(stream, ta, tb, p, grid);
-  if (gelu && residual && !rotary) return launch_one<BN, true, true, false>(stream, ta, tb, p, grid);
+template <int BN, bool D>
+int32_t launch_bn(cudaStream_t stream, const Maps& m, const GemmParams& p, int grid, bool gelu, bool residual,
+                  bool rotary) {
+  if (rotary && !gelu && !residual) return launch_one<BN, false, false, true, D>(stream, m, p, grid);
+  if (gelu && !residual && !rotary) return launch_one<BN, true, false, false, D>(stream, m, p, grid);
+  if (residual && !gelu && !rotary) return launch_one<BN, false, true, false, D>(stream, m, p, grid);
+  if (!gelu && !residual && !rotary) return launch_one<BN, false, false, false, D>(stream, m, p, grid);
+  if (gelu && residual && !rotary) return launch_one<BN, true, true, false, D>(stream, m, p, grid);
   return MR_ERR_BAD_SHAPE;  // rotary never combines with gelu/residual on this path
 }
 
@@ -442,9 +629,21 @@ extern "C" int32_t mr_gemm_epilogue(mr_stream_t stream_, const MrGemmDesc* d, co
   p.num_k_blocks = ceil_div(d->K, kBK);
   const int grid = p.num_tiles < sms ? p.num_tiles : sms;
 
-  CUtensorMap ta, tb;
-  MR_REQUIRE(make_tmap_2d(&ta, A, d->M, d->K, d->lda, kBM, kBK), MR_ERR_DRIVER);
-  MR_REQUIRE(make_tmap_2d(&tb, W, d->N, d->K, d->K, bn, kBK), MR_ERR_DRIVER);
-  if (bn == 256) return launch_bn<256>(stream, ta, tb, p, grid, gelu, residual, rotary);
-  return launch_bn<128>(stream, ta, tb, p, grid, gelu, residual, rotary);
+  Maps m;
+  MR_REQUIRE(make_tmap_2d(&m.a, A, d->M, d->K, d->lda, kBM, kBK), MR_ERR_DRIVER);
+  MR_REQUIRE(make_tmap_2d(&m.b, W, d->N, d->K, d->K, bn, kBK), MR_ERR_DRIVER);
+  // fp32 output and row-remapped output keep per-thread global accesses; everything else is staged
+  // through shared memory and moved by TMA
+  const bool direct = p.out_f32 || d->seq_in != 0;
+  if (direct) {
+    m.out = m.a;
+    m.res = m.a;
+    if (bn == 256) return launch_bn<256, true>(stream, m, p, grid, gelu, residual, rotary);
+    return launch_bn<128, true>(stream, m, p, grid, gelu, residual, rotary);
+  }
+  MR_REQUIRE(make_tmap_2d(&m.out, out[0], d->M, d->N, d->ldd, 32, 64), MR_ERR_DRIVER);
+  m.res = m.out;
+  if (residual) MR_REQUIRE(make_tmap_2d(&m.res, in[3], d->M, d->N, d->ldd, 32, 64), MR_ERR_DRIVER);
+  if (bn == 256) return launch_bn<256, false>(stream, m, p, grid, gelu, residual, rotary);
+  return launch_bn<128, false>(stream, m, p, grid, gelu, residual, rotary);
 }

@@ -279,14 +279,51 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16_f32_ex(int m, int n, int 
   return umma_idesc_bf16_f32(m, n) | (static_cast<uint32_t>(b_mn_major) << 16);
 }
 
+// Register re-distribution between warpgroups (all 4 warps of a warpgroup must execute it).
+template <int N>
+__device__ __forceinline__ void setmaxnreg_inc() {
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
+}
+template <int N>
+__device__ __forceinline__ void setmaxnreg_dec() {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
+}
+
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
 
+// volatile flavour: keeps its program-order position relative to other volatile asm statements
+__device__ __forceinline__ float ex2_approx_v(float x) {
+  float y;
+  asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+__device__ __forceinline__ void named_bar_arrive(uint32_t id, uint32_t nthreads) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// Named barrier over `nthreads` threads that also AND-reduces a predicate across them.
+__device__ __forceinline__ bool __syncthreads_and_named(int pred, uint32_t id, uint32_t nthreads) {
+  uint32_t r;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %3, 0;\n\t"
+      "bar.red.and.pred q, %1, %2, p;\n\t"
+      "selp.u32 %0, 1, 0, q;\n\t"
+      "}\n"
+      : "=r"(r)
+      : "r"(id), "r"(nthreads), "r"(pred)
+      : "memory");
+  return r != 0;
 }
 
 }  // namespace mr

@@ -181,6 +181,32 @@ def test_attention_masked(cuda, lib, B, T, H, algo):
            _attn_ref(qkv, B, T, H, valid, group), 2e-2, 2e-2, "valid+group")
 
 
+@pytest.mark.parametrize("B,T,H,L", [(2, 1120, 128, 160), (3, 400, 128, 130), (2, 288, 256, 144)])
+def test_attention_joint_style_mask(cuda, lib, B, T, H, L):
+    """Joint-encoder layout: padding only inside the first L (text) positions, every later (vision) key valid, so
+    most key blocks take the mask-free fast path while invalid QUERY rows (uniform attention) cross them."""
+    g = torch.Generator().manual_seed(T + L)
+    qkv = _bf(torch.randn(B * T, 3 * H, generator=g)).to(cuda)
+    qkv.view(B * T, 3, H)[:, 0] *= 0.35
+    valid = torch.ones(B, T, dtype=torch.uint8)
+    valid[:, 40:L] = (torch.rand(B, L - 40, generator=g) > 0.5).to(torch.uint8)
+    valid[1, 20:L] = 0
+    valid = valid.to(cuda).contiguous()
+    ref = _attn_ref(qkv, B, T, H, valid)
+    for algo in (1, 2):
+        _close(lib.attention(qkv, B, T, H, valid=valid.view(-1), algo=algo), ref, 2e-2, 2e-2, f"joint mask algo {algo}")
+
+
+def test_attention_many_items_persistent(cuda, lib):
+    """More work items than SMs, odd and even numbers of query tiles: exercises the persistent loop, the Q double
+    buffer, the K/V ring wrap-around and pairs whose second tile is absent."""
+    g = torch.Generator().manual_seed(99)
+    for B, T, H in [(40, 241, 768), (9, 300, 256), (3, 1120, 768)]:
+        qkv = _bf(torch.randn(B * T, 3 * H, generator=g)).to(cuda)
+        qkv.view(B * T, 3, H)[:, 0] *= 0.35
+        _close(lib.attention(qkv, B, T, H, algo=2), _attn_ref(qkv, B, T, H), 2e-2, 2e-2, f"persistent T={T}")
+
+
 @pytest.mark.parametrize("rows,H", [(1000, 768), (333, 1024), (50, 128)])
 def test_layernorm(cuda, lib, rows, H):
     g = torch.Generator().manual_seed(6)

@@ -69,7 +69,7 @@ int64_t mr_launch_count(void);
  * MR_EPI_ROTARY_QKV: N == 3*hidden; for columns c < 2*hidden with (c % 64) < 32 the value is
  * multiplied by rot[(r % rot_rows) * 32 + (c % 64)]; columns c < hidden are then multiplied by
  * q_scale.
- * Constraints: K % 8 == 0, lda % 8 == 0, N % 8 == 0, ldd % 8 == 0, all pointers 16-byte aligned.
+ * Constraints: K % 8 == 0, lda % 8 == 0, ldd % 8 == 0 (N itself is arbitrary), all pointers 16-byte aligned.
  * ------------------------------------------------------------------------------------------ */
 enum {
   MR_EPI_BIAS = 1,
@@ -217,6 +217,14 @@ typedef struct MrAssembleDesc {
   int32_t cls_offset;     /* 1: leave row 0 of every sequence free for a CLS token (span encoder,
                              modeling.py:311-326); the output then has T + 1 rows per sequence,
                              valid[b, 0] = 1 and rot[b, 0] is the zero-coordinate row */
+  /* Source-row maps for the pretraining forward (pretrain_model.py:97-135), which feeds the SAME encoder
+     outputs to several joint sequences; they avoid materialising the reference's repeat / tile copies:
+       audio row of sequence b  = b / aud_div                         (jnp.repeat(audio_seq, aud_div, axis=0))
+       vision row of sequence b = (b / (vis_group * vis_tile)) * vis_group + b % vis_group
+                                                                       (jnp.tile(imgs_seq, [1, vis_tile, 1, 1]))
+     0 in aud_div / vis_tile means identity (row b). */
+  int32_t aud_div;
+  int32_t vis_group, vis_tile;
 } MrAssembleDesc;
 int32_t mr_embed_assemble(mr_stream_t stream, const MrAssembleDesc* d, const void* const* in, void* const* out,
                           void* workspace, size_t workspace_bytes);
@@ -236,7 +244,8 @@ int32_t mr_rotary_table(mr_stream_t stream, const MrRotaryDesc* d, const void* c
 /* ------------------------------------------------------------------------------------------
  * mr_unit_normalize: y = x / sqrt(sum(x^2) + 1e-5) * scale in fp32 (modeling.py:570-578; the
  * optional scale is exp(log_scale/2) of pretrain_model.py:251-253).
- *   in[0] x f32 or bf16 [rows, H]; out[0] y f32 or bf16 [rows, H]
+ *   in[0] x f32 or bf16 [rows_in, H]; in[1] row_idx i32 [rows] optional gather (y[r] = f(x[row_idx[r]]), the
+ *   `x[batch_indexer, best_idxs]` selections of pretrain_model.py:176-182,229-230); out[0] y f32 or bf16 [rows, H]
  * ------------------------------------------------------------------------------------------ */
 typedef struct MrNormalizeDesc {
   int32_t rows, H;
@@ -255,6 +264,7 @@ int32_t mr_unit_normalize(mr_stream_t stream, const MrNormalizeDesc* d, const vo
 typedef struct MrSegmentPoolDesc {
   int32_t B, L, H, S;
   int32_t v_f32;
+  int32_t accumulate; /* 1: add to pooled / count instead of overwriting (the t2sp sum, pretrain_model.py:190-191) */
 } MrSegmentPoolDesc;
 int32_t mr_segment_pool(mr_stream_t stream, const MrSegmentPoolDesc* d, const void* const* in, void* const* out,
                         void* workspace, size_t workspace_bytes);
@@ -273,6 +283,16 @@ typedef struct MrContrastiveDesc {
 int32_t mr_contrastive_lse_fwd(mr_stream_t stream, const MrContrastiveDesc* d, const void* const* in,
                                void* const* out, void* workspace, size_t workspace_bytes);
 size_t mr_contrastive_lse_fwd_workspace_bytes(const MrContrastiveDesc* d);
+
+/* ------------------------------------------------------------------------------------------
+ * mr_contrastive_reduce: the scalar tail of one direction of loss_fn_given_preds
+ * (pretrain_model.py:295-300):
+ *   out[0] = mean_i(lse[i] - numer[i])
+ *   out[1 + s] = sum_i((lse[i] - numer[i]) * [sources[i] == s]) / (count_s + 1e-5),  s = 0, 1, 2
+ *   in[0] lse f32 [n]; in[1] numer f32 [n]; in[2] sources i32 [n] optional; out[0] f32 [4]
+ * ------------------------------------------------------------------------------------------ */
+int32_t mr_contrastive_reduce(mr_stream_t stream, const MrContrastiveDesc* d, const void* const* in,
+                              void* const* out, void* workspace, size_t workspace_bytes);
 
 /* ------------------------------------------------------------------------------------------
  * mr_row_dot: logits[r] = x[r] . w  (finetune `proj` head H -> 1, no bias;

@@ -54,7 +54,8 @@ class WindowDesc(C.Structure):
 class AssembleDesc(C.Structure):
     _fields_ = [("B", C.c_int32), ("L", C.c_int32), ("H", C.c_int32), ("n_aud", C.c_int32), ("n_vis", C.c_int32),
                 ("pool_h", C.c_int32), ("pool_w", C.c_int32), ("T", C.c_int32), ("vocab", C.c_int32),
-                ("audio_token_length", C.c_int32), ("cls_offset", C.c_int32)]
+                ("audio_token_length", C.c_int32), ("cls_offset", C.c_int32), ("aud_div", C.c_int32),
+                ("vis_group", C.c_int32), ("vis_tile", C.c_int32)]
 
 
 class RotaryDesc(C.Structure):
@@ -67,7 +68,8 @@ class NormalizeDesc(C.Structure):
 
 
 class SegmentPoolDesc(C.Structure):
-    _fields_ = [("B", C.c_int32), ("L", C.c_int32), ("H", C.c_int32), ("S", C.c_int32), ("v_f32", C.c_int32)]
+    _fields_ = [("B", C.c_int32), ("L", C.c_int32), ("H", C.c_int32), ("S", C.c_int32), ("v_f32", C.c_int32),
+                ("accumulate", C.c_int32)]
 
 
 class ContrastiveDesc(C.Structure):
@@ -92,6 +94,7 @@ ENTRY_POINTS = {
     "mr_unit_normalize": NormalizeDesc,
     "mr_segment_pool": SegmentPoolDesc,
     "mr_contrastive_lse_fwd": ContrastiveDesc,
+    "mr_contrastive_reduce": ContrastiveDesc,
     "mr_row_dot": RowDotDesc,
 }
 WORKSPACE_FNS = {
@@ -100,6 +103,8 @@ WORKSPACE_FNS = {
     "mr_contrastive_lse_fwd_workspace_bytes": ContrastiveDesc,
 }
 MISC_FNS = ["mr_check_device", "mr_abi_version", "mr_status_string", "mr_launch_count"]
+
+ABI_VERSION = 2  # must equal mr_abi_version() of the loaded library (struct layouts above)
 
 _lib = None
 
@@ -127,6 +132,9 @@ def load() -> C.CDLL:
     lib.mr_status_string.restype = C.c_char_p
     lib.mr_status_string.argtypes = [C.c_int32]
     lib.mr_launch_count.restype = C.c_int64
+    if lib.mr_abi_version() != ABI_VERSION:
+        raise MrError(f"{_LIB_PATH} has ABI version {lib.mr_abi_version()}, this package needs {ABI_VERSION}: "
+                      f"rebuild with `python -m merlot_reserve_b200.build --force`")
     _lib = lib
     return lib
 
@@ -281,17 +289,23 @@ def window_attention(q, kv, B, T, H, mode, win, n_win, grid_h=0, grid_w=0) -> to
 
 
 def embed_assemble(tokens, emb, *, H, seg_idx=None, aud_ptr=None, audio=None, vision=None, tok_emb=None, n_aud=0,
-                   n_vis=0, pool_h=0, pool_w=0, T=None, audio_token_length=6, cls_offset=0):
+                   n_vis=0, pool_h=0, pool_w=0, T=None, audio_token_length=6, cls_offset=0, aud_div=0, vis_group=0,
+                   vis_tile=0, out=None):
+    """`out` = (x, rot, valid) views to fill (rows of a larger joint batch); allocated when None."""
     B, L = tokens.shape
     T = T if T is not None else L + n_vis
     dev = tokens.device
     rows = B * (T + cls_offset)
-    x = torch.empty((rows, H), dtype=torch.bfloat16, device=dev)
-    rot = torch.empty((rows, 32), dtype=torch.float32, device=dev)
-    valid = torch.empty((rows,), dtype=torch.uint8, device=dev)
+    if out is None:
+        x = torch.empty((rows, H), dtype=torch.bfloat16, device=dev)
+        rot = torch.empty((rows, 32), dtype=torch.float32, device=dev)
+        valid = torch.empty((rows,), dtype=torch.uint8, device=dev)
+    else:
+        x, rot, valid = out
+        assert x.numel() == rows * H and rot.numel() == rows * 32 and valid.numel() == rows
     d = AssembleDesc(B=B, L=L, H=H, n_aud=n_aud, n_vis=n_vis, pool_h=pool_h, pool_w=pool_w, T=T,
                      vocab=(emb.shape[0] if emb is not None else 1), audio_token_length=audio_token_length,
-                     cls_offset=cls_offset)
+                     cls_offset=cls_offset, aud_div=aud_div, vis_group=vis_group, vis_tile=vis_tile)
     _call("mr_embed_assemble", d, [tokens, seg_idx, aud_ptr, emb, audio, vision, tok_emb], [x, rot, valid])
     return x, rot, valid
 
@@ -303,19 +317,28 @@ def rotary_table(coords: torch.Tensor) -> torch.Tensor:
     return out
 
 
-def unit_normalize(x: torch.Tensor, scale: float = 1.0, out_f32: bool = True) -> torch.Tensor:
-    rows, H = x.shape
-    out = torch.empty((rows, H), dtype=torch.float32 if out_f32 else torch.bfloat16, device=x.device)
-    d = NormalizeDesc(rows=rows, H=H, in_f32=int(x.dtype == torch.float32), out_f32=int(out_f32), scale=scale)
-    _call("mr_unit_normalize", d, [x], [out])
+def unit_normalize(x: torch.Tensor, scale: float = 1.0, out_f32: bool = True, row_idx=None, out=None) -> torch.Tensor:
+    """y[r] = x[row_idx[r]] / sqrt(|x[row_idx[r]]|^2 + 1e-5) * scale (row_idx None: identity)."""
+    H = x.shape[-1]
+    rows = x.shape[0] if row_idx is None else row_idx.numel()
+    if out is None:
+        out = torch.empty((rows, H), dtype=torch.float32 if out_f32 else torch.bfloat16, device=x.device)
+    d = NormalizeDesc(rows=rows, H=H, in_f32=int(x.dtype == torch.float32), out_f32=int(out.dtype == torch.float32),
+                      scale=scale)
+    _call("mr_unit_normalize", d, [x, row_idx], [out])
     return out
 
 
-def segment_pool(do_pool: torch.Tensor, idx: torch.Tensor, v: torch.Tensor, S: int):
+def segment_pool(do_pool: torch.Tensor, idx: torch.Tensor, v: torch.Tensor, S: int, accumulate_into=None):
+    """one_hot_pool; `accumulate_into` = (pooled, count) of an earlier call to add to."""
     B, L, H = v.shape
-    pooled = torch.empty((B, S, H), dtype=torch.float32, device=v.device)
-    count = torch.empty((B, S), dtype=torch.float32, device=v.device)
-    d = SegmentPoolDesc(B=B, L=L, H=H, S=S, v_f32=int(v.dtype == torch.float32))
+    if accumulate_into is None:
+        pooled = torch.empty((B, S, H), dtype=torch.float32, device=v.device)
+        count = torch.empty((B, S), dtype=torch.float32, device=v.device)
+    else:
+        pooled, count = accumulate_into
+    d = SegmentPoolDesc(B=B, L=L, H=H, S=S, v_f32=int(v.dtype == torch.float32),
+                        accumulate=int(accumulate_into is not None))
     _call("mr_segment_pool", d, [do_pool, idx, v], [pooled, count])
     return pooled, count
 
@@ -329,6 +352,13 @@ def contrastive_lse(x: torch.Tensor, y_all: torch.Tensor, y_pos: torch.Tensor):
     numer = torch.empty((n,), dtype=torch.float32, device=x.device)
     _call("mr_contrastive_lse_fwd", d, [x, y_all, y_pos], [lse, numer], ws)
     return lse, numer
+
+
+def contrastive_reduce(lse: torch.Tensor, numer: torch.Tensor, sources=None) -> torch.Tensor:
+    """[mean(lse - numer), per-source means x3] (pretrain_model.py:295-300)."""
+    out = torch.empty((4,), dtype=torch.float32, device=lse.device)
+    _call("mr_contrastive_reduce", ContrastiveDesc(n=lse.numel(), n_all=0, H=0), [lse, numer, sources], [out])
+    return out
 
 
 def row_dot(x: torch.Tensor, w: torch.Tensor, row_idx=None, rows=None) -> torch.Tensor:

@@ -579,7 +579,7 @@ extern "C" int32_t mr_gemm_epilogue(mr_stream_t stream_, const MrGemmDesc* d, co
   MR_REQUIRE(d->M >= 0 && d->N > 0 && d->K > 0, MR_ERR_BAD_SHAPE);
   if (d->M == 0) return MR_OK;
   MR_REQUIRE(d->K % 8 == 0 && d->lda % 8 == 0 && d->lda >= d->K, MR_ERR_BAD_SHAPE);
-  MR_REQUIRE(d->N % 8 == 0 && d->ldd % 8 == 0 && d->ldd >= d->N, MR_ERR_BAD_SHAPE);
+  MR_REQUIRE(d->ldd % 8 == 0 && d->ldd >= d->N, MR_ERR_BAD_SHAPE);
   MR_REQUIRE(aligned16(A) && aligned16(W) && aligned16(out[0]), MR_ERR_MISALIGNED);
   const bool bias = d->epilogue & MR_EPI_BIAS, gelu = d->epilogue & MR_EPI_GELU;
   const bool residual = d->epilogue & MR_EPI_RESIDUAL, rotary = d->epilogue & MR_EPI_ROTARY_QKV;

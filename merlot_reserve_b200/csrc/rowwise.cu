@@ -287,8 +287,9 @@ embed_assemble_kernel(const int32_t* __restrict__ tokens, const int32_t* __restr
       }
       const int sub = max(cnt - 1, 0) % d.audio_token_length;
       const int ptr = max(aud_ptr[static_cast<size_t>(b) * d.L + t], 0);
+      const int ab = d.aud_div > 1 ? b / d.aud_div : b;
       src = reinterpret_cast<const uint4*>(
-          audio + ((static_cast<size_t>(b) * d.n_aud + ptr) * d.audio_token_length + sub) * d.H);
+          audio + ((static_cast<size_t>(ab) * d.n_aud + ptr) * d.audio_token_length + sub) * d.H);
       from_audio = true;
     }
     if (!from_audio) {
@@ -302,7 +303,8 @@ embed_assemble_kernel(const int32_t* __restrict__ tokens, const int32_t* __restr
   } else if (t < d.L + d.n_vis) {
     const int v = t - d.L;
     ok = 1;
-    src = reinterpret_cast<const uint4*>(vision + (static_cast<size_t>(b) * d.n_vis + v) * d.H);
+    const int vb = d.vis_tile > 0 ? (b / (d.vis_group * d.vis_tile)) * d.vis_group + b % d.vis_group : b;
+    src = reinterpret_cast<const uint4*>(vision + (static_cast<size_t>(vb) * d.n_vis + v) * d.H);
     const int per = d.pool_h * d.pool_w;
     const int pos = v % per;
     const float base_scale = 1.0f / (static_cast<float>(max(d.pool_h, d.pool_w)) + 1.0f);
@@ -327,21 +329,23 @@ embed_assemble_kernel(const int32_t* __restrict__ tokens, const int32_t* __restr
 // ---------------------------------------------------------------------------------------------
 template <bool kInF32, bool kOutF32>
 __global__ void __launch_bounds__(kRowThreads)
-unit_normalize_kernel(const void* __restrict__ x_, void* __restrict__ y_, int rows, int H, float scale) {
+unit_normalize_kernel(const void* __restrict__ x_, const int32_t* __restrict__ row_idx, void* __restrict__ y_,
+                      int rows, int H, float scale) {
   const int row = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
+  const size_t in_row = row_idx ? static_cast<size_t>(row_idx[row]) : static_cast<size_t>(row);
   float ss = 0.f;
   for (int c = lane; c < H; c += 32) {
-    const float v = kInF32 ? static_cast<const float*>(x_)[static_cast<size_t>(row) * H + c]
-                           : __bfloat162float(static_cast<const bf16*>(x_)[static_cast<size_t>(row) * H + c]);
+    const float v = kInF32 ? static_cast<const float*>(x_)[in_row * H + c]
+                           : __bfloat162float(static_cast<const bf16*>(x_)[in_row * H + c]);
     ss += v * v;
   }
   ss = warp_sum(ss);
   const float inv = scale / sqrtf(ss + 1e-5f);
   for (int c = lane; c < H; c += 32) {
-    const float v = kInF32 ? static_cast<const float*>(x_)[static_cast<size_t>(row) * H + c]
-                           : __bfloat162float(static_cast<const bf16*>(x_)[static_cast<size_t>(row) * H + c]);
+    const float v = kInF32 ? static_cast<const float*>(x_)[in_row * H + c]
+                           : __bfloat162float(static_cast<const bf16*>(x_)[in_row * H + c]);
     if (kOutF32)
       static_cast<float*>(y_)[static_cast<size_t>(row) * H + c] = v * inv;
     else
@@ -361,7 +365,8 @@ segment_pool_kernel(const uint8_t* __restrict__ do_pool, const int32_t* __restri
   if (gw >= d.B * d.S) return;
   const int b = gw / d.S, s = gw % d.S;
   float* dst = pooled + static_cast<size_t>(gw) * d.H;
-  for (int c = lane; c < d.H; c += 32) dst[c] = 0.f;
+  if (!d.accumulate)
+    for (int c = lane; c < d.H; c += 32) dst[c] = 0.f;
   int cnt = 0;
   for (int base = 0; base < d.L; base += 32) {
     const int l = base + lane;
@@ -376,7 +381,7 @@ segment_pool_kernel(const uint8_t* __restrict__ do_pool, const int32_t* __restri
         dst[c] += kVF32 ? static_cast<const float*>(v_)[off + c] : __bfloat162float(static_cast<const bf16*>(v_)[off + c]);
     }
   }
-  if (lane == 0) count[gw] = static_cast<float>(cnt);
+  if (lane == 0) count[gw] = (d.accumulate ? count[gw] : 0.f) + static_cast<float>(cnt);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -384,11 +389,11 @@ segment_pool_kernel(const uint8_t* __restrict__ do_pool, const int32_t* __restri
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kRowThreads)
 row_lse_kernel(const float* __restrict__ logits, const bf16* __restrict__ x, const bf16* __restrict__ ypos,
-               float* __restrict__ lse, float* __restrict__ numer, int n, int n_all, int H) {
+               float* __restrict__ lse, float* __restrict__ numer, int n, int n_all, int ld, int H) {
   const int row = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= n) return;
-  const float* lr = logits + static_cast<size_t>(row) * n_all;
+  const float* lr = logits + static_cast<size_t>(row) * ld;
   float m = -INFINITY;
   for (int c = lane; c < n_all; c += 32) m = fmaxf(m, lr[c]);
   m = warp_max(m);
@@ -402,6 +407,43 @@ row_lse_kernel(const float* __restrict__ logits, const bf16* __restrict__ x, con
   if (lane == 0) {
     lse[row] = m + logf(s);
     numer[row] = dot;
+  }
+}
+
+// One block: out[0] = mean(lse - numer); out[1 + s] = sum((lse - numer) [src == s]) / (count_s + 1e-5).
+__global__ void __launch_bounds__(256)
+contrastive_reduce_kernel(const float* __restrict__ lse, const float* __restrict__ numer,
+                          const int32_t* __restrict__ sources, float* __restrict__ out, int n) {
+  float acc[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // total, per-source sums [3], per-source counts [3]
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float v = lse[i] - numer[i];
+    acc[0] += v;
+    if (sources) {
+      const int s = sources[i];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        if (s == k) {
+          acc[1 + k] += v;
+          acc[4 + k] += 1.f;
+        }
+      }
+    }
+  }
+  __shared__ float red[7][8];
+#pragma unroll
+  for (int k = 0; k < 7; ++k) {
+    const float w = warp_sum(acc[k]);
+    if ((threadIdx.x & 31) == 0) red[k][threadIdx.x >> 5] = w;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tot[7];
+    for (int k = 0; k < 7; ++k) {
+      tot[k] = 0.f;
+      for (int w = 0; w < 8; ++w) tot[k] += red[k][w];
+    }
+    out[0] = tot[0] / static_cast<float>(n);
+    for (int k = 0; k < 3; ++k) out[1 + k] = tot[1 + k] / (tot[4 + k] + 1e-5f);
   }
 }
 
@@ -533,6 +575,7 @@ extern "C" int32_t mr_embed_assemble(mr_stream_t stream_, const MrAssembleDesc* 
   MR_REQUIRE(aligned16(out[0]) && aligned16(out[1]), MR_ERR_MISALIGNED);
   if (d->B == 0) return MR_OK;
   MR_REQUIRE(d->cls_offset == 0 || d->cls_offset == 1, MR_ERR_BAD_SHAPE);
+  MR_REQUIRE(d->aud_div >= 0 && d->vis_tile >= 0 && (d->vis_tile == 0 || d->vis_group > 0), MR_ERR_BAD_SHAPE);
   const int64_t rows = static_cast<int64_t>(d->B) * (d->T + d->cls_offset);
   embed_assemble_kernel<<<static_cast<unsigned>(ceil_div64(rows, kWarpsPerBlock)), kRowThreads, 0,
                           static_cast<cudaStream_t>(stream_)>>>(
@@ -551,14 +594,15 @@ extern "C" int32_t mr_unit_normalize(mr_stream_t stream_, const MrNormalizeDesc*
   if (d->rows == 0) return MR_OK;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const int grid = ceil_div(d->rows, kWarpsPerBlock);
+  const int32_t* ridx = static_cast<const int32_t*>(in[1]);
   if (d->in_f32 && d->out_f32)
-    unit_normalize_kernel<true, true><<<grid, kRowThreads, 0, stream>>>(in[0], out[0], d->rows, d->H, d->scale);
+    unit_normalize_kernel<true, true><<<grid, kRowThreads, 0, stream>>>(in[0], ridx, out[0], d->rows, d->H, d->scale);
   else if (d->in_f32)
-    unit_normalize_kernel<true, false><<<grid, kRowThreads, 0, stream>>>(in[0], out[0], d->rows, d->H, d->scale);
+    unit_normalize_kernel<true, false><<<grid, kRowThreads, 0, stream>>>(in[0], ridx, out[0], d->rows, d->H, d->scale);
   else if (d->out_f32)
-    unit_normalize_kernel<false, true><<<grid, kRowThreads, 0, stream>>>(in[0], out[0], d->rows, d->H, d->scale);
+    unit_normalize_kernel<false, true><<<grid, kRowThreads, 0, stream>>>(in[0], ridx, out[0], d->rows, d->H, d->scale);
   else
-    unit_normalize_kernel<false, false><<<grid, kRowThreads, 0, stream>>>(in[0], out[0], d->rows, d->H, d->scale);
+    unit_normalize_kernel<false, false><<<grid, kRowThreads, 0, stream>>>(in[0], ridx, out[0], d->rows, d->H, d->scale);
   return after_launch();
 }
 
@@ -587,7 +631,7 @@ extern "C" size_t mr_contrastive_lse_fwd_workspace_bytes(const MrContrastiveDesc
 extern "C" int32_t mr_contrastive_lse_fwd(mr_stream_t stream_, const MrContrastiveDesc* d, const void* const* in,
                                           void* const* out, void* workspace, size_t workspace_bytes) {
   MR_REQUIRE(d && in && out && in[0] && in[1] && in[2] && out[0] && out[1], MR_ERR_NULL_POINTER);
-  MR_REQUIRE(d->n >= 0 && d->n_all > 0 && d->H > 0 && d->H % 8 == 0 && d->n_all % 8 == 0, MR_ERR_BAD_SHAPE);
+  MR_REQUIRE(d->n >= 0 && d->n_all > 0 && d->H > 0 && d->H % 8 == 0, MR_ERR_BAD_SHAPE);
   if (d->n == 0) return MR_OK;
   MR_REQUIRE(workspace && workspace_bytes >= mr_contrastive_lse_fwd_workspace_bytes(d), MR_ERR_WORKSPACE);
   // logits[n, n_all] = x . y_all^T on the tensor cores (fp32 out), then a row LSE.
@@ -596,7 +640,7 @@ extern "C" int32_t mr_contrastive_lse_fwd(mr_stream_t stream_, const MrContrasti
   g.N = d->n_all;
   g.K = d->H;
   g.lda = d->H;
-  g.ldd = d->n_all;
+  g.ldd = (d->n_all + 7) / 8 * 8;
   g.epilogue = MR_EPI_OUT_F32;
   const void* gin[5] = {in[0], in[1], nullptr, nullptr, nullptr};
   void* gout[1] = {workspace};
@@ -604,7 +648,17 @@ extern "C" int32_t mr_contrastive_lse_fwd(mr_stream_t stream_, const MrContrasti
   if (st != MR_OK) return st;
   row_lse_kernel<<<ceil_div(d->n, kWarpsPerBlock), kRowThreads, 0, static_cast<cudaStream_t>(stream_)>>>(
       static_cast<const float*>(workspace), static_cast<const bf16*>(in[0]), static_cast<const bf16*>(in[2]),
-      static_cast<float*>(out[0]), static_cast<float*>(out[1]), d->n, d->n_all, d->H);
+      static_cast<float*>(out[0]), static_cast<float*>(out[1]), d->n, d->n_all, g.ldd, d->H);
+  return after_launch();
+}
+
+extern "C" int32_t mr_contrastive_reduce(mr_stream_t stream_, const MrContrastiveDesc* d, const void* const* in,
+                                         void* const* out, void*, size_t) {
+  MR_REQUIRE(d && in && out && in[0] && in[1] && out[0], MR_ERR_NULL_POINTER);
+  MR_REQUIRE(d->n > 0, MR_ERR_BAD_SHAPE);
+  contrastive_reduce_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream_)>>>(
+      static_cast<const float*>(in[0]), static_cast<const float*>(in[1]), static_cast<const int32_t*>(in[2]),
+      static_cast<float*>(out[0]), d->n);
   return after_launch();
 }
 

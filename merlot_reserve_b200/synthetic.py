@@ -189,3 +189,128 @@ def round_tree_bf16(tree):
 
 def clone_tree(tree):
     return copy.deepcopy(tree)
+
+
+# ------------------------------------------------------------------------------------------------
+# pretraining batch (BASELINE.json configs[2]; SURVEY.md §8d cfg 3)
+# ------------------------------------------------------------------------------------------------
+MASKAUDIO, LTOVPOOL = 4, 6
+
+
+def synthetic_pretrain_batch(config: Dict, batch: int, seed: int = 1) -> Dict:
+    """One per-device pretraining batch in the layout `MerlotReservePretrainer.__call__` takes
+    (pretrain/pretrain_model.py:38-93; shapes from pretrain/dataloader.py:545-700):
+
+      images [b, nseg*hw, 768], audio_clips [b, nseg*3*60, 65], video_src_index [b, G, nseg/G],
+      text2audio / audio2text (+ '/audio_ptr', '/text_ptr') [b, G, lang_seq_len],
+      audio_text_matching (+ '/audio_ptr'), random_text (+ '/text_ptr') [b, 1, seq_len], text_spans [b, n_spans, 15].
+
+    Per example the two text2audio rows carry 12 [MASK, MASKAUDIO] pairs (text spans 0..11), the two audio2text
+    rows 12 MASKs (12..23), random_text 38 MASKs (24..61) -- the reference's counters (dataloader.py:557,589,647).
+    The reference draws two things from a JAX PRNG inside the forward (pretrain_model.py:28,219); they are supplied
+    as inputs instead: '_rng/split_audio2text', '_rng/split_text2audio' [b*G] (= `split_from_here`) and
+    '_rng/gumbel_u' [b, n_spans] (the uniform draw of the Gumbel top-k)."""
+    m, d = config["model"], config["data"]
+    gh, gw = m["output_grid"]
+    hw = gh * gw
+    nseg, G, nsub = d["num_segments"], d["num_segment_groups"], d["num_audio_subsegments"]
+    per_group = nseg // G
+    n_aud = nseg * nsub
+    Ltxt, Lseq, atl = d["lang_seq_len"], d["seq_len"], m["audio_token_length"]
+    n_trg = int(n_aud * d["mask_rate"])                       # 12 masked audio spans per example and task
+    budget = d["text_span_budget"]
+    n_spans = 2 * n_trg + budget                               # 62
+    rng = np.random.default_rng(7000003 * seed + 11)
+    out = {k: [] for k in ("images", "audio_clips", "video_src_index", "text2audio", "text2audio/audio_ptr",
+                           "text2audio/text_ptr", "audio2text", "audio2text/audio_ptr", "audio2text/text_ptr",
+                           "audio_text_matching", "audio_text_matching/audio_ptr", "random_text",
+                           "random_text/text_ptr", "text_spans")}
+
+    def pad_rows(rows, length):
+        toks = np.zeros((length,), np.int32)
+        ap = np.full((length,), -1, np.int32)
+        tp = np.full((length,), -1, np.int32)
+        rows = rows[:length]
+        if rows:
+            a = np.asarray(rows, dtype=np.int32)
+            toks[:len(rows)], ap[:len(rows)], tp[:len(rows)] = a[:, 0], a[:, 1], a[:, 2]
+        return toks, ap, tp
+
+    for _ in range(batch):
+        out["images"].append(rng.random((nseg * hw, 768), dtype=np.float32))
+        a = np.abs(rng.standard_normal((n_aud * m["audio_seq_length"], 65), dtype=np.float32)) * np.float32(1.5)
+        a[:, 64] = 1.0
+        out["audio_clips"].append(a)
+        vsrc = np.ones((G, per_group), np.int32)
+        vsrc[-1, per_group // 2 + 1:] = 2                       # two videos packed in the last group
+        out["video_src_index"].append(vsrc)
+
+        t2a = {k: [] for k in ("t", "a", "p")}
+        a2t = {k: [] for k in ("t", "a", "p")}
+        per_g = n_trg // G
+        for g in range(G):
+            subs = np.arange(g * per_group * nsub, (g + 1) * per_group * nsub)
+            # --- text2audio: text everywhere, masked spans become [MASK, MASKAUDIO] ---
+            masked = set(rng.choice(subs, size=per_g, replace=False).tolist())
+            rows, k = [], g * per_g
+            for s in subs:
+                if s in masked:
+                    rows += [(MASK, s, k), (MASKAUDIO, s, k)]
+                    k += 1
+                else:
+                    rows += [(int(t), s, -1) for t in rng.integers(10, VOCAB, size=int(rng.integers(3, 7)))]
+            t, ap, tp = pad_rows(rows, Ltxt)
+            t2a["t"].append(t), t2a["a"].append(ap), t2a["p"].append(tp)
+            # --- audio2text: audio spans, a few textified neighbours, masked spans become MASK ---
+            masked = set(rng.choice(subs, size=per_g, replace=False).tolist())
+            rows, k = [], n_trg + g * per_g
+            for s in subs:
+                if s in masked:
+                    rows.append((MASK, s, k))
+                    k += 1
+                elif rng.random() < 0.25:
+                    rows += [(int(t), s, -1) for t in rng.integers(10, VOCAB, size=int(rng.integers(3, 7)))]
+                else:
+                    rows += [(AUDIOSPAN, s, -1)] * atl
+            t, ap, tp = pad_rows(rows, Ltxt)
+            a2t["t"].append(t), a2t["a"].append(ap), a2t["p"].append(tp)
+        for name, dct in (("text2audio", t2a), ("audio2text", a2t)):
+            out[name].append(np.stack(dct["t"])), out[name + "/audio_ptr"].append(np.stack(dct["a"]))
+            out[name + "/text_ptr"].append(np.stack(dct["p"]))
+
+        # --- audio_text_matching: aux text, then per segment LTOVPOOL + 3 x 6 AUDIOSPAN (dataloader.py:605-620) ---
+        rows = [(int(t), -1, -1) for t in rng.integers(10, VOCAB, size=int(rng.integers(20, 60)))]
+        for i in range(nseg):
+            rows.append((LTOVPOOL, i * nsub, -1))
+            for j in range(nsub):
+                rows += [(AUDIOSPAN, i * nsub + j, -1)] * atl
+        t, ap, _ = pad_rows(rows, Lseq)
+        out["audio_text_matching"].append(t[None]), out["audio_text_matching/audio_ptr"].append(ap[None])
+
+        # --- random_text: `budget` MASKs spread through plain text ---
+        rows, k = [], 2 * n_trg
+        n_txt = min(Lseq - 8, 10 * budget)
+        mask_at = set(rng.choice(np.arange(2, n_txt), size=budget, replace=False).tolist())
+        for i in range(n_txt):
+            if i in mask_at:
+                rows.append((MASK, -1, k))
+                k += 1
+            else:
+                rows.append((int(rng.integers(10, VOCAB)), -1, -1))
+        t, _, tp = pad_rows(rows, Lseq)
+        out["random_text"].append(t[None]), out["random_text/text_ptr"].append(tp[None])
+
+        spans = np.zeros((n_spans, m["text_span_length"]), np.int32)
+        for i in range(n_spans):
+            n = int(rng.integers(1, m["text_span_length"] + 1))
+            spans[i, :n] = rng.integers(10, VOCAB, size=n)
+        spans[int(rng.integers(2 * n_trg, n_spans))] = 0        # one empty span: exercises the is_valid filter
+        out["text_spans"].append(spans)
+
+    res = {k: np.stack(v, 0) for k, v in out.items()}
+    split = np.full((2, batch * G), per_group, np.int32)        # per_group == "no split" (pretrain_model.py:31-33)
+    split[0, 0] = per_group // 2
+    split[1, -1] = 2
+    res["_rng/split_audio2text"], res["_rng/split_text2audio"] = split[0], split[1]
+    res["_rng/gumbel_u"] = rng.random((batch, n_spans), dtype=np.float32) * np.float32(0.999) + np.float32(5e-4)
+    return res

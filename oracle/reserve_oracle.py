@@ -486,6 +486,126 @@ class OracleMerlotReserve:
         return (pooled @ _t(proj_kernel).reshape(-1, 1)).reshape(B, n_cand)
 
 
+    # --- pretraining forward (pretrain/pretrain_model.py:38-259) ---
+    @staticmethod
+    def _augment_video_src_idx(video_src_idx, split_from_here):
+        """pretrain_model.py:9-36 with the PRNG draw `split_from_here` [B] (values 1..L; L = no split) supplied."""
+        B, L = video_src_idx.shape
+        if L == 1:
+            return video_src_idx
+        split_mask = split_from_here[:, None] <= torch.arange(L)[None]
+        return torch.where(split_mask, video_src_idx + 4 * L, video_src_idx)
+
+    def pretrain_forward(self, batch):
+        """MerlotReservePretrainer.__call__ (pretrain_model.py:38-259), fp32.  The two PRNG draws of the reference
+        are inputs: batch['_rng/split_audio2text'], ['_rng/split_text2audio'] (`split_from_here`, :28) and
+        ['_rng/gumbel_u'] (the uniform of :219).  jnp.argsort / lax.top_k tie order: stable, lower index first."""
+        d = self.data
+        G, nsub = d["num_segment_groups"], d["num_audio_subsegments"]
+        Ltxt, Lseq = d["lang_seq_len"], d["seq_len"]
+        H = self.hidden_size
+        lng = lambda x: torch.as_tensor(np.asarray(x)).long()
+        images = _t(batch["images"])
+        b, nseg_hw, pp3 = images.shape
+        hw = self.output_grid_h * self.output_grid_w
+        nseg = nseg_hw // hw
+        per_group = nseg // G
+        imgs_enc = self.vision_encoder(images.reshape(b * nseg, hw, pp3))                                   # :53
+        hw1 = hw // (self.vit_pooling_ratio ** 2)
+        imgs_seq = imgs_enc["seq_attnpool"].reshape(b, G, per_group * hw1, H)                               # :56-57
+        vis_len = imgs_seq.shape[-2]
+        audio_enc = self.audio_encoder(_t(batch["audio_clips"]).reshape(b * nseg * nsub, self.audio_seq_length, -1))
+        n_aud = nseg * nsub
+        audio_seq = audio_enc["seq_attnpool"].reshape(b, n_aud, self.audio_token_length, H)                 # :72-73
+        audio_cls = audio_enc["cls"].reshape(b, n_aud, H)                                                   # :74
+        bt = {}
+        for k1 in ("text2audio", "audio2text"):                                                             # :77-80
+            for k2 in ("", "/audio_ptr", "/text_ptr"):
+                bt[k1 + k2] = lng(batch[k1 + k2]).reshape(-1, Ltxt)
+        for k in ("random_text", "random_text/text_ptr", "audio_text_matching", "audio_text_matching/audio_ptr"):
+            bt[k] = lng(batch[k]).reshape(-1, Lseq)                                                         # :82-83
+        text_spans = lng(batch["text_spans"]).reshape(-1, self.cfg["text_span_length"])                     # :85
+        vsi = lng(batch["video_src_index"]).reshape(-1, per_group)                                          # :92
+        n_a2t, n_t2a = d["num_audio2text_seqs"], d["num_text2audio_seqs"]
+
+        def tiled_vsi(n):
+            return vsi.reshape(b, G, per_group).repeat(1, n, 1).reshape(-1, per_group)
+
+        fdiv = lambda a, q: torch.div(a, q, rounding_mode="floor")
+        mm = {}
+        mm["audio2text"] = self.prepare_multimodal_inputs(                                                  # :99-113
+            tokens=bt["audio2text"], token_segment_idx=torch.remainder(fdiv(bt["audio2text/audio_ptr"], nsub), per_group),
+            vision_input=imgs_seq.repeat(1, n_a2t, 1, 1).reshape(-1, vis_len, H),
+            audio_spans=audio_seq.repeat_interleave(G * n_a2t, dim=0), audio_pointers=bt["audio2text/audio_ptr"],
+            padding_len=Lseq,
+            video_src_idx=self._augment_video_src_idx(tiled_vsi(n_a2t), lng(batch["_rng/split_audio2text"])))
+        atm = bt["audio_text_matching"]
+        mm["audio_text_matching"] = self.prepare_multimodal_inputs(                                         # :115-122
+            tokens=atm, token_segment_idx=torch.cumsum((atm == LTOVPOOL).long(), -1), audio_spans=audio_seq,
+            audio_pointers=bt["audio_text_matching/audio_ptr"], padding_len=Lseq)
+        mm["text2audio"] = self.prepare_multimodal_inputs(                                                  # :125-137
+            tokens=bt["text2audio"], token_segment_idx=torch.remainder(fdiv(bt["text2audio/audio_ptr"], nsub), per_group),
+            vision_input=imgs_seq.repeat(1, n_t2a, 1, 1).reshape(-1, vis_len, H),
+            audio_pointers=bt["text2audio/audio_ptr"], padding_len=Lseq,
+            video_src_idx=self._augment_video_src_idx(tiled_vsi(n_t2a), lng(batch["_rng/split_text2audio"])))
+        mm["random_text"] = self.prepare_multimodal_inputs(tokens=bt["random_text"], padding_len=Lseq)      # :138
+        keys = sorted(mm)                                                                                   # :140
+        x = torch.cat([mm[k]["x"] for k in keys], 0)
+        coords = torch.cat([mm[k]["rotary_coords"] for k in keys], 0)
+        mask = torch.cat([mm[k]["attention_mask"] for k in keys], 0)
+        sizes = [mm[k]["x"].shape[0] for k in keys]
+        joint = self.joint_proj(self.joint_transformer(x, coords, mask)["seq"])                             # :150-151
+        mo = dict(zip(keys, torch.split(joint, sizes, 0)))
+        mo["text2audio"] = mo["text2audio"][:, :Ltxt]                                                       # :154-155
+        mo["audio2text"] = mo["audio2text"][:, :Ltxt]
+
+        is_pool = atm == LTOVPOOL                                                                           # :160-165
+        a2v = one_hot_pool(is_pool, torch.cumsum(is_pool.long(), -1) - 1, mo["audio_text_matching"],
+                           nseg)["x"].reshape(b * nseg, H)
+        t2a = one_hot_pool(bt["text2audio"] == MASKAUDIO, bt["text2audio/audio_ptr"], mo["text2audio"], n_aud,
+                           real_bsize=b)                                                                    # :170-176
+        n_trg = int(n_aud * d["mask_rate"]) * n_t2a                                                         # :178
+        is_selected = t2a["idx_oh"].sum(1)
+        idx_sort = torch.sort(-is_selected, dim=-1, stable=True)[1]                                         # :181
+        best = idx_sort[:, :n_trg].reshape(b * n_trg)
+        bi = torch.arange(b).repeat_interleave(n_trg)
+        t2a_sel = t2a["x"][bi, best]
+        a2t_sel = audio_cls[bi, best]
+        extra = idx_sort[:, n_trg:].reshape(b * (n_aud - n_trg))
+        a2t_extra = audio_cls[torch.arange(b).repeat_interleave(n_aud - n_trg), extra]                      # :188-190
+
+        n_spans = text_spans.shape[0] // b                                                                  # :195
+        t2sp = {}
+        for k in ("audio2text", "text2audio", "random_text"):
+            r = one_hot_pool(bt[k] == MASK, bt[f"{k}/text_ptr"], mo[k], n_spans, real_bsize=b)
+            t2sp[k] = {"x": r["x"], "count": r["idx_oh"].sum(1)}
+        sel = t2sp["text2audio"]["x"] + t2sp["audio2text"]["x"] + t2sp["random_text"]["x"]                  # :206
+        ct = t2sp["text2audio"]["count"] + t2sp["audio2text"]["count"] + t2sp["random_text"]["count"]
+        src = torch.stack([torch.zeros_like(ct), t2sp["text2audio"]["count"], t2sp["audio2text"]["count"],
+                           t2sp["random_text"]["count"]], -1).argmax(-1) - 1                                # :208-209
+        is_valid = (text_spans != PADDING).any(-1).reshape(b, n_spans) & (ct > 0.0)                         # :212-214
+        logits_for_pred = is_valid.float() * 1e6 + math.log(4.0) * (t2sp["text2audio"]["count"] + t2sp["audio2text"]["count"])
+        z = -torch.log(-torch.log(_t(batch["_rng/gumbel_u"])))                                              # :219-220
+        n_inc = d["num_text_spans_to_include"]
+        score = (logits_for_pred + z).reshape(-1)
+        best = torch.sort(-score, stable=True)[1][:n_inc * b]                                               # :227 (top_k)
+        t2sp_sel = sel.reshape(b * n_spans, H)[best]
+        t2sp_src = src.reshape(b * n_spans)[best]
+        sp2t_sel = self.span_encoder(self.token_encoder(text_spans[best]), text_spans[best] != PADDING)     # :232-233
+        scales = _t(self.params["contrastive_scales"]).clamp(max=math.log(100.0))                           # :236
+        out = {
+            "imgs_to_audio": {"x": a2v, "y": imgs_enc["cls"], "log_scale": scales[0]},
+            "text_to_audio": {"x": t2a_sel, "y": a2t_sel, "y_extra": a2t_extra, "log_scale": scales[1]},
+            "stuff_to_span": {"x": t2sp_sel, "y": sp2t_sel, "log_scale": scales[2], "_sources": t2sp_src},
+        }
+        for k in out:                                                                                       # :243-257
+            temp = torch.exp(out[k].pop("log_scale") / 2.0)
+            for k2 in ("x", "y", "y_extra"):
+                if k2 in out[k]:
+                    out[k][k2] = unit_normalize(out[k][k2]) * temp
+        return out
+
+
 def unit_normalize(x):
     """modeling.py:570-578."""
     x = x.float()
@@ -512,6 +632,9 @@ def contrastive_loss(preds: Dict[str, Dict[str, torch.Tensor]], gather=None):
         x, y = d["x"].float(), d["y"].float()
         numer = (x * y).sum(-1)
         info[name] = torch.zeros(())
+        if "_sources" in d:
+            for k in ("text2audio", "audio2text", "random_text"):
+                info[f"_{name}_from_{k}"] = torch.zeros(())
         for a, b in ("xy", "yx"):
             xa, yb = d[a].float(), d[b].float()
             if f"{b}_extra" in d:
@@ -519,4 +642,8 @@ def contrastive_loss(preds: Dict[str, Dict[str, torch.Tensor]], gather=None):
             logits = xa @ gather(yb).T
             lse = torch.logsumexp(logits, -1)
             info[name] = info[name] + (lse - numer).mean() / 2.0
-    return sum(info.values()), info
+            if "_sources" in d:
+                for i, k in enumerate(("text2audio", "audio2text", "random_text")):
+                    m = (d["_sources"] == i).float()
+                    info[f"_{name}_from_{k}"] = info[f"_{name}_from_{k}"] + ((lse - numer) * m).sum() / (m.sum() + 1e-5) / 2.0
+    return sum(v for k, v in info.items() if not k.startswith("_")), info

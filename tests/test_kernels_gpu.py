@@ -328,3 +328,73 @@ def test_rotary_table_and_assemble(cuda, lib):
     _close(x, ref_x.to(cuda), 1e-6, 1e-6, "assembled x")
     _close(rot, O.rotary_scale_table(mm["rotary_coords"][0]).to(cuda), 3e-5, 1e-5, "assembled rot")
     assert torch.equal(valid.cpu().bool(), mm["is_valid"][0])
+
+
+@pytest.mark.parametrize("M,N,K", [(96, 12, 128), (50, 100, 64), (300, 188, 768)])
+def test_gemm_ragged_n(cuda, lib, M, N, K):
+    """N need not be a multiple of 8 (contrastive logits against 12 b / 188 b targets): only ldd is padded."""
+    g = torch.Generator().manual_seed(N)
+    a = _bf(torch.randn(M, K, generator=g)).to(cuda)
+    w = _bf(torch.randn(N, K, generator=g) * 0.05).to(cuda)
+    ld = (N + 7) // 8 * 8
+    out = torch.full((M, ld), 7.0, device=cuda)
+    lib.gemm(a, w, out=out[:, :N] if ld == N else out)
+    d = lib.GemmDesc(M=M, N=N, K=K, lda=K, ldd=ld, epilogue=lib.EPI_OUT_F32, algo=0, q_scale=1.0)
+    lib._call("mr_gemm_epilogue", d, [a, w, None, None, None], [out])
+    _close(out[:, :N], a.float() @ w.float().t(), 2e-3, 1e-3, "ragged N")
+    assert (out[:, N:] == 7.0).all()          # the padding columns are never written
+
+
+def test_pretrain_row_kernels(cuda, lib):
+    """The additions of the pretraining forward: gathered unit_normalize, accumulating segment pool, the source
+    row maps of embed_assemble, the scalar loss reduction (pretrain_model.py:97-135,176-230,295-300)."""
+    g = torch.Generator().manual_seed(12)
+    x = torch.randn(40, 256, generator=g).to(cuda)
+    idx = torch.tensor([5, 5, 39, 0, 17], dtype=torch.int32, device=cuda)
+    ref = x[idx.long()]
+    ref = 3.0 * ref / torch.sqrt((ref * ref).sum(-1, keepdim=True) + 1e-5)
+    got = lib.unit_normalize(x, scale=3.0, out_f32=False, row_idx=idx)
+    assert got.dtype == torch.bfloat16 and got.shape == (5, 256)
+    _close(got, ref, 1e-2, 1e-2, "gathered unit_normalize")
+
+    B, L, H, S = 2, 40, 128, 5
+    v1, v2 = torch.randn(B, L, H, generator=g).to(cuda), torch.randn(B, L, H, generator=g).to(cuda)
+    dp1 = (torch.rand(B, L, generator=g) > 0.5).to(torch.uint8).to(cuda)
+    dp2 = (torch.rand(B, L, generator=g) > 0.5).to(torch.uint8).to(cuda)
+    ix = torch.randint(0, S, (B, L), generator=g).to(torch.int32).to(cuda)
+    acc = lib.segment_pool(dp1, ix, v1, S)
+    lib.segment_pool(dp2, ix, v2, S, accumulate_into=acc)
+    oh = lambda dp: ((ix[..., None] == torch.arange(S, device=cuda)) & dp.bool()[..., None]).float()
+    _close(acc[0], torch.einsum("bls,blh->bsh", oh(dp1), v1) + torch.einsum("bls,blh->bsh", oh(dp2), v2), 1e-5, 1e-5, "acc pool")
+    assert torch.equal(acc[1], oh(dp1).sum(1) + oh(dp2).sum(1))
+
+    n = 300
+    lse, numer = torch.randn(n, generator=g).to(cuda) + 5, torch.randn(n, generator=g).to(cuda)
+    src = torch.randint(-1, 3, (n,), generator=g).to(torch.int32).to(cuda)
+    red = lib.contrastive_reduce(lse, numer, src).cpu()
+    dlt = (lse - numer).cpu()
+    assert abs(float(red[0]) - float(dlt.mean())) < 1e-5
+    for s in range(3):
+        m = (src.cpu() == s).float()
+        assert abs(float(red[1 + s]) - float((dlt * m).sum() / (m.sum() + 1e-5))) < 1e-4
+    assert abs(float(lib.contrastive_reduce(lse, numer)[0]) - float(dlt.mean())) < 1e-5
+
+    # source row maps: sequence r reads audio row r // aud_div and vision row (r // (G n)) G + r % G
+    Hh, Ltok, n_vis, n_aud = 64, 8, 6, 4
+    Bv, G, tile = 2, 2, 3
+    R = Bv * G * tile
+    emb = _bf(torch.randn(50, Hh, generator=g)).to(cuda)
+    vis = _bf(torch.randn(Bv * G, n_vis, Hh, generator=g)).to(cuda)
+    aud = _bf(torch.randn(Bv, n_aud, 6, Hh, generator=g)).to(cuda)
+    toks = torch.randint(6, 50, (R, Ltok), generator=g).to(torch.int32)
+    toks[:, 2:5] = 5
+    ptr = torch.randint(0, n_aud, (R, Ltok), generator=g).to(torch.int32)
+    xo, _, _ = lib.embed_assemble(toks.to(cuda), emb, H=Hh, seg_idx=torch.zeros_like(toks).to(cuda), aud_ptr=ptr.to(cuda),
+                                  audio=aud, vision=vis, n_aud=n_aud, n_vis=n_vis, pool_h=2, pool_w=3, T=Ltok + n_vis,
+                                  aud_div=G * tile, vis_group=G, vis_tile=tile)
+    xo = xo.view(R, Ltok + n_vis, Hh)
+    for r in range(R):
+        vb = (r // (G * tile)) * G + r % G
+        assert torch.equal(xo[r, Ltok:], vis[vb])
+        for t in range(2, 5):
+            assert torch.equal(xo[r, t], aud[r // (G * tile), ptr[r, t], t - 2])

@@ -70,13 +70,26 @@ int64_t mr_launch_count(void);
  * multiplied by rot[(r % rot_rows) * 32 + (c % 64)]; columns c < hidden are then multiplied by
  * q_scale.
  * Constraints: K % 8 == 0, lda % 8 == 0, ldd % 8 == 0 (N itself is arbitrary), all pointers 16-byte aligned.
+ *
+ * LayerNorm folding (TransformerLayer, modeling.py:272-279: `Dense(LN(x))`).  With W' = gamma (.) W,
+ *   LN(x) W + b = rstd_r (x W' - mu_r colsum(W')) + (beta W + b),
+ * so the pre-LN GEMMs (qkv, MLP intermediate) read the residual stream x directly and apply the row
+ * statistics in the epilogue; the LayerNorm kernel, its [M, H] output and the re-read of it disappear.
+ *   MR_EPI_LN_IN:     in[1] = W' (bf16 [N, K]), in[2] = beta W + b (f32 [N]), in[5] = stats f32 [K/64][M][2],
+ *                     in[6] = colsum(W') f32 [N]; mu = sum/K, var = sumsq/K - mu^2 (flax LayerNorm), eps = ln_eps.
+ *   MR_EPI_STATS_OUT: out[1] = stats f32 [N/64][M][2]: for each output row and each 64-column slab the sum and
+ *                     the sum of squares of the bf16-ROUNDED outputs (N % 64 == 0).  The residual GEMMs
+ *                     (attn_proj, MLP out) produce x, so they produce the statistics of the next LayerNorm.
+ * Both need the bf16, un-remapped output path (no MR_EPI_OUT_F32, seq_in == 0).
  * ------------------------------------------------------------------------------------------ */
 enum {
   MR_EPI_BIAS = 1,
   MR_EPI_GELU = 2,       /* x * sigmoid(1.702 x)  (modeling.py:240) */
   MR_EPI_RESIDUAL = 4,
   MR_EPI_ROTARY_QKV = 8,
-  MR_EPI_OUT_F32 = 16
+  MR_EPI_OUT_F32 = 16,
+  MR_EPI_LN_IN = 32,     /* A is the UN-normalised residual stream; LayerNorm is folded into the GEMM (below) */
+  MR_EPI_STATS_OUT = 64  /* also emit per-row (sum, sum of squares) partials of the bf16 output (below) */
 };
 
 enum { MR_GEMM_ALGO_TCGEN05 = 0, MR_GEMM_ALGO_SIMT_DEBUG = 1 };
@@ -92,6 +105,7 @@ typedef struct MrGemmDesc {
   int32_t algo;     /* MR_GEMM_ALGO_* ; SIMT_DEBUG is a slow CUDA-core kernel kept for bisecting */
   float q_scale;
   int32_t num_sms;  /* 0 = use every SM of the current device */
+  float ln_eps;     /* MR_EPI_LN_IN */
 } MrGemmDesc;
 
 int32_t mr_gemm_epilogue(mr_stream_t stream, const MrGemmDesc* d, const void* const* in, void* const* out,
@@ -127,6 +141,8 @@ size_t mr_attention_fwd_workspace_bytes(const MrAttentionDesc* d);
  * mr_layernorm_fwd: flax LayerNorm(eps) (modeling.py:272,277,360,366): fp32 statistics,
  * var = E[x^2] - E[x]^2, y = (x - mean) * rsqrt(var + eps) * gamma + beta.
  *   in[0] x bf16 [rows_in, ldx]; in[1] gamma f32 [H]; in[2] beta f32 [H]; out[0] y bf16 [rows, H]
+ *   out[1] (only when emit_stats) stats f32 [H/64][rows][2] of the bf16-rounded y, in the MR_EPI_STATS_OUT layout (slab 0
+ *   carries the whole row, the other slabs are zero): lets `pre_ln` (modeling.py:360) feed layer 0's folded LN.
  * Row map: output row r reads input row  seq_out == 0 ? r : (r / seq_out) * seq_in + (r % seq_out) + row_off
  * (used to normalise only the first L rows of every joint sequence / only the CLS row).
  * ------------------------------------------------------------------------------------------ */
@@ -136,6 +152,7 @@ typedef struct MrLayerNormDesc {
   int32_t ldx;
   int32_t seq_in, seq_out, row_off;
   float eps;
+  int32_t emit_stats; /* 1: out[1] is written (see above) */
 } MrLayerNormDesc;
 
 int32_t mr_layernorm_fwd(mr_stream_t stream, const MrLayerNormDesc* d, const void* const* in, void* const* out,

@@ -14,7 +14,7 @@ import torch
 
 _LIB_PATH = Path(__file__).resolve().parent / "lib" / "libmreserve_b200.so"
 
-EPI_BIAS, EPI_GELU, EPI_RESIDUAL, EPI_ROTARY_QKV, EPI_OUT_F32 = 1, 2, 4, 8, 16
+EPI_BIAS, EPI_GELU, EPI_RESIDUAL, EPI_ROTARY_QKV, EPI_OUT_F32, EPI_LN_IN, EPI_STATS_OUT = 1, 2, 4, 8, 16, 32, 64
 ALGO_TCGEN05, ALGO_SIMT_DEBUG = 0, 1
 
 
@@ -26,7 +26,7 @@ class GemmDesc(C.Structure):
     _fields_ = [("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32), ("lda", C.c_int32), ("ldd", C.c_int32),
                 ("epilogue", C.c_int32), ("seq_in", C.c_int32), ("seq_out", C.c_int32), ("row_off", C.c_int32),
                 ("rot_rows", C.c_int32), ("hidden", C.c_int32), ("algo", C.c_int32), ("q_scale", C.c_float),
-                ("num_sms", C.c_int32)]
+                ("num_sms", C.c_int32), ("ln_eps", C.c_float)]
 
 
 class AttentionDesc(C.Structure):
@@ -35,7 +35,7 @@ class AttentionDesc(C.Structure):
 
 class LayerNormDesc(C.Structure):
     _fields_ = [("rows", C.c_int32), ("H", C.c_int32), ("ldx", C.c_int32), ("seq_in", C.c_int32),
-                ("seq_out", C.c_int32), ("row_off", C.c_int32), ("eps", C.c_float)]
+                ("seq_out", C.c_int32), ("row_off", C.c_int32), ("eps", C.c_float), ("emit_stats", C.c_int32)]
 
 
 class CastDesc(C.Structure):
@@ -104,7 +104,7 @@ WORKSPACE_FNS = {
 }
 MISC_FNS = ["mr_check_device", "mr_abi_version", "mr_status_string", "mr_launch_count"]
 
-ABI_VERSION = 2  # must equal mr_abi_version() of the loaded library (struct layouts above)
+ABI_VERSION = 3  # must equal mr_abi_version() of the loaded library (struct layouts above)
 
 _lib = None
 
@@ -209,8 +209,10 @@ def _work(name: str, d):
 # ------------------------------------------------------------------------------------------------
 def gemm(a: torch.Tensor, w: torch.Tensor, *, bias=None, residual=None, rot=None, out=None, gelu=False,
          out_f32=False, hidden=0, q_scale=1.0, seq_in=0, seq_out=0, row_off=0, out_rows=None, M=None, lda=None,
-         algo=ALGO_TCGEN05) -> torch.Tensor:
-    """D = epilogue(A @ W^T).  a: bf16 [M, K] (or strided rows via M / lda), w: bf16 [N, K]."""
+         algo=ALGO_TCGEN05, ln_stats=None, ln_colsum=None, ln_eps=1e-5, stats_out=None) -> torch.Tensor:
+    """D = epilogue(A @ W^T).  a: bf16 [M, K] (or strided rows via M / lda), w: bf16 [N, K].
+    ln_stats / ln_colsum: fold LayerNorm(a) into the GEMM (w must be the gamma-scaled weight, bias = beta W + b);
+    stats_out: f32 [N/64, M, 2] buffer receiving the row statistics of the (bf16) output."""
     assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16
     N, K = w.shape
     if M is None:
@@ -231,10 +233,14 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias=None, residual=None, rot=None
         epi |= EPI_ROTARY_QKV
     if out.dtype == torch.float32:
         epi |= EPI_OUT_F32
+    if ln_stats is not None:
+        epi |= EPI_LN_IN
+    if stats_out is not None:
+        epi |= EPI_STATS_OUT
     d = GemmDesc(M=M, N=N, K=K, lda=lda, ldd=out.shape[-1], epilogue=epi, seq_in=seq_in, seq_out=seq_out,
                  row_off=row_off, rot_rows=(rot.shape[0] if rot is not None else 0), hidden=hidden, algo=algo,
-                 q_scale=q_scale, num_sms=0)
-    _call("mr_gemm_epilogue", d, [a, w, bias, residual, rot], [out])
+                 q_scale=q_scale, num_sms=0, ln_eps=ln_eps)
+    _call("mr_gemm_epilogue", d, [a, w, bias, residual, rot, ln_stats, ln_colsum], [out, stats_out])
     return out
 
 
@@ -249,14 +255,15 @@ def attention(qkv: torch.Tensor, B: int, T: int, H: int, valid=None, group=None,
 
 
 def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, rows=None, H=None, ldx=None, seq_in=0,
-              seq_out=0, row_off=0, eps=1e-5, out=None) -> torch.Tensor:
+              seq_out=0, row_off=0, eps=1e-5, out=None, stats_out=None) -> torch.Tensor:
     H = H or x.shape[-1]
     rows = rows if rows is not None else x.numel() // H
     ldx = ldx or H
     if out is None:
         out = torch.empty((rows, H), dtype=torch.bfloat16, device=x.device)
-    d = LayerNormDesc(rows=rows, H=H, ldx=ldx, seq_in=seq_in, seq_out=seq_out, row_off=row_off, eps=eps)
-    _call("mr_layernorm_fwd", d, [x, gamma, beta], [out])
+    d = LayerNormDesc(rows=rows, H=H, ldx=ldx, seq_in=seq_in, seq_out=seq_out, row_off=row_off, eps=eps,
+                      emit_stats=int(stats_out is not None))
+    _call("mr_layernorm_fwd", d, [x, gamma, beta], [out, stats_out])
     return out
 
 

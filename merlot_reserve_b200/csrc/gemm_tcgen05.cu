@@ -21,6 +21,8 @@
 //
 // The arithmetic this replaces is flax Dense/DenseGeneral (+ the elementwise ops around it) at the
 // reference call sites listed in include/mreserve_b200.h.
+#include <type_traits>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -46,6 +48,12 @@ struct GemmParams {
   const float* rot;
   void* D;
   int num_n_tiles, num_tiles, num_k_blocks;
+  // LayerNorm folded into the GEMM (see the header): consumer side reads per-row partial (sum, sum of squares),
+  // producer side writes them for its own (bf16-rounded) output rows.
+  const float2* stats_in;   // [K / 64][M]
+  const float* ln_s;        // [N] column sums of the gamma-scaled weight
+  float2* stats_out;        // [ceil(N / 64)][M]
+  float ln_eps;
 };
 
 constexpr int kBoxBytes = 32 * 128;  // one epilogue staging box: 32 rows x 64 bf16, 128B swizzle
@@ -76,7 +84,27 @@ __device__ __forceinline__ int map_row(int r, int seq_in, int seq_out, int row_o
   return seq_in == 0 ? r : (r / seq_in) * seq_out + (r % seq_in) + row_off;
 }
 
-template <int BN, bool kGelu, bool kResidual, bool kRotary, bool kDirect>
+// Loads 8 consecutive fp32 column values (bias / colsum vectors).  kFull: the whole 64-column box is in range,
+// two 16-byte loads that every lane of the warp shares (one L1 wavefront each); otherwise element-wise guarded.
+template <bool kFull>
+__device__ __forceinline__ void load_cols8(const float* __restrict__ v, int c, int n, float (&o)[8]) {
+  if constexpr (kFull) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(v + c));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(v + c + 4));
+    o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w;
+    o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
+  } else {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) o[q] = (c + q < n) ? __ldg(v + c + q) : 0.f;
+  }
+}
+
+// kBias / kLn / kStats are compile-time on the staged path so that the unrolled epilogue body is branch free and
+// ptxas can hoist the (L1-resident) per-column vector loads ahead of their uses; with run-time flags every 8-column
+// step sat behind its own reconvergence point and the epilogue became latency bound (profiles/ncu_gemm_r01j.md).
+// The direct path keeps run-time p.bias_on (small GEMMs only).
+template <int BN, bool kGelu, bool kResidual, bool kRotary, bool kDirect, bool kBias = false, bool kLn = false,
+          bool kStats = false>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res,
@@ -130,9 +158,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   // Rotary (QKV) GEMMs: every CTA owns a CONTIGUOUS range instead, so consecutive tiles of a CTA share the row
   // block and the per-row rotary scales stay in registers (K = hidden there: 148 live A blocks fit the L2).
   const int tiles_per_cta = (p.num_tiles + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
-  const int tile_step = kRotary ? 1 : static_cast<int>(gridDim.x);
-  const int tile_begin = kRotary ? static_cast<int>(blockIdx.x) * tiles_per_cta : static_cast<int>(blockIdx.x);
-  const int tile_end = kRotary ? min(tile_begin + tiles_per_cta, p.num_tiles) : p.num_tiles;
+  // LN-consuming GEMMs (K = hidden as well) use the contiguous schedule too: the row statistics stay in registers.
+  constexpr bool contiguous = kRotary || kLn;
+  const int tile_step = contiguous ? 1 : static_cast<int>(gridDim.x);
+  const int tile_begin = contiguous ? static_cast<int>(blockIdx.x) * tiles_per_cta : static_cast<int>(blockIdx.x);
+  const int tile_end = contiguous ? min(tile_begin + tiles_per_cta, p.num_tiles) : p.num_tiles;
 
   if (warp_idx == 0) {
     // ===================== TMA producer =====================
@@ -212,12 +242,29 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       uint32_t res_phase = 0;
       float rot[kRotary ? 32 : 1];
       int rot_m = -1;
+      float ln_mu = 0.f, ln_rstd = 1.f;        // LayerNorm statistics of this thread's row (LN-consuming GEMMs)
+      int ln_m = -1;
       for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
         const int m_blk = tile / p.num_n_tiles;
         const int n_blk = tile % p.num_n_tiles;
         const int row0 = m_blk * kBM + quarter * 32;
         const int r = row0 + lane;
         const int col_base = n_blk * BN + col_half * (BN / 2);
+        if (kLn && m_blk != ln_m) {
+          ln_m = m_blk;
+          float s1 = 0.f, s2 = 0.f;
+          if (r < p.M) {
+            const int parts = p.K >> 6;
+            for (int q = 0; q < parts; ++q) {
+              const float2 t = __ldg(p.stats_in + static_cast<size_t>(q) * p.M + r);
+              s1 += t.x;
+              s2 += t.y;
+            }
+          }
+          const float inv_k = 1.0f / static_cast<float>(p.K);
+          ln_mu = s1 * inv_k;
+          ln_rstd = rsqrtf(s2 * inv_k - ln_mu * ln_mu + p.ln_eps);
+        }
 
         // Work that does not depend on the accumulator goes first: residual box 0 and the rotary row.
         if (lane == 0) {
@@ -290,53 +337,75 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             res_phase ^= 1;
           }
           const bool full_box = col0 + 64 <= p.N;
+          float st_sum = 0.f, st_sq = 0.f;
+          auto box_body = [&](auto full_tag) {
+            constexpr bool kFull = decltype(full_tag)::value;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float f[8];
+            for (int j = 0; j < 8; ++j) {
+              float f[8];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) f[q] = __uint_as_float(v[8 * j + q]);
-            const int c = col0 + 8 * j;
-            if (p.bias_on) {
-              if (full_box) {
-                const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + c));
-                const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + c + 4));
-                f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
-                f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
-              } else {
+              for (int q = 0; q < 8; ++q) f[q] = __uint_as_float(v[8 * j + q]);
+              const int c = col0 + 8 * j;
+              if constexpr (kLn) {
+                // LN(x) W = rstd (x W' - mu colsum(W')): W' = gamma-scaled weight, beta W + b is the bias below
+                float sv[8];
+                load_cols8<kFull>(p.ln_s, c, p.N, sv);
 #pragma unroll
-                for (int q = 0; q < 8; ++q)
-                  if (c + q < p.N) f[q] += __ldg(p.bias + c + q);
+                for (int q = 0; q < 8; ++q) f[q] = (f[q] - ln_mu * sv[q]) * ln_rstd;
+              }
+              if constexpr (kBias) {
+                float bv[8];
+                load_cols8<kFull>(p.bias, c, p.N, bv);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) f[q] += bv[q];
+              }
+              if constexpr (kRotary) {
+                // a box is exactly one head: [q heads | k heads | v heads]; first 32 dims of q/k heads are scaled
+                if (j < 4 && col0 < 2 * p.hidden) {
+#pragma unroll
+                  for (int q = 0; q < 8; ++q) f[q] *= rot[8 * j + q];
+                }
+                if (col0 < p.hidden) {
+#pragma unroll
+                  for (int q = 0; q < 8; ++q) f[q] *= p.q_scale;
+                }
+              }
+              if constexpr (kGelu) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) f[q] = gelu_sigmoid(f[q]);
+              }
+              uint4* cell = reinterpret_cast<uint4*>(my_row + ((j ^ sw) << 4));
+              if constexpr (kResidual) {
+                const uint4 rr = *cell;
+                f[0] += bf16_lo(rr.x); f[1] += bf16_hi(rr.x);
+                f[2] += bf16_lo(rr.y); f[3] += bf16_hi(rr.y);
+                f[4] += bf16_lo(rr.z); f[5] += bf16_hi(rr.z);
+                f[6] += bf16_lo(rr.w); f[7] += bf16_hi(rr.w);
+              }
+              uint4 o;
+              o.x = pack_bf16(f[0], f[1]);
+              o.y = pack_bf16(f[2], f[3]);
+              o.z = pack_bf16(f[4], f[5]);
+              o.w = pack_bf16(f[6], f[7]);
+              *cell = o;
+              if constexpr (kStats) {
+                // statistics of the ROUNDED values: exactly what the consuming GEMM will read back as x
+                const uint32_t ow[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  const float a = bf16_lo(ow[q]), b = bf16_hi(ow[q]);
+                  st_sum += a + b;
+                  st_sq = fmaf(a, a, fmaf(b, b, st_sq));
+                }
               }
             }
-            if constexpr (kRotary) {
-              // a box is exactly one head: [q heads | k heads | v heads]; first 32 dims of q/k heads are scaled
-              if (j < 4 && col0 < 2 * p.hidden) {
-#pragma unroll
-                for (int q = 0; q < 8; ++q) f[q] *= rot[8 * j + q];
-              }
-              if (col0 < p.hidden) {
-#pragma unroll
-                for (int q = 0; q < 8; ++q) f[q] *= p.q_scale;
-              }
-            }
-            if constexpr (kGelu) {
-#pragma unroll
-              for (int q = 0; q < 8; ++q) f[q] = gelu_sigmoid(f[q]);
-            }
-            uint4* cell = reinterpret_cast<uint4*>(my_row + ((j ^ sw) << 4));
-            if constexpr (kResidual) {
-              const uint4 rr = *cell;
-              f[0] += bf16_lo(rr.x); f[1] += bf16_hi(rr.x);
-              f[2] += bf16_lo(rr.y); f[3] += bf16_hi(rr.y);
-              f[4] += bf16_lo(rr.z); f[5] += bf16_hi(rr.z);
-              f[6] += bf16_lo(rr.w); f[7] += bf16_hi(rr.w);
-            }
-            uint4 o;
-            o.x = pack_bf16(f[0], f[1]);
-            o.y = pack_bf16(f[2], f[3]);
-            o.z = pack_bf16(f[4], f[5]);
-            o.w = pack_bf16(f[6], f[7]);
-            *cell = o;
+          };
+          if (full_box)
+            box_body(std::true_type{});
+          else
+            box_body(std::false_type{});
+          if constexpr (kStats) {
+            if (r < p.M) p.stats_out[static_cast<size_t>(col0 >> 6) * p.M + r] = make_float2(st_sum, st_sq);
           }
           fence_proxy_async_smem();            // generic-proxy smem writes -> visible to the TMA (async proxy)
           __syncwarp();
@@ -538,9 +607,9 @@ struct Maps {
   CUtensorMap a, b, out, res;
 };
 
-template <int BN, bool G, bool R, bool Q, bool D>
+template <int BN, bool G, bool R, bool Q, bool D, bool B = false, bool L = false, bool S = false>
 int32_t launch_one(cudaStream_t stream, const Maps& m, const GemmParams& p, int grid) {
-  auto kern = gemm_tcgen05_kernel<BN, G, R, Q, D>;
+  auto kern = gemm_tcgen05_kernel<BN, G, R, Q, D, B, L, S>;
   static bool attr_set = false;  // benign race: the attribute is idempotent
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::kSmemBytes);
@@ -551,15 +620,49 @@ int32_t launch_one(cudaStream_t stream, const Maps& m, const GemmParams& p, int 
   return after_launch();
 }
 
-template <int BN, bool D>
-int32_t launch_bn(cudaStream_t stream, const Maps& m, const GemmParams& p, int grid, bool gelu, bool residual,
-                  bool rotary) {
-  if (rotary && !gelu && !residual) return launch_one<BN, false, false, true, D>(stream, m, p, grid);
-  if (gelu && !residual && !rotary) return launch_one<BN, true, false, false, D>(stream, m, p, grid);
-  if (residual && !gelu && !rotary) return launch_one<BN, false, true, false, D>(stream, m, p, grid);
-  if (!gelu && !residual && !rotary) return launch_one<BN, false, false, false, D>(stream, m, p, grid);
-  if (gelu && residual && !rotary) return launch_one<BN, true, true, false, D>(stream, m, p, grid);
+struct Epi {
+  bool gelu, residual, rotary, bias, ln, stats;
+};
+
+// direct path (fp32 or row-remapped output): bias is a run-time flag, no LN fold / statistics
+template <int BN>
+int32_t launch_direct(cudaStream_t stream, const Maps& m, const GemmParams& p, int grid, const Epi& e) {
+  if (e.ln || e.stats) return MR_ERR_BAD_SHAPE;
+  if (e.rotary && !e.gelu && !e.residual) return launch_one<BN, false, false, true, true>(stream, m, p, grid);
+  if (e.gelu && !e.residual && !e.rotary) return launch_one<BN, true, false, false, true>(stream, m, p, grid);
+  if (e.residual && !e.gelu && !e.rotary) return launch_one<BN, false, true, false, true>(stream, m, p, grid);
+  if (!e.gelu && !e.residual && !e.rotary) return launch_one<BN, false, false, false, true>(stream, m, p, grid);
+  if (e.gelu && e.residual && !e.rotary) return launch_one<BN, true, true, false, true>(stream, m, p, grid);
   return MR_ERR_BAD_SHAPE;  // rotary never combines with gelu/residual on this path
+}
+
+// staged path (bf16 output through shared memory + TMA store): every flag is compile time
+template <int BN, bool G, bool R, bool Q>
+int32_t launch_staged_bls(cudaStream_t stream, const Maps& m, const GemmParams& p, int grid, const Epi& e) {
+  if (e.ln && e.stats) return MR_ERR_BAD_SHAPE;
+  if (e.ln) {
+    if (!e.bias || R) return MR_ERR_BAD_SHAPE;   // the folded LayerNorm always carries beta W (+ b) as its bias
+    if constexpr (!R) return launch_one<BN, G, R, Q, false, true, true, false>(stream, m, p, grid);
+  }
+  if (e.stats) {
+    if (G || Q) return MR_ERR_BAD_SHAPE;
+    if constexpr (!G && !Q) {
+      if (e.bias) return launch_one<BN, G, R, Q, false, true, false, true>(stream, m, p, grid);
+      return launch_one<BN, G, R, Q, false, false, false, true>(stream, m, p, grid);
+    }
+  }
+  if (e.bias) return launch_one<BN, G, R, Q, false, true, false, false>(stream, m, p, grid);
+  return launch_one<BN, G, R, Q, false, false, false, false>(stream, m, p, grid);
+}
+
+template <int BN>
+int32_t launch_staged(cudaStream_t stream, const Maps& m, const GemmParams& p, int grid, const Epi& e) {
+  if (e.rotary && !e.gelu && !e.residual) return launch_staged_bls<BN, false, false, true>(stream, m, p, grid, e);
+  if (e.gelu && !e.residual && !e.rotary) return launch_staged_bls<BN, true, false, false>(stream, m, p, grid, e);
+  if (e.residual && !e.gelu && !e.rotary) return launch_staged_bls<BN, false, true, false>(stream, m, p, grid, e);
+  if (!e.gelu && !e.residual && !e.rotary) return launch_staged_bls<BN, false, false, false>(stream, m, p, grid, e);
+  if (e.gelu && e.residual && !e.rotary) return launch_staged_bls<BN, true, true, false>(stream, m, p, grid, e);
+  return MR_ERR_BAD_SHAPE;
 }
 
 }  // namespace
@@ -608,6 +711,22 @@ extern "C" int32_t mr_gemm_epilogue(mr_stream_t stream_, const MrGemmDesc* d, co
   p.residual = static_cast<const bf16*>(in[3]);
   p.rot = static_cast<const float*>(in[4]);
   p.D = out[0];
+  const bool ln_in = d->epilogue & MR_EPI_LN_IN, stats_out = d->epilogue & MR_EPI_STATS_OUT;
+  const bool direct_path = p.out_f32 || d->seq_in != 0;
+  if (ln_in) {
+    MR_REQUIRE(in[5] && in[6], MR_ERR_NULL_POINTER);
+    MR_REQUIRE(aligned16(in[5]) && aligned16(in[6]), MR_ERR_MISALIGNED);
+    MR_REQUIRE(d->K % 64 == 0 && d->N % 8 == 0 && !direct_path && d->algo == MR_GEMM_ALGO_TCGEN05, MR_ERR_BAD_SHAPE);
+    p.stats_in = static_cast<const float2*>(in[5]);
+    p.ln_s = static_cast<const float*>(in[6]);
+    p.ln_eps = d->ln_eps;
+  }
+  if (stats_out) {
+    MR_REQUIRE(out[1], MR_ERR_NULL_POINTER);
+    MR_REQUIRE(aligned16(out[1]), MR_ERR_MISALIGNED);
+    MR_REQUIRE(d->N % 64 == 0 && !direct_path && d->algo == MR_GEMM_ALGO_TCGEN05, MR_ERR_BAD_SHAPE);
+    p.stats_out = static_cast<float2*>(out[1]);
+  }
 
   if (d->algo == MR_GEMM_ALGO_SIMT_DEBUG) {
     const int64_t total = static_cast<int64_t>(d->M) * d->N;
@@ -634,16 +753,17 @@ extern "C" int32_t mr_gemm_epilogue(mr_stream_t stream_, const MrGemmDesc* d, co
   MR_REQUIRE(make_tmap_2d(&m.b, W, d->N, d->K, d->K, bn, kBK), MR_ERR_DRIVER);
   // fp32 output and row-remapped output keep per-thread global accesses; everything else is staged
   // through shared memory and moved by TMA
-  const bool direct = p.out_f32 || d->seq_in != 0;
+  const bool direct = direct_path;
+  const Epi epi{gelu, residual, rotary, bias, ln_in, stats_out};
   if (direct) {
     m.out = m.a;
     m.res = m.a;
-    if (bn == 256) return launch_bn<256, true>(stream, m, p, grid, gelu, residual, rotary);
-    return launch_bn<128, true>(stream, m, p, grid, gelu, residual, rotary);
+    if (bn == 256) return launch_direct<256>(stream, m, p, grid, epi);
+    return launch_direct<128>(stream, m, p, grid, epi);
   }
   MR_REQUIRE(make_tmap_2d(&m.out, out[0], d->M, d->N, d->ldd, 32, 64), MR_ERR_DRIVER);
   m.res = m.out;
   if (residual) MR_REQUIRE(make_tmap_2d(&m.res, in[3], d->M, d->N, d->ldd, 32, 64), MR_ERR_DRIVER);
-  if (bn == 256) return launch_bn<256, false>(stream, m, p, grid, gelu, residual, rotary);
-  return launch_bn<128, false>(stream, m, p, grid, gelu, residual, rotary);
+  if (bn == 256) return launch_staged<256>(stream, m, p, grid, epi);
+  return launch_staged<128>(stream, m, p, grid, epi);
 }

@@ -44,7 +44,7 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 template <int kVec>
 __global__ void __launch_bounds__(kRowThreads)
 layernorm_kernel(const bf16* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
-                 bf16* __restrict__ y, MrLayerNormDesc d) {
+                 bf16* __restrict__ y, float2* __restrict__ stats, MrLayerNormDesc d) {
   const int row = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= d.rows) return;
@@ -73,6 +73,7 @@ layernorm_kernel(const bf16* __restrict__ x, const float* __restrict__ gamma, co
     const float mean = s * inv_h;
     const float var = s2 * inv_h - mean * mean;
     const float rstd = rsqrtf(var + d.eps);
+    float os = 0.f, os2 = 0.f;   // statistics of the rounded output (folded LayerNorm of the next GEMM)
 #pragma unroll
     for (int i = 0; i < kVec; ++i) {
       float f[8];
@@ -86,7 +87,23 @@ layernorm_kernel(const bf16* __restrict__ x, const float* __restrict__ gamma, co
       const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
       for (int j = 0; j < 8; ++j) f[j] = (f[j] - mean) * (rstd * g[j]) + b[j];
-      dst[lane + 32 * i] = pack8(f);
+      const uint4 o = pack8(f);
+      dst[lane + 32 * i] = o;
+      if (stats != nullptr) {
+        unpack8(o, f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          os += f[j];
+          os2 = fmaf(f[j], f[j], os2);
+        }
+      }
+    }
+    if (stats != nullptr) {
+      os = warp_sum(os);
+      os2 = warp_sum(os2);
+      const int parts = d.H >> 6;
+      if (lane < parts)
+        stats[static_cast<size_t>(lane) * d.rows + row] = lane == 0 ? make_float2(os, os2) : make_float2(0.f, 0.f);
     }
   } else {
     const int nvec = d.H / 8;
@@ -110,7 +127,27 @@ layernorm_kernel(const bf16* __restrict__ x, const float* __restrict__ gamma, co
       unpack8(__ldg(src + v), f);
 #pragma unroll
       for (int j = 0; j < 8; ++j) f[j] = (f[j] - mean) * (rstd * gamma[v * 8 + j]) + beta[v * 8 + j];
-      dst[v] = pack8(f);
+      const uint4 o = pack8(f);
+      dst[v] = o;
+    }
+    if (stats != nullptr) {
+      // generic-H path: second pass over the rounded output just written by this warp
+      __syncwarp();
+      float os = 0.f, os2 = 0.f;
+      for (int v = lane; v < nvec; v += 32) {
+        float f[8];
+        unpack8(dst[v], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          os += f[j];
+          os2 = fmaf(f[j], f[j], os2);
+        }
+      }
+      os = warp_sum(os);
+      os2 = warp_sum(os2);
+      const int parts = d.H >> 6;
+      for (int q = lane; q < parts; q += 32)
+        stats[static_cast<size_t>(q) * d.rows + row] = q == 0 ? make_float2(os, os2) : make_float2(0.f, 0.f);
     }
   }
 }
@@ -476,13 +513,15 @@ extern "C" int32_t mr_layernorm_fwd(mr_stream_t stream_, const MrLayerNormDesc* 
   const float* g = static_cast<const float*>(in[1]);
   const float* b = static_cast<const float*>(in[2]);
   bf16* y = static_cast<bf16*>(out[0]);
+  float2* stats = d->emit_stats ? static_cast<float2*>(out[1]) : nullptr;
+  if (d->emit_stats) MR_REQUIRE(stats && d->H % 64 == 0 && aligned16(stats), MR_ERR_BAD_SHAPE);
   const int grid = ceil_div(d->rows, kWarpsPerBlock);
   if (d->H == 768)
-    layernorm_kernel<3><<<grid, kRowThreads, 0, stream>>>(x, g, b, y, *d);
+    layernorm_kernel<3><<<grid, kRowThreads, 0, stream>>>(x, g, b, y, stats, *d);
   else if (d->H == 1024)
-    layernorm_kernel<4><<<grid, kRowThreads, 0, stream>>>(x, g, b, y, *d);
+    layernorm_kernel<4><<<grid, kRowThreads, 0, stream>>>(x, g, b, y, stats, *d);
   else
-    layernorm_kernel<0><<<grid, kRowThreads, 0, stream>>>(x, g, b, y, *d);
+    layernorm_kernel<0><<<grid, kRowThreads, 0, stream>>>(x, g, b, y, stats, *d);
   return after_launch();
 }
 

@@ -89,9 +89,24 @@ def _f(x) -> torch.Tensor:
     return torch.as_tensor(np.asarray(x), dtype=torch.float32).reshape(-1).cuda().contiguous()
 
 
+def _w_ln(kernel, in_features: int, ln: Dict, bias):
+    """Folds the LayerNorm in front of a Dense into its weights (include/mreserve_b200.h, MR_EPI_LN_IN):
+    LN(x) W + b = rstd (x W' - mu colsum(W')) + (beta W + b) with W' = gamma (.) W.  Returns
+    (W' bf16 [N, K], colsum(W') f32 [N] of the bf16-ROUNDED W' so that the mean term cancels exactly, beta W + b)."""
+    k = torch.as_tensor(np.asarray(kernel), dtype=torch.float32).reshape(in_features, -1)
+    gamma = torch.as_tensor(np.asarray(ln["scale"]), dtype=torch.float32).reshape(-1)
+    beta = torch.as_tensor(np.asarray(ln["bias"]), dtype=torch.float32).reshape(-1)
+    wt = (k * gamma[:, None]).t().contiguous().to(torch.bfloat16)
+    colsum = wt.float().sum(1)
+    b = beta.double() @ k.double()
+    if bias is not None:
+        b = b + torch.as_tensor(np.asarray(bias), dtype=torch.float64).reshape(-1)
+    return wt.cuda().contiguous(), colsum.cuda().contiguous(), b.float().cuda().contiguous()
+
+
 class _PackedEncoder:
-    def __init__(self, p: Dict, H: int, num_layers: int, add_cls: bool):
-        self.H, self.num_layers, self.add_cls = H, num_layers, add_cls
+    def __init__(self, p: Dict, H: int, num_layers: int, add_cls: bool, fuse_ln: bool = True):
+        self.H, self.num_layers, self.add_cls, self.fuse_ln = H, num_layers, add_cls, fuse_ln
         self.pre_ln = (_f(p["pre_ln"]["scale"]), _f(p["pre_ln"]["bias"]))
         self.final_ln = (_f(p["final_ln"]["scale"]), _f(p["final_ln"]["bias"]))
         if add_cls:
@@ -101,14 +116,17 @@ class _PackedEncoder:
         for i in range(num_layers):
             lp = p[f"layer_{i:02d}"]
             a, m = lp["attention_layer"], lp["mlp_layer"]
-            self.layers.append(dict(
-                ln1=(_f(lp["pre_attn_ln"]["scale"]), _f(lp["pre_attn_ln"]["bias"])),
-                wqkv=_w(a["qkv"]["kernel"], H), bqkv=_f(a["qkv"]["bias"]),
-                wo=_w(a["attn_proj"]["kernel"], H),
-                ln2=(_f(lp["pre_mlp_ln"]["scale"]), _f(lp["pre_mlp_ln"]["bias"])),
-                w1=_w(m["intermediate"]["kernel"], H), b1=_f(m["intermediate"]["bias"]),
-                w2=_w(m["out"]["kernel"], 4 * H),
-            ))
+            layer = dict(wo=_w(a["attn_proj"]["kernel"], H), w2=_w(m["out"]["kernel"], 4 * H))
+            if fuse_ln:
+                layer["wqkv"], layer["sqkv"], layer["bqkv"] = _w_ln(a["qkv"]["kernel"], H, lp["pre_attn_ln"], a["qkv"]["bias"])
+                layer["w1"], layer["s1"], layer["b1"] = _w_ln(m["intermediate"]["kernel"], H, lp["pre_mlp_ln"],
+                                                              m["intermediate"]["bias"])
+            else:
+                layer.update(ln1=(_f(lp["pre_attn_ln"]["scale"]), _f(lp["pre_attn_ln"]["bias"])),
+                             wqkv=_w(a["qkv"]["kernel"], H), bqkv=_f(a["qkv"]["bias"]),
+                             ln2=(_f(lp["pre_mlp_ln"]["scale"]), _f(lp["pre_mlp_ln"]["bias"])),
+                             w1=_w(m["intermediate"]["kernel"], H), b1=_f(m["intermediate"]["bias"]))
+            self.layers.append(layer)
 
 
 class _PackedPool:
@@ -122,23 +140,23 @@ class _PackedPool:
 class _Packed:
     """Device-resident weights of one parameter tree."""
 
-    def __init__(self, params: Dict, cfg: Dict):
+    def __init__(self, params: Dict, cfg: Dict, fuse_ln: bool = True):
         H = cfg["hidden_size"]
         self.H = H
         if "vision_encoder" in params:
             v = params["vision_encoder"]
             self.vis_emb = (_w(v["embedding"]["kernel"], (cfg["vit_patch_size"] ** 2) * 3), _f(v["embedding"]["bias"]))
-            self.vis = _PackedEncoder(v["transformer"], H, cfg["vit_num_layers"], True)
+            self.vis = _PackedEncoder(v["transformer"], H, cfg["vit_num_layers"], True, fuse_ln)
             self.vis_pool = _PackedPool(v["seq_attnpool"], H)
         if "audio_encoder" in params:
             a = params["audio_encoder"]
             kin = cfg["audio_patch_size"] * 65
             self.aud_emb = (_w(a["embedding"]["kernel"], kin, _AUDIO_K_PAD), _f(a["embedding"]["bias"]))
-            self.aud = _PackedEncoder(a["transformer"], H, cfg["audio_num_layers"], True)
+            self.aud = _PackedEncoder(a["transformer"], H, cfg["audio_num_layers"], True, fuse_ln)
             self.aud_pool = _PackedPool(a["seq_attnpool"], H)
         if "span_encoder" in params:
-            self.span = _PackedEncoder(params["span_encoder"]["transformer"], H, cfg["span_num_layers"], True)
-        self.joint = _PackedEncoder(params["joint_transformer"], H, cfg["joint_num_layers"], False)
+            self.span = _PackedEncoder(params["span_encoder"]["transformer"], H, cfg["span_num_layers"], True, fuse_ln)
+        self.joint = _PackedEncoder(params["joint_transformer"], H, cfg["joint_num_layers"], False, fuse_ln)
         self.tok_emb = torch.as_tensor(np.asarray(params["token_encoder"]["Embed_0"]["embedding"]),
                                        dtype=torch.float32).to(torch.bfloat16).cuda().contiguous()
         if "head" in params:
@@ -166,6 +184,9 @@ class MerlotReserve:
             raise ValueError("the B200 kernels require size_per_head == 64")
         self.hidden_size = config["hidden_size"]
         self.audio_pooling_ratio = config["audio_seq_length"] // (config["audio_token_length"] * config["audio_patch_size"])
+        # Fold every pre-attention / pre-MLP LayerNorm into the GEMM that consumes it (MR_EPI_LN_IN); False keeps
+        # the separate LayerNorm kernel (same arithmetic up to rounding; kept for bisecting in tests).
+        self.fuse_layernorm = True
         self._packed_cache: Dict[int, _Packed] = {}
         self._bound: Optional[_Packed] = None
         self._tables: Dict[Any, torch.Tensor] = {}
@@ -191,7 +212,7 @@ class MerlotReserve:
         L.require_b200(torch.cuda.current_device() if torch.cuda.is_available() else 0)
         key = id(params)
         if key not in self._packed_cache:
-            self._packed_cache[key] = _Packed(params, self.config)
+            self._packed_cache[key] = _Packed(params, self.config, self.fuse_layernorm)
             self._packed_cache[key]._keepalive = params
         self._bound = self._packed_cache[key]
         return self
@@ -235,11 +256,24 @@ class MerlotReserve:
                  valid: Optional[torch.Tensor] = None, group: Optional[torch.Tensor] = None) -> torch.Tensor:
         H, M = enc.H, B * T
         dev = x.device
-        x = L.layernorm(x, *enc.pre_ln)
-        h = torch.empty((M, H), dtype=torch.bfloat16, device=dev)
         qkv = torch.empty((M, 3 * H), dtype=torch.bfloat16, device=dev)
         ctx = torch.empty((M, H), dtype=torch.bfloat16, device=dev)
         u = torch.empty((M, 4 * H), dtype=torch.bfloat16, device=dev)
+        if enc.fuse_ln:
+            # row statistics of the residual stream travel beside it: written by pre_ln and by the two residual
+            # GEMMs of a layer, consumed by the GEMM behind the next LayerNorm (no LayerNorm launches in the loop)
+            stats = torch.empty((H // 64, M, 2), dtype=torch.float32, device=dev)
+            x = L.layernorm(x, *enc.pre_ln, stats_out=stats)
+            for lw in enc.layers:
+                L.gemm(x, lw["wqkv"], bias=lw["bqkv"], rot=rot, hidden=H, q_scale=0.125, out=qkv, ln_stats=stats,
+                       ln_colsum=lw["sqkv"])
+                L.attention(qkv, B, T, H, valid=valid, group=group, out=ctx)
+                L.gemm(ctx, lw["wo"], residual=x, out=x, stats_out=stats)
+                L.gemm(x, lw["w1"], bias=lw["b1"], gelu=True, out=u, ln_stats=stats, ln_colsum=lw["s1"])
+                L.gemm(u, lw["w2"], residual=x, out=x, stats_out=stats)
+            return x  # before final_ln
+        x = L.layernorm(x, *enc.pre_ln)
+        h = torch.empty((M, H), dtype=torch.bfloat16, device=dev)
         for lw in enc.layers:
             L.layernorm(x, *lw["ln1"], out=h)
             L.gemm(h, lw["wqkv"], bias=lw["bqkv"], rot=rot, hidden=H, q_scale=0.125, out=qkv)

@@ -398,3 +398,65 @@ def test_pretrain_row_kernels(cuda, lib):
         assert torch.equal(xo[r, Ltok:], vis[vb])
         for t in range(2, 5):
             assert torch.equal(xo[r, t], aud[r // (G * tile), ptr[r, t], t - 2])
+
+
+@pytest.mark.parametrize("M,H,N,mode", [(1000, 768, 2304, "rotary"), (300, 1024, 4096, "gelu"), (77, 128, 384, "plain"),
+                                        (4000, 768, 3072, "gelu")])
+def test_gemm_layernorm_fold(cuda, lib, M, H, N, mode):
+    """MR_EPI_LN_IN / MR_EPI_STATS_OUT: Dense(LayerNorm(x)) with the LayerNorm folded into the GEMM epilogue, fed
+    by row statistics that (a) the LayerNorm kernel and (b) a residual GEMM emit for their own bf16 outputs.
+    Reference: flax LayerNorm in fp32 (var = E[x^2] - E[x]^2, eps 1e-5) then the fp32 matmul (modeling.py:272-279)."""
+    g = torch.Generator().manual_seed(M + N)
+    gamma = (1 + 0.1 * torch.randn(H, generator=g))
+    beta = 0.1 * torch.randn(H, generator=g)
+    W = torch.randn(H, N, generator=g) * 0.05          # flax layout [in, out]
+    b = 0.1 * torch.randn(N, generator=g)
+    wt = (W * gamma[:, None]).t().contiguous().to(torch.bfloat16)
+    colsum = wt.float().sum(1).to(cuda)
+    bias = (beta @ W + b).to(cuda)
+
+    def ref_of(x_bf16):
+        x = x_bf16.float().cpu()
+        mu = x.mean(-1, keepdim=True)
+        var = (x * x).mean(-1, keepdim=True) - mu * mu
+        h = (x - mu) * torch.rsqrt(var + 1e-5) * gamma + beta
+        return h @ W + b
+
+    # (a) x comes out of a LayerNorm kernel that also emits the statistics; rows carry a large common offset
+    x0 = _bf(torch.randn(M, H, generator=g) * 2 + 3 * torch.randn(M, 1, generator=g)).to(cuda)
+    g0, b0 = (1 + 0.1 * torch.randn(H, generator=g)).to(cuda), (0.5 + 0.1 * torch.randn(H, generator=g)).to(cuda)
+    stats = torch.full((H // 64, M, 2), float("nan"), device=cuda)
+    x = lib.layernorm(x0, g0, b0, stats_out=stats)
+    xs = x.float()
+    _close(stats.sum(0)[:, 0], xs.sum(-1), 1e-2, 1e-4, "LN stats sum")
+    _close(stats.sum(0)[:, 1], (xs * xs).sum(-1), 1e-2, 1e-4, "LN stats sumsq")
+    kw = {}
+    ref = ref_of(x)
+    if mode == "rotary":
+        hid = N // 3
+        rot = (torch.rand(7, 32, generator=g) * 2 - 1).to(cuda)
+        kw = dict(rot=rot, hidden=hid, q_scale=0.125)
+        r = ref.clone().view(M, 3, hid // 64, 64)
+        sc = rot.cpu()[torch.arange(M) % 7]
+        r[:, :2, :, :32] *= sc[:, None, None, :]
+        r[:, 0] *= 0.125
+        ref = r.view(M, N)
+    elif mode == "gelu":
+        kw = dict(gelu=True)
+        ref = ref * torch.sigmoid(1.702 * ref)
+    got = lib.gemm(x, wt.to(cuda), bias=bias, ln_stats=stats, ln_colsum=colsum, **kw)
+    _close(got.cpu(), ref, 3e-2, 2e-2, f"LN-folded gemm ({mode}) on LayerNorm-kernel statistics")
+
+    # (b) x comes out of a residual GEMM that emits the statistics of its rounded output
+    if N % 64 == 0:
+        a = _bf(torch.randn(M, 256, generator=g)).to(cuda)
+        w2 = _bf(torch.randn(H, 256, generator=g) * 0.1).to(cuda)
+        stats2 = torch.full((H // 64, M, 2), float("nan"), device=cuda)
+        x2 = x.clone()
+        lib.gemm(a, w2, residual=x2, out=x2, stats_out=stats2)
+        xs = x2.float()
+        _close(x2, x.float() + a.float() @ w2.float().t(), 5e-2, 2e-2, "residual gemm")
+        _close(stats2.sum(0)[:, 0], xs.sum(-1), 1e-2, 1e-4, "gemm stats sum")
+        _close(stats2.sum(0)[:, 1], (xs * xs).sum(-1), 1e-2, 1e-4, "gemm stats sumsq")
+        got = lib.gemm(x2, wt.to(cuda), bias=bias, ln_stats=stats2, ln_colsum=colsum)
+        _close(got.cpu(), ref_of(x2), 3e-2, 2e-2, "LN-folded gemm on GEMM statistics")

@@ -141,3 +141,17 @@ def test_input_validation(setup):
         model.embed_video(clip["images"], clip["audio_clips"][:5], clip["tokens"], clip["subseg_idxs"])
     with pytest.raises(ValueError):
         model.embed_video(clip["images"], clip["audio_clips"], clip["tokens"], clip["subseg_idxs"][:10])
+
+
+def test_layernorm_fold_matches_separate_layernorm(setup):
+    """The default path folds every pre-attention / pre-MLP LayerNorm into the consuming GEMM; the unfused path
+    (separate LayerNorm kernel) must give the same embeddings, and both must match the oracle."""
+    cfg, params, model, orc = setup
+    clip = synthetic_clip(cfg, nseg=4, seed=13)
+    fused = model.apply({"params": params}, **clip, method=model.embed_video)
+    plain = MerlotReserve.from_config(cfg)
+    plain.fuse_layernorm = False
+    unfused = plain.apply({"params": params}, **clip, method=plain.embed_video)
+    assert _cos(fused, unfused).min() >= 0.999
+    ref = orc.embed_video(**clip)
+    assert _cos(fused, ref).min() >= COS_MIN and _cos(unfused, ref).min() >= COS_MIN

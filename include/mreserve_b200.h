@@ -106,6 +106,8 @@ typedef struct MrGemmDesc {
   float q_scale;
   int32_t num_sms;  /* 0 = use every SM of the current device */
   float ln_eps;     /* MR_EPI_LN_IN */
+  int32_t algo_pair; /* 0 = auto, 1 = force CTA pairs (cta_group::2, 256 x 256 tiles), 2 = never; pairs need the
+                        staged bf16 output path and a 256-wide tile, otherwise the field is ignored */
 } MrGemmDesc;
 
 int32_t mr_gemm_epilogue(mr_stream_t stream, const MrGemmDesc* d, const void* const* in, void* const* out,

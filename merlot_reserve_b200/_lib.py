@@ -26,7 +26,7 @@ class GemmDesc(C.Structure):
     _fields_ = [("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32), ("lda", C.c_int32), ("ldd", C.c_int32),
                 ("epilogue", C.c_int32), ("seq_in", C.c_int32), ("seq_out", C.c_int32), ("row_off", C.c_int32),
                 ("rot_rows", C.c_int32), ("hidden", C.c_int32), ("algo", C.c_int32), ("q_scale", C.c_float),
-                ("num_sms", C.c_int32), ("ln_eps", C.c_float)]
+                ("num_sms", C.c_int32), ("ln_eps", C.c_float), ("algo_pair", C.c_int32)]
 
 
 class AttentionDesc(C.Structure):
@@ -104,7 +104,11 @@ WORKSPACE_FNS = {
 }
 MISC_FNS = ["mr_check_device", "mr_abi_version", "mr_status_string", "mr_launch_count"]
 
-ABI_VERSION = 3  # must equal mr_abi_version() of the loaded library (struct layouts above)
+# MrGemmDesc.algo_pair used when a call does not say: 0 auto, 1 force CTA pairs, 2 never (MR_GEMM_PAIR overrides)
+import os as _os
+GEMM_PAIR_DEFAULT = int(_os.environ.get("MR_GEMM_PAIR", "0"))
+
+ABI_VERSION = 4  # must equal mr_abi_version() of the loaded library (struct layouts above)
 
 _lib = None
 
@@ -209,11 +213,13 @@ def _work(name: str, d):
 # ------------------------------------------------------------------------------------------------
 def gemm(a: torch.Tensor, w: torch.Tensor, *, bias=None, residual=None, rot=None, out=None, gelu=False,
          out_f32=False, hidden=0, q_scale=1.0, seq_in=0, seq_out=0, row_off=0, out_rows=None, M=None, lda=None,
-         algo=ALGO_TCGEN05, ln_stats=None, ln_colsum=None, ln_eps=1e-5, stats_out=None) -> torch.Tensor:
+         algo=ALGO_TCGEN05, ln_stats=None, ln_colsum=None, ln_eps=1e-5, stats_out=None, pair=None) -> torch.Tensor:
     """D = epilogue(A @ W^T).  a: bf16 [M, K] (or strided rows via M / lda), w: bf16 [N, K].
     ln_stats / ln_colsum: fold LayerNorm(a) into the GEMM (w must be the gamma-scaled weight, bias = beta W + b);
     stats_out: f32 [N/64, M, 2] buffer receiving the row statistics of the (bf16) output."""
     assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16
+    if pair is None:
+        pair = GEMM_PAIR_DEFAULT
     N, K = w.shape
     if M is None:
         M = a.shape[0]
@@ -239,7 +245,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias=None, residual=None, rot=None
         epi |= EPI_STATS_OUT
     d = GemmDesc(M=M, N=N, K=K, lda=lda, ldd=out.shape[-1], epilogue=epi, seq_in=seq_in, seq_out=seq_out,
                  row_off=row_off, rot_rows=(rot.shape[0] if rot is not None else 0), hidden=hidden, algo=algo,
-                 q_scale=q_scale, num_sms=0, ln_eps=ln_eps)
+                 q_scale=q_scale, num_sms=0, ln_eps=ln_eps, algo_pair=pair)
     _call("mr_gemm_epilogue", d, [a, w, bias, residual, rot, ln_stats, ln_colsum], [out, stats_out])
     return out
 

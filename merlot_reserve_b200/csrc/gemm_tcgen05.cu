@@ -58,11 +58,15 @@ struct GemmParams {
 
 constexpr int kBoxBytes = 32 * 128;  // one epilogue staging box: 32 rows x 64 bf16, 128B swizzle
 
-template <int BN>
+// kCtas = 2: CTA pair (cta_group::2).  The pair owns a 256 x BN tile: each CTA stages its own 128 rows of A and
+// HALF of the W tile (BN / 2 rows); the leader issues 256 x BN x 16 MMAs that read both CTAs' shared memory and
+// write each CTA's half of the accumulator into its own TMEM.  Per CTA and k-block that is 32 KB of L2 -> SMEM
+// traffic instead of 48 KB, and the smaller stages allow a 6-deep ring.
+template <int BN, int kCtas = 1>
 struct Cfg {
-  static constexpr int kStages = BN == 256 ? 4 : 6;
+  static constexpr int kStages = (BN == 256 && kCtas == 1) ? 4 : 6;
   static constexpr int kABytes = kBM * kBK * 2;
-  static constexpr int kBBytes = BN * kBK * 2;
+  static constexpr int kBBytes = (BN / kCtas) * kBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTmemCols = 2 * BN;  // two accumulator stages
   static constexpr int kOutBytes = kEpiWarps * kBoxBytes;
@@ -104,12 +108,15 @@ __device__ __forceinline__ void load_cols8(const float* __restrict__ v, int c, i
 // step sat behind its own reconvergence point and the epilogue became latency bound (profiles/ncu_gemm_r01j.md).
 // The direct path keeps run-time p.bias_on (small GEMMs only).
 template <int BN, bool kGelu, bool kResidual, bool kRotary, bool kDirect, bool kBias = false, bool kLn = false,
-          bool kStats = false>
+          bool kStats = false, int kCtas = 1>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res,
                     const GemmParams p) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, kCtas>;
+  constexpr bool kPair = kCtas == 2;
+  static_assert(!(kPair && kDirect) && (!kPair || BN == 256), "CTA pairs: staged 256-wide tiles only");
+  const uint32_t cta_rank = kPair ? cluster_ctarank() : 0u;   // 0 = leader (issues the MMAs of the pair)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
@@ -139,17 +146,25 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full_bar[a], 1);
-      mbar_init(&tmem_empty_bar[a], kEpiWarps);
+      mbar_init(&tmem_empty_bar[a], kEpiWarps * kCtas);   // pair: the leader's barrier collects both CTAs' epilogues
     }
     for (int w = 0; w < kEpiWarps; ++w) mbar_init(&res_bar[w], 1);
     fence_mbar_init();
   }
   if (warp_idx == 2) {
-    tmem_alloc(tmem_slot, C::kTmemCols);
-    tmem_relinquish();
+    if constexpr (kPair) {
+      tmem_alloc_pair(tmem_slot, C::kTmemCols);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(tmem_slot, C::kTmemCols);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (kPair)
+    cluster_sync_all();       // both CTAs' barriers are initialised before any remote arrive / TMA credit
+  else
+    __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -157,11 +172,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   // CTAs that share an A row block run at the same time and a long-K A block is fetched from HBM once.
   // Rotary (QKV) GEMMs: every CTA owns a CONTIGUOUS range instead, so consecutive tiles of a CTA share the row
   // block and the per-row rotary scales stay in registers (K = hidden there: 148 live A blocks fit the L2).
-  const int tiles_per_cta = (p.num_tiles + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+  // CTA pairs: the schedule is over PAIR tiles (256 rows); CTA `cta_rank` owns row block 2 * m_pair + cta_rank.
+  const int num_workers = static_cast<int>(gridDim.x) / kCtas;
+  const int worker = static_cast<int>(blockIdx.x) / kCtas;
+  const int tiles_per_cta = (p.num_tiles + num_workers - 1) / num_workers;
   // LN-consuming GEMMs (K = hidden as well) use the contiguous schedule too: the row statistics stay in registers.
   constexpr bool contiguous = kRotary || kLn;
-  const int tile_step = contiguous ? 1 : static_cast<int>(gridDim.x);
-  const int tile_begin = contiguous ? static_cast<int>(blockIdx.x) * tiles_per_cta : static_cast<int>(blockIdx.x);
+  const int tile_step = contiguous ? 1 : num_workers;
+  const int tile_begin = contiguous ? worker * tiles_per_cta : worker;
   const int tile_end = contiguous ? min(tile_begin + tiles_per_cta, p.num_tiles) : p.num_tiles;
 
   if (warp_idx == 0) {
@@ -170,16 +188,24 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
-        const int m_blk = tile / p.num_n_tiles;
+        const int m_blk = (tile / p.num_n_tiles) * kCtas + static_cast<int>(cta_rank);
         const int n_blk = tile % p.num_n_tiles;
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * C::kStageBytes;
           uint8_t* sb = sa + C::kABytes;
-          mbar_arrive_expect_tx(&full_bar[stage], C::kStageBytes);
           // activations are streamed once per N-sweep; weights are re-read by every M block
+          if constexpr (kPair) {
+            // both CTAs load into their own ring slot; all bytes are credited to the leader's barrier
+            if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * C::kStageBytes);
+            tma_load_2d_pair(&tmap_a, &full_bar[stage], sa, kb * kBK, m_blk * kBM, kEvictNormal);
+            tma_load_2d_pair(&tmap_b, &full_bar[stage], sb, kb * kBK, n_blk * BN + static_cast<int>(cta_rank) * (BN / 2),
+                             kEvictLast);
+          } else {
+          mbar_arrive_expect_tx(&full_bar[stage], C::kStageBytes);
           tma_load_2d(&tmap_a, &full_bar[stage], sa, kb * kBK, m_blk * kBM, kEvictNormal);
           tma_load_2d(&tmap_b, &full_bar[stage], sb, kb * kBK, n_blk * BN, kEvictLast);
+          }
           if (++stage == C::kStages) {
             stage = 0;
             phase ^= 1;
@@ -189,8 +215,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
   } else if (warp_idx == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16_f32(kBM, BN);
+    if (lane == 0 && cta_rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16_f32(kBM * kCtas, BN);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -209,15 +235,20 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll
           for (int k = 0; k < kBK / kUmmaK; ++k) {
             // advancing 16 bf16 = 32 bytes along K inside the 128-byte swizzle row: +2 in 16-byte units
-            umma_bf16_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            if constexpr (kPair)
+              umma_bf16_ss_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            else
+              umma_bf16_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);  // frees the ring slot once these MMAs have read it
+          // frees the ring slot (in both CTAs of a pair) once these MMAs have read it
+          if constexpr (kPair) umma_commit_pair(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
           if (++stage == C::kStages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&tmem_full_bar[acc]);  // accumulator complete
+        // accumulator complete (each CTA's epilogue reads its own half from its own TMEM)
+        if constexpr (kPair) umma_commit_pair(&tmem_full_bar[acc]); else umma_commit(&tmem_full_bar[acc]);
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1;
@@ -245,7 +276,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       float ln_mu = 0.f, ln_rstd = 1.f;        // LayerNorm statistics of this thread's row (LN-consuming GEMMs)
       int ln_m = -1;
       for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
-        const int m_blk = tile / p.num_n_tiles;
+        const int m_blk = (tile / p.num_n_tiles) * kCtas + static_cast<int>(cta_rank);
         const int n_blk = tile % p.num_n_tiles;
         const int row0 = m_blk * kBM + quarter * 32;
         const int r = row0 + lane;
@@ -326,10 +357,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             }
           }
           if (box == kBoxes - 1) {
-            // all TMEM reads of this accumulator stage are done: hand it back to the MMA warp
+            // all TMEM reads of this accumulator stage are done: hand it back to the (leader's) MMA warp
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+            if (lane == 0) {
+              if constexpr (kPair)
+                mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty_bar[acc]), 0));
+              else
+                mbar_arrive(&tmem_empty_bar[acc]);
+            }
           }
           if (!box_ok) continue;
           if constexpr (kResidual) {
@@ -564,10 +600,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (kPair)
+    cluster_sync_all();       // the leader's MMAs read the peer's shared memory: neither CTA may retire early
+  else
+    __syncthreads();
   if (warp_idx == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, C::kTmemCols);
+    if constexpr (kPair)
+      tmem_dealloc_pair(tmem_base, C::kTmemCols);
+    else
+      tmem_dealloc(tmem_base, C::kTmemCols);
   }
 }
 
@@ -607,17 +649,35 @@ struct Maps {
   CUtensorMap a, b, out, res;
 };
 
-template <int BN, bool G, bool R, bool Q, bool D, bool B = false, bool L = false, bool S = false>
+template <int BN, bool G, bool R, bool Q, bool D, bool B = false, bool L = false, bool S = false, int P = 1>
 int32_t launch_one(cudaStream_t stream, const Maps& m, const GemmParams& p, int grid) {
-  auto kern = gemm_tcgen05_kernel<BN, G, R, Q, D, B, L, S>;
+  auto kern = gemm_tcgen05_kernel<BN, G, R, Q, D, B, L, S, P>;
   static bool attr_set = false;  // benign race: the attribute is idempotent
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN, P>::kSmemBytes);
     if (e != cudaSuccess) return cuda_status(e);
     attr_set = true;
   }
-  kern<<<grid, kThreads, Cfg<BN>::kSmemBytes, stream>>>(m.a, m.b, m.out, m.res, p);
-  return after_launch();
+  if constexpr (P == 2) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(static_cast<unsigned>(grid));
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = Cfg<BN, P>::kSmemBytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, m.a, m.b, m.out, m.res, p);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return cuda_status(e != cudaSuccess ? e : cudaGetLastError());
+  } else {
+    kern<<<grid, kThreads, Cfg<BN>::kSmemBytes, stream>>>(m.a, m.b, m.out, m.res, p);
+    return after_launch();
+  }
 }
 
 struct Epi {
@@ -637,31 +697,31 @@ int32_t launch_direct(cudaStream_t stream, const Maps& m, const GemmParams& p, i
 }
 
 // staged path (bf16 output through shared memory + TMA store): every flag is compile time
-template <int BN, bool G, bool R, bool Q>
+template <int BN, bool G, bool R, bool Q, int P>
 int32_t launch_staged_bls(cudaStream_t stream, const Maps& m, const GemmParams& p, int grid, const Epi& e) {
   if (e.ln && e.stats) return MR_ERR_BAD_SHAPE;
   if (e.ln) {
     if (!e.bias || R) return MR_ERR_BAD_SHAPE;   // the folded LayerNorm always carries beta W (+ b) as its bias
-    if constexpr (!R) return launch_one<BN, G, R, Q, false, true, true, false>(stream, m, p, grid);
+    if constexpr (!R) return launch_one<BN, G, R, Q, false, true, true, false, P>(stream, m, p, grid);
   }
   if (e.stats) {
     if (G || Q) return MR_ERR_BAD_SHAPE;
     if constexpr (!G && !Q) {
-      if (e.bias) return launch_one<BN, G, R, Q, false, true, false, true>(stream, m, p, grid);
-      return launch_one<BN, G, R, Q, false, false, false, true>(stream, m, p, grid);
+      if (e.bias) return launch_one<BN, G, R, Q, false, true, false, true, P>(stream, m, p, grid);
+      return launch_one<BN, G, R, Q, false, false, false, true, P>(stream, m, p, grid);
     }
   }
-  if (e.bias) return launch_one<BN, G, R, Q, false, true, false, false>(stream, m, p, grid);
-  return launch_one<BN, G, R, Q, false, false, false, false>(stream, m, p, grid);
+  if (e.bias) return launch_one<BN, G, R, Q, false, true, false, false, P>(stream, m, p, grid);
+  return launch_one<BN, G, R, Q, false, false, false, false, P>(stream, m, p, grid);
 }
 
-template <int BN>
+template <int BN, int P = 1>
 int32_t launch_staged(cudaStream_t stream, const Maps& m, const GemmParams& p, int grid, const Epi& e) {
-  if (e.rotary && !e.gelu && !e.residual) return launch_staged_bls<BN, false, false, true>(stream, m, p, grid, e);
-  if (e.gelu && !e.residual && !e.rotary) return launch_staged_bls<BN, true, false, false>(stream, m, p, grid, e);
-  if (e.residual && !e.gelu && !e.rotary) return launch_staged_bls<BN, false, true, false>(stream, m, p, grid, e);
-  if (!e.gelu && !e.residual && !e.rotary) return launch_staged_bls<BN, false, false, false>(stream, m, p, grid, e);
-  if (e.gelu && e.residual && !e.rotary) return launch_staged_bls<BN, true, true, false>(stream, m, p, grid, e);
+  if (e.rotary && !e.gelu && !e.residual) return launch_staged_bls<BN, false, false, true, P>(stream, m, p, grid, e);
+  if (e.gelu && !e.residual && !e.rotary) return launch_staged_bls<BN, true, false, false, P>(stream, m, p, grid, e);
+  if (e.residual && !e.gelu && !e.rotary) return launch_staged_bls<BN, false, true, false, P>(stream, m, p, grid, e);
+  if (!e.gelu && !e.residual && !e.rotary) return launch_staged_bls<BN, false, false, false, P>(stream, m, p, grid, e);
+  if (e.gelu && e.residual && !e.rotary) return launch_staged_bls<BN, true, true, false, P>(stream, m, p, grid, e);
   return MR_ERR_BAD_SHAPE;
 }
 
@@ -764,6 +824,14 @@ extern "C" int32_t mr_gemm_epilogue(mr_stream_t stream_, const MrGemmDesc* d, co
   MR_REQUIRE(make_tmap_2d(&m.out, out[0], d->M, d->N, d->ldd, 32, 64), MR_ERR_DRIVER);
   m.res = m.out;
   if (residual) MR_REQUIRE(make_tmap_2d(&m.res, in[3], d->M, d->N, d->ldd, 32, 64), MR_ERR_DRIVER);
+  // CTA pairs (cta_group::2, 256 x 256 pair tiles) whenever every pair of SMs gets at least one pair tile
+  const int pair_tiles = ceil_div(d->M, 2 * kBM) * p.num_n_tiles;
+  if (bn == 256 && d->algo_pair != 2 && sms >= 2 && (d->algo_pair == 1 || pair_tiles >= sms / 2)) {
+    p.num_tiles = pair_tiles;
+    const int pairs = pair_tiles < sms / 2 ? pair_tiles : sms / 2;
+    MR_REQUIRE(make_tmap_2d(&m.b, W, d->N, d->K, d->K, bn / 2, kBK), MR_ERR_DRIVER);
+    return launch_staged<256, 2>(stream, m, p, 2 * pairs, epi);
+  }
   if (bn == 256) return launch_staged<256>(stream, m, p, grid, epi);
   return launch_staged<128>(stream, m, p, grid, epi);
 }

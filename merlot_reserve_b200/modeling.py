@@ -459,10 +459,65 @@ class MerlotReserve:
         enc = self._audio(a.reshape(-1, self.config["audio_seq_length"], 65))["seq_attnpool"]
         return _ret(enc.reshape(*lead, self.config["audio_token_length"], self.hidden_size), as_np)
 
+    # --------------------------------------------------------------------------------------------
+    # host inputs: the pixel patches are 94 % of the bytes a step moves over PCIe, so when `images` is a PINNED
+    # host tensor it is copied in chunks on a side stream while the audio encoder and the previous chunks' ViT
+    # layers run (per-chunk events); everything else is small and goes on the compute stream.
+    # --------------------------------------------------------------------------------------------
+    _H2D_CHUNKS = None      # None: chosen per call (below); an int forces that many chunks
+
+    def _h2d_chunks(self, n_frames: int, n_bytes: int, n_audio: int) -> int:
+        """Fewest chunks that keep the copy hidden: the copy of chunk 0 runs under the audio encoder; every ViT
+        pass over a chunk costs a few launch tails, so one chunk is best whenever the audio branch (estimated at
+        1 PFLOP/s) outlasts the whole copy (estimated at 50 GB/s)."""
+        if self._H2D_CHUNKS is not None:
+            return max(1, min(self._H2D_CHUNKS, n_frames))
+        H, T = self.hidden_size, self.config["audio_seq_length"] // self.config["audio_patch_size"] + 1
+        t_audio = n_audio * self.config["audio_num_layers"] * (24.0 * T * H * H + 4.0 * T * T * H) / 1.0e15
+        t_copy = n_bytes / 50e9
+        want = 1 if t_audio >= t_copy else (2 if t_audio >= t_copy / 2 else 4)
+        return max(1, min(want, n_frames // 64 if n_frames >= 64 else 1))
+
+    def _vision_from_pinned(self, img_host: torch.Tensor, between=None, n_audio: int = 0) -> torch.Tensor:
+        """img_host: pinned fp32 [N, hw, 768] -> seq_attnpool [N, hw/4, H].  `between()` (the audio branch) is
+        enqueued on the compute stream after the copies have been queued and before the first chunk is awaited."""
+        main = torch.cuda.current_stream()
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream()
+            self._staging, self._staging_free = None, None
+        cs = self._copy_stream
+        if self._staging is None or self._staging.shape != img_host.shape:
+            self._staging = torch.empty(img_host.shape, dtype=torch.float32, device="cuda")
+            self._staging_free = None
+            cs.wait_stream(main)
+        if self._staging_free is not None:
+            cs.wait_event(self._staging_free)       # the previous call has finished reading the staging buffer
+        N = img_host.shape[0]
+        n_chunks = self._h2d_chunks(N, img_host.numel() * 4, n_audio)
+        bounds = [(i * N // n_chunks, (i + 1) * N // n_chunks) for i in range(n_chunks)]
+        events = []
+        with torch.cuda.stream(cs):
+            for a, b in bounds:
+                self._staging[a:b].copy_(img_host[a:b], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(cs)
+                events.append(ev)
+        mid = between() if between is not None else None
+        outs = []
+        for (a, b), ev in zip(bounds, events):
+            main.wait_event(ev)
+            outs.append(self._vision(self._staging[a:b])["seq_attnpool"])
+        self._staging_free = torch.cuda.Event()
+        self._staging_free.record(main)
+        return (outs[0] if len(outs) == 1 else torch.cat(outs, 0)), mid
+
     def batch_embed_video(self, images, audio_clips, tokens, subseg_idxs):
         """modeling.py:845-846 (vmap of embed_video): images [B, nseg, hw, 768], audio_clips
         [B, 3 nseg, 60, 65], tokens / subseg_idxs [B, L] -> [B, L, H] fp32 unit vectors."""
         as_np = _is_np(images, audio_clips, tokens, subseg_idxs)
+        if (isinstance(images, torch.Tensor) and not images.is_cuda and images.is_pinned()
+                and images.dtype == torch.float32 and images.dim() == 4 and images.is_contiguous()):
+            return self._batch_embed_video_pinned(images, audio_clips, tokens, subseg_idxs)
         img = _dev(images, torch.float32)
         aud = _dev(audio_clips, torch.float32)
         tok = _dev(tokens, torch.int32)
@@ -482,6 +537,33 @@ class MerlotReserve:
         seg = torch.div(sub, 3, rounding_mode="floor").to(torch.int32)
         out = self._joint_embed(tok, seg, vision=imgs_enc, audio=audio_enc, aud_ptr=sub)
         return _ret(out, as_np)
+
+    def _batch_embed_video_pinned(self, images, audio_clips, tokens, subseg_idxs):
+        """batch_embed_video for pinned host inputs: same arithmetic, H2D of the patches overlapped with compute."""
+        B, nseg, hw, pp3 = images.shape
+        H = self.hidden_size
+        if pp3 != 768:
+            raise ValueError("images must be pre-patchified to 768 features (modeling.py:817)")
+        if tuple(audio_clips.shape) != (B, 3 * nseg, self.config["audio_seq_length"], 65):
+            raise ValueError(f"audio_clips must be [B, {3 * nseg}, {self.config['audio_seq_length']}, 65] "
+                             f"(modeling.py:819-822), got {tuple(audio_clips.shape)}")
+        if tuple(tokens.shape) != tuple(subseg_idxs.shape) or len(tokens.shape) != 2 or tokens.shape[0] != B:
+            raise ValueError("tokens and subseg_idxs must both be [B, L] (modeling.py:824-826)")
+
+        # the small inputs go first: H2D copies of all streams share one copy engine and are served in order, so an
+        # audio copy queued behind the 755 MB of patches would stall the audio encoder until they have landed
+        aud = _dev(audio_clips, torch.float32)
+        tok = _dev(tokens, torch.int32)
+        sub = _dev(subseg_idxs, torch.int32)
+
+        def audio_branch():
+            enc = self._audio(aud.reshape(B * 3 * nseg, aud.shape[2], 65))["seq_attnpool"]
+            return enc.reshape(B, 3 * nseg, self.config["audio_token_length"], H)
+
+        imgs_enc, audio_enc = self._vision_from_pinned(images.view(B * nseg, hw, pp3), between=audio_branch,
+                                                        n_audio=B * 3 * nseg)
+        seg = torch.div(sub, 3, rounding_mode="floor").to(torch.int32)
+        return self._joint_embed(tok, seg, vision=imgs_enc.reshape(B, nseg * hw // 4, H), audio=audio_enc, aud_ptr=sub)
 
     def embed_video(self, images, audio_clips, tokens, subseg_idxs):
         """modeling.py:806-843: one clip -> [L, H]."""

@@ -460,3 +460,48 @@ def test_gemm_layernorm_fold(cuda, lib, M, H, N, mode):
         _close(stats2.sum(0)[:, 1], (xs * xs).sum(-1), 1e-2, 1e-4, "gemm stats sumsq")
         got = lib.gemm(x2, wt.to(cuda), bias=bias, ln_stats=stats2, ln_colsum=colsum)
         _close(got.cpu(), ref_of(x2), 3e-2, 2e-2, "LN-folded gemm on GEMM statistics")
+
+
+@pytest.mark.parametrize("M", [19000, 19000 + 100, 19000 + 200, 256 * 74])
+@pytest.mark.parametrize("mode", ["plain", "bias", "gelu", "residual_stats", "rotary_ln"])
+def test_gemm_cta_pairs(cuda, lib, M, mode):
+    """cta_group::2 path (256 x 256 pair tiles, leader-issued MMAs over both CTAs' shared memory) against the
+    single-CTA path and the fp32 reference, for every epilogue of the transformer layer; M tails that leave the
+    second CTA of the last pair partially or completely out of range."""
+    H = 768
+    g = torch.Generator().manual_seed(M)
+    a = _bf(torch.randn(M, H, generator=g)).to(cuda)
+    N = {"plain": 768, "bias": 1024, "gelu": 3072, "residual_stats": 768, "rotary_ln": 2304}[mode]
+    w = _bf(torch.randn(N, H, generator=g) * 0.05).to(cuda)
+    b = torch.randn(N, generator=g).to(cuda)
+    outs = {}
+    for pair in (1, 2):
+        if mode == "plain":
+            outs[pair] = lib.gemm(a, w, pair=pair)
+        elif mode == "bias":
+            outs[pair] = lib.gemm(a, w, bias=b, pair=pair)
+        elif mode == "gelu":
+            outs[pair] = lib.gemm(a, w, bias=b, gelu=True, pair=pair)
+        elif mode == "residual_stats":
+            x = _bf(torch.randn(M, N, generator=torch.Generator().manual_seed(1))).to(cuda)
+            st = torch.zeros((N // 64, M, 2), device=cuda)
+            lib.gemm(a, w, residual=x, out=x, stats_out=st, pair=pair)
+            outs[pair] = (x, st)
+        else:
+            st = torch.zeros((H // 64, M, 2), device=cuda)
+            xs = a.float()
+            st[0, :, 0], st[0, :, 1] = xs.sum(-1), (xs * xs).sum(-1)
+            rot = (torch.rand(241, 32, generator=torch.Generator().manual_seed(2)) * 2 - 1).to(cuda)
+            outs[pair] = lib.gemm(a, w, bias=b, rot=rot, hidden=H, q_scale=0.125, ln_stats=st,
+                                  ln_colsum=w.float().sum(1).contiguous(), pair=pair)
+    if mode == "residual_stats":
+        assert torch.equal(outs[1][0], outs[2][0]) and torch.equal(outs[1][1], outs[2][1])
+        x0 = _bf(torch.randn(M, N, generator=torch.Generator().manual_seed(1))).to(cuda).float()
+        _close(outs[1][0], x0 + a.float() @ w.float().t(), 5e-2, 2e-2, "pair residual")
+    else:
+        assert torch.equal(outs[1], outs[2]), f"{mode}: pair and single-CTA results differ"
+        if mode in ("plain", "bias", "gelu"):
+            ref = a.float() @ w.float().t() + (b if mode != "plain" else 0)
+            if mode == "gelu":
+                ref = ref * torch.sigmoid(1.702 * ref)
+            _close(outs[1], ref, 3e-2, 2e-2, f"pair {mode}")

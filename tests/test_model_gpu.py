@@ -155,3 +155,19 @@ def test_layernorm_fold_matches_separate_layernorm(setup):
     assert _cos(fused, unfused).min() >= 0.999
     ref = orc.embed_video(**clip)
     assert _cos(fused, ref).min() >= COS_MIN and _cos(unfused, ref).min() >= COS_MIN
+
+
+def test_pinned_host_inputs_take_the_overlapped_path_and_match(setup):
+    """bench.py's e2e leg: pinned host tensors -> chunked H2D on a side stream overlapped with compute; results
+    must equal the resident-input path bit for bit (same kernels, same chunk-independent arithmetic)."""
+    cfg, params, model, orc = setup
+    model.bind(params)
+    batch = synthetic_batch(cfg, 40, nseg=4, seed=17)          # 160 frames -> 2 H2D chunks
+    pinned = {k: torch.from_numpy(v).pin_memory() for k, v in batch.items()}
+    model._H2D_CHUNKS = 2
+    a = model.batch_embed_video(**pinned)
+    b = model.batch_embed_video(**{k: torch.from_numpy(v).cuda() for k, v in batch.items()})
+    model._H2D_CHUNKS = None
+    a2 = model.batch_embed_video(**pinned)                     # staging buffer reuse, automatic chunk count
+    torch.cuda.synchronize()
+    assert a.is_cuda and torch.equal(a, b) and torch.equal(a2, b)

@@ -161,6 +161,34 @@ int32_t mr_layernorm_fwd(mr_stream_t stream, const MrLayerNormDesc* d, const voi
                          void* workspace, size_t workspace_bytes);
 
 /* ------------------------------------------------------------------------------------------
+ * mr_transformer_encode: the whole layer stack of TransformerEncoder (modeling.py:283-376, without the CLS
+ * prepend before it and the final_ln / cls_proj after it) as one call: pre_ln, then per layer the qkv GEMM
+ * (LayerNorm folded in, rotary + 1/sqrt(d) epilogue), fused attention, attn_proj (+ residual), MLP-up (LayerNorm
+ * folded in, GELU), MLP-down (+ residual).  The vision, audio, span and joint encoders are this call with their own
+ * B, T, rotary table and masks -- it is what one jax.ffi custom call per encoder binds.
+ *
+ *   in[0] x       bf16 [B*T, H]     input tokens (CLS row already in place), before pre_ln
+ *   in[1] rot     f32  [rot_rows, 32]  rotary scale table (rot_rows == T for the static tables, B*T per-row)
+ *   in[2] valid   u8   [B*T]        optional (modeling.py:343-358)
+ *   in[3] group   i32  [B*T]        optional video_src ids (modeling.py:743-756)
+ *   in[4], in[5]  pre_ln gamma, beta f32 [H]
+ *   in[6 + 8 l + i], layer l:  i = 0 wqkv' bf16 [3H, H] (gamma-scaled, transposed), 1 bqkv' f32 [3H] (beta W + b),
+ *                 2 colsum(wqkv') f32 [3H], 3 wo bf16 [H, H], 4 w1' bf16 [4H, H], 5 b1' f32 [4H],
+ *                 6 colsum(w1') f32 [4H], 7 w2 bf16 [H, 4H]      (see MR_EPI_LN_IN for the primed quantities)
+ *   out[0] x_out  bf16 [B*T, H]     residual stream after the last layer (may alias in[0])
+ *   workspace: mr_transformer_encode_workspace_bytes(desc)  (qkv, ctx, MLP hidden, row statistics)
+ * ------------------------------------------------------------------------------------------ */
+typedef struct MrEncoderDesc {
+  int32_t B, T, H;
+  int32_t num_layers;
+  int32_t rot_rows;
+  float ln_eps;
+} MrEncoderDesc;
+int32_t mr_transformer_encode(mr_stream_t stream, const MrEncoderDesc* d, const void* const* in, void* const* out,
+                              void* workspace, size_t workspace_bytes);
+size_t mr_transformer_encode_workspace_bytes(const MrEncoderDesc* d);
+
+/* ------------------------------------------------------------------------------------------
  * mr_cast_pad: f32 [rows, cols] -> bf16 [rows, ld_out] (zero padded columns).  Stages the
  * fp32 pixel patches (modeling.py:402 casts to module dtype) and the [B,30,130] audio patches
  * (:453; K=130 is padded to a TMA-legal pitch).

@@ -38,6 +38,11 @@ class LayerNormDesc(C.Structure):
                 ("seq_out", C.c_int32), ("row_off", C.c_int32), ("eps", C.c_float), ("emit_stats", C.c_int32)]
 
 
+class EncoderDesc(C.Structure):
+    _fields_ = [("B", C.c_int32), ("T", C.c_int32), ("H", C.c_int32), ("num_layers", C.c_int32),
+                ("rot_rows", C.c_int32), ("ln_eps", C.c_float)]
+
+
 class CastDesc(C.Structure):
     _fields_ = [("rows", C.c_int64), ("cols", C.c_int32), ("ld_out", C.c_int32)]
 
@@ -85,6 +90,7 @@ ENTRY_POINTS = {
     "mr_gemm_epilogue": GemmDesc,
     "mr_attention_fwd": AttentionDesc,
     "mr_layernorm_fwd": LayerNormDesc,
+    "mr_transformer_encode": EncoderDesc,
     "mr_cast_pad": CastDesc,
     "mr_fill_cls": FillClsDesc,
     "mr_window_mean": WindowDesc,
@@ -100,6 +106,7 @@ ENTRY_POINTS = {
 WORKSPACE_FNS = {
     "mr_gemm_epilogue_workspace_bytes": GemmDesc,
     "mr_attention_fwd_workspace_bytes": AttentionDesc,
+    "mr_transformer_encode_workspace_bytes": EncoderDesc,
     "mr_contrastive_lse_fwd_workspace_bytes": ContrastiveDesc,
 }
 MISC_FNS = ["mr_check_device", "mr_abi_version", "mr_status_string", "mr_launch_count"]
@@ -108,7 +115,7 @@ MISC_FNS = ["mr_check_device", "mr_abi_version", "mr_status_string", "mr_launch_
 import os as _os
 GEMM_PAIR_DEFAULT = int(_os.environ.get("MR_GEMM_PAIR", "0"))
 
-ABI_VERSION = 4  # must equal mr_abi_version() of the loaded library (struct layouts above)
+ABI_VERSION = 5  # must equal mr_abi_version() of the loaded library (struct layouts above)
 
 _lib = None
 
@@ -248,6 +255,17 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias=None, residual=None, rot=None
                  q_scale=q_scale, num_sms=0, ln_eps=ln_eps, algo_pair=pair)
     _call("mr_gemm_epilogue", d, [a, w, bias, residual, rot, ln_stats, ln_colsum], [out, stats_out])
     return out
+
+
+def transformer_encode(x: torch.Tensor, rot: torch.Tensor, pre_ln, layer_ptrs: Sequence[torch.Tensor], B: int, T: int,
+                       H: int, valid=None, group=None, eps=1e-5) -> torch.Tensor:
+    """In-place layer stack (mr_transformer_encode).  layer_ptrs: 8 tensors per layer, in the header's order."""
+    n_layers = len(layer_ptrs) // 8
+    d = EncoderDesc(B=B, T=T, H=H, num_layers=n_layers, rot_rows=rot.shape[0], ln_eps=eps)
+    nbytes = load().mr_transformer_encode_workspace_bytes(C.byref(d))
+    ws = torch.empty((nbytes,), dtype=torch.uint8, device=x.device)
+    _call("mr_transformer_encode", d, [x, rot, valid, group, pre_ln[0], pre_ln[1], *layer_ptrs], [x], ws)
+    return x
 
 
 ATTN_AUTO, ATTN_MMA_SYNC, ATTN_TCGEN05 = 0, 1, 2

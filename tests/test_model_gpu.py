@@ -171,3 +171,19 @@ def test_pinned_host_inputs_take_the_overlapped_path_and_match(setup):
     a2 = model.batch_embed_video(**pinned)                     # staging buffer reuse, automatic chunk count
     torch.cuda.synchronize()
     assert a.is_cuda and torch.equal(a, b) and torch.equal(a2, b)
+
+
+def test_composite_encoder_call_equals_step_by_step(setup, lib):
+    """mr_transformer_encode (one C call per encoder) enqueues the same kernels as the Python-composed layer loop
+    that bench.py uses for per-launch timing: results must be bit-identical."""
+    cfg, params, model, orc = setup
+    clip = synthetic_clip(cfg, nseg=3, seed=19)
+    a = model.apply({"params": params}, **clip, method=model.embed_video)
+    lib.PROFILE = []
+    try:
+        b = model.apply({"params": params}, **clip, method=model.embed_video)
+        names = {n for n, *_ in lib.PROFILE}
+    finally:
+        lib.PROFILE = None
+    assert "mr_transformer_encode" not in names and "mr_gemm_epilogue" in names
+    assert np.array_equal(a, b)

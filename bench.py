@@ -38,6 +38,44 @@ NSEG = 16
 METRIC, UNIT = "segments/sec", "segments/s"
 
 
+def _enc_flops(T, layers, H):
+    return layers * (24.0 * T * H * H + 4.0 * T * T * H)
+
+
+def flops_vision_frame(cfg):
+    m = cfg["model"]
+    H = m["hidden_size"]
+    hw = m["output_grid"][0] * m["output_grid"][1]
+    return _enc_flops(hw + 1, m["vit_num_layers"], H) + 2 * hw * 768 * H + 2 * hw * H * H * 2 + 2 * (hw // 4) * H * H * 2
+
+
+def flops_audio_subseg(cfg):
+    m = cfg["model"]
+    H = m["hidden_size"]
+    return _enc_flops(31, m["audio_num_layers"], H) + 2 * 30 * 130 * H + 2 * 30 * H * H * 2 + 2 * 6 * H * H * 2
+
+
+def flops_mc_example(cfg, n_cand=4, L=144):
+    """cfg 5 (finetune/vcr/qa_qar_joint_finetune.py:150-170): one frame, n_cand joint sequences of L + hw/4 rows."""
+    m = cfg["model"]
+    H = m["hidden_size"]
+    hw = m["output_grid"][0] * m["output_grid"][1]
+    return flops_vision_frame(cfg) + n_cand * _enc_flops(L + hw // 4, m["joint_num_layers"], H)
+
+
+def flops_pretrain_example(cfg):
+    """cfg 3 forward (pretrain_model.py:38-259): 16 frames, 48 audio sub-segments, 6 joint sequences of seq_len
+    rows, joint_proj on the pooled rows, 48 spans through the span encoder."""
+    m, d = cfg["model"], cfg["data"]
+    H = m["hidden_size"]
+    G = d["num_segment_groups"]
+    n_joint = G * (d["num_audio2text_seqs"] + d["num_text2audio_seqs"]) + 2
+    joint = n_joint * _enc_flops(d["seq_len"], m["joint_num_layers"], H)
+    span = d["num_text_spans_to_include"] * (_enc_flops(16, m["span_num_layers"], H) + 2 * H * H)
+    return (d["num_segments"] * flops_vision_frame(cfg) + 3 * d["num_segments"] * flops_audio_subseg(cfg) + joint + span
+            + 2.0 * (2 * G * d["lang_seq_len"] + 2 * d["seq_len"]) * H * H)
+
+
 def flops_per_clip(cfg, nseg=NSEG, L=160):
     """Algorithmic FLOPs of embed_video per clip: 24 T H^2 + 4 T^2 H per layer, plus
     patch / audio embeds, the two attention pools and the head."""
@@ -162,10 +200,92 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------
 # B200 arm
 # ------------------------------------------------------------------------------------------------
+def build_workload(args, rank, dev):
+    """Returns the pieces of one benchmark workload: a resident-input step, an end-to-end (pinned host input) step,
+    units and algorithmic FLOPs per step, and the description that goes into `config`."""
+    from merlot_reserve_b200 import MerlotReserve, MerlotReservePretrainer, loss_fn_given_preds
+    from merlot_reserve_b200.synthetic import (load_config, synthetic_batch, synthetic_params,
+                                               synthetic_pretrain_batch)
+    grid = tuple(args.grid) if args.grid else None
+    cfg = load_config(args.config, grid)
+    H = cfg["model"]["hidden_size"]
+    gh, gw = cfg["model"]["output_grid"]
+    params = synthetic_params(cfg, seed=0)
+    pin = lambda d: {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in d.items()}
+    w = {"cfg": cfg, "params": params, "metric": METRIC, "unit": UNIT}
+    if args.workload == "embed_video":
+        B = args.clips
+        model = MerlotReserve.from_config(cfg).bind(params)
+        host = pin(synthetic_batch(cfg, B, nseg=NSEG, seed=1 + 1000 * rank))      # disjoint clips per rank
+        resident = {k: v.to(dev) for k, v in host.items()}
+        out_host = torch.empty((B, 160, H), dtype=torch.float32).pin_memory()
+
+        def step_e2e():
+            out = model.batch_embed_video(**host)             # H2D of every input happens inside the call
+            out_host.copy_(out, non_blocking=True)            # D2H of the step's result
+            torch.cuda.current_stream().synchronize()
+
+        w.update(step=lambda: model.batch_embed_video(**resident), step_e2e=step_e2e, units=B * NSEG,
+                 flops=flops_per_clip(cfg) * B, h2d=sum(v.numel() * v.element_size() for v in host.values()),
+                 d2h=out_host.numel() * 4,
+                 workload=f"reserve-{args.config} zero-shot embed_video (vision+audio+joint encoders, head, "
+                          f"unit_normalize), {B} clips x 16 segments ({gh}x{gw} patches) + 48 audio sub-segments, "
+                          f"L=160, per GPU",
+                 extra={"clips_per_gpu": B, "segments_per_step_per_gpu": B * NSEG})
+    elif args.workload == "mc_scoring":
+        B, n_cand, Ltok = args.clips, 4, 144
+        model = MerlotReserve.from_config(cfg).bind(params)
+        rng = np.random.default_rng(5 + rank)
+        toks = rng.integers(10, 32768, size=(B, n_cand, Ltok)).astype(np.int32)
+        toks[:, :, -1] = 3
+        host = pin({"images": rng.random((B, gh * gw, 768), dtype=np.float32), "tokens": toks})
+        proj = (rng.standard_normal(H) * 0.05).astype(np.float32)
+        resident = {k: v.to(dev) for k, v in host.items()}
+        out_host = torch.empty((B, n_cand), dtype=torch.float32).pin_memory()
+
+        def step_e2e():
+            out = model.score_multiple_choice(host["images"].to(dev, non_blocking=True),
+                                              host["tokens"].to(dev, non_blocking=True), proj)
+            out_host.copy_(out, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+
+        w.update(step=lambda: model.score_multiple_choice(resident["images"], resident["tokens"], proj),
+                 step_e2e=step_e2e, units=B, flops=flops_mc_example(cfg, n_cand, Ltok) * B,
+                 h2d=sum(v.numel() * v.element_size() for v in host.values()), d2h=out_host.numel() * 4,
+                 metric="examples/sec", unit="examples/s",
+                 workload=f"reserve-{args.config} VCR-style multiple-choice scoring (MerlotReserveVCR forward): batch {B}, "
+                          f"1 frame ({gh}x{gw} patches) x {n_cand} candidates, L={Ltok}, proj head, per GPU",
+                 extra={"examples_per_gpu": B})
+    elif args.workload == "pretrain_fwd":
+        b = args.clips
+        model = MerlotReservePretrainer.from_config(cfg).bind(params)
+        host = pin(synthetic_pretrain_batch(cfg, b, seed=1 + 1000 * rank))
+        resident = {k: v.to(dev) for k, v in host.items()}
+        out_host = torch.empty((1,), dtype=torch.float32).pin_memory()
+
+        def fwd(batch):
+            loss, _ = loss_fn_given_preds(model(dict(batch)))    # all-gathers the targets when world > 1
+            return loss
+
+        def step_e2e():
+            out_host.copy_(fwd({k: v.to(dev, non_blocking=True) for k, v in host.items()}).reshape(1), non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+
+        w.update(step=lambda: fwd(resident), step_e2e=step_e2e, units=b, flops=flops_pretrain_example(cfg) * b,
+                 h2d=sum(v.numel() * v.element_size() for v in host.values()), d2h=4,
+                 metric="examples/sec (forward + contrastive loss)", unit="examples/s",
+                 workload=f"reserve-{args.config} contrastive pretraining FORWARD + loss (no backward yet): {b} examples "
+                          f"per GPU (16 frames {gh}x{gw}, 48 audio sub-segments, 6 joint sequences x 640), targets "
+                          f"all-gathered over the ranks",
+                 extra={"examples_per_gpu": b})
+    else:
+        raise ValueError(args.workload)
+    return w
+
+
 def run_b200(args):
     import torch.distributed as dist
-    from merlot_reserve_b200 import MerlotReserve, _lib
-    from merlot_reserve_b200.synthetic import load_config, synthetic_batch, synthetic_params
+    from merlot_reserve_b200 import _lib
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -177,30 +297,15 @@ def run_b200(args):
     dev = torch.device(f"cuda:{local}")
     _lib.require_b200(local)
 
-    cfg = load_config(args.config)
-    H = cfg["model"]["hidden_size"]
-    B = args.clips
-    params = synthetic_params(cfg, seed=0)
-    model = MerlotReserve.from_config(cfg).bind(params)
-    batch = synthetic_batch(cfg, B, nseg=NSEG, seed=1 + 1000 * rank)      # disjoint clips per rank
-    host = {k: torch.from_numpy(v).pin_memory() for k, v in batch.items()}
-    resident = {k: v.to(dev) for k, v in host.items()}
+    w = build_workload(args, rank, dev)
+    cfg, params = w["cfg"], w["params"]
+    step_resident, step_e2e = w["step"], w["step_e2e"]
     torch.cuda.synchronize()
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-
-    def step_resident():
-        return model.batch_embed_video(**resident)
-
-    out_host = torch.empty((B, 160, H), dtype=torch.float32).pin_memory()
-
-    def step_e2e():
-        out = model.batch_embed_video(**host)             # H2D of every input happens inside the call
-        out_host.copy_(out, non_blocking=True)            # D2H of the step's result
-        torch.cuda.current_stream().synchronize()
 
     def timed(fn, steps):
         barrier()
@@ -224,16 +329,15 @@ def run_b200(args):
         total_ms = timed(step_resident, args.steps)
     launches = _lib.launch_count() - launches0
     ms_step = total_ms / args.steps
-    value = world * B * NSEG / (ms_step * 1e-3)
+    value = world * w["units"] / (ms_step * 1e-3)
 
     for _ in range(2):
         step_e2e()
     e2e_ms = timed(step_e2e, args.steps) / args.steps
-    e2e_value = world * B * NSEG / (e2e_ms * 1e-3)
-    h2d = sum(v.numel() * v.element_size() for v in host.values())
-    d2h = out_host.numel() * out_host.element_size()
+    e2e_value = world * w["units"] / (e2e_ms * 1e-3)
 
-    # per-kernel-class timing: CUDA events around every launch of instrumented steps
+    # per-kernel-class timing: CUDA events around every launch of instrumented steps (the model then composes the
+    # layer loop call by call instead of through mr_transformer_encode: same kernels, same order)
     peaks = load_peaks()
     _lib.PROFILE = []
     for _ in range(2):
@@ -259,32 +363,37 @@ def run_b200(args):
                 gemm[k] += d[k]
     achieved = gemm["flops"] / gemm["ms"] / 1e9
     peak = peaks["tflops_sustained"]
+    traffic, traffic_note = None, None
+    tf = ROOT / "profiles" / "gemm_traffic.json"      # dram bytes per launch from the committed ncu --set full capture
+    if tf.exists() and args.workload == "embed_video" and args.config == "base":
+        tj = json.loads(tf.read_text())
+        traffic = tj.get("dram_bytes_per_launch_avg")
+        traffic_note = ("dram__bytes_read+write per launch, mean of the four vision-layer GEMM launches "
+                        "(M = 246784: algorithmic 1.90 / 1.52 / 0.76 / 1.90 GB for down / qkv / out / up); " + tj.get("source", ""))
     roofline = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (all epilogue variants)", "achieved": achieved,
                 "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 "peak_source": f"{peaks['source']} sustained bf16 (kernel timed inside a long step)",
                 "avg_launch_ms": gemm["ms"] / gemm["launches"], "flops_per_launch": gemm["flops"] / gemm["launches"],
-                "share_of_step": gemm["ms"] / prof_ms, "traffic": None}
-    whole = flops_per_clip(cfg) * B / (ms_step * 1e-3) / 1e12
+                "share_of_step": gemm["ms"] / prof_ms, "traffic": traffic, "traffic_note": traffic_note}
+    whole = w["flops"] / (ms_step * 1e-3) / 1e12
 
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.workload == "embed_video":
         val, dt, cores = cpu_oracle_segments_per_s(cfg, params, steps=2, warmup=1, nseg_sample=NSEG)
         cpu = {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"CPU oracle (torch fp32 port of the reference arithmetic; jax not installable): "
                          f"1 clip x {NSEG} segments, 2 timed passes, {dt:.2f} s each"}
     if rank == 0:
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "metric": w["metric"], "value": value, "unit": w["unit"], "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"reserve-{args.config} zero-shot embed_video (vision+audio+joint encoders, head, "
-                                   f"unit_normalize), {B} clips x 16 segments (12x20 patches) + 48 audio "
-                                   f"sub-segments, L=160, per GPU",
-                       "clips_per_gpu": B, "segments_per_step_per_gpu": B * NSEG, "parallelism": f"replicas x{world}",
-                       "l2": "inputs (fp32 patches, 755 MB at 64 clips) and activations exceed the 126 MB L2"},
+            "config": {"workload": w["workload"], **w["extra"], "parallelism": f"replicas x{world}",
+                       "l2": "inputs and activations of a step exceed the 126 MB L2 many times over (fp32 patches "
+                             "alone are 755 MB at 64 Base clips)"},
             "clocks": clk.summary(),
-            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h},
+            "e2e": {"value": e2e_value, "unit": w["unit"], "ms_per_step": e2e_ms, "h2d_bytes_per_step": w["h2d"],
+                    "d2h_bytes_per_step": w["d2h"]},
             "gpu_launches": int(launches),
             "roofline": roofline,
             "whole_step_tflops": whole, "whole_step_frac_of_sustained_peak": whole / peak,
@@ -304,9 +413,15 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="base", choices=["base", "large"])
-    ap.add_argument("--clips", type=int, default=64)
+    ap.add_argument("--clips", type=int, default=None, help="clips / examples per GPU and step")
+    ap.add_argument("--workload", default="embed_video", choices=["embed_video", "mc_scoring", "pretrain_fwd"],
+                    help="embed_video = BASELINE configs[1] (default) / [3] with --config large --grid 18 32; "
+                         "mc_scoring = configs[4]; pretrain_fwd = the forward half of configs[2]")
+    ap.add_argument("--grid", type=int, nargs=2, default=None, help="output_grid override, e.g. 18 32")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    if args.clips is None:
+        args.clips = {"embed_video": 64 if args.config == "base" else 16, "mc_scoring": 128, "pretrain_fwd": 8}[args.workload]
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -178,3 +178,42 @@ def test_base_param_count_matches_survey():
     """Base has 316.4 M parameters."""
     n = count_params(synthetic_params(load_config("base")))
     assert abs(n - 316.4e6) / 316.4e6 < 0.01, n
+
+
+@pytest.mark.parametrize("name,scale", [("tiny_init", 1.0), ("tiny_scale4", 4.0)])
+def test_oracle_pretrain_forward_reproduces_golden(name, scale):
+    """The committed pretraining vectors (tools/make_golden.py) are what the oracle computes today."""
+    from merlot_reserve_b200.synthetic import synthetic_pretrain_batch
+    g = np.load(GOLDEN / f"{name}.npz")
+    cfg = tiny_config()
+    orc = O.OracleMerlotReserve(cfg, synthetic_params(cfg, seed=0, weight_scale=scale))
+    preds = orc.pretrain_forward(synthetic_pretrain_batch(cfg, 2, seed=3))
+    for head, d in preds.items():
+        for k, v in d.items():
+            assert np.allclose(v.numpy(), g[f"pretrain/{head}/{k}"], atol=2e-5), (head, k)
+    loss, info = O.contrastive_loss(preds)
+    assert abs(float(loss) - float(g["pretrain/loss"])) < 1e-4
+    # structure of the forward (pretrain_model.py:170-233): 12 b targets + 36 b extras, 48 b spans, sources in {0,1,2}
+    assert preds["text_to_audio"]["y"].shape[0] == 24 and preds["text_to_audio"]["y_extra"].shape[0] == 72
+    assert preds["stuff_to_span"]["x"].shape[0] == 96 and set(preds["stuff_to_span"]["_sources"].tolist()) <= {0, 1, 2}
+
+
+def test_pretrain_batch_layout():
+    """synthetic_pretrain_batch follows the reference dataloader's pointer conventions (dataloader.py:545-700)."""
+    from merlot_reserve_b200.synthetic import synthetic_pretrain_batch
+    cfg = load_config("base")
+    b = synthetic_pretrain_batch(cfg, 2, seed=9)
+    assert b["images"].shape == (2, 16 * 240, 768) and b["audio_clips"].shape == (2, 48 * 60, 65)
+    assert b["text2audio"].shape == (2, 2, 160) and b["random_text"].shape == (2, 1, 640) and b["text_spans"].shape == (2, 62, 15)
+    for i in range(2):
+        t2a, a2t, rt = b["text2audio"][i], b["audio2text"][i], b["random_text"][i]
+        assert (t2a == 4).sum() == 12 and (t2a == 3).sum() == 12 and (a2t == 3).sum() == 12 and (rt == 3).sum() == 38
+        assert sorted(b["text2audio/text_ptr"][i][t2a == 3].tolist()) == list(range(12))
+        assert sorted(b["audio2text/text_ptr"][i][a2t == 3].tolist()) == list(range(12, 24))
+        assert sorted(b["random_text/text_ptr"][i][rt == 3].tolist()) == list(range(24, 62))
+        atm = b["audio_text_matching"][i, 0]
+        assert (atm == 6).sum() == 16 and (atm == 5).sum() == 16 * 18
+        # masked audio pointers of group g stay inside that group's 24 sub-segments
+        for g in range(2):
+            ptr = b["text2audio/audio_ptr"][i, g][t2a[g] == 4]
+            assert ((ptr >= 24 * g) & (ptr < 24 * (g + 1))).all()

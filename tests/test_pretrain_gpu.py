@@ -72,3 +72,22 @@ def test_loss_kernels_match_oracle_on_same_preds(cuda):
     for k in ref_info:
         assert abs(float(info[k]) - float(ref_info[k])) <= 2e-3, k
     assert abs(float(loss) - float(ref_loss)) <= 5e-3
+
+
+@pytest.mark.parametrize("name,scale", [("tiny_init", 1.0), ("tiny_scale4", 4.0)])
+def test_pretrain_forward_against_committed_golden(cuda, name, scale):
+    """CUDA path vs the committed golden vectors (tests/golden/*.npz, tools/make_golden.py)."""
+    from pathlib import Path
+    g = np.load(Path(__file__).resolve().parent / "golden" / f"{name}.npz")
+    cfg = tiny_config()
+    model = MerlotReservePretrainer.from_config(cfg)
+    got = model.apply({"params": synthetic_params(cfg, seed=0, weight_scale=scale)}, synthetic_pretrain_batch(cfg, 2, seed=3))
+    for head in ("imgs_to_audio", "text_to_audio", "stuff_to_span"):
+        for k, v in got[head].items():
+            ref = torch.from_numpy(g[f"pretrain/{head}/{k}"])
+            if k == "_sources":
+                assert torch.equal(v.cpu().long(), ref.long())
+            else:
+                assert torch.nn.functional.cosine_similarity(v.float().cpu(), ref, dim=-1).min() >= 0.999, (head, k)
+    loss, _ = loss_fn_given_preds(got)
+    assert abs(float(loss) - float(g["pretrain/loss"])) <= 0.1

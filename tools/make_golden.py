@@ -12,8 +12,9 @@ import numpy as np
 
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
-from merlot_reserve_b200.synthetic import synthetic_clip, synthetic_params, synthetic_spans, tiny_config  # noqa: E402
-from oracle.reserve_oracle import MASK, OracleMerlotReserve  # noqa: E402
+from merlot_reserve_b200.synthetic import (synthetic_clip, synthetic_params, synthetic_pretrain_batch,  # noqa: E402
+                                           synthetic_spans, tiny_config)
+from oracle.reserve_oracle import MASK, OracleMerlotReserve, contrastive_loss  # noqa: E402
 
 
 def golden_case(weight_scale: float):
@@ -40,6 +41,15 @@ def golden_case(weight_scale: float):
         "audio_checksum": np.float64(clip["audio_clips"].astype(np.float64).sum()),
         "weight_scale": np.float32(weight_scale),
     }
+    # pretraining forward + loss (pretrain/pretrain_model.py:38-303) on synthetic_pretrain_batch(cfg, 2, seed=3)
+    preds = orc.pretrain_forward(synthetic_pretrain_batch(cfg, 2, seed=3))
+    loss, info = contrastive_loss(preds)
+    for head, d in preds.items():
+        for k, v in d.items():
+            out[f"pretrain/{head}/{k}"] = v.numpy().astype(np.int32 if k == "_sources" else np.float32)
+    out["pretrain/loss"] = np.float32(loss)
+    for k, v in info.items():
+        out[f"pretrain/loss_info/{k}"] = np.float32(v)
     return out
 
 

@@ -108,6 +108,16 @@ typedef struct MrGemmDesc {
   float ln_eps;     /* MR_EPI_LN_IN */
   int32_t algo_pair; /* 0 = auto, 1 = force CTA pairs (cta_group::2, 256 x 256 tiles), 2 = never; pairs need the
                         staged bf16 output path and a 256-wide tile, otherwise the field is ignored */
+  /* Backward GEMMs: operands given TRANSPOSED (MN-major for the tensor core, no transposed copies in HBM):
+       trans_a: in[0] is A^T, bf16 [K, lda >= M]        trans_b: in[1] is W^T, bf16 [K, ldb >= N]
+     dgrad  dX[M, K_f] = dY[M, N_f] . W[N_f, K_f]:  A = dY, in[1] = the forward's packed W with trans_b = 1;
+     wgrad  dW[N_f, K_f] = dY^T . X:                in[0] = dY with trans_a = 1, in[1] = X with trans_b = 1
+     (the reduction then runs over the M_f token rows: use split_k).  Plain epilogue only (bias on the fp32 path).
+     split_k > 1: the K range is cut in split_k parts, fp32 partials go to the workspace
+     (mr_gemm_epilogue_workspace_bytes) and are summed in a fixed order by a second kernel. */
+  int32_t trans_a, trans_b;
+  int32_t ldb;       /* row pitch of in[1] in elements; 0 = dense (K, or N when trans_b) */
+  int32_t split_k;
 } MrGemmDesc;
 
 int32_t mr_gemm_epilogue(mr_stream_t stream, const MrGemmDesc* d, const void* const* in, void* const* out,

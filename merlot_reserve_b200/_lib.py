@@ -26,7 +26,8 @@ class GemmDesc(C.Structure):
     _fields_ = [("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32), ("lda", C.c_int32), ("ldd", C.c_int32),
                 ("epilogue", C.c_int32), ("seq_in", C.c_int32), ("seq_out", C.c_int32), ("row_off", C.c_int32),
                 ("rot_rows", C.c_int32), ("hidden", C.c_int32), ("algo", C.c_int32), ("q_scale", C.c_float),
-                ("num_sms", C.c_int32), ("ln_eps", C.c_float), ("algo_pair", C.c_int32)]
+                ("num_sms", C.c_int32), ("ln_eps", C.c_float), ("algo_pair", C.c_int32),
+                ("trans_a", C.c_int32), ("trans_b", C.c_int32), ("ldb", C.c_int32), ("split_k", C.c_int32)]
 
 
 class AttentionDesc(C.Structure):
@@ -115,7 +116,7 @@ MISC_FNS = ["mr_check_device", "mr_abi_version", "mr_status_string", "mr_launch_
 import os as _os
 GEMM_PAIR_DEFAULT = int(_os.environ.get("MR_GEMM_PAIR", "0"))
 
-ABI_VERSION = 5  # must equal mr_abi_version() of the loaded library (struct layouts above)
+ABI_VERSION = 6  # must equal mr_abi_version() of the loaded library (struct layouts above)
 
 _lib = None
 
@@ -389,6 +390,28 @@ def contrastive_reduce(lse: torch.Tensor, numer: torch.Tensor, sources=None) -> 
     """[mean(lse - numer), per-source means x3] (pretrain_model.py:295-300)."""
     out = torch.empty((4,), dtype=torch.float32, device=lse.device)
     _call("mr_contrastive_reduce", ContrastiveDesc(n=lse.numel(), n_all=0, H=0), [lse, numer, sources], [out])
+    return out
+
+
+def gemm_bwd(a: torch.Tensor, b: torch.Tensor, *, trans_a=False, trans_b=False, out_f32=True, split_k=0, out=None,
+             bias=None) -> torch.Tensor:
+    """Backward GEMMs on transposed (MN-major) operands, D [M, N] = op(a) . op(b):
+       trans_a: a is [K, M] (else [M, K]);  trans_b: b is [K, N] (else [N, K]).
+    dgrad: gemm_bwd(dY, W_packed, trans_b=True);  wgrad (packed layout): gemm_bwd(dY, X, trans_a=True, trans_b=True)."""
+    assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16 and a.is_contiguous() and b.is_contiguous()
+    K, M = a.shape if trans_a else (a.shape[1], a.shape[0])
+    Kb, N = b.shape if trans_b else (b.shape[1], b.shape[0])
+    assert K == Kb, (a.shape, b.shape)
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.float32 if out_f32 else torch.bfloat16, device=a.device)
+    epi = (EPI_OUT_F32 if out.dtype == torch.float32 else 0) | (EPI_BIAS if bias is not None else 0)
+    d = GemmDesc(M=M, N=N, K=K, lda=a.shape[1], ldd=out.shape[-1], epilogue=epi, algo=ALGO_TCGEN05, q_scale=1.0,
+                 trans_a=int(trans_a), trans_b=int(trans_b), ldb=b.shape[1], split_k=split_k)
+    ws = None
+    if split_k > 1:
+        nbytes = load().mr_gemm_epilogue_workspace_bytes(C.byref(d))
+        ws = torch.empty((nbytes,), dtype=torch.uint8, device=a.device)
+    _call("mr_gemm_epilogue", d, [a, b, bias, None, None, None, None], [out, None], ws)
     return out
 
 

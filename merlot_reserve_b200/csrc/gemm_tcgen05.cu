@@ -54,6 +54,10 @@ struct GemmParams {
   const float* ln_s;        // [N] column sums of the gamma-scaled weight
   float2* stats_out;        // [ceil(N / 64)][M]
   float ln_eps;
+  // split-K (direct fp32 path only): work item = (tile, split); split s reduces k-blocks [s * kb_per_split, ...) and
+  // writes its partial to D + s * split_stride elements
+  int splits, kb_per_split;
+  size_t split_stride;
 };
 
 constexpr int kBoxBytes = 32 * 128;  // one epilogue staging box: 32 rows x 64 bf16, 128B swizzle
@@ -108,7 +112,7 @@ __device__ __forceinline__ void load_cols8(const float* __restrict__ v, int c, i
 // step sat behind its own reconvergence point and the epilogue became latency bound (profiles/ncu_gemm_r01j.md).
 // The direct path keeps run-time p.bias_on (small GEMMs only).
 template <int BN, bool kGelu, bool kResidual, bool kRotary, bool kDirect, bool kBias = false, bool kLn = false,
-          bool kStats = false, int kCtas = 1>
+          bool kStats = false, int kCtas = 1, int kTrans = 0>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res,
@@ -116,6 +120,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   using C = Cfg<BN, kCtas>;
   constexpr bool kPair = kCtas == 2;
   static_assert(!(kPair && kDirect) && (!kPair || BN == 256), "CTA pairs: staged 256-wide tiles only");
+  // kTrans bit 0: A is MN-major (given as [K, M], the backward's "A^T"); bit 1: B is MN-major (given as [K, N]).
+  // An MN-major operand is staged as 64-column slabs of [64 k-rows x 128 B] (one TMA box each, 128B swizzle):
+  // slab stride = LBO = 8 KB, 8-row groups inside a slab = SBO = 1 KB, one K=16 MMA step = 2 KB further.
+  constexpr bool kAmn = (kTrans & 1) != 0, kBmn = (kTrans & 2) != 0;
+  static_assert(!(kPair && kTrans != 0), "MN-major operands: single-CTA tiles only");
   const uint32_t cta_rank = kPair ? cluster_ctarank() : 0u;   // 0 = leader (issues the MMAs of the pair)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -173,6 +182,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   // Rotary (QKV) GEMMs: every CTA owns a CONTIGUOUS range instead, so consecutive tiles of a CTA share the row
   // block and the per-row rotary scales stay in registers (K = hidden there: 148 live A blocks fit the L2).
   // CTA pairs: the schedule is over PAIR tiles (256 rows); CTA `cta_rank` owns row block 2 * m_pair + cta_rank.
+  // split-K exists on the direct path only; elsewhere these fold to constants
+  const int splits = kDirect ? p.splits : 1;
+  const int kb_per_split = kDirect ? p.kb_per_split : p.num_k_blocks;
   const int num_workers = static_cast<int>(gridDim.x) / kCtas;
   const int worker = static_cast<int>(blockIdx.x) / kCtas;
   const int tiles_per_cta = (p.num_tiles + num_workers - 1) / num_workers;
@@ -188,9 +200,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
-        const int m_blk = (tile / p.num_n_tiles) * kCtas + static_cast<int>(cta_rank);
-        const int n_blk = tile % p.num_n_tiles;
-        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+        const int mn = tile / splits, split = tile % splits;
+        const int m_blk = (mn / p.num_n_tiles) * kCtas + static_cast<int>(cta_rank);
+        const int n_blk = mn % p.num_n_tiles;
+        const int kb_end = min((split + 1) * kb_per_split, p.num_k_blocks);
+        for (int kb = split * kb_per_split; kb < kb_end; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * C::kStageBytes;
           uint8_t* sb = sa + C::kABytes;
@@ -203,8 +217,20 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                              kEvictLast);
           } else {
           mbar_arrive_expect_tx(&full_bar[stage], C::kStageBytes);
-          tma_load_2d(&tmap_a, &full_bar[stage], sa, kb * kBK, m_blk * kBM, kEvictNormal);
-          tma_load_2d(&tmap_b, &full_bar[stage], sb, kb * kBK, n_blk * BN, kEvictLast);
+          if constexpr (kAmn) {
+#pragma unroll
+            for (int i = 0; i < kBM / 64; ++i)
+              tma_load_2d(&tmap_a, &full_bar[stage], sa + i * 8192, m_blk * kBM + 64 * i, kb * kBK, kEvictNormal);
+          } else {
+            tma_load_2d(&tmap_a, &full_bar[stage], sa, kb * kBK, m_blk * kBM, kEvictNormal);
+          }
+          if constexpr (kBmn) {
+#pragma unroll
+            for (int i = 0; i < BN / 64; ++i)
+              tma_load_2d(&tmap_b, &full_bar[stage], sb + i * 8192, n_blk * BN + 64 * i, kb * kBK, kEvictLast);
+          } else {
+            tma_load_2d(&tmap_b, &full_bar[stage], sb, kb * kBK, n_blk * BN, kEvictLast);
+          }
           }
           if (++stage == C::kStages) {
             stage = 0;
@@ -216,7 +242,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   } else if (warp_idx == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0 && cta_rank == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16_f32(kBM * kCtas, BN);
+      constexpr uint32_t idesc = umma_idesc_bf16_f32(kBM * kCtas, BN) | (kAmn ? (1u << 15) : 0u) | (kBmn ? (1u << 16) : 0u);
+      constexpr uint64_t kLboMn = static_cast<uint64_t>((8192 >> 4) - 1) << 16;   // LBO field holds 1 for K-major
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -225,20 +252,25 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
-        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+        const int split = tile % splits;
+        const int kb_begin = split * kb_per_split, kb_end = min(kb_begin + kb_per_split, p.num_k_blocks);
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * C::kStageBytes);
           const uint32_t sb = sa + C::kABytes;
-          const uint64_t adesc = umma_desc_k_sw128(sa);
-          const uint64_t bdesc = umma_desc_k_sw128(sb);
+          const uint64_t adesc = umma_desc_k_sw128(sa) + (kAmn ? kLboMn : 0);
+          const uint64_t bdesc = umma_desc_k_sw128(sb) + (kBmn ? kLboMn : 0);
 #pragma unroll
           for (int k = 0; k < kBK / kUmmaK; ++k) {
-            // advancing 16 bf16 = 32 bytes along K inside the 128-byte swizzle row: +2 in 16-byte units
+            // one K=16 step: K-major = 32 bytes along the 128-byte swizzle row (+2 in 16-byte units);
+            // MN-major = 16 k-rows x 128 B = 2 KB further into every slab (+128)
+            const uint64_t ad = adesc + (kAmn ? 128 : 2) * k, bd = bdesc + (kBmn ? 128 : 2) * k;
+            const uint32_t accum = (kb != kb_begin || k != 0) ? 1u : 0u;
             if constexpr (kPair)
-              umma_bf16_ss_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+              umma_bf16_ss_pair(d_tmem, ad, bd, idesc, accum);
             else
-              umma_bf16_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+              umma_bf16_ss(d_tmem, ad, bd, idesc, accum);
           }
           // frees the ring slot (in both CTAs of a pair) once these MMAs have read it
           if constexpr (kPair) umma_commit_pair(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
@@ -276,8 +308,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       float ln_mu = 0.f, ln_rstd = 1.f;        // LayerNorm statistics of this thread's row (LN-consuming GEMMs)
       int ln_m = -1;
       for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
-        const int m_blk = (tile / p.num_n_tiles) * kCtas + static_cast<int>(cta_rank);
-        const int n_blk = tile % p.num_n_tiles;
+        const int mn = tile;                     // no split-K on the staged path
+        const int m_blk = (mn / p.num_n_tiles) * kCtas + static_cast<int>(cta_rank);
+        const int n_blk = mn % p.num_n_tiles;
         const int row0 = m_blk * kBM + quarter * 32;
         const int r = row0 + lane;
         const int col_base = n_blk * BN + col_half * (BN / 2);
@@ -458,8 +491,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       if (lane == 0) tma_store_wait<0>();      // all bulk stores complete before the CTA retires its smem
     } else
     for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
-      const int m_blk = tile / p.num_n_tiles;
-      const int n_blk = tile % p.num_n_tiles;
+      const int mn = tile / splits, split = tile % splits;
+      const int m_blk = mn / p.num_n_tiles;
+      const int n_blk = mn % p.num_n_tiles;
       const int r = m_blk * kBM + quarter * 32 + lane;
       const bool row_ok = r < p.M;
       const int out_row = map_row(r, p.seq_in, p.seq_out, p.row_off);
@@ -565,7 +599,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           }
         }
         if (p.out_f32) {
-          float* dst = reinterpret_cast<float*>(p.D) + static_cast<size_t>(out_row) * p.ldd + col0;
+          float* dst = reinterpret_cast<float*>(p.D) + static_cast<size_t>(split) * p.split_stride +
+                       static_cast<size_t>(out_row) * p.ldd + col0;
           if (full_chunk) {
 #pragma unroll
             for (int j = 0; j < 8; ++j)
@@ -649,9 +684,9 @@ struct Maps {
   CUtensorMap a, b, out, res;
 };
 
-template <int BN, bool G, bool R, bool Q, bool D, bool B = false, bool L = false, bool S = false, int P = 1>
+template <int BN, bool G, bool R, bool Q, bool D, bool B = false, bool L = false, bool S = false, int P = 1, int T = 0>
 int32_t launch_one(cudaStream_t stream, const Maps& m, const GemmParams& p, int grid) {
-  auto kern = gemm_tcgen05_kernel<BN, G, R, Q, D, B, L, S, P>;
+  auto kern = gemm_tcgen05_kernel<BN, G, R, Q, D, B, L, S, P, T>;
   static bool attr_set = false;  // benign race: the attribute is idempotent
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN, P>::kSmemBytes);
@@ -683,6 +718,49 @@ int32_t launch_one(cudaStream_t stream, const Maps& m, const GemmParams& p, int 
 struct Epi {
   bool gelu, residual, rotary, bias, ln, stats;
 };
+
+// MN-major ("transposed") operands: the backward GEMMs.  Plain epilogue only (optional run-time bias on the direct
+// path); trans = 1 (A^T given), 2 (B^T given, i.e. dgrad on the forward's packed weights), 3 (both: wgrad).
+template <int BN>
+int32_t launch_trans(cudaStream_t stream, const Maps& m, const GemmParams& p, int grid, int trans, bool direct) {
+  if (direct) {
+    if (trans == 1) return launch_one<BN, false, false, false, true, false, false, false, 1, 1>(stream, m, p, grid);
+    if (trans == 2) return launch_one<BN, false, false, false, true, false, false, false, 1, 2>(stream, m, p, grid);
+    return launch_one<BN, false, false, false, true, false, false, false, 1, 3>(stream, m, p, grid);
+  }
+  if (trans == 1) return launch_one<BN, false, false, false, false, false, false, false, 1, 1>(stream, m, p, grid);
+  if (trans == 2) return launch_one<BN, false, false, false, false, false, false, false, 1, 2>(stream, m, p, grid);
+  return launch_one<BN, false, false, false, false, false, false, false, 1, 3>(stream, m, p, grid);
+}
+
+// out[r, c] = sum_s partial[s][r, c]  (split-K second stage; deterministic order)
+template <bool kOutF32>
+__global__ void __launch_bounds__(256)
+splitk_reduce_kernel(const float* __restrict__ part, void* __restrict__ out, int M, int N, int ldd, int splits,
+                     size_t split_stride) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int n4 = (N + 3) / 4;
+  if (i >= static_cast<int64_t>(M) * n4) return;
+  const int r = static_cast<int>(i / n4), c = static_cast<int>(i % n4) * 4;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int s = 0; s < splits; ++s) {
+    const float* src = part + static_cast<size_t>(s) * split_stride + static_cast<size_t>(r) * ldd + c;
+    if (c + 4 <= N) {
+      const float4 v = *reinterpret_cast<const float4*>(src);
+      acc[0] += v.x; acc[1] += v.y; acc[2] += v.z; acc[3] += v.w;
+    } else {
+      for (int q = 0; q < 4; ++q)
+        if (c + q < N) acc[q] += src[q];
+    }
+  }
+  for (int q = 0; q < 4; ++q) {
+    if (c + q >= N) break;
+    if (kOutF32)
+      static_cast<float*>(out)[static_cast<size_t>(r) * ldd + c + q] = acc[q];
+    else
+      static_cast<bf16*>(out)[static_cast<size_t>(r) * ldd + c + q] = __float2bfloat16(acc[q]);
+  }
+}
 
 // direct path (fp32 or row-remapped output): bias is a run-time flag, no LN fold / statistics
 template <int BN>
@@ -729,10 +807,13 @@ int32_t launch_staged(cudaStream_t stream, const Maps& m, const GemmParams& p, i
 
 }  // namespace mr
 
-extern "C" size_t mr_gemm_epilogue_workspace_bytes(const MrGemmDesc*) { return 0; }
+extern "C" size_t mr_gemm_epilogue_workspace_bytes(const MrGemmDesc* d) {
+  if (!d || d->split_k <= 1) return 0;
+  return static_cast<size_t>(d->split_k) * static_cast<size_t>(d->M) * static_cast<size_t>(d->ldd) * sizeof(float);
+}
 
 extern "C" int32_t mr_gemm_epilogue(mr_stream_t stream_, const MrGemmDesc* d, const void* const* in,
-                                    void* const* out, void*, size_t) {
+                                    void* const* out, void* workspace, size_t workspace_bytes) {
   using namespace mr;
   MR_REQUIRE(d && in && out, MR_ERR_NULL_POINTER);
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -741,7 +822,13 @@ extern "C" int32_t mr_gemm_epilogue(mr_stream_t stream_, const MrGemmDesc* d, co
   MR_REQUIRE(A && W && out[0], MR_ERR_NULL_POINTER);
   MR_REQUIRE(d->M >= 0 && d->N > 0 && d->K > 0, MR_ERR_BAD_SHAPE);
   if (d->M == 0) return MR_OK;
-  MR_REQUIRE(d->K % 8 == 0 && d->lda % 8 == 0 && d->lda >= d->K, MR_ERR_BAD_SHAPE);
+  const int trans = (d->trans_a ? 1 : 0) | (d->trans_b ? 2 : 0);
+  const int ldb = d->ldb > 0 ? d->ldb : (d->trans_b ? d->N : d->K);
+  if (d->trans_a)
+    MR_REQUIRE(d->M % 8 == 0 && d->lda % 8 == 0 && d->lda >= d->M, MR_ERR_BAD_SHAPE);   // A given as [K, M]
+  else
+    MR_REQUIRE(d->K % 8 == 0 && d->lda % 8 == 0 && d->lda >= d->K, MR_ERR_BAD_SHAPE);
+  MR_REQUIRE(ldb % 8 == 0 && ldb >= (d->trans_b ? d->N : d->K), MR_ERR_BAD_SHAPE);
   MR_REQUIRE(d->ldd % 8 == 0 && d->ldd >= d->N, MR_ERR_BAD_SHAPE);
   MR_REQUIRE(aligned16(A) && aligned16(W) && aligned16(out[0]), MR_ERR_MISALIGNED);
   const bool bias = d->epilogue & MR_EPI_BIAS, gelu = d->epilogue & MR_EPI_GELU;
@@ -771,6 +858,7 @@ extern "C" int32_t mr_gemm_epilogue(mr_stream_t stream_, const MrGemmDesc* d, co
   p.residual = static_cast<const bf16*>(in[3]);
   p.rot = static_cast<const float*>(in[4]);
   p.D = out[0];
+  p.splits = 1;
   const bool ln_in = d->epilogue & MR_EPI_LN_IN, stats_out = d->epilogue & MR_EPI_STATS_OUT;
   const bool direct_path = p.out_f32 || d->seq_in != 0;
   if (ln_in) {
@@ -806,11 +894,56 @@ extern "C" int32_t mr_gemm_epilogue(mr_stream_t stream_, const MrGemmDesc* d, co
   p.num_n_tiles = ceil_div(d->N, bn);
   p.num_tiles = m_tiles * p.num_n_tiles;
   p.num_k_blocks = ceil_div(d->K, kBK);
+  p.kb_per_split = p.num_k_blocks;
+  const int splits = d->split_k > 1 ? (d->split_k < p.num_k_blocks ? d->split_k : p.num_k_blocks) : 1;
+  if (splits > 1) {
+    // partial sums go to the workspace (fp32, [splits][M][ldd]); a second kernel adds them up in a fixed order
+    MR_REQUIRE(!(gelu || residual || rotary || bias || ln_in || stats_out), MR_ERR_BAD_SHAPE);
+    MR_REQUIRE(d->seq_in == 0, MR_ERR_BAD_SHAPE);
+    MR_REQUIRE(workspace && workspace_bytes >= mr_gemm_epilogue_workspace_bytes(d), MR_ERR_WORKSPACE);
+    MR_REQUIRE(aligned16(workspace), MR_ERR_MISALIGNED);
+    p.splits = splits;
+    p.kb_per_split = ceil_div(p.num_k_blocks, splits);
+    p.split_stride = static_cast<size_t>(d->M) * d->ldd;
+    p.D = workspace;
+    p.out_f32 = 1;
+    p.num_tiles *= splits;
+  }
   const int grid = p.num_tiles < sms ? p.num_tiles : sms;
 
   Maps m;
-  MR_REQUIRE(make_tmap_2d(&m.a, A, d->M, d->K, d->lda, kBM, kBK), MR_ERR_DRIVER);
-  MR_REQUIRE(make_tmap_2d(&m.b, W, d->N, d->K, d->K, bn, kBK), MR_ERR_DRIVER);
+  if (d->trans_a)
+    MR_REQUIRE(make_tmap_2d(&m.a, A, d->K, d->M, d->lda, 64, 64), MR_ERR_DRIVER);
+  else
+    MR_REQUIRE(make_tmap_2d(&m.a, A, d->M, d->K, d->lda, kBM, kBK), MR_ERR_DRIVER);
+  if (d->trans_b)
+    MR_REQUIRE(make_tmap_2d(&m.b, W, d->K, d->N, ldb, 64, 64), MR_ERR_DRIVER);
+  else
+    MR_REQUIRE(make_tmap_2d(&m.b, W, d->N, d->K, ldb, bn, kBK), MR_ERR_DRIVER);
+  if (trans != 0) {
+    MR_REQUIRE(!(gelu || residual || rotary || ln_in || stats_out) && (direct_path || !bias), MR_ERR_BAD_SHAPE);
+    int32_t st;
+    if (direct_path || splits > 1) {
+      m.out = m.a;
+      m.res = m.a;
+      st = bn == 256 ? launch_trans<256>(stream, m, p, grid, trans, true) : launch_trans<128>(stream, m, p, grid, trans, true);
+    } else {
+      MR_REQUIRE(make_tmap_2d(&m.out, out[0], d->M, d->N, d->ldd, 32, 64), MR_ERR_DRIVER);
+      m.res = m.out;
+      st = bn == 256 ? launch_trans<256>(stream, m, p, grid, trans, false) : launch_trans<128>(stream, m, p, grid, trans, false);
+    }
+    if (st != MR_OK || splits == 1) return st;
+    const int64_t total = static_cast<int64_t>(d->M) * ((d->N + 3) / 4);
+    const unsigned blocks = static_cast<unsigned>(ceil_div64(total, 256));
+    if (d->epilogue & MR_EPI_OUT_F32)
+      splitk_reduce_kernel<true><<<blocks, 256, 0, stream>>>(static_cast<const float*>(workspace), out[0], d->M, d->N,
+                                                             d->ldd, splits, p.split_stride);
+    else
+      splitk_reduce_kernel<false><<<blocks, 256, 0, stream>>>(static_cast<const float*>(workspace), out[0], d->M, d->N,
+                                                              d->ldd, splits, p.split_stride);
+    return after_launch();
+  }
+  MR_REQUIRE(splits == 1, MR_ERR_BAD_SHAPE);   // split-K is offered for the backward (transposed-operand) GEMMs
   // fp32 output and row-remapped output keep per-thread global accesses; everything else is staged
   // through shared memory and moved by TMA
   const bool direct = direct_path;
@@ -826,7 +959,7 @@ extern "C" int32_t mr_gemm_epilogue(mr_stream_t stream_, const MrGemmDesc* d, co
   if (residual) MR_REQUIRE(make_tmap_2d(&m.res, in[3], d->M, d->N, d->ldd, 32, 64), MR_ERR_DRIVER);
   // CTA pairs (cta_group::2, 256 x 256 pair tiles) whenever every pair of SMs gets at least one pair tile
   const int pair_tiles = ceil_div(d->M, 2 * kBM) * p.num_n_tiles;
-  if (bn == 256 && d->algo_pair != 2 && sms >= 2 && (d->algo_pair == 1 || pair_tiles >= sms / 2)) {
+  if (bn == 256 && trans == 0 && d->algo_pair != 2 && sms >= 2 && (d->algo_pair == 1 || pair_tiles >= sms / 2)) {
     p.num_tiles = pair_tiles;
     const int pairs = pair_tiles < sms / 2 ? pair_tiles : sms / 2;
     MR_REQUIRE(make_tmap_2d(&m.b, W, d->N, d->K, d->K, bn / 2, kBK), MR_ERR_DRIVER);

@@ -505,3 +505,41 @@ def test_gemm_cta_pairs(cuda, lib, M, mode):
             if mode == "gelu":
                 ref = ref * torch.sigmoid(1.702 * ref)
             _close(outs[1], ref, 3e-2, 2e-2, f"pair {mode}")
+
+
+@pytest.mark.parametrize("M,N,K", [(1000, 768, 3072), (333, 200, 136), (4096, 768, 768), (128, 256, 64)])
+def test_gemm_dgrad_transposed_b(cuda, lib, M, N, K):
+    """dgrad form: D[M, N] = A[M, K] . Bt[K, N] with Bt consumed MN-major straight from its [K, N] layout
+    (dX = dY . W on the forward's packed [N_f, K_f] weights, no transposed copy)."""
+    g = torch.Generator().manual_seed(M + K)
+    a = _bf(torch.randn(M, K, generator=g)).to(cuda)
+    bt = _bf(torch.randn(K, N, generator=g) * 0.05).to(cuda)
+    ref = a.float() @ bt.float()
+    _close(lib.gemm_bwd(a, bt, trans_b=True), ref, 2e-3, 1e-3, "dgrad f32")
+    _close(lib.gemm_bwd(a, bt, trans_b=True, out_f32=False), ref, 3e-2, 1e-2, "dgrad bf16 (staged)")
+
+
+@pytest.mark.parametrize("M,N,K,split", [(768, 3072, 5000, 0), (768, 3072, 5000, 4), (2304, 768, 30848, 8), (136, 200, 333, 0),
+                                         (136, 200, 333, 3), (128, 256, 64, 0), (3072, 768, 777 * 8, 5)])
+def test_gemm_wgrad_both_transposed(cuda, lib, M, N, K, split):
+    """wgrad form: D[M, N] = At[K, M]^T . Bt[K, N] (dW = dY^T . X, reduction over the token rows), both operands
+    MN-major, optional split-K with a deterministic second-stage sum."""
+    g = torch.Generator().manual_seed(M + K + split)
+    at = _bf(torch.randn(K, M, generator=g)).to(cuda)
+    bt = _bf(torch.randn(K, N, generator=g) * 0.05).to(cuda)
+    ref = at.float().t() @ bt.float()
+    got = lib.gemm_bwd(at, bt, trans_a=True, trans_b=True, split_k=split)
+    _close(got, ref, 5e-3 * math.sqrt(K / 64), 2e-3, f"wgrad split={split}")
+    if split:
+        assert torch.equal(got, lib.gemm_bwd(at, bt, trans_a=True, trans_b=True, split_k=split))   # deterministic
+        _close(lib.gemm_bwd(at, bt, trans_a=True, trans_b=True, split_k=split, out_f32=False), ref,
+               5e-2 * math.sqrt(K / 64), 1e-2, "wgrad bf16 out")
+
+
+def test_gemm_transposed_a_only(cuda, lib):
+    g = torch.Generator().manual_seed(5)
+    K, M, N = 520, 264, 392
+    at = _bf(torch.randn(K, M, generator=g)).to(cuda)
+    w = _bf(torch.randn(N, K, generator=g) * 0.05).to(cuda)
+    b = torch.randn(N, generator=g).to(cuda)
+    _close(lib.gemm_bwd(at, w, trans_a=True, bias=b), at.float().t() @ w.float().t() + b, 2e-3, 1e-3, "A^T . W^T + b")

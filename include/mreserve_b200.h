@@ -69,7 +69,7 @@ int64_t mr_launch_count(void);
  * MR_EPI_ROTARY_QKV: N == 3*hidden; for columns c < 2*hidden with (c % 64) < 32 the value is
  * multiplied by rot[(r % rot_rows) * 32 + (c % 64)]; columns c < hidden are then multiplied by
  * q_scale.
- * Constraints: K % 8 == 0, lda % 8 == 0, ldd % 8 == 0 (N itself is arbitrary), all pointers 16-byte aligned.
+ * Constraints: lda % 8 == 0, ldb % 8 == 0, ldd % 8 == 0 (row pitches; M, N, K are arbitrary), pointers 16-byte aligned.
  *
  * LayerNorm folding (TransformerLayer, modeling.py:272-279: `Dense(LN(x))`).  With W' = gamma (.) W,
  *   LN(x) W + b = rstd_r (x W' - mu_r colsum(W')) + (beta W + b),
@@ -336,6 +336,8 @@ int32_t mr_segment_pool(mr_stream_t stream, const MrSegmentPoolDesc* d, const vo
  * ------------------------------------------------------------------------------------------ */
 typedef struct MrContrastiveDesc {
   int32_t n, n_all, H;
+  int32_t pos_off;   /* _bwd: column of y_all holding row 0's positive (rank * n for the rank-major all-gather) */
+  float grad_scale;  /* _bwd: upstream gradient times 1 / (2 n) (pretrain_model.py:295) */
 } MrContrastiveDesc;
 int32_t mr_contrastive_lse_fwd(mr_stream_t stream, const MrContrastiveDesc* d, const void* const* in,
                                void* const* out, void* workspace, size_t workspace_bytes);
@@ -350,6 +352,56 @@ size_t mr_contrastive_lse_fwd_workspace_bytes(const MrContrastiveDesc* d);
  * ------------------------------------------------------------------------------------------ */
 int32_t mr_contrastive_reduce(mr_stream_t stream, const MrContrastiveDesc* d, const void* const* in,
                               void* const* out, void* workspace, size_t workspace_bytes);
+
+/* ------------------------------------------------------------------------------------------
+ * Backward entries (pretrain_model.py:306-340 differentiates the whole forward with jax.value_and_grad; these are
+ * the op-level gradients the forward kernels above need).  GEMM gradients are mr_gemm_epilogue with trans_a /
+ * trans_b / split_k.
+ *
+ * mr_layernorm_bwd: in[0] dy bf16 [rows, H]; in[1] x bf16 [rows, H] (the LayerNorm INPUT; statistics are
+ *   recomputed); in[2] gamma f32 [H]; in[3] dres bf16 [rows, H] optional, added to dx (gradient of the residual
+ *   branch that bypasses the LayerNorm); out[0] dx bf16 [rows, H]; out[1] dgamma f32 [H]; out[2] dbeta f32 [H].
+ *   Uses MrLayerNormDesc {rows, H, ldx = H, eps}; workspace mr_layernorm_bwd_workspace_bytes.
+ * mr_gelu: mode 0: out[0] = x sigmoid(1.702 x) (modeling.py:240); mode 1: out[0] = dy * d/dx of that.
+ *   in[0] x bf16 [n]; in[1] dy bf16 [n] (mode 1); out[0] bf16 [n]
+ * mr_colsum: out[0] f32 [cols] = column sums of in[0] bf16 [rows, ld] (bias gradients).
+ * mr_rotary_bwd: backward of the qkv epilogue's element-wise factors, in place on out[0] = d(qkv) bf16
+ *   [rows, 3 hidden]; in[0] = the forward's rotary table f32 [rot_rows, 32].
+ * mr_contrastive_lse_bwd: one direction of the loss gradient.  in[0] x bf16 [n, H]; in[1] y_all bf16 [n_all, H];
+ *   in[2] lse f32 [n] (forward); out[0] dx f32 [n, H]; out[1] dy_all f32 [n_all, H] (to be reduce-scattered to
+ *   the ranks that own the rows).  d(logits) = grad_scale (softmax - onehot(pos_off + i)) is formed in bf16 and both
+ *   products run on the tensor cores.
+ * mr_unit_normalize_bwd: in[0] x (forward input, f32 if in_f32 else bf16) [rows_in, H]; in[1] dy (f32 if out_f32
+ *   else bf16) [rows, H]; in[2] row_idx i32 [rows] optional (the forward's gather); out[0] dx f32 [rows_in, H]
+ *   (rows that are not referenced keep their previous contents: zero the buffer first when gathering).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct MrElementwiseDesc {
+  int64_t n;
+  int32_t mode;
+} MrElementwiseDesc;
+typedef struct MrColsumDesc {
+  int32_t rows, cols, ld;
+} MrColsumDesc;
+typedef struct MrRotaryBwdDesc {
+  int64_t rows;
+  int32_t hidden, rot_rows;
+  float q_scale;
+} MrRotaryBwdDesc;
+int32_t mr_layernorm_bwd(mr_stream_t stream, const MrLayerNormDesc* d, const void* const* in, void* const* out,
+                         void* workspace, size_t workspace_bytes);
+size_t mr_layernorm_bwd_workspace_bytes(const MrLayerNormDesc* d);
+int32_t mr_gelu(mr_stream_t stream, const MrElementwiseDesc* d, const void* const* in, void* const* out,
+                void* workspace, size_t workspace_bytes);
+int32_t mr_colsum(mr_stream_t stream, const MrColsumDesc* d, const void* const* in, void* const* out, void* workspace,
+                  size_t workspace_bytes);
+size_t mr_colsum_workspace_bytes(const MrColsumDesc* d);
+int32_t mr_rotary_bwd(mr_stream_t stream, const MrRotaryBwdDesc* d, const void* const* in, void* const* out,
+                      void* workspace, size_t workspace_bytes);
+int32_t mr_contrastive_lse_bwd(mr_stream_t stream, const MrContrastiveDesc* d, const void* const* in, void* const* out,
+                               void* workspace, size_t workspace_bytes);
+size_t mr_contrastive_lse_bwd_workspace_bytes(const MrContrastiveDesc* d);
+int32_t mr_unit_normalize_bwd(mr_stream_t stream, const MrNormalizeDesc* d, const void* const* in, void* const* out,
+                              void* workspace, size_t workspace_bytes);
 
 /* ------------------------------------------------------------------------------------------
  * mr_row_dot: logits[r] = x[r] . w  (finetune `proj` head H -> 1, no bias;

@@ -79,7 +79,20 @@ class SegmentPoolDesc(C.Structure):
 
 
 class ContrastiveDesc(C.Structure):
-    _fields_ = [("n", C.c_int32), ("n_all", C.c_int32), ("H", C.c_int32)]
+    _fields_ = [("n", C.c_int32), ("n_all", C.c_int32), ("H", C.c_int32), ("pos_off", C.c_int32),
+                ("grad_scale", C.c_float)]
+
+
+class ElementwiseDesc(C.Structure):
+    _fields_ = [("n", C.c_int64), ("mode", C.c_int32)]
+
+
+class ColsumDesc(C.Structure):
+    _fields_ = [("rows", C.c_int32), ("cols", C.c_int32), ("ld", C.c_int32)]
+
+
+class RotaryBwdDesc(C.Structure):
+    _fields_ = [("rows", C.c_int64), ("hidden", C.c_int32), ("rot_rows", C.c_int32), ("q_scale", C.c_float)]
 
 
 class RowDotDesc(C.Structure):
@@ -103,11 +116,20 @@ ENTRY_POINTS = {
     "mr_contrastive_lse_fwd": ContrastiveDesc,
     "mr_contrastive_reduce": ContrastiveDesc,
     "mr_row_dot": RowDotDesc,
+    "mr_layernorm_bwd": LayerNormDesc,
+    "mr_gelu": ElementwiseDesc,
+    "mr_colsum": ColsumDesc,
+    "mr_rotary_bwd": RotaryBwdDesc,
+    "mr_contrastive_lse_bwd": ContrastiveDesc,
+    "mr_unit_normalize_bwd": NormalizeDesc,
 }
 WORKSPACE_FNS = {
     "mr_gemm_epilogue_workspace_bytes": GemmDesc,
     "mr_attention_fwd_workspace_bytes": AttentionDesc,
     "mr_transformer_encode_workspace_bytes": EncoderDesc,
+    "mr_layernorm_bwd_workspace_bytes": LayerNormDesc,
+    "mr_colsum_workspace_bytes": ColsumDesc,
+    "mr_contrastive_lse_bwd_workspace_bytes": ContrastiveDesc,
     "mr_contrastive_lse_fwd_workspace_bytes": ContrastiveDesc,
 }
 MISC_FNS = ["mr_check_device", "mr_abi_version", "mr_status_string", "mr_launch_count"]
@@ -116,7 +138,7 @@ MISC_FNS = ["mr_check_device", "mr_abi_version", "mr_status_string", "mr_launch_
 import os as _os
 GEMM_PAIR_DEFAULT = int(_os.environ.get("MR_GEMM_PAIR", "0"))
 
-ABI_VERSION = 6  # must equal mr_abi_version() of the loaded library (struct layouts above)
+ABI_VERSION = 7  # must equal mr_abi_version() of the loaded library (struct layouts above)
 
 _lib = None
 
@@ -421,3 +443,61 @@ def row_dot(x: torch.Tensor, w: torch.Tensor, row_idx=None, rows=None) -> torch.
     out = torch.empty((rows,), dtype=torch.float32, device=x.device)
     _call("mr_row_dot", RowDotDesc(rows=rows, H=H), [x, w, row_idx], [out])
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# backward wrappers
+# ------------------------------------------------------------------------------------------------
+def _ws(fn_name: str, desc, device) -> torch.Tensor:
+    n = getattr(load(), fn_name)(C.byref(desc))
+    return torch.empty((max(int(n), 16),), dtype=torch.uint8, device=device)
+
+
+def layernorm_bwd(dy: torch.Tensor, x: torch.Tensor, gamma: torch.Tensor, dres=None, eps=1e-5):
+    """-> (dx bf16 [rows, H] (+ dres), dgamma f32 [H], dbeta f32 [H])."""
+    rows, H = x.shape
+    d = LayerNormDesc(rows=rows, H=H, ldx=H, eps=eps)
+    dx = torch.empty_like(x)
+    dg = torch.empty((H,), dtype=torch.float32, device=x.device)
+    db = torch.empty((H,), dtype=torch.float32, device=x.device)
+    _call("mr_layernorm_bwd", d, [dy, x, gamma, dres], [dx, dg, db], _ws("mr_layernorm_bwd_workspace_bytes", d, x.device))
+    return dx, dg, db
+
+
+def gelu(x: torch.Tensor, dy=None) -> torch.Tensor:
+    """dy None: x sigmoid(1.702 x); else dy * gelu'(x)."""
+    out = torch.empty_like(x)
+    _call("mr_gelu", ElementwiseDesc(n=x.numel(), mode=int(dy is not None)), [x, dy], [out])
+    return out
+
+
+def colsum(x: torch.Tensor) -> torch.Tensor:
+    rows, cols = x.shape
+    d = ColsumDesc(rows=rows, cols=cols, ld=cols)
+    out = torch.empty((cols,), dtype=torch.float32, device=x.device)
+    _call("mr_colsum", d, [x], [out], _ws("mr_colsum_workspace_bytes", d, x.device))
+    return out
+
+
+def rotary_bwd(dqkv: torch.Tensor, rot: torch.Tensor, hidden: int, q_scale: float = 0.125) -> torch.Tensor:
+    _call("mr_rotary_bwd", RotaryBwdDesc(rows=dqkv.shape[0], hidden=hidden, rot_rows=rot.shape[0], q_scale=q_scale),
+          [rot], [dqkv])
+    return dqkv
+
+
+def contrastive_lse_bwd(x: torch.Tensor, y_all: torch.Tensor, lse: torch.Tensor, pos_off: int, grad_scale: float):
+    n, H = x.shape
+    d = ContrastiveDesc(n=n, n_all=y_all.shape[0], H=H, pos_off=pos_off, grad_scale=grad_scale)
+    dx = torch.empty((n, H), dtype=torch.float32, device=x.device)
+    dy = torch.empty((y_all.shape[0], H), dtype=torch.float32, device=x.device)
+    _call("mr_contrastive_lse_bwd", d, [x, y_all, lse], [dx, dy], _ws("mr_contrastive_lse_bwd_workspace_bytes", d, x.device))
+    return dx, dy
+
+
+def unit_normalize_bwd(x: torch.Tensor, dy: torch.Tensor, scale: float = 1.0, row_idx=None) -> torch.Tensor:
+    H = x.shape[-1]
+    rows = dy.shape[0]
+    dx = torch.zeros((x.shape[0], H), dtype=torch.float32, device=x.device)
+    d = NormalizeDesc(rows=rows, H=H, in_f32=int(x.dtype == torch.float32), out_f32=int(dy.dtype == torch.float32), scale=scale)
+    _call("mr_unit_normalize_bwd", d, [x, dy, row_idx], [dx])
+    return dx

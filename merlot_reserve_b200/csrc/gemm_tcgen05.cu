@@ -824,10 +824,8 @@ extern "C" int32_t mr_gemm_epilogue(mr_stream_t stream_, const MrGemmDesc* d, co
   if (d->M == 0) return MR_OK;
   const int trans = (d->trans_a ? 1 : 0) | (d->trans_b ? 2 : 0);
   const int ldb = d->ldb > 0 ? d->ldb : (d->trans_b ? d->N : d->K);
-  if (d->trans_a)
-    MR_REQUIRE(d->M % 8 == 0 && d->lda % 8 == 0 && d->lda >= d->M, MR_ERR_BAD_SHAPE);   // A given as [K, M]
-  else
-    MR_REQUIRE(d->K % 8 == 0 && d->lda % 8 == 0 && d->lda >= d->K, MR_ERR_BAD_SHAPE);
+  // only the row PITCHES must be multiples of 8 elements (16 bytes, TMA); M, N, K themselves are arbitrary
+  MR_REQUIRE(d->lda % 8 == 0 && d->lda >= (d->trans_a ? d->M : d->K), MR_ERR_BAD_SHAPE);
   MR_REQUIRE(ldb % 8 == 0 && ldb >= (d->trans_b ? d->N : d->K), MR_ERR_BAD_SHAPE);
   MR_REQUIRE(d->ldd % 8 == 0 && d->ldd >= d->N, MR_ERR_BAD_SHAPE);
   MR_REQUIRE(aligned16(A) && aligned16(W) && aligned16(out[0]), MR_ERR_MISALIGNED);

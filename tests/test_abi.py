@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol(lib):
     assert len(names) >= 20
     for n in names:
         assert hasattr(cdll, n), f"{n} declared in the header but not exported"
-    assert cdll.mr_abi_version() == 6
+    assert cdll.mr_abi_version() == 7
     assert lib.launch_count() >= 0
 
 
@@ -38,7 +38,8 @@ def test_struct_sizes_match_c(lib, tmp_path):
                "MrCastDesc": lib.CastDesc, "MrFillClsDesc": lib.FillClsDesc, "MrWindowDesc": lib.WindowDesc,
                "MrAssembleDesc": lib.AssembleDesc, "MrRotaryDesc": lib.RotaryDesc, "MrNormalizeDesc": lib.NormalizeDesc,
                "MrSegmentPoolDesc": lib.SegmentPoolDesc, "MrContrastiveDesc": lib.ContrastiveDesc,
-               "MrRowDotDesc": lib.RowDotDesc, "MrEncoderDesc": lib.EncoderDesc}
+               "MrRowDotDesc": lib.RowDotDesc, "MrEncoderDesc": lib.EncoderDesc, "MrElementwiseDesc": lib.ElementwiseDesc,
+               "MrColsumDesc": lib.ColsumDesc, "MrRotaryBwdDesc": lib.RotaryBwdDesc}
     src = tmp_path / "sz.c"
     body = "\n".join(f'  printf("{n} %zu\\n", sizeof({n}));' for n in structs)
     src.write_text(f'#include <stdio.h>\n#include "mreserve_b200.h"\nint main(void) {{\n{body}\n  return 0;\n}}\n')
@@ -53,7 +54,7 @@ def test_struct_sizes_match_c(lib, tmp_path):
 def test_argument_validation_without_gpu(lib):
     """Bad descriptors are rejected before anything touches the device."""
     cdll = lib.load()
-    d = lib.GemmDesc(M=4, N=8, K=12, lda=12, ldd=8)  # K % 8 != 0
+    d = lib.GemmDesc(M=4, N=8, K=16, lda=12, ldd=8)  # row pitch smaller than K
     arr = (C.c_void_p * 5)(16, 16, None, None, None)
     out = (C.c_void_p * 1)(16)
     assert cdll.mr_gemm_epilogue(None, C.byref(d), arr, out, None, 0) == -1

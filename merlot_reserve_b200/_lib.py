@@ -31,7 +31,7 @@ class GemmDesc(C.Structure):
 
 
 class AttentionDesc(C.Structure):
-    _fields_ = [("B", C.c_int32), ("T", C.c_int32), ("H", C.c_int32), ("algo", C.c_int32)]
+    _fields_ = [("B", C.c_int32), ("T", C.c_int32), ("H", C.c_int32), ("algo", C.c_int32), ("emit_lse", C.c_int32)]
 
 
 class LayerNormDesc(C.Structure):
@@ -103,6 +103,7 @@ class RowDotDesc(C.Structure):
 ENTRY_POINTS = {
     "mr_gemm_epilogue": GemmDesc,
     "mr_attention_fwd": AttentionDesc,
+    "mr_attention_bwd": AttentionDesc,
     "mr_layernorm_fwd": LayerNormDesc,
     "mr_transformer_encode": EncoderDesc,
     "mr_cast_pad": CastDesc,
@@ -126,6 +127,7 @@ ENTRY_POINTS = {
 WORKSPACE_FNS = {
     "mr_gemm_epilogue_workspace_bytes": GemmDesc,
     "mr_attention_fwd_workspace_bytes": AttentionDesc,
+    "mr_attention_bwd_workspace_bytes": AttentionDesc,
     "mr_transformer_encode_workspace_bytes": EncoderDesc,
     "mr_layernorm_bwd_workspace_bytes": LayerNormDesc,
     "mr_colsum_workspace_bytes": ColsumDesc,
@@ -138,7 +140,7 @@ MISC_FNS = ["mr_check_device", "mr_abi_version", "mr_status_string", "mr_launch_
 import os as _os
 GEMM_PAIR_DEFAULT = int(_os.environ.get("MR_GEMM_PAIR", "0"))
 
-ABI_VERSION = 7  # must equal mr_abi_version() of the loaded library (struct layouts above)
+ABI_VERSION = 8  # must equal mr_abi_version() of the loaded library (struct layouts above)
 
 _lib = None
 
@@ -294,11 +296,22 @@ def transformer_encode(x: torch.Tensor, rot: torch.Tensor, pre_ln, layer_ptrs: S
 ATTN_AUTO, ATTN_MMA_SYNC, ATTN_TCGEN05 = 0, 1, 2
 
 
-def attention(qkv: torch.Tensor, B: int, T: int, H: int, valid=None, group=None, out=None, algo=ATTN_AUTO) -> torch.Tensor:
+def attention(qkv: torch.Tensor, B: int, T: int, H: int, valid=None, group=None, out=None, algo=ATTN_AUTO, lse=None) -> torch.Tensor:
+    """lse: optional f32 [B, H/64, T] buffer that receives the row log-sum-exp (needed by attention_bwd)."""
     if out is None:
         out = torch.empty((B * T, H), dtype=torch.bfloat16, device=qkv.device)
-    _call("mr_attention_fwd", AttentionDesc(B=B, T=T, H=H, algo=algo), [qkv, valid, group], [out])
+    _call("mr_attention_fwd", AttentionDesc(B=B, T=T, H=H, algo=algo, emit_lse=int(lse is not None)), [qkv, valid, group],
+          [out, lse])
     return out
+
+
+def attention_bwd(qkv: torch.Tensor, dctx: torch.Tensor, ctx: torch.Tensor, lse: torch.Tensor, B: int, T: int, H: int,
+                  valid=None, group=None) -> torch.Tensor:
+    d = AttentionDesc(B=B, T=T, H=H)
+    dqkv = torch.empty_like(qkv)
+    _call("mr_attention_bwd", d, [qkv, dctx, ctx, lse, valid, group], [dqkv],
+          _ws("mr_attention_bwd_workspace_bytes", d, qkv.device))
+    return dqkv
 
 
 def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, rows=None, H=None, ldx=None, seq_in=0,

@@ -39,7 +39,7 @@ __device__ __forceinline__ void load_tile(bf16* s, const bf16* __restrict__ qkv,
 
 __global__ void __launch_bounds__(kAttnThreads)
 attention_fwd_kernel(const bf16* __restrict__ qkv, const uint8_t* __restrict__ valid, const int32_t* __restrict__ group,
-                     bf16* __restrict__ out, int B, int T, int H) {
+                     bf16* __restrict__ out, float* __restrict__ lse_out, int B, int T, int H) {
   __shared__ __align__(128) bf16 sQ[kBlockM * kD];
   __shared__ __align__(128) bf16 sK[2][kBlockN * kD];
   __shared__ __align__(128) bf16 sV[2][kBlockN * kD];
@@ -219,6 +219,9 @@ attention_fwd_kernel(const bf16* __restrict__ qkv, const uint8_t* __restrict__ v
       l += __shfl_xor_sync(0xffffffffu, l, 1);
       l += __shfl_xor_sync(0xffffffffu, l, 2);
       inv[r] = l > 0.f ? 1.0f / l : 0.f;
+      // row log-sum-exp of the masked scores, kept for the backward pass (mr_attention_bwd)
+      if (lse_out != nullptr && tq == 0 && qrow[r] < T)
+        lse_out[(static_cast<size_t>(b) * nh + h) * T + qrow[r]] = (m_run[r] == -INFINITY ? 0.f : m_run[r]) + (l > 0.f ? logf(l) : 0.f);
     }
 #pragma unroll
     for (int dt = 0; dt < 8; ++dt) {
@@ -246,7 +249,7 @@ attention_fwd_kernel(const bf16* __restrict__ qkv, const uint8_t* __restrict__ v
 
 namespace mr {
 int32_t launch_attention_tc(cudaStream_t stream, const bf16* qkv, const uint8_t* valid, const int32_t* group,
-                            bf16* out, int B, int T, int H);
+                            bf16* out, float* lse, int B, int T, int H);
 }
 
 extern "C" size_t mr_attention_fwd_workspace_bytes(const MrAttentionDesc*) { return 0; }
@@ -259,10 +262,12 @@ extern "C" int32_t mr_attention_fwd(mr_stream_t stream_, const MrAttentionDesc* 
   MR_REQUIRE(aligned16(in[0]) && aligned16(out[0]), MR_ERR_MISALIGNED);
   if (d->B == 0) return MR_OK;
   MR_REQUIRE(d->algo >= MR_ATTN_ALGO_AUTO && d->algo <= MR_ATTN_ALGO_TCGEN05, MR_ERR_BAD_SHAPE);
+  float* lse = d->emit_lse ? static_cast<float*>(out[1]) : nullptr;
+  MR_REQUIRE(!d->emit_lse || lse, MR_ERR_NULL_POINTER);
   if (d->algo == MR_ATTN_ALGO_TCGEN05 || (d->algo == MR_ATTN_ALGO_AUTO && d->T > 64)) {
     return launch_attention_tc(static_cast<cudaStream_t>(stream_), static_cast<const bf16*>(in[0]),
                                static_cast<const uint8_t*>(in[1]), static_cast<const int32_t*>(in[2]),
-                               static_cast<bf16*>(out[0]), d->B, d->T, d->H);
+                               static_cast<bf16*>(out[0]), lse, d->B, d->T, d->H);
   }
   const int nh = d->H / 64;
   const int nqb = ceil_div(d->T, kBlockM);
@@ -270,6 +275,6 @@ extern "C" int32_t mr_attention_fwd(mr_stream_t stream_, const MrAttentionDesc* 
   MR_REQUIRE(blocks < (int64_t(1) << 31), MR_ERR_BAD_SHAPE);
   attention_fwd_kernel<<<static_cast<unsigned>(blocks), kAttnThreads, 0, static_cast<cudaStream_t>(stream_)>>>(
       static_cast<const bf16*>(in[0]), static_cast<const uint8_t*>(in[1]), static_cast<const int32_t*>(in[2]),
-      static_cast<bf16*>(out[0]), d->B, d->T, d->H);
+      static_cast<bf16*>(out[0]), lse, d->B, d->T, d->H);
   return after_launch();
 }

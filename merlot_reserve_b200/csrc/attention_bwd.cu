@@ -1,0 +1,371 @@
+// mr_attention_bwd: gradient of the fused attention (apply_attention, modeling.py:188-200) w.r.t. q, k, v.
+//
+// Flash-attention style: P is recomputed from q, k and the forward's row log-sum-exp, never stored.
+//   prep kernel : D[b, h, t] = sum_d dO . O                                  (one warp per (row, head))
+//   main kernel : one CTA per (sequence, head, 64-key block j), loop over 64-query blocks i:
+//                   S = Q_i K_j^T ; P = exp(S - lse_i) (masked) ; dP = dO_i V_j^T ; dS = P (dP - D_i)
+//                   dV_j += P^T dO_i ; dK_j += dS^T Q_i            (fp32 register accumulators, written once)
+//                   dQ_i += dS K_j                                 (fp32 atomics into the workspace)
+//   convert     : dQ fp32 -> bf16 into the q columns of d(qkv)
+// mma.sync m16n8k16 bf16 with fp32 accumulation (the tcgen05 version of this kernel is future work; the forward
+// for T > 64 already runs on tcgen05).  q arrives pre-scaled by 1/sqrt(d) and rotary-scaled (qkv GEMM epilogue), so
+// the gradients produced here are w.r.t. those scaled values; mr_rotary_bwd applies the same factors afterwards.
+// Mask semantics follow the forward: key validity + group ids; a query row whose mask is all false attended
+// uniformly to all T keys, and its gradient is the one of that uniform distribution (S := 0, lse = ln T).
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace mr {
+namespace {
+
+constexpr int kBlk = 64;
+constexpr int kD = 64;
+constexpr int kThreadsB = 128;
+constexpr int kTile = kBlk * kD;   // elements
+constexpr int kInfoOob = static_cast<int>(0x80000000u);
+constexpr int kInfoInvalid = static_cast<int>(0x80000001u);
+
+__device__ __forceinline__ int swz(int row, int chunk) { return row * kD + ((chunk ^ (row & 7)) << 3); }
+
+__device__ __forceinline__ void load_tile(bf16* s, const bf16* __restrict__ src, size_t seq_base, int row0, int T, int ld,
+                                          int col0, int tid) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int i = tid + kThreadsB * k;
+    const int row = i >> 3, ch = i & 7;
+    const int t = row0 + row;
+    const bool ok = t < T;
+    cp_async_16(s + swz(row, ch), src + (seq_base + static_cast<size_t>(ok ? t : T - 1)) * ld + col0 + ch * 8, ok);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+attn_bwd_prep_kernel(const bf16* __restrict__ dout, const bf16* __restrict__ out, float* __restrict__ Dsum, int B, int T,
+                     int H) {
+  const int nh = H / kD;
+  const int64_t gw = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (gw >= static_cast<int64_t>(B) * T * nh) return;
+  const int h = static_cast<int>(gw % nh);
+  const int64_t row = gw / nh;   // b * T + t
+  const size_t off = static_cast<size_t>(row) * H + h * kD;
+  const uint32_t a = reinterpret_cast<const uint32_t*>(dout + off)[lane];
+  const uint32_t b = reinterpret_cast<const uint32_t*>(out + off)[lane];
+  float v = bf16_lo(a) * bf16_lo(b) + bf16_hi(a) * bf16_hi(b);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if (lane == 0) {
+    const int b_ = static_cast<int>(row / T), t = static_cast<int>(row % T);
+    Dsum[(static_cast<size_t>(b_) * nh + h) * T + t] = v;
+  }
+}
+
+__global__ void __launch_bounds__(kThreadsB)
+attention_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dout, const float* __restrict__ lse,
+                     const float* __restrict__ Dsum, const uint8_t* __restrict__ valid, const int32_t* __restrict__ group,
+                     bf16* __restrict__ dqkv, float* __restrict__ dq_acc, int B, int T, int H) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  bf16* sK = reinterpret_cast<bf16*>(smem_raw);
+  bf16* sV = sK + kTile;
+  bf16* sQ = sV + kTile;          // [2]
+  bf16* sdO = sQ + 2 * kTile;     // [2]
+  bf16* sP = sdO + 2 * kTile;
+  bf16* sdS = sP + kTile;
+  float* sLse = reinterpret_cast<float*>(sdS + kTile);   // [2][64]
+  float* sD = sLse + 2 * kBlk;                           // [2][64]
+  int* sKInfo = reinterpret_cast<int*>(sD + 2 * kBlk);   // [64]
+  int* sQInfo = sKInfo + kBlk;                           // [2][64]: group id, or kInfoInvalid / kInfoOob
+
+  const int nh = H / kD;
+  const int nkb = (T + kBlk - 1) / kBlk;
+  const int jb = blockIdx.x % nkb;
+  const int h = (blockIdx.x / nkb) % nh;
+  const int b = blockIdx.x / (nkb * nh);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, tq = lane & 3;
+  const int ld = 3 * H;
+  const size_t seq_base = static_cast<size_t>(b) * T;
+  const int k0 = jb * kBlk;
+  const size_t stat_base = (static_cast<size_t>(b) * nh + h) * T;
+
+  auto load_q_side = [&](int buf, int qb) {
+    load_tile(sQ + buf * kTile, qkv, seq_base, qb * kBlk, T, ld, h * kD, tid);
+    load_tile(sdO + buf * kTile, dout, seq_base, qb * kBlk, T, H, h * kD, tid);
+    if (tid < kBlk) {
+      const int t = qb * kBlk + tid;
+      float l = 0.f, dsum = 0.f;
+      int info = kInfoOob;
+      if (t < T) {
+        l = lse[stat_base + t];
+        dsum = Dsum[stat_base + t];
+        const bool v = valid ? (valid[seq_base + t] != 0) : true;
+        info = v ? (group ? group[seq_base + t] : 0) : kInfoInvalid;
+      }
+      sLse[buf * kBlk + tid] = l;
+      sD[buf * kBlk + tid] = dsum;
+      sQInfo[buf * kBlk + tid] = info;
+    }
+  };
+
+  load_tile(sK, qkv, seq_base, k0, T, ld, H + h * kD, tid);
+  load_tile(sV, qkv, seq_base, k0, T, ld, 2 * H + h * kD, tid);
+  if (tid < kBlk) {
+    const int kidx = k0 + tid;
+    int info = kInfoOob;
+    if (kidx < T) {
+      const bool v = valid ? (valid[seq_base + kidx] != 0) : true;
+      info = v ? (group ? group[seq_base + kidx] : 0) : kInfoInvalid;
+    }
+    sKInfo[tid] = info;
+  }
+  load_q_side(0, 0);
+  cp_async_commit();
+
+  float dk[8][4], dv[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      dk[i][j] = 0.f;
+      dv[i][j] = 0.f;
+    }
+
+  const int nqb = nkb;
+  for (int qb = 0; qb < nqb; ++qb) {
+    const int buf = qb & 1;
+    if (qb + 1 < nqb) {
+      load_q_side(buf ^ 1, qb + 1);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    const bf16* q_s = sQ + buf * kTile;
+    const bf16* do_s = sdO + buf * kTile;
+
+    // ---- S = Q K^T and dP = dO V^T for this warp's 16 query rows ----
+    float s[8][4], dp[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        s[i][j] = 0.f;
+        dp[i][j] = 0.f;
+      }
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      uint32_t qf[4], of[4];
+      {
+        const int row = warp * 16 + (lane & 15);
+        const int ch = 2 * ks + (lane >> 4);
+        ldmatrix_x4(smem_u32(q_s + swz(row, ch)), qf[0], qf[1], qf[2], qf[3]);
+        ldmatrix_x4(smem_u32(do_s + swz(row, ch)), of[0], of[1], of[2], of[3]);
+      }
+#pragma unroll
+      for (int n16 = 0; n16 < 4; ++n16) {
+        const int mat = lane >> 3;
+        const int row = n16 * 16 + (mat >> 1) * 8 + (lane & 7);
+        const int ch = 2 * ks + (mat & 1);
+        uint32_t r0, r1, r2, r3;
+        ldmatrix_x4(smem_u32(sK + swz(row, ch)), r0, r1, r2, r3);
+        mma_bf16_16816(s[2 * n16], qf, r0, r1);
+        mma_bf16_16816(s[2 * n16 + 1], qf, r2, r3);
+        ldmatrix_x4(smem_u32(sV + swz(row, ch)), r0, r1, r2, r3);
+        mma_bf16_16816(dp[2 * n16], of, r0, r1);
+        mma_bf16_16816(dp[2 * n16 + 1], of, r2, r3);
+      }
+    }
+    // ---- P = exp(S - lse) under the mask, dS = P (dP - D); both to shared memory as bf16 [q][key] ----
+    {
+      const int rl[2] = {warp * 16 + g, warp * 16 + g + 8};
+      float lrow[2], drow[2];
+      int qinfo[2];
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        lrow[r] = sLse[buf * kBlk + rl[r]];
+        drow[r] = sD[buf * kBlk + rl[r]];
+        qinfo[r] = sQInfo[buf * kBlk + rl[r]];
+      }
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int r = e >> 1;
+          const int kinfo = sKInfo[nt * 8 + tq * 2 + (e & 1)];
+          float p;
+          if (qinfo[r] == kInfoOob || kinfo == kInfoOob) {
+            p = 0.f;
+          } else if (qinfo[r] == kInfoInvalid) {
+            p = __expf(-lrow[r]);                      // uniform row: S := 0 for every key of the sequence
+          } else {
+            p = (kinfo == qinfo[r]) ? __expf(s[nt][e] - lrow[r]) : 0.f;
+          }
+          s[nt][e] = p;
+          dp[nt][e] = p * (dp[nt][e] - drow[r]);
+        }
+        const int c = tq * 2;
+        *reinterpret_cast<uint32_t*>(sP + swz(rl[0], nt) + c) = pack_bf16(s[nt][0], s[nt][1]);
+        *reinterpret_cast<uint32_t*>(sP + swz(rl[1], nt) + c) = pack_bf16(s[nt][2], s[nt][3]);
+        *reinterpret_cast<uint32_t*>(sdS + swz(rl[0], nt) + c) = pack_bf16(dp[nt][0], dp[nt][1]);
+        *reinterpret_cast<uint32_t*>(sdS + swz(rl[1], nt) + c) = pack_bf16(dp[nt][2], dp[nt][3]);
+      }
+    }
+    // ---- dQ_i (this warp's 16 rows) = dS K_j : A from registers, B = K[key][d] transposed on load ----
+    {
+      float dq[8][4];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dq[i][j] = 0.f;
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        uint32_t pa[4];
+        pa[0] = pack_bf16(dp[2 * kk][0], dp[2 * kk][1]);
+        pa[1] = pack_bf16(dp[2 * kk][2], dp[2 * kk][3]);
+        pa[2] = pack_bf16(dp[2 * kk + 1][0], dp[2 * kk + 1][1]);
+        pa[3] = pack_bf16(dp[2 * kk + 1][2], dp[2 * kk + 1][3]);
+#pragma unroll
+        for (int d16 = 0; d16 < 4; ++d16) {
+          const int mat = lane >> 3;
+          const int row = kk * 16 + (mat & 1) * 8 + (lane & 7);
+          const int ch = 2 * d16 + (mat >> 1);
+          uint32_t r0, r1, r2, r3;
+          ldmatrix_x4_trans(smem_u32(sK + swz(row, ch)), r0, r1, r2, r3);
+          mma_bf16_16816(dq[2 * d16], pa, r0, r1);
+          mma_bf16_16816(dq[2 * d16 + 1], pa, r2, r3);
+        }
+      }
+      const int t0 = qb * kBlk + warp * 16 + g, t1 = t0 + 8;
+#pragma unroll
+      for (int dt = 0; dt < 8; ++dt) {
+        const int col = h * kD + dt * 8 + tq * 2;
+        if (t0 < T) {
+          float* dst = dq_acc + (seq_base + t0) * H + col;
+          atomicAdd(dst, dq[dt][0]);
+          atomicAdd(dst + 1, dq[dt][1]);
+        }
+        if (t1 < T) {
+          float* dst = dq_acc + (seq_base + t1) * H + col;
+          atomicAdd(dst, dq[dt][2]);
+          atomicAdd(dst + 1, dq[dt][3]);
+        }
+      }
+    }
+    __syncthreads();   // P / dS of all 64 query rows are in shared memory
+    // ---- dV_j += P^T dO_i ; dK_j += dS^T Q_i  (this warp's 16 keys; A = transposed load of [q][key]) ----
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {   // 16 query rows per step
+      uint32_t pa[4], sa[4];
+      {
+        const int mat = lane >> 3;
+        const int row = ks * 16 + (mat >> 1) * 8 + (lane & 7);   // query index (the k of this product)
+        const int ch = 2 * warp + (mat & 1);                     // key chunk (the m of this product)
+        ldmatrix_x4_trans(smem_u32(sP + swz(row, ch)), pa[0], pa[1], pa[2], pa[3]);
+        ldmatrix_x4_trans(smem_u32(sdS + swz(row, ch)), sa[0], sa[1], sa[2], sa[3]);
+      }
+#pragma unroll
+      for (int d16 = 0; d16 < 4; ++d16) {
+        const int mat = lane >> 3;
+        const int row = ks * 16 + (mat & 1) * 8 + (lane & 7);
+        const int ch = 2 * d16 + (mat >> 1);
+        uint32_t r0, r1, r2, r3;
+        ldmatrix_x4_trans(smem_u32(do_s + swz(row, ch)), r0, r1, r2, r3);
+        mma_bf16_16816(dv[2 * d16], pa, r0, r1);
+        mma_bf16_16816(dv[2 * d16 + 1], pa, r2, r3);
+        ldmatrix_x4_trans(smem_u32(q_s + swz(row, ch)), r0, r1, r2, r3);
+        mma_bf16_16816(dk[2 * d16], sa, r0, r1);
+        mma_bf16_16816(dk[2 * d16 + 1], sa, r2, r3);
+      }
+    }
+    __syncthreads();   // before the next iteration overwrites sP / sdS and prefetches into this buffer's sibling
+  }
+
+  // ---- write dK_j, dV_j (bf16) into the k / v columns of d(qkv) ----
+  const int kr0 = k0 + warp * 16 + g, kr1 = kr0 + 8;
+#pragma unroll
+  for (int dt = 0; dt < 8; ++dt) {
+    const int col = h * kD + dt * 8 + tq * 2;
+    if (kr0 < T) {
+      bf16* row = dqkv + (seq_base + kr0) * ld;
+      *reinterpret_cast<uint32_t*>(row + H + col) = pack_bf16(dk[dt][0], dk[dt][1]);
+      *reinterpret_cast<uint32_t*>(row + 2 * H + col) = pack_bf16(dv[dt][0], dv[dt][1]);
+    }
+    if (kr1 < T) {
+      bf16* row = dqkv + (seq_base + kr1) * ld;
+      *reinterpret_cast<uint32_t*>(row + H + col) = pack_bf16(dk[dt][2], dk[dt][3]);
+      *reinterpret_cast<uint32_t*>(row + 2 * H + col) = pack_bf16(dv[dt][2], dv[dt][3]);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+dq_convert_kernel(const float* __restrict__ dq_acc, bf16* __restrict__ dqkv, int64_t rows, int H) {
+  const int vec_per_row = H / 8;
+  const int64_t total = rows * vec_per_row;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = i / vec_per_row;
+    const int c = static_cast<int>(i % vec_per_row) * 8;
+    const float4 a = *reinterpret_cast<const float4*>(dq_acc + r * H + c);
+    const float4 b = *reinterpret_cast<const float4*>(dq_acc + r * H + c + 4);
+    uint4 o;
+    o.x = pack_bf16(a.x, a.y);
+    o.y = pack_bf16(a.z, a.w);
+    o.z = pack_bf16(b.x, b.y);
+    o.w = pack_bf16(b.z, b.w);
+    *reinterpret_cast<uint4*>(dqkv + r * 3 * H + c) = o;
+  }
+}
+
+constexpr int kBwdSmem = (2 + 2 + 2 + 2) * kTile * 2 + 4 * kBlk * 4 + 3 * kBlk * 4;
+
+}  // namespace
+}  // namespace mr
+
+extern "C" size_t mr_attention_bwd_workspace_bytes(const MrAttentionDesc* d) {
+  if (!d || d->B <= 0 || d->T <= 0 || d->H <= 0) return 0;
+  const size_t rows = static_cast<size_t>(d->B) * d->T;
+  return rows * d->H * sizeof(float) + rows * (d->H / 64) * sizeof(float);
+}
+
+extern "C" int32_t mr_attention_bwd(mr_stream_t stream_, const MrAttentionDesc* d, const void* const* in, void* const* out,
+                                    void* workspace, size_t workspace_bytes) {
+  using namespace mr;
+  MR_REQUIRE(d && in && out && in[0] && in[1] && in[2] && in[3] && out[0], MR_ERR_NULL_POINTER);
+  MR_REQUIRE(d->B >= 0 && d->T > 0 && d->H > 0 && d->H % 64 == 0, MR_ERR_BAD_SHAPE);
+  if (d->B == 0) return MR_OK;
+  MR_REQUIRE(workspace && workspace_bytes >= mr_attention_bwd_workspace_bytes(d), MR_ERR_WORKSPACE);
+  MR_REQUIRE(aligned16(in[0]) && aligned16(in[1]) && aligned16(in[2]) && aligned16(out[0]) && aligned16(workspace),
+             MR_ERR_MISALIGNED);
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const int nh = d->H / 64;
+  const int64_t rows = static_cast<int64_t>(d->B) * d->T;
+  float* dq_acc = static_cast<float*>(workspace);
+  float* Dsum = dq_acc + rows * d->H;
+  cudaError_t e = cudaMemsetAsync(dq_acc, 0, static_cast<size_t>(rows) * d->H * sizeof(float), stream);
+  if (e != cudaSuccess) return cuda_status(e);
+  attn_bwd_prep_kernel<<<static_cast<unsigned>(ceil_div64(rows * nh, 8)), 256, 0, stream>>>(
+      static_cast<const bf16*>(in[1]), static_cast<const bf16*>(in[2]), Dsum, d->B, d->T, d->H);
+  int32_t st = after_launch();
+  if (st != MR_OK) return st;
+  static bool attr_set = false;
+  if (!attr_set) {
+    e = cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem);
+    if (e != cudaSuccess) return cuda_status(e);
+    attr_set = true;
+  }
+  const int nkb = ceil_div(d->T, kBlk);
+  const int64_t blocks = static_cast<int64_t>(d->B) * nh * nkb;
+  MR_REQUIRE(blocks < (int64_t(1) << 31), MR_ERR_BAD_SHAPE);
+  attention_bwd_kernel<<<static_cast<unsigned>(blocks), kThreadsB, kBwdSmem, stream>>>(
+      static_cast<const bf16*>(in[0]), static_cast<const bf16*>(in[1]), static_cast<const float*>(in[3]), Dsum,
+      static_cast<const uint8_t*>(in[4]), static_cast<const int32_t*>(in[5]), static_cast<bf16*>(out[0]), dq_acc, d->B,
+      d->T, d->H);
+  st = after_launch();
+  if (st != MR_OK) return st;
+  int64_t cblocks = ceil_div64(rows * (d->H / 8), 256);
+  if (cblocks > 148 * 16) cblocks = 148 * 16;
+  dq_convert_kernel<<<static_cast<unsigned>(cblocks), 256, 0, stream>>>(dq_acc, static_cast<bf16*>(out[0]), rows, d->H);
+  return after_launch();
+}

@@ -67,6 +67,7 @@ struct AttnParams {
   const uint8_t* valid;
   const int32_t* group;
   bf16* out;
+  float* lse;   // optional [B, nh, T]: natural-log row log-sum-exp of the masked scores (for mr_attention_bwd)
   int B, T, H, nh, nqb, npairs, nkb;
   int num_items;
 };
@@ -416,6 +417,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnPara
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&o_free[wg]);     // the next item's first PV may overwrite O
+      if (p.lse != nullptr && q_in)
+        p.lse[(static_cast<size_t>(it.b) * p.nh + it.h) * p.T + q] = (m2 + (l > 0.f ? log2f(l) : 0.f)) * 0.6931471805599453f;
       if (q_in) {
         uint4* dst = reinterpret_cast<uint4*>(p.out + (static_cast<size_t>(seq_base) + q) * p.H + it.h * kD);
 #pragma unroll
@@ -436,13 +439,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnPara
 
 // Called by mr_attention_fwd (attention.cu) when T is long enough for 128-wide tiles.
 int32_t launch_attention_tc(cudaStream_t stream, const bf16* qkv, const uint8_t* valid, const int32_t* group,
-                            bf16* out, int B, int T, int H) {
+                            bf16* out, float* lse, int B, int T, int H) {
   CUtensorMap tm;
   if (!make_tmap_2d(&tm, qkv, static_cast<int64_t>(B) * T, 3 * H, 3 * H, 128, kD)) return MR_ERR_DRIVER;
   AttnParams p{};
   p.valid = valid;
   p.group = group;
   p.out = out;
+  p.lse = lse;
   p.B = B;
   p.T = T;
   p.H = H;

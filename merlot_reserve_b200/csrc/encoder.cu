@@ -98,7 +98,7 @@ extern "C" int32_t mr_transformer_encode(mr_stream_t stream, const MrEncoderDesc
     }
     {  // ctx = softmax(q k^T + mask) v             modeling.py:188-200
       const void* ain[3] = {qkv, valid, group};
-      void* aout[1] = {ctx};
+      void* aout[2] = {ctx, nullptr};
       if ((st = mr_attention_fwd(stream, &a, ain, aout, nullptr, 0)) != MR_OK) return st;
     }
     {  // x += ctx Wo                                modeling.py:235,275

@@ -65,7 +65,7 @@ ffi::Error AttentionImpl(cudaStream_t stream, ffi::Buffer<ffi::BF16> qkv, ffi::B
   MrAttentionDesc d{B, T, H, MR_ATTN_ALGO_AUTO};
   const void* in[3] = {qkv.untyped_data(), valid.element_count() ? valid.untyped_data() : nullptr,
                        group.element_count() ? group.untyped_data() : nullptr};
-  void* out[1] = {ctx->untyped_data()};
+  void* out[2] = {ctx->untyped_data(), nullptr};
   return to_error(mr_attention_fwd(stream, &d, in, out, nullptr, 0), "mr_attention_fwd");
 }
 

@@ -98,3 +98,143 @@ def test_unit_normalize_bwd(cuda, lib):
     dyf = torch.randn(40, 256, generator=g)
     y.backward(dyf)
     _close(lib.unit_normalize_bwd(xb.to(cuda), dyf.to(cuda)), xr.grad, 1e-4, 1e-3, "unit_normalize bwd")
+
+
+def _attn_ref_autograd(qkv, dctx, B, T, H, valid=None, group=None):
+    """fp32 torch restatement of apply_attention (modeling.py:188-200) with the reference's 0 / -1e10 bias, and its
+    autograd gradient w.r.t. qkv (q is already scaled by 1/8 and rotary-scaled in qkv, as the kernels get it)."""
+    nh = H // 64
+    x = qkv.float().cpu().clone().requires_grad_(True)
+    q, k, v = x.view(B, T, 3, nh, 64).unbind(2)
+    s = torch.einsum("bqhd,bkhd->bhqk", q, k)
+    if valid is not None or group is not None:
+        m = torch.ones(B, T, T, dtype=torch.bool)
+        if valid is not None:
+            vv = valid.cpu().bool().view(B, T)
+            m &= vv[:, :, None] & vv[:, None, :]
+        if group is not None:
+            gg = group.cpu().view(B, T)
+            m &= gg[:, :, None] == gg[:, None, :]
+        s = s + torch.where(m, 0.0, -1e10)[:, None]
+    w = torch.softmax(s, -1)
+    ctx = torch.einsum("bhqk,bkhd->bqhd", w, v).reshape(B * T, H)
+    ctx.backward(dctx.float().cpu())
+    return ctx.detach(), x.grad, torch.logsumexp(s, -1).detach()
+
+
+@pytest.mark.parametrize("B,T,H,masked", [(3, 241, 128, False), (5, 31, 128, False), (4, 16, 128, True), (2, 640, 128, True),
+                                          (2, 200, 256, True), (1, 64, 64, False)])
+def test_attention_bwd(cuda, lib, B, T, H, masked):
+    g = torch.Generator().manual_seed(B * 1000 + T)
+    qkv = _bf(torch.randn(B * T, 3 * H, generator=g) * 0.8)
+    qkv[:, :H] *= 0.35                                   # q carries the 1/sqrt(d) scale already
+    dctx = _bf(torch.randn(B * T, H, generator=g))
+    valid = group = None
+    if masked:
+        valid = torch.ones(B, T, dtype=torch.uint8)
+        for b in range(B):
+            valid[b, T - 3 - 7 * b:] = 0                 # right padding, different per sequence
+        group = (torch.arange(T)[None] >= (T // 2 + torch.arange(B)[:, None])).to(torch.int32) + 1
+        group[valid == 0] = -1
+        dctx.view(B, T, H)[valid == 0] = 0               # outputs of padded rows are never used downstream
+    ref_ctx, ref_dqkv, ref_lse = _attn_ref_autograd(qkv, dctx, B, T, H, valid, group)
+    dev = lambda t: None if t is None else t.to(cuda).contiguous().view(-1)
+    for algo in ([1, 2] if T > 64 else [1]):
+        lse = torch.empty(B, H // 64, T, device=cuda)
+        ctx = lib.attention(qkv.to(cuda), B, T, H, valid=dev(valid), group=dev(group), algo=algo, lse=lse)
+        _close(ctx, ref_ctx, 2e-2, 2e-2, f"ctx algo {algo}")
+        ok = torch.ones(B, T, dtype=torch.bool) if valid is None else valid.bool()
+        _close(lse.cpu().permute(0, 2, 1)[ok], ref_lse.permute(0, 2, 1)[ok], 2e-3, 1e-3, f"lse algo {algo}")
+        dqkv = lib.attention_bwd(qkv.to(cuda), dctx.to(cuda), ctx, lse, B, T, H, valid=dev(valid), group=dev(group))
+        scale = ref_dqkv.abs().max().item()
+        _close(dqkv, ref_dqkv, 2e-2 * scale + 1e-3, 3e-2, f"dqkv algo {algo}")
+
+
+def test_transformer_layer_backward_composition(cuda, lib):
+    """One pre-LN transformer layer (modeling.py:259-280) forward + backward composed from the C-ABI kernels
+    (unfused LayerNorm path), against torch autograd of the fp32 oracle layer: dx and every parameter gradient."""
+    from merlot_reserve_b200.synthetic import _encoder_params
+    from oracle import reserve_oracle as O
+    import numpy as np
+    H, B, T = 128, 6, 50
+    rng = np.random.default_rng(0)
+    lp = _encoder_params(rng, H, 1, False, 4.0)["layer_00"]
+    g = torch.Generator().manual_seed(0)
+    x0 = _bf(torch.randn(B, T, H, generator=g))
+    dout = _bf(torch.randn(B, T, H, generator=g) * 0.1)
+    coords = torch.rand(T, 1, generator=g) * 2 - 1
+    valid = torch.ones(B, T, dtype=torch.bool)
+    valid[:, T - 4:] = False
+    dout[~valid] = 0
+
+    # ---- oracle + autograd ----
+    def leaf(a):
+        return O._t(a).clone().requires_grad_(True)
+    P = {"pre_attn_ln": {k: leaf(v) for k, v in lp["pre_attn_ln"].items()},
+         "pre_mlp_ln": {k: leaf(v) for k, v in lp["pre_mlp_ln"].items()},
+         "attention_layer": {"qkv": {k: leaf(v) for k, v in lp["attention_layer"]["qkv"].items()},
+                             "attn_proj": {"kernel": leaf(lp["attention_layer"]["attn_proj"]["kernel"])}},
+         "mlp_layer": {"intermediate": {k: leaf(v) for k, v in lp["mlp_layer"]["intermediate"].items()},
+                       "out": {"kernel": leaf(lp["mlp_layer"]["out"]["kernel"])}}}
+    xr = x0.float().clone().requires_grad_(True)
+    bias = torch.where(valid[:, None, :, None] & valid[:, None, None, :], 0.0, -1e10)
+    y = O.transformer_layer(xr, P, O.rotary_sinusoids(coords), bias)
+    y.backward(dout.float())
+
+    # ---- kernels ----
+    from merlot_reserve_b200.modeling import _w, _f
+    M = B * T
+    a, m = lp["attention_layer"], lp["mlp_layer"]
+    wqkv, bqkv, wo = _w(a["qkv"]["kernel"], H), _f(a["qkv"]["bias"]), _w(a["attn_proj"]["kernel"], H)
+    w1, b1, w2 = _w(m["intermediate"]["kernel"], H), _f(m["intermediate"]["bias"]), _w(m["out"]["kernel"], 4 * H)
+    g1, be1 = _f(lp["pre_attn_ln"]["scale"]), _f(lp["pre_attn_ln"]["bias"])
+    g2, be2 = _f(lp["pre_mlp_ln"]["scale"]), _f(lp["pre_mlp_ln"]["bias"])
+    rot = lib.rotary_table(coords.to(cuda).contiguous())
+    vld = valid.to(torch.uint8).to(cuda).view(-1)
+    x = x0.to(cuda).view(M, H)
+    # forward, keeping what the backward needs
+    h1 = lib.layernorm(x, g1, be1)
+    qkv = lib.gemm(h1, wqkv, bias=bqkv, rot=rot, hidden=H, q_scale=0.125)
+    lse = torch.empty(B, H // 64, T, device=cuda)
+    ctx = lib.attention(qkv, B, T, H, valid=vld, lse=lse)
+    xm = lib.gemm(ctx, wo, residual=x)
+    h2 = lib.layernorm(xm, g2, be2)
+    up = lib.gemm(h2, w1, bias=b1)
+    u = lib.gelu(up)
+    yk = lib.gemm(u, w2, residual=xm)
+    _close(yk.view(B, T, H)[valid], y.detach()[valid], 6e-2, 3e-2, "layer forward")
+    # backward
+    dy = dout.to(cuda).view(M, H)
+    du = lib.gemm_bwd(dy, w2, trans_b=True, out_f32=False)                 # [M, 4H]
+    dw2 = lib.gemm_bwd(dy, u, trans_a=True, trans_b=True, split_k=2)       # packed layout [H, 4H]
+    dup = lib.gelu(up, du)
+    dh2 = lib.gemm_bwd(dup, w1, trans_b=True, out_f32=False)
+    dw1 = lib.gemm_bwd(dup, h2, trans_a=True, trans_b=True)
+    db1 = lib.colsum(dup)
+    dxm, dg2, dbe2 = lib.layernorm_bwd(dh2, xm, g2, dres=dy)
+    dctx = lib.gemm_bwd(dxm, wo, trans_b=True, out_f32=False)
+    dwo = lib.gemm_bwd(dxm, ctx, trans_a=True, trans_b=True)
+    dqkv = lib.attention_bwd(qkv, dctx, ctx, lse, B, T, H, valid=vld)
+    lib.rotary_bwd(dqkv, rot, H)
+    dh1 = lib.gemm_bwd(dqkv, wqkv, trans_b=True, out_f32=False)
+    dwqkv = lib.gemm_bwd(dqkv, h1, trans_a=True, trans_b=True)
+    dbqkv = lib.colsum(dqkv)
+    dx, dg1, dbe1 = lib.layernorm_bwd(dh1, x, g1, dres=dxm)
+
+    def chk(got, ref, what, tol=4e-2):
+        ref = ref.detach().float()
+        s = ref.abs().max().item() + 1e-6
+        err = (got.float().cpu() - ref).abs().max().item()
+        assert err <= tol * s, f"{what}: max err {err:.4g} vs scale {s:.4g}"
+    chk(dx.view(B, T, H)[valid], xr.grad[valid], "dx")
+    # packed weights are [out, in]: compare with the flax [in, out] gradients transposed
+    chk(dw2, P["mlp_layer"]["out"]["kernel"].grad.t(), "dW2")
+    chk(dw1, P["mlp_layer"]["intermediate"]["kernel"].grad.t(), "dW1")
+    chk(db1, P["mlp_layer"]["intermediate"]["bias"].grad, "db1")
+    chk(dwo, P["attention_layer"]["attn_proj"]["kernel"].grad.reshape(H, H).t(), "dWo")
+    chk(dwqkv, P["attention_layer"]["qkv"]["kernel"].grad.reshape(H, 3 * H).t(), "dWqkv")
+    chk(dbqkv, P["attention_layer"]["qkv"]["bias"].grad.reshape(-1), "dbqkv")
+    chk(dg2, P["pre_mlp_ln"]["scale"].grad, "dgamma2")
+    chk(dbe2, P["pre_mlp_ln"]["bias"].grad, "dbeta2")
+    chk(dg1, P["pre_attn_ln"]["scale"].grad, "dgamma1")
+    chk(dbe1, P["pre_attn_ln"]["bias"].grad, "dbeta1")

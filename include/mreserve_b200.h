@@ -413,6 +413,24 @@ int32_t mr_contrastive_lse_bwd(mr_stream_t stream, const MrContrastiveDesc* d, c
 size_t mr_contrastive_lse_bwd_workspace_bytes(const MrContrastiveDesc* d);
 int32_t mr_unit_normalize_bwd(mr_stream_t stream, const MrNormalizeDesc* d, const void* const* in, void* const* out,
                               void* workspace, size_t workspace_bytes);
+/* mr_segment_pool_bwd: in[0] do_pool u8 [B, L]; in[1] idx i32 [B, L]; in[2] dpooled f32 [B, S, H]; out[0] dv bf16 [B, L, H].
+ * mr_embed_assemble_bwd (same descriptor as the forward): in[0] tokens; in[1] aud_ptr (optional); in[2] dx bf16
+ *   [B, T (+1), H]; out[0] d_emb f32 [vocab, H] (optional), out[1] d_audio f32 [B / aud_div, n_aud, 6, H] (optional),
+ *   out[2] d_vision f32 [vision rows, n_vis, H] (optional) -- all ACCUMULATED with atomics: zero them first.
+ * mr_window_attention_bwd: in[0] q, in[1] kv (forward inputs), in[2] dctx bf16 [B*n_win, H];
+ *   out[0] dq bf16 [B*n_win, H]; out[1] dkv bf16 [B*T, 2H] (every row written; CLS rows zero).
+ * mr_window_mean_bwd: out[0] dx bf16 [B*T, H] += in[0] dq_in bf16 [B*n_win, H] / win on the window's token rows.
+ * mr_add: out[0] bf16 [n] = in[0] bf16 + in[1] (bf16, or f32 when mode == 1). */
+int32_t mr_segment_pool_bwd(mr_stream_t stream, const MrSegmentPoolDesc* d, const void* const* in, void* const* out,
+                            void* workspace, size_t workspace_bytes);
+int32_t mr_embed_assemble_bwd(mr_stream_t stream, const MrAssembleDesc* d, const void* const* in, void* const* out,
+                              void* workspace, size_t workspace_bytes);
+int32_t mr_window_attention_bwd(mr_stream_t stream, const MrWindowDesc* d, const void* const* in, void* const* out,
+                                void* workspace, size_t workspace_bytes);
+int32_t mr_window_mean_bwd(mr_stream_t stream, const MrWindowDesc* d, const void* const* in, void* const* out,
+                           void* workspace, size_t workspace_bytes);
+int32_t mr_add(mr_stream_t stream, const MrElementwiseDesc* d, const void* const* in, void* const* out, void* workspace,
+               size_t workspace_bytes);
 
 /* ------------------------------------------------------------------------------------------
  * mr_row_dot: logits[r] = x[r] . w  (finetune `proj` head H -> 1, no bias;

@@ -123,6 +123,11 @@ ENTRY_POINTS = {
     "mr_rotary_bwd": RotaryBwdDesc,
     "mr_contrastive_lse_bwd": ContrastiveDesc,
     "mr_unit_normalize_bwd": NormalizeDesc,
+    "mr_segment_pool_bwd": SegmentPoolDesc,
+    "mr_embed_assemble_bwd": AssembleDesc,
+    "mr_window_attention_bwd": WindowDesc,
+    "mr_window_mean_bwd": WindowDesc,
+    "mr_add": ElementwiseDesc,
 }
 WORKSPACE_FNS = {
     "mr_gemm_epilogue_workspace_bytes": GemmDesc,
@@ -140,7 +145,7 @@ MISC_FNS = ["mr_check_device", "mr_abi_version", "mr_status_string", "mr_launch_
 import os as _os
 GEMM_PAIR_DEFAULT = int(_os.environ.get("MR_GEMM_PAIR", "0"))
 
-ABI_VERSION = 8  # must equal mr_abi_version() of the loaded library (struct layouts above)
+ABI_VERSION = 9  # must equal mr_abi_version() of the loaded library (struct layouts above)
 
 _lib = None
 
@@ -514,3 +519,42 @@ def unit_normalize_bwd(x: torch.Tensor, dy: torch.Tensor, scale: float = 1.0, ro
     d = NormalizeDesc(rows=rows, H=H, in_f32=int(x.dtype == torch.float32), out_f32=int(dy.dtype == torch.float32), scale=scale)
     _call("mr_unit_normalize_bwd", d, [x, dy, row_idx], [dx])
     return dx
+
+
+def segment_pool_bwd(do_pool: torch.Tensor, idx: torch.Tensor, dpooled: torch.Tensor, L: int) -> torch.Tensor:
+    B, S, H = dpooled.shape
+    dv = torch.empty((B, L, H), dtype=torch.bfloat16, device=dpooled.device)
+    _call("mr_segment_pool_bwd", SegmentPoolDesc(B=B, L=L, H=H, S=S), [do_pool, idx, dpooled], [dv])
+    return dv
+
+
+def embed_assemble_bwd(tokens, dx, *, H, vocab, d_emb=None, aud_ptr=None, d_audio=None, d_vision=None, n_aud=0, n_vis=0,
+                       T=None, audio_token_length=6, cls_offset=0, aud_div=0, vis_group=0, vis_tile=0) -> None:
+    """Accumulates (atomics) into d_emb [vocab, H], d_audio, d_vision (all f32, zero-initialised by the caller)."""
+    B, L = tokens.shape
+    T = T if T is not None else L + n_vis
+    d = AssembleDesc(B=B, L=L, H=H, n_aud=n_aud if d_audio is not None else 0, n_vis=n_vis if d_vision is not None else 0,
+                     pool_h=1, pool_w=1, T=T, vocab=vocab, audio_token_length=audio_token_length, cls_offset=cls_offset,
+                     aud_div=aud_div, vis_group=vis_group, vis_tile=vis_tile)
+    if d_vision is None and n_vis:
+        d.n_vis = 0
+        d.T = T            # rows beyond L are simply skipped
+    _call("mr_embed_assemble_bwd", d, [tokens, aud_ptr, dx], [d_emb, d_audio, d_vision])
+
+
+def window_attention_bwd(q, kv, dctx, B, T, H, mode, win, n_win, grid_h=0, grid_w=0):
+    dq = torch.empty_like(q)
+    dkv = torch.empty_like(kv)
+    _call("mr_window_attention_bwd", _window_desc(B, T, H, mode, win, n_win, grid_h, grid_w), [q, kv, dctx], [dq, dkv])
+    return dq, dkv
+
+
+def window_mean_bwd(dq_in, dx, B, T, H, mode, win, n_win, grid_h=0, grid_w=0) -> None:
+    _call("mr_window_mean_bwd", _window_desc(B, T, H, mode, win, n_win, grid_h, grid_w), [dq_in], [dx])
+
+
+def add(a: torch.Tensor, b: torch.Tensor, out=None) -> torch.Tensor:
+    """bf16 a + (bf16 | f32) b -> bf16."""
+    out = torch.empty_like(a) if out is None else out
+    _call("mr_add", ElementwiseDesc(n=a.numel(), mode=int(b.dtype == torch.float32)), [a, b], [out])
+    return out

@@ -247,22 +247,30 @@ rotary_bwd_kernel(bf16* __restrict__ dqkv, const float* __restrict__ rot, int64_
 // pos_off + i of y_all (this rank's block of the rank-major all-gather).  One warp per row.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreadsRow)
-contrastive_dlogits_kernel(const float* __restrict__ logits, const float* __restrict__ lse, bf16* __restrict__ dl, int n,
-                           int n_all, int ld_logits, int ld_out, int pos_off, float w) {
+contrastive_dlogits_kernel(const float* __restrict__ logits, const float* __restrict__ lse, bf16* __restrict__ dl_a,
+                           bf16* __restrict__ dl_b, int n, int n_all, int ld, int pos_off, float w) {
+  // d(logits) is a difference of nearly equal numbers whenever the embeddings are close to each other (e.g. right
+  // after initialisation): a single bf16 would lose the gradient, so it is kept as hi + lo bf16 pairs.
+  //   dl_a [n, 2 ld]: (hi | lo) side by side  -> dx     = dl_a . [Y; Y]
+  //   dl_b [2 n, ld]: hi rows then lo rows     -> dy_all = dl_b^T . [X; X]
   const int row = blockIdx.x * kWarps + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= n) return;
-  const float* lr = logits + static_cast<size_t>(row) * ld_logits;
+  const float* lr = logits + static_cast<size_t>(row) * ld;
   const float l = lse[row];
-  bf16* o = dl + static_cast<size_t>(row) * ld_out;
-  for (int c = lane; c < ld_out; c += 32) {
+  for (int c = lane; c < ld; c += 32) {
     float v = 0.f;
     if (c < n_all) {
       v = __expf(lr[c] - l);
       if (c == pos_off + row) v -= 1.0f;
       v *= w;
     }
-    o[c] = __float2bfloat16(v);
+    const bf16 hi = __float2bfloat16(v);
+    const bf16 lo = __float2bfloat16(v - __bfloat162float(hi));
+    dl_a[static_cast<size_t>(row) * 2 * ld + c] = hi;
+    dl_a[static_cast<size_t>(row) * 2 * ld + ld + c] = lo;
+    dl_b[static_cast<size_t>(row) * ld + c] = hi;
+    dl_b[static_cast<size_t>(n + row) * ld + c] = lo;
   }
 }
 
@@ -298,6 +306,176 @@ unit_normalize_bwd_kernel(const void* __restrict__ x_, const void* __restrict__ 
   const float a = scale * rsqrtf(r2);
   const float b = dot / r2;
   for (int c = lane; c < H; c += 32) dx[xr * H + c] = a * (DY(c) - X(c) * b);
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// one_hot_pool backward (modeling.py:541-567): dv[b, l] = do_pool[b, l] ? dpooled[b, idx[b, l]] : 0.  Warp per (b, l).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreadsRow)
+segment_pool_bwd_kernel(const uint8_t* __restrict__ do_pool, const int32_t* __restrict__ idx,
+                        const float* __restrict__ dpooled, bf16* __restrict__ dv, MrSegmentPoolDesc d) {
+  const int64_t gw = static_cast<int64_t>(blockIdx.x) * kWarps + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (gw >= static_cast<int64_t>(d.B) * d.L) return;
+  const int b = static_cast<int>(gw / d.L);
+  const int s = idx[gw];
+  const bool hit = do_pool[gw] != 0 && s >= 0 && s < d.S;
+  const float* src = dpooled + (static_cast<size_t>(b) * d.S + (hit ? s : 0)) * d.H;
+  bf16* dst = dv + static_cast<size_t>(gw) * d.H;
+  for (int c = lane; c < d.H; c += 32) dst[c] = __float2bfloat16(hit ? src[c] : 0.f);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Joint-input assembly backward (prepare_multimodal_inputs, modeling.py:651-758): every row of dx goes to where the
+// forward took the row from -- the token embedding table, an audio span row or a (possibly shared) vision row.
+// fp32 atomics: several sequences share audio / vision rows (pretrain_model.py:104-109) and tokens repeat.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreadsRow)
+embed_assemble_bwd_kernel(const int32_t* __restrict__ tokens, const int32_t* __restrict__ aud_ptr,
+                          const bf16* __restrict__ dx, float* __restrict__ d_emb, float* __restrict__ d_audio,
+                          float* __restrict__ d_vision, MrAssembleDesc d) {
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * kWarps + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  const int t_out = d.T + d.cls_offset;
+  if (row >= static_cast<int64_t>(d.B) * t_out) return;
+  const int b = static_cast<int>(row / t_out), t = static_cast<int>(row % t_out) - d.cls_offset;
+  float* dst = nullptr;
+  if (t < 0) return;                       // CLS slot: handled by the caller (gradient of the cls parameter)
+  if (t < d.L) {
+    const int32_t* trow = tokens + static_cast<size_t>(b) * d.L;
+    const int tok = trow[t];
+    if (aud_ptr != nullptr && d_audio != nullptr && tok == 5) {
+      int cnt = 0;
+      for (int base = 0; base <= t; base += 32) {
+        const int i = base + lane;
+        cnt += __popc(__ballot_sync(0xffffffffu, (i <= t) && (trow[i] == 5)));
+      }
+      const int sub = max(cnt - 1, 0) % d.audio_token_length;
+      const int ptr = max(aud_ptr[static_cast<size_t>(b) * d.L + t], 0);
+      const int ab = d.aud_div > 1 ? b / d.aud_div : b;
+      dst = d_audio + ((static_cast<size_t>(ab) * d.n_aud + ptr) * d.audio_token_length + sub) * d.H;
+    } else if (d_emb != nullptr) {
+      dst = d_emb + static_cast<size_t>(min(max(tok, 0), d.vocab - 1)) * d.H;
+    }
+  } else if (t < d.L + d.n_vis && d_vision != nullptr) {
+    const int vb = d.vis_tile > 0 ? (b / (d.vis_group * d.vis_tile)) * d.vis_group + b % d.vis_group : b;
+    dst = d_vision + (static_cast<size_t>(vb) * d.n_vis + (t - d.L)) * d.H;
+  }
+  if (dst == nullptr) return;
+  const bf16* src = dx + static_cast<size_t>(row) * d.H;
+  for (int c = lane; c < d.H; c += 32) atomicAdd(dst + c, __bfloat162float(src[c]));
+}
+
+// ---------------------------------------------------------------------------------------------
+// Attention-pool backward (flax MultiHeadDotProductAttention with one mean query per window; modeling.py:413-429,
+// :464-475).  One warp per (window, head), lane owns 2 of the 64 head dims; the softmax over <= 8 keys is recomputed.
+//   dq[w] and dkv[token] (k | v) are written by exactly one warp each; CLS rows of dkv are zeroed by window 0.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int win_token(const MrWindowDesc& d, int w, int j) {
+  if (d.mode == 0) return w * d.win + j;
+  const int w2 = d.grid_w / 2;
+  const int y = w / w2, x = w % w2;
+  return (2 * y + (j >> 1)) * d.grid_w + 2 * x + (j & 1);
+}
+
+__global__ void __launch_bounds__(kThreadsRow)
+window_attention_bwd_kernel(const bf16* __restrict__ q, const bf16* __restrict__ kv, const bf16* __restrict__ dctx,
+                            bf16* __restrict__ dq, bf16* __restrict__ dkv, MrWindowDesc d) {
+  const int nh = d.H / 64;
+  const int64_t gw = static_cast<int64_t>(blockIdx.x) * kWarps + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (gw >= static_cast<int64_t>(d.B) * d.n_win * nh) return;
+  const int h = static_cast<int>(gw % nh);
+  const int64_t bw = gw / nh;
+  const int b = static_cast<int>(bw / d.n_win), w = static_cast<int>(bw % d.n_win);
+  const uint32_t qq = reinterpret_cast<const uint32_t*>(q + static_cast<size_t>(bw) * d.H + h * 64)[lane];
+  const uint32_t gg = reinterpret_cast<const uint32_t*>(dctx + static_cast<size_t>(bw) * d.H + h * 64)[lane];
+  const float q0 = bf16_lo(qq) * 0.125f, q1 = bf16_hi(qq) * 0.125f;
+  const float g0 = bf16_lo(gg), g1 = bf16_hi(gg);
+  float sc[8], k0[8], k1[8], v0[8], v1[8], dp[8];
+  float m = -INFINITY;
+  for (int j = 0; j < d.win; ++j) {
+    const size_t row = static_cast<size_t>(b) * d.T + 1 + win_token(d, w, j);
+    const bf16* kr = kv + row * (2 * d.H) + h * 64;
+    const uint32_t kk = reinterpret_cast<const uint32_t*>(kr)[lane];
+    const uint32_t vv = reinterpret_cast<const uint32_t*>(kr + d.H)[lane];
+    k0[j] = bf16_lo(kk); k1[j] = bf16_hi(kk);
+    v0[j] = bf16_lo(vv); v1[j] = bf16_hi(vv);
+    sc[j] = wsum(q0 * k0[j] + q1 * k1[j]);
+    dp[j] = wsum(g0 * v0[j] + g1 * v1[j]);
+    m = fmaxf(m, sc[j]);
+  }
+  float l = 0.f;
+  for (int j = 0; j < d.win; ++j) {
+    sc[j] = __expf(sc[j] - m);
+    l += sc[j];
+  }
+  const float inv = 1.0f / l;
+  float dsum = 0.f;
+  for (int j = 0; j < d.win; ++j) {
+    sc[j] *= inv;                 // p_j
+    dsum += sc[j] * dp[j];
+  }
+  float dq0 = 0.f, dq1 = 0.f;
+  for (int j = 0; j < d.win; ++j) {
+    const float ds = sc[j] * (dp[j] - dsum);
+    dq0 += ds * k0[j];
+    dq1 += ds * k1[j];
+    const size_t row = static_cast<size_t>(b) * d.T + 1 + win_token(d, w, j);
+    bf16* o = dkv + row * (2 * d.H) + h * 64;
+    reinterpret_cast<uint32_t*>(o)[lane] = pack_bf16(ds * q0, ds * q1);              // dk = ds * (q / 8)
+    reinterpret_cast<uint32_t*>(o + d.H)[lane] = pack_bf16(sc[j] * g0, sc[j] * g1);  // dv = p * dctx
+  }
+  reinterpret_cast<uint32_t*>(dq + static_cast<size_t>(bw) * d.H + h * 64)[lane] = pack_bf16(dq0 * 0.125f, dq1 * 0.125f);
+  if (w == 0) {                    // CLS row of this sequence takes no part in the pool
+    bf16* o = dkv + static_cast<size_t>(b) * d.T * (2 * d.H) + h * 64;
+    reinterpret_cast<uint32_t*>(o)[lane] = 0u;
+    reinterpret_cast<uint32_t*>(o + d.H)[lane] = 0u;
+  }
+}
+
+// dx[b, 1 + tok(w, j)] += dq_in[b, w] / win  (backward of the window mean); one thread per 8 columns of a token row.
+__global__ void __launch_bounds__(256)
+window_mean_bwd_kernel(const bf16* __restrict__ dq_in, bf16* __restrict__ dx, MrWindowDesc d) {
+  const int vec_per_row = d.H / 8;
+  const int64_t total = static_cast<int64_t>(d.B) * d.n_win * d.win * vec_per_row;
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int v = static_cast<int>(i % vec_per_row);
+  int64_t r = i / vec_per_row;
+  const int j = static_cast<int>(r % d.win);
+  r /= d.win;
+  const int w = static_cast<int>(r % d.n_win), b = static_cast<int>(r / d.n_win);
+  float a[8], g[8];
+  unpack8b(__ldg(reinterpret_cast<const uint4*>(dq_in + (static_cast<size_t>(b) * d.n_win + w) * d.H) + v), g);
+  uint4* cell = reinterpret_cast<uint4*>(dx + (static_cast<size_t>(b) * d.T + 1 + win_token(d, w, j)) * d.H) + v;
+  unpack8b(*cell, a);
+  const float inv = 1.0f / static_cast<float>(d.win);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) a[k] += g[k] * inv;
+  *cell = pack8b(a);
+}
+
+// y (bf16) = a (bf16) + b (f32 or bf16): gradient accumulation of two branches.  One thread per 8 elements.
+template <bool kBF32>
+__global__ void __launch_bounds__(256)
+add_kernel(const bf16* __restrict__ a, const void* __restrict__ b_, bf16* __restrict__ y, int64_t nvec) {
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    float f[8], g[8];
+    unpack8b(__ldg(reinterpret_cast<const uint4*>(a) + i), f);
+    if (kBF32) {
+      const float4 u = __ldg(reinterpret_cast<const float4*>(b_) + 2 * i);
+      const float4 w = __ldg(reinterpret_cast<const float4*>(b_) + 2 * i + 1);
+      g[0] = u.x; g[1] = u.y; g[2] = u.z; g[3] = u.w; g[4] = w.x; g[5] = w.y; g[6] = w.z; g[7] = w.w;
+    } else {
+      unpack8b(__ldg(reinterpret_cast<const uint4*>(b_) + i), g);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) f[k] += g[k];
+    reinterpret_cast<uint4*>(y)[i] = pack8b(f);
+  }
 }
 
 }  // namespace
@@ -391,10 +569,27 @@ extern "C" int32_t mr_rotary_bwd(mr_stream_t stream_, const MrRotaryBwdDesc* d, 
   return after_launch();
 }
 
+namespace {
+struct LseBwdCarve {
+  size_t logits, dl_a, dl_b, y2, x2, total;
+};
+LseBwdCarve lse_bwd_carve(const MrContrastiveDesc* d) {
+  const size_t ld = (static_cast<size_t>(d->n_all) + 7) / 8 * 8, n = d->n, H = d->H;
+  auto al = [](size_t v) { return (v + 255) / 256 * 256; };
+  LseBwdCarve c;
+  c.logits = 0;
+  c.dl_a = c.logits + al(n * ld * sizeof(float));
+  c.dl_b = c.dl_a + al(n * 2 * ld * sizeof(bf16));
+  c.y2 = c.dl_b + al(2 * n * ld * sizeof(bf16));
+  c.x2 = c.y2 + al(2 * ld * H * sizeof(bf16));
+  c.total = c.x2 + al(2 * n * H * sizeof(bf16));
+  return c;
+}
+}  // namespace
+
 extern "C" size_t mr_contrastive_lse_bwd_workspace_bytes(const MrContrastiveDesc* d) {
-  if (!d) return 0;
-  const size_t ld = (static_cast<size_t>(d->n_all) + 7) / 8 * 8;
-  return static_cast<size_t>(d->n) * ld * (sizeof(float) + sizeof(bf16));
+  if (!d || d->n <= 0 || d->n_all <= 0 || d->H <= 0) return 0;
+  return lse_bwd_carve(d).total;
 }
 
 // One direction of the loss: dx = w (softmax(x y_all^T) y_all - y_pos'), dy_all = w (softmax^T x) with the positive
@@ -406,10 +601,23 @@ extern "C" int32_t mr_contrastive_lse_bwd(mr_stream_t stream_, const MrContrasti
   MR_REQUIRE(d->n > 0 && d->n_all > 0 && d->H > 0 && d->H % 8 == 0 && d->pos_off >= 0 && d->pos_off + d->n <= d->n_all,
              MR_ERR_BAD_SHAPE);
   MR_REQUIRE(workspace && workspace_bytes >= mr_contrastive_lse_bwd_workspace_bytes(d), MR_ERR_WORKSPACE);
+  MR_REQUIRE(aligned16(workspace), MR_ERR_MISALIGNED);
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const int ld = (d->n_all + 7) / 8 * 8;
-  float* logits = static_cast<float*>(workspace);
-  bf16* dl = reinterpret_cast<bf16*>(logits + static_cast<size_t>(d->n) * ld);
+  const LseBwdCarve c = lse_bwd_carve(d);
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  float* logits = reinterpret_cast<float*>(ws + c.logits);
+  bf16* dl_a = reinterpret_cast<bf16*>(ws + c.dl_a);
+  bf16* dl_b = reinterpret_cast<bf16*>(ws + c.dl_b);
+  bf16* y2 = reinterpret_cast<bf16*>(ws + c.y2);
+  bf16* x2 = reinterpret_cast<bf16*>(ws + c.x2);
+  const size_t ybytes = static_cast<size_t>(d->n_all) * d->H * sizeof(bf16), xbytes = static_cast<size_t>(d->n) * d->H * sizeof(bf16);
+  cudaError_t e = cudaMemsetAsync(y2, 0, static_cast<size_t>(2) * ld * d->H * sizeof(bf16), stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(y2, in[1], ybytes, cudaMemcpyDeviceToDevice, stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(y2 + static_cast<size_t>(ld) * d->H, in[1], ybytes, cudaMemcpyDeviceToDevice, stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(x2, in[0], xbytes, cudaMemcpyDeviceToDevice, stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(x2 + static_cast<size_t>(d->n) * d->H, in[0], xbytes, cudaMemcpyDeviceToDevice, stream);
+  if (e != cudaSuccess) return cuda_status(e);
   // logits = x . y_all^T (recomputed: cheaper than keeping [n, n_all] fp32 alive since the forward)
   MrGemmDesc g{};
   g.M = d->n;
@@ -425,37 +633,37 @@ extern "C" int32_t mr_contrastive_lse_bwd(mr_stream_t stream_, const MrContrasti
     if (st != MR_OK) return st;
   }
   contrastive_dlogits_kernel<<<ceil_div(d->n, kWarps), kThreadsRow, 0, stream>>>(
-      logits, static_cast<const float*>(in[2]), dl, d->n, d->n_all, ld, ld, d->pos_off, d->grad_scale);
+      logits, static_cast<const float*>(in[2]), dl_a, dl_b, d->n, d->n_all, ld, d->pos_off, d->grad_scale);
   int32_t st = after_launch();
   if (st != MR_OK) return st;
-  // dx[n, H] = dl[n, n_all] . y_all[n_all, H]            (dgrad form: B given as [K, N])
+  // dx[n, H] = (hi | lo)[n, 2 ld] . [Y; Y][2 ld, H]      (dgrad form: B given as [K, N])
   MrGemmDesc gx{};
   gx.M = d->n;
   gx.N = d->H;
-  gx.K = d->n_all;      // the < 8 padding columns of dl are beyond K: clipped by the tensor map
-  gx.lda = ld;
+  gx.K = 2 * ld;
+  gx.lda = 2 * ld;
   gx.ldd = d->H;
   gx.ldb = d->H;
   gx.trans_b = 1;
   gx.epilogue = MR_EPI_OUT_F32;
   {
-    const void* gin[7] = {dl, in[1], nullptr, nullptr, nullptr, nullptr, nullptr};
+    const void* gin[7] = {dl_a, y2, nullptr, nullptr, nullptr, nullptr, nullptr};
     void* gout[2] = {out[0], nullptr};
     st = mr_gemm_epilogue(stream_, &gx, gin, gout, nullptr, 0);
     if (st != MR_OK) return st;
   }
-  // dy_all[n_all, H] = dl^T[n_all, n] . x[n, H]            (wgrad form: both operands given as [K, *])
+  // dy_all[n_all, H] = [hi; lo]^T [n_all, 2 n] . [X; X][2 n, H]   (wgrad form: both operands given as [K, *])
   MrGemmDesc gy{};
   gy.M = d->n_all;
   gy.N = d->H;
-  gy.K = d->n;
+  gy.K = 2 * d->n;
   gy.lda = ld;
   gy.ldd = d->H;
   gy.ldb = d->H;
   gy.trans_a = 1;
   gy.trans_b = 1;
   gy.epilogue = MR_EPI_OUT_F32;
-  const void* gin[7] = {dl, in[0], nullptr, nullptr, nullptr, nullptr, nullptr};
+  const void* gin[7] = {dl_b, x2, nullptr, nullptr, nullptr, nullptr, nullptr};
   void* gout[2] = {out[1], nullptr};
   return mr_gemm_epilogue(stream_, &gy, gin, gout, nullptr, 0);
 }
@@ -478,5 +686,77 @@ extern "C" int32_t mr_unit_normalize_bwd(mr_stream_t stream_, const MrNormalizeD
     unit_normalize_bwd_kernel<false, true><<<grid, kThreadsRow, 0, stream>>>(in[0], in[1], ridx, dx, d->rows, d->H, d->scale);
   else
     unit_normalize_bwd_kernel<false, false><<<grid, kThreadsRow, 0, stream>>>(in[0], in[1], ridx, dx, d->rows, d->H, d->scale);
+  return after_launch();
+}
+
+extern "C" int32_t mr_segment_pool_bwd(mr_stream_t stream_, const MrSegmentPoolDesc* d, const void* const* in,
+                                       void* const* out, void*, size_t) {
+  MR_REQUIRE(d && in && out && in[0] && in[1] && in[2] && out[0], MR_ERR_NULL_POINTER);
+  MR_REQUIRE(d->B >= 0 && d->L > 0 && d->H > 0 && d->S > 0, MR_ERR_BAD_SHAPE);
+  if (d->B == 0) return MR_OK;
+  const int64_t warps = static_cast<int64_t>(d->B) * d->L;
+  segment_pool_bwd_kernel<<<static_cast<unsigned>(ceil_div64(warps, kWarps)), kThreadsRow, 0,
+                            static_cast<cudaStream_t>(stream_)>>>(
+      static_cast<const uint8_t*>(in[0]), static_cast<const int32_t*>(in[1]), static_cast<const float*>(in[2]),
+      static_cast<bf16*>(out[0]), *d);
+  return after_launch();
+}
+
+extern "C" int32_t mr_embed_assemble_bwd(mr_stream_t stream_, const MrAssembleDesc* d, const void* const* in,
+                                         void* const* out, void*, size_t) {
+  MR_REQUIRE(d && in && out && in[0] && in[2], MR_ERR_NULL_POINTER);
+  MR_REQUIRE(d->B >= 0 && d->L > 0 && d->H > 0 && d->T >= d->L + d->n_vis && d->vocab > 0, MR_ERR_BAD_SHAPE);
+  MR_REQUIRE(d->cls_offset == 0 || d->cls_offset == 1, MR_ERR_BAD_SHAPE);
+  if (d->B == 0) return MR_OK;
+  const int64_t rows = static_cast<int64_t>(d->B) * (d->T + d->cls_offset);
+  embed_assemble_bwd_kernel<<<static_cast<unsigned>(ceil_div64(rows, kWarps)), kThreadsRow, 0,
+                              static_cast<cudaStream_t>(stream_)>>>(
+      static_cast<const int32_t*>(in[0]), d->n_aud > 0 ? static_cast<const int32_t*>(in[1]) : nullptr,
+      static_cast<const bf16*>(in[2]), static_cast<float*>(out[0]), d->n_aud > 0 ? static_cast<float*>(out[1]) : nullptr,
+      d->n_vis > 0 ? static_cast<float*>(out[2]) : nullptr, *d);
+  return after_launch();
+}
+
+extern "C" int32_t mr_window_attention_bwd(mr_stream_t stream_, const MrWindowDesc* d, const void* const* in,
+                                           void* const* out, void*, size_t) {
+  MR_REQUIRE(d && in && out && in[0] && in[1] && in[2] && out[0] && out[1], MR_ERR_NULL_POINTER);
+  MR_REQUIRE(d->B >= 0 && d->T > 0 && d->H > 0 && d->H % 64 == 0 && d->win > 0 && d->win <= 8 && d->n_win > 0 &&
+                 (d->mode == 0 || (d->mode == 1 && d->win == 4)),
+             MR_ERR_BAD_SHAPE);
+  if (d->B == 0) return MR_OK;
+  const int64_t warps = static_cast<int64_t>(d->B) * d->n_win * (d->H / 64);
+  window_attention_bwd_kernel<<<static_cast<unsigned>(ceil_div64(warps, kWarps)), kThreadsRow, 0,
+                                static_cast<cudaStream_t>(stream_)>>>(
+      static_cast<const bf16*>(in[0]), static_cast<const bf16*>(in[1]), static_cast<const bf16*>(in[2]),
+      static_cast<bf16*>(out[0]), static_cast<bf16*>(out[1]), *d);
+  return after_launch();
+}
+
+extern "C" int32_t mr_window_mean_bwd(mr_stream_t stream_, const MrWindowDesc* d, const void* const* in, void* const* out,
+                                      void*, size_t) {
+  MR_REQUIRE(d && in && out && in[0] && out[0], MR_ERR_NULL_POINTER);
+  MR_REQUIRE(d->B >= 0 && d->T > 0 && d->H > 0 && d->H % 8 == 0 && d->win > 0 && d->n_win > 0, MR_ERR_BAD_SHAPE);
+  if (d->B == 0) return MR_OK;
+  const int64_t total = static_cast<int64_t>(d->B) * d->n_win * d->win * (d->H / 8);
+  window_mean_bwd_kernel<<<static_cast<unsigned>(ceil_div64(total, 256)), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
+      static_cast<const bf16*>(in[0]), static_cast<bf16*>(out[0]), *d);
+  return after_launch();
+}
+
+extern "C" int32_t mr_add(mr_stream_t stream_, const MrElementwiseDesc* d, const void* const* in, void* const* out, void*,
+                          size_t) {
+  MR_REQUIRE(d && in && out && in[0] && in[1] && out[0], MR_ERR_NULL_POINTER);
+  MR_REQUIRE(d->n >= 0 && d->n % 8 == 0 && (d->mode == 0 || d->mode == 1), MR_ERR_BAD_SHAPE);
+  if (d->n == 0) return MR_OK;
+  const int64_t nvec = d->n / 8;
+  int64_t blocks = ceil_div64(nvec, 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (d->mode == 1)
+    add_kernel<true><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(static_cast<const bf16*>(in[0]), in[1],
+                                                                        static_cast<bf16*>(out[0]), nvec);
+  else
+    add_kernel<false><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(static_cast<const bf16*>(in[0]), in[1],
+                                                                         static_cast<bf16*>(out[0]), nvec);
   return after_launch();
 }

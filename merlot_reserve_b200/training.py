@@ -1,0 +1,480 @@
+"""Forward + backward of the contrastive pretraining step on the B200 kernels (pretrain/pretrain_model.py:306-340).
+
+The reference gets its gradients from `jax.value_and_grad` over `MerlotReservePretrainer.__call__` +
+`loss_fn_given_preds`; here the same chain rule is written out over the C-ABI kernels: every GEMM gradient is
+`mr_gemm_epilogue` with transposed (MN-major) operands and split-K, attention uses `mr_attention_bwd`, the row ops
+have their `_bwd` entries, and the gather / pool / assembly steps scatter their gradients back with the `_bwd`
+kernels of include/mreserve_b200.h.  torch only owns memory, prepares integer indices, and runs the collectives.
+
+`PretrainStep.loss_and_grads(batch)` returns the loss, the loss_info dict and the parameter gradients as a flat
+dict keyed by the reference's flax parameter paths ('vision_encoder/transformer/layer_00/mlp_layer/out/kernel', ...),
+each in the flax layout and fp32, so that they compare one to one with `jax.grad` (tests use torch autograd over the
+CPU oracle).  Training runs the un-folded LayerNorm path (the folded weights of the inference path are functions of
+gamma / beta and would have to be re-packed every step).
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from .modeling import LTOVPOOL, MASK, MASKAUDIO, PADDING, _AUDIO_K_PAD, _PackedEncoder, _PackedPool, _dev
+from .pretrain_model import MerlotReservePretrainer, gather_contrastive_targets
+
+BF16 = torch.bfloat16
+
+
+def _split_k(rows: int) -> int:
+    """wgrad reduces over the token rows: enough K parts to occupy the SMs, at least ~2k rows per part."""
+    return int(max(1, min(16, rows // 2048)))
+
+
+def _wgrad(dy: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
+    """dW in the packed [out, in] layout = dy^T [out, rows] . x [rows, in]."""
+    return L.gemm_bwd(dy, x, trans_a=True, trans_b=True, split_k=_split_k(dy.shape[0]))
+
+
+def _dgrad(dy: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
+    """dx bf16 [rows, in] = dy [rows, out] . W [out, in] (the forward's packed weight, consumed MN-major)."""
+    return L.gemm_bwd(dy, w, trans_b=True, out_f32=False)
+
+
+class _Grads:
+    """Accumulates parameter gradients (fp32, packed layout) under flax-style path names."""
+
+    def __init__(self):
+        self.g: Dict[str, torch.Tensor] = {}
+
+    def add(self, name: str, t: torch.Tensor):
+        t = t.float() if t.dtype != torch.float32 else t
+        if name in self.g:
+            self.g[name] += t
+        else:
+            self.g[name] = t
+
+
+class PretrainStep:
+    def __init__(self, config: Dict, params: Dict):
+        self.model = MerlotReservePretrainer.from_config(config)
+        self.model.fuse_layernorm = False
+        self.model.bind(params)
+        self.params = params
+        self.cfg = self.model.config
+        self.H = self.model.hidden_size
+
+    # --------------------------------------------------------------------------------------------
+    # transformer encoder with a tape (modeling.py:283-376)
+    # --------------------------------------------------------------------------------------------
+    def _enc_fwd(self, x0: torch.Tensor, enc: _PackedEncoder, B: int, T: int, rot, valid=None, group=None):
+        H = enc.H
+        x = L.layernorm(x0, *enc.pre_ln)
+        tape = {"x0": x0, "layers": [], "B": B, "T": T, "rot": rot, "valid": valid, "group": group}
+        for lw in enc.layers:
+            h1 = L.layernorm(x, *lw["ln1"])
+            qkv = L.gemm(h1, lw["wqkv"], bias=lw["bqkv"], rot=rot, hidden=H, q_scale=0.125)
+            lse = torch.empty((B, H // 64, T), dtype=torch.float32, device=x.device)
+            ctx = L.attention(qkv, B, T, H, valid=valid, group=group, lse=lse)
+            xm = L.gemm(ctx, lw["wo"], residual=x)
+            h2 = L.layernorm(xm, *lw["ln2"])
+            up = L.gemm(h2, lw["w1"], bias=lw["b1"])
+            u = L.gelu(up)
+            xn = L.gemm(u, lw["w2"], residual=xm)
+            tape["layers"].append((x, h1, qkv, lse, ctx, xm, h2, up, u))
+            x = xn
+        return x, tape
+
+    def _enc_bwd(self, dx: torch.Tensor, tape, enc: _PackedEncoder, G: _Grads, prefix: str) -> torch.Tensor:
+        H, B, T = enc.H, tape["B"], tape["T"]
+        for i in reversed(range(len(enc.layers))):
+            lw = enc.layers[i]
+            x, h1, qkv, lse, ctx, xm, h2, up, u = tape["layers"][i]
+            p = f"{prefix}/layer_{i:02d}"
+            du = _dgrad(dx, lw["w2"])
+            G.add(f"{p}/mlp_layer/out/kernel", _wgrad(dx, u))
+            dup = L.gelu(up, du)
+            dh2 = _dgrad(dup, lw["w1"])
+            G.add(f"{p}/mlp_layer/intermediate/kernel", _wgrad(dup, h2))
+            G.add(f"{p}/mlp_layer/intermediate/bias", L.colsum(dup))
+            dxm, dg, db = L.layernorm_bwd(dh2, xm, lw["ln2"][0], dres=dx)
+            G.add(f"{p}/pre_mlp_ln/scale", dg)
+            G.add(f"{p}/pre_mlp_ln/bias", db)
+            dctx = _dgrad(dxm, lw["wo"])
+            G.add(f"{p}/attention_layer/attn_proj/kernel", _wgrad(dxm, ctx))
+            dqkv = L.attention_bwd(qkv, dctx, ctx, lse, B, T, H, valid=tape["valid"], group=tape["group"])
+            L.rotary_bwd(dqkv, tape["rot"], H)
+            dh1 = _dgrad(dqkv, lw["wqkv"])
+            G.add(f"{p}/attention_layer/qkv/kernel", _wgrad(dqkv, h1))
+            G.add(f"{p}/attention_layer/qkv/bias", L.colsum(dqkv))
+            dx, dg, db = L.layernorm_bwd(dh1, x, lw["ln1"][0], dres=dxm)
+            G.add(f"{p}/pre_attn_ln/scale", dg)
+            G.add(f"{p}/pre_attn_ln/bias", db)
+        dx0, dg, db = L.layernorm_bwd(dx, tape["x0"], enc.pre_ln[0])
+        G.add(f"{prefix}/pre_ln/scale", dg)
+        G.add(f"{prefix}/pre_ln/bias", db)
+        return dx0
+
+    # --- final_ln + cls_proj (modeling.py:366-372) ---
+    def _final_fwd(self, x_last, enc: _PackedEncoder, B, T, want_cls):
+        xf = L.layernorm(x_last, *enc.final_ln)
+        cls_rows = cls_out = None
+        if want_cls:
+            cls_rows = xf.view(B, T, enc.H)[:, 0].contiguous()
+            cls_out = L.gemm(cls_rows, enc.cls_proj[0], bias=enc.cls_proj[1])
+        return xf, cls_rows, cls_out
+
+    def _final_bwd(self, dxf, d_cls_out, x_last, cls_rows, enc, B, T, G: _Grads, prefix):
+        """dxf: gradient w.r.t. the final_ln output [B*T, H] bf16 (modified in place); d_cls_out bf16 [B, H] or None."""
+        if d_cls_out is not None:
+            G.add(f"{prefix}/cls_proj/kernel", _wgrad(d_cls_out, cls_rows))
+            G.add(f"{prefix}/cls_proj/bias", L.colsum(d_cls_out))
+            d_rows = _dgrad(d_cls_out, enc.cls_proj[0])
+            v = dxf.view(B, T, enc.H)
+            v[:, 0] = L.add(v[:, 0].contiguous(), d_rows)
+        dx_last, dg, db = L.layernorm_bwd(dxf, x_last, enc.final_ln[0])
+        G.add(f"{prefix}/final_ln/scale", dg)
+        G.add(f"{prefix}/final_ln/bias", db)
+        return dx_last
+
+    # --- attention pools (modeling.py:413-429, :464-475) ---
+    def _pool_fwd(self, xf, pool: _PackedPool, B, T, geom):
+        H = self.H
+        q_in = L.window_mean(xf, B, T, H, *geom)
+        q = L.gemm(q_in, pool.wq, bias=pool.bq)
+        kv = L.gemm(xf, pool.wkv, bias=pool.bkv)
+        ctxp = L.window_attention(q, kv, B, T, H, *geom)
+        return L.gemm(ctxp, pool.wo, bias=pool.bo), (q_in, q, kv, ctxp)
+
+    def _pool_bwd(self, d_pooled, xf, saved, pool: _PackedPool, B, T, geom, G: _Grads, prefix) -> torch.Tensor:
+        H = self.H
+        q_in, q, kv, ctxp = saved
+        G.add(f"{prefix}/out/kernel", _wgrad(d_pooled, ctxp))
+        G.add(f"{prefix}/out/bias", L.colsum(d_pooled))
+        d_ctxp = _dgrad(d_pooled, pool.wo)
+        dq, dkv = L.window_attention_bwd(q, kv, d_ctxp, B, T, H, *geom)
+        dwkv = _wgrad(dkv, xf)                       # [2H, H]: key rows then value rows
+        dbkv = L.colsum(dkv)
+        G.add(f"{prefix}/key/kernel", dwkv[:H])
+        G.add(f"{prefix}/value/kernel", dwkv[H:])
+        G.add(f"{prefix}/key/bias", dbkv[:H])
+        G.add(f"{prefix}/value/bias", dbkv[H:])
+        dxf = _dgrad(dkv, pool.wkv)
+        G.add(f"{prefix}/query/kernel", _wgrad(dq, q_in))
+        G.add(f"{prefix}/query/bias", L.colsum(dq))
+        dq_in = _dgrad(dq, pool.wq)
+        L.window_mean_bwd(dq_in, dxf, B, T, H, *geom)
+        return dxf
+
+    # --- embedding front ends ---
+    def _embed_rows_bwd(self, dx0, a, B, T, G: _Grads, prefix):
+        """Backward of `x0[:, 1:] = a . W_emb + b`, `x0[:, 0] = cls` (modeling.py:402,316-320)."""
+        H = self.H
+        v = dx0.view(B, T, H)
+        G.add(f"{prefix}/transformer/cls", v[:, 0].float().sum(0))
+        dxe = v[:, 1:].reshape(-1, H).contiguous()
+        G.add(f"{prefix}/embedding/kernel", _wgrad(dxe, a))          # [H, K (padded)]
+        G.add(f"{prefix}/embedding/bias", L.colsum(dxe))
+
+    # --------------------------------------------------------------------------------------------
+    def loss_and_grads(self, batch: Dict, group=None):
+        import torch.distributed as dist
+        m, p, H = self.model, self.model._p, self.H
+        cfg, data = self.cfg, self.cfg["data"]
+        G_, nsub = data["num_segment_groups"], data["num_audio_subsegments"]
+        Ltxt, Lseq = data["lang_seq_len"], data["seq_len"]
+        n_a2t, n_t2a = data["num_audio2text_seqs"], data["num_text2audio_seqs"]
+        gh, gw = m.output_grid_h, m.output_grid_w
+        hw, atl = gh * gw, cfg["audio_token_length"]
+        G = _Grads()
+
+        images = _dev(batch["images"], torch.float32)
+        dev = images.device
+        b, nseg_hw, pp3 = images.shape
+        nseg = nseg_hw // hw
+        per_group, n_aud = nseg // G_, nseg * nsub
+        i32 = lambda k, cols: _dev(batch[k], torch.int32).reshape(-1, cols).contiguous()
+
+        # ================================ forward ================================
+        # ---- vision (modeling.py:391-430) ----
+        Bv, Tv = b * nseg, hw + 1
+        av = L.cast_pad(images.reshape(Bv * hw, pp3), Bv * hw, pp3, pp3)
+        xv0 = torch.empty((Bv * Tv, H), dtype=BF16, device=dev)
+        L.gemm(av, p.vis_emb[0], bias=p.vis_emb[1], out=xv0, seq_in=hw, seq_out=Tv, row_off=1)
+        L.fill_cls(xv0, p.vis.cls, Bv, Tv, H)
+        xv_last, tape_v = self._enc_fwd(xv0, p.vis, Bv, Tv, m._table("vision"))
+        xvf, v_cls_rows, v_cls = self._final_fwd(xv_last, p.vis, Bv, Tv, True)
+        geom_v = (1, 4, (gh // 2) * (gw // 2), gh, gw)
+        v_pooled, v_pool_saved = self._pool_fwd(xvf, p.vis_pool, Bv, Tv, geom_v)
+        hw1 = hw // 4
+        vis_len = per_group * hw1
+        imgs_seq = v_pooled.view(b * G_, vis_len, H)
+
+        # ---- audio (modeling.py:443-476) ----
+        audio = _dev(batch["audio_clips"], torch.float32).reshape(b * n_aud, cfg["audio_seq_length"], -1)
+        Ba, na = audio.shape[0], cfg["audio_seq_length"] // cfg["audio_patch_size"]
+        Ta = na + 1
+        aa = L.cast_pad(audio.reshape(Ba * na, -1), Ba * na, cfg["audio_patch_size"] * 65, _AUDIO_K_PAD)
+        xa0 = torch.empty((Ba * Ta, H), dtype=BF16, device=dev)
+        L.gemm(aa, p.aud_emb[0], bias=p.aud_emb[1], out=xa0, seq_in=na, seq_out=Ta, row_off=1)
+        L.fill_cls(xa0, p.aud.cls, Ba, Ta, H)
+        xa_last, tape_a = self._enc_fwd(xa0, p.aud, Ba, Ta, m._table("audio"))
+        xaf, a_cls_rows, audio_cls = self._final_fwd(xa_last, p.aud, Ba, Ta, True)
+        r = m.audio_pooling_ratio
+        geom_a = (0, r, na // r, 0, 0)
+        a_pooled, a_pool_saved = self._pool_fwd(xaf, p.aud_pool, Ba, Ta, geom_a)
+        audio_seq = a_pooled.view(b, n_aud, atl, H)
+
+        # ---- joint inputs (pretrain_model.py:97-144) ----
+        tok = {k: i32(k, Ltxt) for k in ("text2audio", "text2audio/audio_ptr", "text2audio/text_ptr", "audio2text",
+                                         "audio2text/audio_ptr", "audio2text/text_ptr")}
+        tok.update({k: i32(k, Lseq) for k in ("random_text", "random_text/text_ptr", "audio_text_matching",
+                                              "audio_text_matching/audio_ptr")})
+        text_spans = i32("text_spans", cfg["text_span_length"])
+        n_spans = text_spans.shape[0] // b
+        vsi = _dev(batch["video_src_index"], torch.int64).reshape(b, G_, per_group)
+        rng = m._draw_rng(batch, b * G_ * max(n_a2t, n_t2a), per_group, b, n_spans, dev)
+        rows = {"audio2text": b * G_ * n_a2t, "audio_text_matching": b, "random_text": b, "text2audio": b * G_ * n_t2a}
+        keys = sorted(rows)
+        R = sum(rows.values())
+        xj0 = torch.empty((R * Lseq, H), dtype=BF16, device=dev)
+        rotj = torch.empty((R * Lseq, 32), dtype=torch.float32, device=dev)
+        validj = torch.empty((R * Lseq,), dtype=torch.uint8, device=dev)
+        groupj = torch.zeros((R, Lseq), dtype=torch.int32, device=dev)
+        start, r0 = {}, 0
+        for k in keys:
+            start[k] = r0
+            r0 += rows[k]
+        sl = lambda k: slice(start[k] * Lseq, (start[k] + rows[k]) * Lseq)
+        views = lambda k: (xj0[sl(k)], rotj[sl(k)], validj[sl(k)])
+        hp, wp = gh // 2, gw // 2
+        vis_seg = torch.arange(per_group, device=dev).repeat_interleave(hw1)
+
+        def video_src(seg_idx, n_seqs, split):
+            v = vsi.repeat(1, n_seqs, 1).reshape(-1, per_group)
+            v = m._augment_video_src_idx(v, split.to(torch.int64))
+            parts = [torch.gather(v, 1, seg_idx.long()), torch.gather(v, 1, vis_seg[None].expand(v.shape[0], -1))]
+            pad = Lseq - Ltxt - vis_len
+            if pad > 0:
+                parts.append(torch.full((v.shape[0], pad), -1, dtype=torch.int64, device=dev))
+            return torch.cat(parts, 1).to(torch.int32)
+
+        asm = {}          # per key: kwargs shared by the forward assembly and its backward
+        for k, n_seqs, use_audio in (("audio2text", n_a2t, True), ("text2audio", n_t2a, False)):
+            ptr = tok[k + "/audio_ptr"]
+            seg = torch.remainder(torch.div(ptr, nsub, rounding_mode="floor"), per_group).to(torch.int32).contiguous()
+            asm[k] = dict(aud_ptr=ptr if use_audio else None, n_aud=n_aud if use_audio else 0, n_vis=vis_len, T=Lseq,
+                          audio_token_length=atl, aud_div=G_ * n_seqs, vis_group=G_, vis_tile=n_seqs)
+            L.embed_assemble(tok[k], p.tok_emb, H=H, seg_idx=seg, audio=audio_seq if use_audio else None, vision=imgs_seq,
+                             pool_h=hp, pool_w=wp, out=views(k), **asm[k])
+            groupj[start[k]:start[k] + rows[k]] = video_src(seg, n_seqs, rng["_rng/split_" + k])
+        atm = tok["audio_text_matching"]
+        is_pool = atm == LTOVPOOL
+        pool_cum = torch.cumsum(is_pool.to(torch.int32), -1).to(torch.int32)
+        asm["audio_text_matching"] = dict(aud_ptr=tok["audio_text_matching/audio_ptr"], n_aud=n_aud, T=Lseq,
+                                          audio_token_length=atl)
+        L.embed_assemble(atm, p.tok_emb, H=H, seg_idx=pool_cum.contiguous(), audio=audio_seq,
+                         out=views("audio_text_matching"), **asm["audio_text_matching"])
+        asm["random_text"] = dict(T=Lseq)
+        L.embed_assemble(tok["random_text"], p.tok_emb, H=H, out=views("random_text"), **asm["random_text"])
+
+        xj_last, tape_j = self._enc_fwd(xj0, p.joint, R, Lseq, rotj, valid=validj, group=groupj.reshape(-1))
+        xjf, _, _ = self._final_fwd(xj_last, p.joint, R, Lseq, False)
+        mo_all = L.gemm(xjf, p.head[0], bias=p.head[1])                      # joint_proj on every row (:151), bf16
+        mo = {k: mo_all[sl(k)].view(rows[k], Lseq, H) for k in keys}
+
+        # ---- pools and selections (pretrain_model.py:160-233); text2audio / audio2text pool over all 640 rows of a
+        #      sequence with do_pool false beyond lang_seq_len, which equals the reference's [:, :lang_seq_len] slice ----
+        def pad_to_seq(t, fill):
+            return torch.nn.functional.pad(t, (0, Lseq - t.shape[1]), value=fill).contiguous()
+
+        pools = []        # (do_pool u8 [b, l2], idx [b, l2], key, S, which pooled gradient it receives)
+
+        def pool(do_pool, idx, k, S, acc=None, tag=None):
+            l2 = (rows[k] * Lseq) // b
+            dp = do_pool.to(torch.uint8).reshape(b, l2).contiguous()
+            ix = idx.reshape(b, l2).contiguous()
+            pools.append((dp, ix, k, S, tag))
+            return L.segment_pool(dp, ix, mo[k].reshape(b, l2, H), S, accumulate_into=acc)
+
+        a2v, _ = pool(is_pool, pool_cum - 1, "audio_text_matching", nseg, tag="a2v")
+        t2a_tok = pad_to_seq(tok["text2audio"], 0)
+        t2a_x, is_selected = pool(t2a_tok == MASKAUDIO, pad_to_seq(tok["text2audio/audio_ptr"], -1), "text2audio", n_aud,
+                                  tag="t2a")
+        n_trg = int(n_aud * data["mask_rate"]) * n_t2a
+        idx_sort = torch.sort(-is_selected, dim=-1, stable=True)[1]
+        base = (torch.arange(b, device=dev) * n_aud)[:, None]
+        best_rows = (idx_sort[:, :n_trg] + base).reshape(-1).to(torch.int32).contiguous()
+        extra_rows = (idx_sort[:, n_trg:] + base).reshape(-1).to(torch.int32).contiguous()
+        counts, sel = {}, None
+        for k in ("text2audio", "audio2text", "random_text"):
+            tk = tok[k] if tok[k].shape[1] == Lseq else pad_to_seq(tok[k], 0)
+            pk = tok[k + "/text_ptr"] if tok[k].shape[1] == Lseq else pad_to_seq(tok[k + "/text_ptr"], -1)
+            if sel is None:
+                sel = pool(tk == MASK, pk, k, n_spans, tag="t2sp")
+                counts[k] = sel[1].clone()
+            else:
+                before = sel[1].clone()
+                pool(tk == MASK, pk, k, n_spans, acc=sel, tag="t2sp")
+                counts[k] = sel[1] - before
+        t2sp_x, t2sp_ct = sel
+        src = torch.stack([torch.zeros_like(t2sp_ct), counts["text2audio"], counts["audio2text"],
+                           counts["random_text"]], -1).argmax(-1) - 1
+        is_valid = (text_spans != PADDING).any(-1).reshape(b, n_spans) & (t2sp_ct > 0)
+        logits_for_pred = is_valid.float() * 1e6 + math.log(4.0) * (counts["text2audio"] + counts["audio2text"])
+        z = -torch.log(-torch.log(rng["_rng/gumbel_u"].float()))
+        n_inc = data["num_text_spans_to_include"]
+        best = torch.sort(-(logits_for_pred + z).reshape(-1), stable=True)[1][:n_inc * b]
+        best32 = best.to(torch.int32).contiguous()
+
+        # ---- span encoder (modeling.py:488-504) on the selected spans ----
+        spans_sel = text_spans[best].contiguous()
+        Bs, Ts = spans_sel.shape[0], spans_sel.shape[1] + 1
+        xs0, _, valid_s = L.embed_assemble(spans_sel, p.tok_emb, H=H, cls_offset=1)
+        L.fill_cls(xs0, p.span.cls, Bs, Ts, H)
+        xs_last, tape_s = self._enc_fwd(xs0, p.span, Bs, Ts, m._table("span"), valid=valid_s)
+        xsf, s_cls_rows, sp_cls = self._final_fwd(xs_last, p.span, Bs, Ts, True)
+
+        # ---- heads: unit_normalize * exp(scale / 2) -> bf16 (pretrain_model.py:236-257) ----
+        ls_raw = p.contrastive_scales.astype(np.float32)
+        ls = np.minimum(ls_raw, np.float32(math.log(100.0)))
+        temp = [float(np.exp(v / 2.0)) for v in ls]
+        un = lambda v, s, idx=None: L.unit_normalize(v.reshape(-1, H), scale=s, out_f32=False, row_idx=idx)
+        heads = {                       # name -> {field: (normalised output, source tensor, row gather, temperature)}
+            "imgs_to_audio": {"x": (a2v, None), "y": (v_cls, None)},
+            "text_to_audio": {"x": (t2a_x, best_rows), "y": (audio_cls, best_rows), "y_extra": (audio_cls, extra_rows)},
+            "stuff_to_span": {"x": (t2sp_x, best32), "y": (sp_cls, None)},
+        }
+        preds = {}
+        for hi, (name, fields) in enumerate(heads.items()):
+            preds[name] = {f: un(srct, temp[hi], idx) for f, (srct, idx) in fields.items()}
+        preds["stuff_to_span"]["_sources"] = src.reshape(-1)[best].to(torch.int32).contiguous()
+
+        # ---- loss forward (pretrain_model.py:262-303) ----
+        world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+        rank = dist.get_rank(group) if world > 1 else 0
+        jobs = gather_contrastive_targets(preds, group)
+        info, lses = {}, []
+        for name, x, y_pos, y_all in jobs:
+            lse, numer = L.contrastive_lse(x, y_all, y_pos)
+            lses.append(lse)
+            red = L.contrastive_reduce(lse, numer, preds[name].get("_sources"))
+            info[name] = info.get(name, 0.0) + red[0] / 2.0
+            if "_sources" in preds[name]:
+                for i, k in enumerate(("text2audio", "audio2text", "random_text")):
+                    key = f"_{name}_from_{k}"
+                    info[key] = info.get(key, 0.0) + red[1 + i] / 2.0
+        loss = sum(v for k, v in info.items() if not k.startswith("_"))
+
+        # ================================ backward ================================
+        # ---- loss: d(preds) (fp32); the gradients w.r.t. gathered targets go back to the ranks that own the rows ----
+        dpred = {name: {f: torch.zeros(t.shape, dtype=torch.float32, device=dev) for f, t in d.items() if f != "_sources"}
+                 for name, d in preds.items()}
+        dy_alls = []
+        for (name, x, y_pos, y_all), lse in zip(jobs, lses):
+            n = x.shape[0]
+            n_own = y_all.shape[0] // world
+            dx, dy_all = L.contrastive_lse_bwd(x, y_all, lse, rank * n_own, 1.0 / (2.0 * n))
+            dy_alls.append((name, x, dx, dy_all, n_own))
+        if world > 1:
+            flat = torch.cat([d[3].reshape(-1) for d in dy_alls])
+            dist.all_reduce(flat, group=group)               # every rank contributed to every rank's targets
+            off = 0
+            new = []
+            for name, x, dx, dy_all, n_own in dy_alls:
+                new.append((name, x, dx, flat[off:off + dy_all.numel()].view_as(dy_all), n_own))
+                off += dy_all.numel()
+            dy_alls = new
+        for ji, (name, x, dx, dy_all, n_own) in enumerate(dy_alls):
+            k1, k2 = ("x", "y") if ji % 2 == 0 else ("y", "x")
+            dpred[name][k1] += dx
+            own = dy_all[rank * n_own:(rank + 1) * n_own]
+            n2 = preds[name][k2].shape[0]
+            dpred[name][k2] += own[:n2]
+            if (k2 + "_extra") in preds[name]:
+                dpred[name][k2 + "_extra"] += own[n2:]
+
+        # ---- unit_normalize backward (+ scatter through the row gathers); d(contrastive_scales) ----
+        dsrc: Dict[int, torch.Tensor] = {}
+        dscale = torch.zeros(3, dtype=torch.float32, device=dev)
+        for hi, (name, fields) in enumerate(heads.items()):
+            for f, (srct, idx) in fields.items():
+                g_out = dpred[name][f]
+                d = L.unit_normalize_bwd(srct.reshape(-1, H), g_out, scale=temp[hi], row_idx=idx)
+                key = id(srct)
+                dsrc[key] = dsrc[key] + d if key in dsrc else d
+                # y = exp(s / 2) * unit(x):  dL/ds = 0.5 * sum(dy * y), zero where the clip at log(100) is active
+                if ls_raw[hi] <= math.log(100.0):
+                    dscale[hi] += 0.5 * (g_out * preds[name][f].float()).sum()
+        G.add("contrastive_scales", dscale)
+        d_a2v, d_vcls, d_t2ax = dsrc[id(a2v)], dsrc[id(v_cls)], dsrc[id(t2a_x)]
+        d_acls, d_t2sp, d_spcls = dsrc[id(audio_cls)], dsrc[id(t2sp_x)], dsrc[id(sp_cls)]
+
+        # ---- span encoder ----
+        dxsf = torch.zeros_like(xsf)
+        dxs_last = self._final_bwd(dxsf, d_spcls.to(BF16), xs_last, s_cls_rows, p.span, Bs, Ts, G, "span_encoder/transformer")
+        dxs0 = self._enc_bwd(dxs_last, tape_s, p.span, G, "span_encoder/transformer")
+        G.add("span_encoder/transformer/cls", dxs0.view(Bs, Ts, H)[:, 0].float().sum(0))
+        d_tok_emb = torch.zeros(p.tok_emb.shape, dtype=torch.float32, device=dev)
+        L.embed_assemble_bwd(spans_sel, dxs0, H=H, vocab=p.tok_emb.shape[0], d_emb=d_tok_emb, cls_offset=1)
+
+        # ---- pools -> joint_proj -> joint transformer ----
+        dmo_all = torch.zeros_like(mo_all)
+        dpooled = {"a2v": d_a2v.view(b, nseg, H), "t2a": d_t2ax.view(b, n_aud, H), "t2sp": d_t2sp.view(b, n_spans, H)}
+        for dp, ix, k, S, tag in pools:
+            l2 = dp.shape[1]
+            dv = L.segment_pool_bwd(dp, ix, dpooled[tag].contiguous(), l2).view(-1, H)
+            L.add(dmo_all[sl(k)], dv, out=dmo_all[sl(k)])
+        G.add("head/kernel", _wgrad(dmo_all, xjf))
+        G.add("head/bias", L.colsum(dmo_all))
+        dxjf = _dgrad(dmo_all, p.head[0])
+        dxj_last = self._final_bwd(dxjf, None, xj_last, None, p.joint, R, Lseq, G, "joint_transformer")
+        dxj0 = self._enc_bwd(dxj_last, tape_j, p.joint, G, "joint_transformer")
+        d_audio_seq = torch.zeros(audio_seq.shape, dtype=torch.float32, device=dev)
+        d_imgs_seq = torch.zeros(imgs_seq.shape, dtype=torch.float32, device=dev)
+        for k in keys:
+            kw = asm[k]
+            L.embed_assemble_bwd(tok[k], dxj0[sl(k)], H=H, vocab=p.tok_emb.shape[0], d_emb=d_tok_emb,
+                                 d_audio=d_audio_seq if kw.get("n_aud", 0) else None,
+                                 d_vision=d_imgs_seq if kw.get("n_vis", 0) else None, **kw)
+        G.add("token_encoder/Embed_0/embedding", d_tok_emb)
+
+        # ---- audio encoder ----
+        dxaf = self._pool_bwd(d_audio_seq.view(-1, H).to(BF16), xaf, a_pool_saved, p.aud_pool, Ba, Ta, geom_a, G,
+                              "audio_encoder/seq_attnpool")
+        dxa_last = self._final_bwd(dxaf, d_acls.to(BF16), xa_last, a_cls_rows, p.aud, Ba, Ta, G, "audio_encoder/transformer")
+        dxa0 = self._enc_bwd(dxa_last, tape_a, p.aud, G, "audio_encoder/transformer")
+        self._embed_rows_bwd(dxa0, aa, Ba, Ta, G, "audio_encoder")
+
+        # ---- vision encoder ----
+        dxvf = self._pool_bwd(d_imgs_seq.view(-1, H).to(BF16), xvf, v_pool_saved, p.vis_pool, Bv, Tv, geom_v, G,
+                              "vision_encoder/seq_attnpool")
+        dxv_last = self._final_bwd(dxvf, d_vcls.to(BF16), xv_last, v_cls_rows, p.vis, Bv, Tv, G, "vision_encoder/transformer")
+        dxv0 = self._enc_bwd(dxv_last, tape_v, p.vis, G, "vision_encoder/transformer")
+        self._embed_rows_bwd(dxv0, av, Bv, Tv, G, "vision_encoder")
+        if getattr(self, "_keep_locals", False):
+            self._dbg = dict(locals())
+        return loss, info, G.g
+
+    # --------------------------------------------------------------------------------------------
+    def grads_to_flax(self, g: Dict[str, torch.Tensor]) -> Dict[str, np.ndarray]:
+        """Packed-layout gradients -> the flax shapes of the reference's parameter tree (numpy, fp32)."""
+        out = {}
+        H = self.H
+
+        def shape_of(path):
+            node = self.params
+            for part in path.split("/"):
+                node = node[part]
+            return np.asarray(node).shape
+
+        for name, t in g.items():
+            shp = shape_of(name)
+            t = t.detach().float()
+            if name.endswith("kernel"):
+                t = t.t()                                    # packed [out, in] -> flax [in, out]
+                if name == "audio_encoder/embedding/kernel":
+                    t = t[: shp[0] * shp[1]]                 # drop the K padding rows
+            out[name] = t.reshape(shp).cpu().numpy()
+        return out

@@ -238,3 +238,69 @@ def test_transformer_layer_backward_composition(cuda, lib):
     chk(dbe2, P["pre_mlp_ln"]["bias"].grad, "dbeta2")
     chk(dg1, P["pre_attn_ln"]["scale"].grad, "dgamma1")
     chk(dbe1, P["pre_attn_ln"]["bias"].grad, "dbeta1")
+
+
+def test_glue_backward_kernels(cuda, lib):
+    """segment_pool / embed_assemble / attention-pool backward against torch autograd of the same gather-scatter ops."""
+    g = torch.Generator().manual_seed(21)
+    # one_hot_pool backward
+    B, Lq, H, S = 3, 40, 64, 6
+    dp = (torch.rand(B, Lq, generator=g) > 0.5)
+    ix = torch.randint(-1, S + 1, (B, Lq), generator=g).to(torch.int32)
+    dpooled = torch.randn(B, S, H, generator=g)
+    v = torch.randn(B, Lq, H, generator=g).requires_grad_(True)
+    oh = ((ix[..., None] == torch.arange(S)) & dp[..., None]).float()
+    torch.einsum("bls,blh->bsh", oh, v).backward(dpooled)
+    got = lib.segment_pool_bwd(dp.to(torch.uint8).to(cuda), ix.to(cuda), dpooled.to(cuda), Lq)
+    _close(got, v.grad, 1e-2, 1e-2, "segment_pool bwd")
+
+    # attention pool backward (2x2 windows, mode 1) vs autograd of the flax-MHA restatement
+    Bp, gh, gw, Hp = 2, 4, 6, 128
+    T, nw, nh = gh * gw + 1, (gh // 2) * (gw // 2), Hp // 64
+    q = _bf(torch.randn(Bp * nw, Hp, generator=g))
+    kv = _bf(torch.randn(Bp * T, 2 * Hp, generator=g))
+    dctx = _bf(torch.randn(Bp * nw, Hp, generator=g))
+    qr, kvr = q.float().requires_grad_(True), kv.float().requires_grad_(True)
+    idx = torch.tensor([[1 + (2 * (w // (gw // 2)) + (j >> 1)) * gw + 2 * (w % (gw // 2)) + (j & 1) for j in range(4)]
+                        for w in range(nw)])
+    kvw = kvr.view(Bp, T, 2, nh, 64)[:, idx]                               # [B, nw, 4, 2, nh, 64]
+    sc = torch.einsum("bwhd,bwjhd->bwhj", qr.view(Bp, nw, nh, 64) / 8.0, kvw[:, :, :, 0])
+    ctx = torch.einsum("bwhj,bwjhd->bwhd", torch.softmax(sc, -1), kvw[:, :, :, 1]).reshape(Bp * nw, Hp)
+    ctx.backward(dctx.float())
+    dq, dkv = lib.window_attention_bwd(q.to(cuda), kv.to(cuda), dctx.to(cuda), Bp, T, Hp, 1, 4, nw, gh, gw)
+    _close(dq, qr.grad, 2e-2, 2e-2, "pool dq")
+    _close(dkv, kvr.grad, 2e-2, 2e-2, "pool dkv")
+    # window mean backward
+    dq_in = _bf(torch.randn(Bp * nw, Hp, generator=g))
+    dx = _bf(torch.randn(Bp * T, Hp, generator=g))
+    ref = dx.float().view(Bp, T, Hp).clone()
+    ref[:, idx.reshape(-1)] += (dq_in.float().view(Bp, nw, 1, Hp) / 4).expand(-1, -1, 4, -1).reshape(Bp, nw * 4, Hp)
+    got = dx.to(cuda).clone()
+    lib.window_mean_bwd(dq_in.to(cuda), got, Bp, T, Hp, 1, 4, nw, gh, gw)
+    _close(got, ref.view(-1, Hp), 2e-2, 1e-2, "window mean bwd")
+
+    # joint assembly backward: rows scatter to the embedding table / audio spans / (shared) vision rows
+    Hh, Ltok, n_vis, n_aud, vocab = 64, 8, 6, 4, 50
+    Bv, G, tile = 2, 2, 3
+    R = Bv * G * tile
+    toks = torch.randint(6, vocab, (R, Ltok), generator=g).to(torch.int32)
+    toks[:, 2:5] = 5
+    ptr = torch.randint(0, n_aud, (R, Ltok), generator=g).to(torch.int32)
+    dxj = _bf(torch.randn(R, Ltok + n_vis, Hh, generator=g))
+    d_emb = torch.zeros(vocab, Hh, device=cuda)
+    d_aud = torch.zeros(Bv, n_aud, 6, Hh, device=cuda)
+    d_vis = torch.zeros(Bv * G, n_vis, Hh, device=cuda)
+    lib.embed_assemble_bwd(toks.to(cuda), dxj.to(cuda).view(-1, Hh), H=Hh, vocab=vocab, d_emb=d_emb, aud_ptr=ptr.to(cuda),
+                           d_audio=d_aud, d_vision=d_vis, n_aud=n_aud, n_vis=n_vis, T=Ltok + n_vis, aud_div=G * tile,
+                           vis_group=G, vis_tile=tile)
+    r_emb, r_aud, r_vis = torch.zeros(vocab, Hh), torch.zeros(Bv, n_aud, 6, Hh), torch.zeros(Bv * G, n_vis, Hh)
+    for r in range(R):
+        for t in range(Ltok):
+            if toks[r, t] == 5:
+                r_aud[r // (G * tile), ptr[r, t], t - 2] += dxj[r, t].float()
+            else:
+                r_emb[toks[r, t]] += dxj[r, t].float()
+        r_vis[(r // (G * tile)) * G + r % G] += dxj[r, Ltok:].float()
+    _close(d_emb, r_emb, 1e-5, 1e-5, "d_emb")
+    _close(d_aud, r_aud, 1e-5, 1e-5, "d_audio")
+    _close(d_vis, r_vis, 1e-5, 1e-5, "d_vision")

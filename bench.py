@@ -278,6 +278,26 @@ def build_workload(args, rank, dev):
                           f"per GPU (16 frames {gh}x{gw}, 48 audio sub-segments, 6 joint sequences x 640), targets "
                           f"all-gathered over the ranks",
                  extra={"examples_per_gpu": b})
+    elif args.workload == "pretrain_step":
+        from merlot_reserve_b200.training import PretrainStep
+        b = args.clips
+        stepper = PretrainStep(cfg, params)
+        host = pin(synthetic_pretrain_batch(cfg, b, seed=1 + 1000 * rank))
+        resident = {k: v.to(dev) for k, v in host.items()}
+        out_host = torch.empty((1,), dtype=torch.float32).pin_memory()
+
+        def step_e2e():
+            loss, _ = stepper.train_step({k: v.to(dev, non_blocking=True) for k, v in host.items()})
+            out_host.copy_(loss.reshape(1), non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+
+        w.update(step=lambda: stepper.train_step(resident), step_e2e=step_e2e, units=b, flops=3.0 * flops_pretrain_example(cfg) * b,
+                 h2d=sum(v.numel() * v.element_size() for v in host.values()), d2h=4,
+                 metric="examples/sec (train step: forward + backward + all-reduce + AdamW)", unit="examples/s",
+                 workload=f"reserve-{args.config} contrastive pretraining train_step (pretrain_model.py:306-340): {b} examples "
+                          f"per GPU (16 frames {gh}x{gw}, 48 audio sub-segments, 6 joint sequences x 640), targets "
+                          f"all-gathered and gradients all-reduced (bf16) over the ranks, fp32-moment AdamW",
+                 extra={"examples_per_gpu": b})
     else:
         raise ValueError(args.workload)
     return w
@@ -414,14 +434,14 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="base", choices=["base", "large"])
     ap.add_argument("--clips", type=int, default=None, help="clips / examples per GPU and step")
-    ap.add_argument("--workload", default="embed_video", choices=["embed_video", "mc_scoring", "pretrain_fwd"],
+    ap.add_argument("--workload", default="embed_video", choices=["embed_video", "mc_scoring", "pretrain_fwd", "pretrain_step"],
                     help="embed_video = BASELINE configs[1] (default) / [3] with --config large --grid 18 32; "
                          "mc_scoring = configs[4]; pretrain_fwd = the forward half of configs[2]")
     ap.add_argument("--grid", type=int, nargs=2, default=None, help="output_grid override, e.g. 18 32")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.clips is None:
-        args.clips = {"embed_video": 64 if args.config == "base" else 16, "mc_scoring": 128, "pretrain_fwd": 8}[args.workload]
+        args.clips = {"embed_video": 64 if args.config == "base" else 16, "mc_scoring": 128, "pretrain_fwd": 8, "pretrain_step": 8}[args.workload]
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -432,6 +432,19 @@ int32_t mr_window_mean_bwd(mr_stream_t stream, const MrWindowDesc* d, const void
 int32_t mr_add(mr_stream_t stream, const MrElementwiseDesc* d, const void* const* in, void* const* out, void* workspace,
                size_t workspace_bytes);
 
+/* mr_adamw: the parameter update of train_step (pretrain_model.py:340 `apply_gradients`; optimizer of
+ * pretrain/optimization.py:158-195 = Adam moments, decoupled weight decay on ndim > 1 parameters, schedule * lr),
+ * with fp32 moments (the reference's bf16-compressed moments, optimization.py:36-51, are a "next" row).
+ *   in[0] g f32 [n]; out[0] p f32 [n] (master, updated in place); out[1] m, out[2] v f32 [n];
+ *   out[3] w bf16 [n] optional working copy (same layout as the master) refreshed from the new p. */
+typedef struct MrAdamWDesc {
+  int64_t n;
+  float lr, beta1, beta2, eps, weight_decay;
+  float grad_scale; /* e.g. 1 / world_size after a SUM all-reduce */
+} MrAdamWDesc;
+int32_t mr_adamw(mr_stream_t stream, const MrAdamWDesc* d, const void* const* in, void* const* out, void* workspace,
+                 size_t workspace_bytes);
+
 /* ------------------------------------------------------------------------------------------
  * mr_row_dot: logits[r] = x[r] . w  (finetune `proj` head H -> 1, no bias;
  * finetune/vcr/qa_qar_joint_finetune.py:163-170), with an optional row gather.

@@ -91,6 +91,11 @@ class ColsumDesc(C.Structure):
     _fields_ = [("rows", C.c_int32), ("cols", C.c_int32), ("ld", C.c_int32)]
 
 
+class AdamWDesc(C.Structure):
+    _fields_ = [("n", C.c_int64), ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
+                ("weight_decay", C.c_float), ("grad_scale", C.c_float)]
+
+
 class RotaryBwdDesc(C.Structure):
     _fields_ = [("rows", C.c_int64), ("hidden", C.c_int32), ("rot_rows", C.c_int32), ("q_scale", C.c_float)]
 
@@ -128,6 +133,7 @@ ENTRY_POINTS = {
     "mr_window_attention_bwd": WindowDesc,
     "mr_window_mean_bwd": WindowDesc,
     "mr_add": ElementwiseDesc,
+    "mr_adamw": AdamWDesc,
 }
 WORKSPACE_FNS = {
     "mr_gemm_epilogue_workspace_bytes": GemmDesc,
@@ -145,7 +151,7 @@ MISC_FNS = ["mr_check_device", "mr_abi_version", "mr_status_string", "mr_launch_
 import os as _os
 GEMM_PAIR_DEFAULT = int(_os.environ.get("MR_GEMM_PAIR", "0"))
 
-ABI_VERSION = 9  # must equal mr_abi_version() of the loaded library (struct layouts above)
+ABI_VERSION = 10  # must equal mr_abi_version() of the loaded library (struct layouts above)
 
 _lib = None
 
@@ -558,3 +564,8 @@ def add(a: torch.Tensor, b: torch.Tensor, out=None) -> torch.Tensor:
     out = torch.empty_like(a) if out is None else out
     _call("mr_add", ElementwiseDesc(n=a.numel(), mode=int(b.dtype == torch.float32)), [a, b], [out])
     return out
+
+
+def adamw(g, p, m, v, w=None, *, lr, beta1=0.9, beta2=0.98, eps=1e-6, weight_decay=0.0, grad_scale=1.0) -> None:
+    d = AdamWDesc(n=p.numel(), lr=lr, beta1=beta1, beta2=beta2, eps=eps, weight_decay=weight_decay, grad_scale=grad_scale)
+    _call("mr_adamw", d, [g], [p, m, v, w])

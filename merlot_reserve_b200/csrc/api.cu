@@ -50,7 +50,7 @@ bool make_tmap_2d(CUtensorMap* m, const void* base, int64_t rows, int cols, int6
 
 }  // namespace mr
 
-extern "C" int32_t mr_abi_version(void) { return 9; }
+extern "C" int32_t mr_abi_version(void) { return 10; }
 
 extern "C" int64_t mr_launch_count(void) { return mr::g_launches.load(std::memory_order_relaxed); }
 

@@ -478,6 +478,31 @@ add_kernel(const bf16* __restrict__ a, const void* __restrict__ b_, bf16* __rest
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// AdamW step of pretrain/optimization.py:54-114,158-195 with fp32 moments: g' = nan_to_num(g) * grad_scale;
+// m = b1 m + (1 - b1) g'; v = b2 v + (1 - b2) g'^2; p -= lr (m / (sqrt(v) + eps) + wd p)  (no bias correction, the
+// reference's default); optionally refreshes the bf16 working copy the GEMMs read.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+adamw_kernel(const float* __restrict__ g, float* __restrict__ p, float* __restrict__ m, float* __restrict__ v,
+             bf16* __restrict__ w, MrAdamWDesc d) {
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < d.n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    float gi = g[i];
+    if (gi != gi) gi = 0.f;                                   // nan_to_num (pretrain_model.py:327)
+    gi = fminf(fmaxf(gi, -3.4028235e38f), 3.4028235e38f) * d.grad_scale;
+    const float mi = d.beta1 * m[i] + (1.0f - d.beta1) * gi;
+    const float vi = d.beta2 * v[i] + (1.0f - d.beta2) * gi * gi;
+    float pi = p[i];
+    pi -= d.lr * (mi / (sqrtf(vi) + d.eps) + d.weight_decay * pi);
+    m[i] = mi;
+    v[i] = vi;
+    p[i] = pi;
+    if (w != nullptr) w[i] = __float2bfloat16(pi);
+  }
+}
+
 }  // namespace
 }  // namespace mr
 
@@ -758,5 +783,18 @@ extern "C" int32_t mr_add(mr_stream_t stream_, const MrElementwiseDesc* d, const
   else
     add_kernel<false><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(static_cast<const bf16*>(in[0]), in[1],
                                                                          static_cast<bf16*>(out[0]), nvec);
+  return after_launch();
+}
+
+extern "C" int32_t mr_adamw(mr_stream_t stream_, const MrAdamWDesc* d, const void* const* in, void* const* out, void*,
+                            size_t) {
+  MR_REQUIRE(d && in && out && in[0] && out[0] && out[1] && out[2], MR_ERR_NULL_POINTER);
+  MR_REQUIRE(d->n >= 0, MR_ERR_BAD_SHAPE);
+  if (d->n == 0) return MR_OK;
+  int64_t blocks = ceil_div64(d->n, 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  adamw_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
+      static_cast<const float*>(in[0]), static_cast<float*>(out[0]), static_cast<float*>(out[1]),
+      static_cast<float*>(out[2]), static_cast<bf16*>(out[3]), *d);
   return after_launch();
 }

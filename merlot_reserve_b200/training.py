@@ -64,6 +64,98 @@ class PretrainStep:
         self.params = params
         self.cfg = self.model.config
         self.H = self.model.hidden_size
+        self._state = None
+
+    # --------------------------------------------------------------------------------------------
+    # train_step (pretrain_model.py:306-340): grads -> nan_to_num -> mean over the data-parallel ranks (bf16, as the
+    # reference's pmean) -> AdamW (pretrain/optimization.py:158-195) on fp32 masters -> refreshed bf16 weights
+    # --------------------------------------------------------------------------------------------
+    def _registry(self) -> Dict[str, Tuple[torch.Tensor, bool]]:
+        """flax parameter path -> (device tensor the kernels read, decays?).  bf16 tensors get an fp32 master."""
+        p, H = self.model._p, self.H
+        reg: Dict[str, Tuple[torch.Tensor, bool]] = {}
+        for prefix, enc in (("vision_encoder/transformer", p.vis), ("audio_encoder/transformer", p.aud),
+                            ("span_encoder/transformer", p.span), ("joint_transformer", p.joint)):
+            reg[f"{prefix}/pre_ln/scale"], reg[f"{prefix}/pre_ln/bias"] = (enc.pre_ln[0], False), (enc.pre_ln[1], False)
+            reg[f"{prefix}/final_ln/scale"], reg[f"{prefix}/final_ln/bias"] = (enc.final_ln[0], False), (enc.final_ln[1], False)
+            if enc.add_cls:
+                reg[f"{prefix}/cls"] = (enc.cls, False)
+                reg[f"{prefix}/cls_proj/kernel"], reg[f"{prefix}/cls_proj/bias"] = (enc.cls_proj[0], True), (enc.cls_proj[1], False)
+            for i, lw in enumerate(enc.layers):
+                q = f"{prefix}/layer_{i:02d}"
+                reg[f"{q}/pre_attn_ln/scale"], reg[f"{q}/pre_attn_ln/bias"] = (lw["ln1"][0], False), (lw["ln1"][1], False)
+                reg[f"{q}/pre_mlp_ln/scale"], reg[f"{q}/pre_mlp_ln/bias"] = (lw["ln2"][0], False), (lw["ln2"][1], False)
+                reg[f"{q}/attention_layer/qkv/kernel"], reg[f"{q}/attention_layer/qkv/bias"] = (lw["wqkv"], True), (lw["bqkv"], True)
+                reg[f"{q}/attention_layer/attn_proj/kernel"] = (lw["wo"], True)
+                reg[f"{q}/mlp_layer/intermediate/kernel"], reg[f"{q}/mlp_layer/intermediate/bias"] = (lw["w1"], True), (lw["b1"], False)
+                reg[f"{q}/mlp_layer/out/kernel"] = (lw["w2"], True)
+        for prefix, pool in (("vision_encoder/seq_attnpool", p.vis_pool), ("audio_encoder/seq_attnpool", p.aud_pool)):
+            reg[f"{prefix}/query/kernel"], reg[f"{prefix}/query/bias"] = (pool.wq, True), (pool.bq, True)
+            reg[f"{prefix}/key/kernel"], reg[f"{prefix}/value/kernel"] = (pool.wkv[:H], True), (pool.wkv[H:], True)
+            reg[f"{prefix}/key/bias"], reg[f"{prefix}/value/bias"] = (pool.bkv[:H], True), (pool.bkv[H:], True)
+            reg[f"{prefix}/out/kernel"], reg[f"{prefix}/out/bias"] = (pool.wo, True), (pool.bo, False)
+        reg["vision_encoder/embedding/kernel"], reg["vision_encoder/embedding/bias"] = (p.vis_emb[0], True), (p.vis_emb[1], False)
+        reg["audio_encoder/embedding/kernel"], reg["audio_encoder/embedding/bias"] = (p.aud_emb[0], True), (p.aud_emb[1], False)
+        reg["token_encoder/Embed_0/embedding"] = (p.tok_emb, True)
+        reg["head/kernel"], reg["head/bias"] = (p.head[0], True), (p.head[1], False)
+        return reg
+
+    def _init_state(self):
+        # decay mask = flax ndim > 1 (optimization.py:182-184): the qkv / pool biases are [heads, 64] in flax
+        st = {}
+        for name, (t, decay) in self._registry().items():
+            master = t if t.dtype == torch.float32 else t.float()
+            st[name] = {"w": t if t.dtype != torch.float32 else None, "p": master,
+                        "m": torch.zeros_like(master), "v": torch.zeros_like(master), "decay": decay}
+        self._state = st
+        self._scale_state = {"m": np.zeros(3, np.float32), "v": np.zeros(3, np.float32)}
+        self.step_count = 0
+
+    def lr_scale(self, step: int, opt: Dict) -> float:
+        """lr_scale_linearwarmup_cosinedecay (optimization.py:117-137)."""
+        nw, nt, final = opt["num_warmup_steps"], opt["num_train_steps"], opt.get("final_lr_scale", 0.02)
+        if step < nw:
+            return step / nw
+        s = min((step - nw) / (nt - nw + 1.0), 1.0)
+        return final + (1.0 - final) * (1.0 - (1.0 - math.cos(math.pi * s)) / 2.0)
+
+    def train_step(self, batch: Dict, opt: Optional[Dict] = None, group=None):
+        """One optimisation step; returns (loss, loss_info) of this rank (0-d CUDA tensors)."""
+        import torch.distributed as dist
+        opt = opt or {"learning_rate": 4e-4, "num_train_steps": 750000, "num_warmup_steps": 3750, "weight_decay_rate": 0.1,
+                      "beta_2": 0.98, "eps": 1e-6}
+        if self._state is None:
+            self._init_state()
+        loss, info, grads = self.loss_and_grads(batch, group=group)
+        world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+        names = sorted(grads)
+        if world > 1:
+            # gradient all-reduce in bf16, one flat bucket (pretrain_model.py:323-333 casts to bf16 before the pmean)
+            flat = torch.cat([grads[n].reshape(-1) for n in names]).to(BF16)
+            dist.all_reduce(flat, group=group)
+            flat = flat.float()
+            off = 0
+            for n in names:
+                k = grads[n].numel()
+                grads[n] = flat[off:off + k].view(grads[n].shape)
+                off += k
+        lr = opt["learning_rate"] * self.lr_scale(self.step_count, opt)
+        b1, b2, eps, wd = opt.get("beta_1", 0.9), opt.get("beta_2", 0.98), opt.get("eps", 1e-8), opt["weight_decay_rate"]
+        for n in names:
+            if n == "contrastive_scales":
+                continue
+            st = self._state[n]
+            g = grads[n].reshape(st["p"].shape)
+            L.adamw(g.contiguous() if not g.is_contiguous() else g, st["p"], st["m"], st["v"], st["w"], lr=lr, beta1=b1,
+                    beta2=b2, eps=eps, weight_decay=wd if st["decay"] else 0.0, grad_scale=1.0 / world)
+        # the three temperatures live on the host (they parameterise kernel launches)
+        gs = np.nan_to_num(grads["contrastive_scales"].cpu().numpy().astype(np.float32)) / world
+        ss, p = self._scale_state, self.model._p
+        ss["m"] = b1 * ss["m"] + (1 - b1) * gs
+        ss["v"] = b2 * ss["v"] + (1 - b2) * gs * gs
+        p.contrastive_scales = (p.contrastive_scales - lr * ss["m"] / (np.sqrt(ss["v"]) + eps)).astype(np.float32)
+        self.step_count += 1
+        return loss, info
 
     # --------------------------------------------------------------------------------------------
     # transformer encoder with a tape (modeling.py:283-376)

@@ -194,6 +194,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   const int tile_begin = contiguous ? worker * tiles_per_cta : worker;
   const int tile_end = contiguous ? min(tile_begin + tiles_per_cta, p.num_tiles) : p.num_tiles;
 
+  // Register re-distribution (staged path): the producer / MMA warpgroup runs single-thread loops, the two epilogue
+  // warpgroups hold 64 accumulator values plus the hoisted per-column vectors per thread.  64 + 2 x 216 registers
+  // per thread-slot fit the 64 K file of the CTA's launch allocation (384 x 168).
+  // (setmaxnreg must dominate the role code it applies to, hence the nesting below.)
+  if (warp_idx < 4) {
+  if constexpr (!kDirect) setmaxnreg_dec<64>();
   if (warp_idx == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
@@ -287,7 +293,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         }
       }
     }
-  } else if (warp_idx >= 4) {
+  }
+  } else {
+    if constexpr (!kDirect) setmaxnreg_inc<216>();
     // ===================== epilogue =====================
     const int ew = warp_idx - 4;
     const int quarter = warp_idx & 3;          // TMEM lane quarter this warp may access

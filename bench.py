@@ -173,23 +173,41 @@ def cpu_oracle_segments_per_s(cfg, params, steps: int, warmup: int, nseg_sample:
     return nseg_sample / dt, dt, torch.get_num_threads()
 
 
+def workload_config(args, world: int):
+    """The `config` object of the JSON line (shared by both arms so that the driver compares like with like)."""
+    from merlot_reserve_b200.synthetic import load_config
+    cfg = load_config(args.config, tuple(args.grid) if args.grid else None)
+    gh, gw = cfg["model"]["output_grid"]
+    B = args.clips
+    return {"workload": f"reserve-{args.config} zero-shot embed_video (vision+audio+joint encoders, head, "
+                        f"unit_normalize), {B} clips x 16 segments ({gh}x{gw} patches) + 48 audio sub-segments, "
+                        f"L=160, per GPU",
+            "clips_per_gpu": B, "segments_per_step_per_gpu": B * NSEG, "parallelism": f"replicas x{world}",
+            "l2": "inputs and activations of a step exceed the 126 MB L2 many times over (fp32 patches "
+                  "alone are 755 MB at 64 Base clips)"}
+
+
 def run_reference(args):
+    """Reference arm: the reference's own implementation of the path cannot be installed here (jax / flax absent, no
+    setup.py), so this times the CPU oracle port of it on all host cores, on a bounded sample (1 clip per step) of
+    the same workload.  Rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    if args.workload != "embed_video":
+        print(json.dumps({"impl": "reference", "unavailable": "the CPU reference arm covers the embed_video workload"}))
+        return
     from merlot_reserve_b200.synthetic import load_config, synthetic_params
-    cfg = load_config(args.config)
+    cfg = load_config(args.config, tuple(args.grid) if args.grid else None)
     params = synthetic_params(cfg, seed=0)
     steps, warmup = min(args.steps, 5), min(args.warmup, 1)
     val, dt, cores = cpu_oracle_segments_per_s(cfg, params, steps, warmup, NSEG)
     sample = (f"CPU oracle (torch fp32 restatement of the reference; jax/flax not installable here): "
-              f"embed_video on 1 clip x {NSEG} segments per step, {steps} steps")
+              f"embed_video on 1 clip x {NSEG} segments per step (of the {args.clips} clips of the workload), {steps} steps")
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"reserve-{args.config} embed_video (vision+audio+joint), 16-segment clips, 12x20 patches, L=160",
-                   "clips_per_step": 1},
+        "dtype": "f32", "data": "synthetic", "config": workload_config(args, int(os.environ.get("WORLD_SIZE", "1"))),
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -408,9 +426,9 @@ def run_b200(args):
             "metric": w["metric"], "value": value, "unit": w["unit"], "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": w["workload"], **w["extra"], "parallelism": f"replicas x{world}",
-                       "l2": "inputs and activations of a step exceed the 126 MB L2 many times over (fp32 patches "
-                             "alone are 755 MB at 64 Base clips)"},
+            "config": workload_config(args, world) if args.workload == "embed_video" else
+                      {"workload": w["workload"], **w["extra"], "parallelism": f"replicas x{world}",
+                       "l2": "inputs and activations of a step exceed the 126 MB L2 many times over"},
             "clocks": clk.summary(),
             "e2e": {"value": e2e_value, "unit": w["unit"], "ms_per_step": e2e_ms, "h2d_bytes_per_step": w["h2d"],
                     "d2h_bytes_per_step": w["d2h"]},

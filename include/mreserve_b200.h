@@ -46,6 +46,9 @@ int32_t mr_abi_version(void);
 const char* mr_status_string(int32_t status);
 /* Number of kernels this library has launched since load (per process, all threads). */
 int64_t mr_launch_count(void);
+/* Diagnostics (not part of the reference-facing path): device buffer of 2*64*8 int64 that receives clock64()
+ * stamps of the softmax phases of CTA 0 in every following tcgen05 attention launch; NULL switches it off. */
+int32_t mr_debug_attention_trace(void* device_buffer);
 
 /* ------------------------------------------------------------------------------------------
  * mr_gemm_epilogue: D = epilogue(A . W^T)      [tcgen05 tensor cores, TMEM accumulators, TMA]

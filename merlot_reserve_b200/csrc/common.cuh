@@ -36,6 +36,12 @@ int device_sm_count();
 // 128-byte swizzle (box_cols * 2 bytes must be 128), zero fill out of bounds.
 bool make_tmap_2d(CUtensorMap* m, const void* base, int64_t rows, int cols, int64_t ld, int box_rows, int box_cols);
 
+// 3-D bf16 tensor map over [batch, rows, cols] (row pitch `ld`, batch pitch `batch_stride` elements), box
+// [1, box_rows, box_cols], 128-byte swizzle.  Rows past `rows` are clipped by the TMA unit, so a tile that
+// overhangs the end of one sequence never touches the next sequence of a concatenated [batch * rows, cols] buffer.
+bool make_tmap_3d(CUtensorMap* m, const void* base, int cols, int rows, int batch, int64_t ld, int64_t batch_stride,
+                  int box_rows, int box_cols);
+
 }  // namespace mr
 
 #define MR_REQUIRE(cond, code) \

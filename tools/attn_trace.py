@@ -12,7 +12,7 @@ from merlot_reserve_b200 import _lib as L  # noqa: E402
 
 which = sys.argv[1] if len(sys.argv) > 1 else "vision"
 B, T, H, masked = {"vision": (1024, 241, 768, False), "joint": (64, 1120, 768, True),
-                   "large_vision": (256, 577, 1024, False), "large_joint": (16, 2464, 1024, True)}[which]
+                   "large_vision": (256, 577, 1024, False), "audio": (3072, 31, 768, False), "large_joint": (16, 2464, 1024, True)}[which]
 torch.cuda.set_device(0)
 lib = L.load()
 lib.mr_debug_attention_trace.argtypes = [C.c_void_p]
@@ -33,6 +33,8 @@ lib.mr_debug_attention_trace(None)
 t = buf.cpu().view(2, 64, 8)
 names = ["wait S", "ld S", "max/mask", "ffma+ex2+pack", "wait PV(j-1)", "rescale O", "st P + arrive"]
 nkb = (T + 127) // 128
+if T <= 64:
+    nkb = 1
 for wg in range(2):
     print(f"tile {wg}: stamps relative to the first; one row per key block (block index within the CTA's stream)")
     t0 = int(t[wg, 0, 0])

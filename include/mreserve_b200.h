@@ -448,6 +448,38 @@ typedef struct MrAdamWDesc {
 int32_t mr_adamw(mr_stream_t stream, const MrAdamWDesc* d, const void* const* in, void* const* out, void* workspace,
                  size_t workspace_bytes);
 
+/* mr_adamw_multi: the whole parameter update of train_step in ONE launch, with the reference's optimizer state
+ * (pretrain/optimization.py:54-114 `scale_by_bfloat16_adam`, :158-195 `construct_train_state`).
+ *   Arenas (same element order, tensor slots start at multiples of 8 elements):
+ *   in[0]  g      f32 or bf16 [n]   flat gradient (bf16 = straight out of the reference's bf16 pmean, pretrain_model.py:329)
+ *   in[1]  table  MrAdamWChunk [n_chunks]  (device memory; built once per model)
+ *   out[0] p      f32 [n]           master parameters, updated in place
+ *   out[1] m      bf16 | f32 [n]    first moment; bf16 when moments_bf16 (optimization.py:72,98)
+ *   out[2] v      bf16 | f32 [n]    second moment; moments_bf16: sign-coded bf16 of nu^3 (optimization.py:36-51)
+ *   Each chunk covers `count` <= MR_ADAMW_CHUNK consecutive elements of ONE tensor starting at arena element `offset`;
+ *   `w` points at the same elements inside the working copy the forward kernels read (bf16, or f32 with
+ *   MR_ADAMW_W_F32; NULL = none) and is refreshed from the new p.  MR_ADAMW_DECAY = flax ndim > 1 (optimization.py:182-184).
+ *   update: g' = nan_to_num(g) grad_scale; m = (1-b1) g' + b1 m; v = (1-b2) g'^2 + b2 decode(v);
+ *           p -= lr ( (m / bias_corr1) / (sqrt(v / bias_corr2) + eps) + wd p )   with the UN-rounded m, v (optimization.py:101-111);
+ *   bias_corr = 1 - beta^t when the reference's do_bias_correction is set, else 1 (its default, optimization.py:165). */
+enum { MR_ADAMW_DECAY = 1, MR_ADAMW_W_F32 = 2 };
+enum { MR_ADAMW_CHUNK = 2048 };
+typedef struct MrAdamWChunk {
+  int64_t offset; /* first arena element of the chunk (multiple of 8) */
+  void* w;        /* working copy of these elements, or NULL */
+  int32_t count;  /* 1 .. MR_ADAMW_CHUNK */
+  int32_t flags;  /* MR_ADAMW_DECAY | MR_ADAMW_W_F32 */
+} MrAdamWChunk;
+typedef struct MrAdamWMultiDesc {
+  int32_t n_chunks;
+  int32_t moments_bf16; /* 1 = reference storage (bf16 mu, coded bf16 nu), 0 = fp32 moments */
+  int32_t grad_bf16;    /* dtype of in[0] */
+  float lr, beta1, beta2, eps, weight_decay, grad_scale, bias_corr1, bias_corr2;
+  float one_minus_beta1, one_minus_beta2; /* (float)(1.0 - (double)beta): rounded once, as a traced python constant is */
+} MrAdamWMultiDesc;
+int32_t mr_adamw_multi(mr_stream_t stream, const MrAdamWMultiDesc* d, const void* const* in, void* const* out,
+                       void* workspace, size_t workspace_bytes);
+
 /* ------------------------------------------------------------------------------------------
  * mr_row_dot: logits[r] = x[r] . w  (finetune `proj` head H -> 1, no bias;
  * finetune/vcr/qa_qar_joint_finetune.py:163-170), with an optional row gather.

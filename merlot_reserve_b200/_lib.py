@@ -96,6 +96,20 @@ class AdamWDesc(C.Structure):
                 ("weight_decay", C.c_float), ("grad_scale", C.c_float)]
 
 
+class AdamWChunk(C.Structure):
+    _fields_ = [("offset", C.c_int64), ("w", C.c_void_p), ("count", C.c_int32), ("flags", C.c_int32)]
+
+
+class AdamWMultiDesc(C.Structure):
+    _fields_ = [("n_chunks", C.c_int32), ("moments_bf16", C.c_int32), ("grad_bf16", C.c_int32), ("lr", C.c_float),
+                ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float), ("weight_decay", C.c_float),
+                ("grad_scale", C.c_float), ("bias_corr1", C.c_float), ("bias_corr2", C.c_float),
+                ("one_minus_beta1", C.c_float), ("one_minus_beta2", C.c_float)]
+
+
+ADAMW_DECAY, ADAMW_W_F32, ADAMW_CHUNK = 1, 2, 2048
+
+
 class RotaryBwdDesc(C.Structure):
     _fields_ = [("rows", C.c_int64), ("hidden", C.c_int32), ("rot_rows", C.c_int32), ("q_scale", C.c_float)]
 
@@ -134,6 +148,7 @@ ENTRY_POINTS = {
     "mr_window_mean_bwd": WindowDesc,
     "mr_add": ElementwiseDesc,
     "mr_adamw": AdamWDesc,
+    "mr_adamw_multi": AdamWMultiDesc,
 }
 WORKSPACE_FNS = {
     "mr_gemm_epilogue_workspace_bytes": GemmDesc,
@@ -145,13 +160,13 @@ WORKSPACE_FNS = {
     "mr_contrastive_lse_bwd_workspace_bytes": ContrastiveDesc,
     "mr_contrastive_lse_fwd_workspace_bytes": ContrastiveDesc,
 }
-MISC_FNS = ["mr_check_device", "mr_abi_version", "mr_status_string", "mr_launch_count"]
+MISC_FNS = ["mr_check_device", "mr_abi_version", "mr_status_string", "mr_launch_count", "mr_debug_attention_trace"]
 
 # MrGemmDesc.algo_pair used when a call does not say: 0 auto, 1 force CTA pairs, 2 never (MR_GEMM_PAIR overrides)
 import os as _os
 GEMM_PAIR_DEFAULT = int(_os.environ.get("MR_GEMM_PAIR", "0"))
 
-ABI_VERSION = 10  # must equal mr_abi_version() of the loaded library (struct layouts above)
+ABI_VERSION = 11  # must equal mr_abi_version() of the loaded library (struct layouts above)
 
 _lib = None
 
@@ -569,3 +584,32 @@ def add(a: torch.Tensor, b: torch.Tensor, out=None) -> torch.Tensor:
 def adamw(g, p, m, v, w=None, *, lr, beta1=0.9, beta2=0.98, eps=1e-6, weight_decay=0.0, grad_scale=1.0) -> None:
     d = AdamWDesc(n=p.numel(), lr=lr, beta1=beta1, beta2=beta2, eps=eps, weight_decay=weight_decay, grad_scale=grad_scale)
     _call("mr_adamw", d, [g], [p, m, v, w])
+
+
+def adamw_chunk_table(slots, device) -> torch.Tensor:
+    """Chunk table of mr_adamw_multi as a device uint8 tensor.  `slots` = [(arena_offset, numel, working-copy tensor
+    or None, decay?)], arena offsets multiples of 8 elements; the working copy must be contiguous (bf16 or fp32)."""
+    import numpy as np
+    rows = []
+    for off, n, w, decay in slots:
+        assert off % 8 == 0 and (w is None or (w.is_contiguous() and w.numel() == n))
+        flags = (ADAMW_DECAY if decay else 0) | (ADAMW_W_F32 if (w is not None and w.dtype == torch.float32) else 0)
+        esz = 0 if w is None else w.element_size()
+        for c0 in range(0, n, ADAMW_CHUNK):
+            rows.append((off + c0, 0 if w is None else w.data_ptr() + c0 * esz, min(ADAMW_CHUNK, n - c0), flags))
+    arr = np.array(rows, dtype=np.dtype([("offset", "<i8"), ("w", "<u8"), ("count", "<i4"), ("flags", "<i4")]))
+    assert arr.dtype.itemsize == C.sizeof(AdamWChunk)
+    return torch.from_numpy(arr.view(np.uint8).reshape(-1).copy()).to(device)
+
+
+def adamw_multi(g, table, p, m, v, *, lr, beta1=0.9, beta2=0.98, eps=1e-8, weight_decay=0.0, grad_scale=1.0,
+                bias_corr1=1.0, bias_corr2=1.0) -> None:
+    """One launch for all parameters (include/mreserve_b200.h: mr_adamw_multi).  Moment dtype selects the storage:
+    bf16 = the reference's compressed moments (pretrain/optimization.py:36-51), fp32 = plain Adam."""
+    assert m.dtype == v.dtype and m.dtype in (torch.bfloat16, torch.float32) and p.dtype == torch.float32
+    assert g.dtype in (torch.bfloat16, torch.float32), g.dtype
+    d = AdamWMultiDesc(n_chunks=table.numel() // C.sizeof(AdamWChunk), moments_bf16=int(m.dtype == torch.bfloat16),
+                       grad_bf16=int(g.dtype == torch.bfloat16), lr=lr, beta1=beta1, beta2=beta2, eps=eps,
+                       weight_decay=weight_decay, grad_scale=grad_scale, bias_corr1=bias_corr1, bias_corr2=bias_corr2,
+                       one_minus_beta1=1.0 - beta1, one_minus_beta2=1.0 - beta2)
+    _call("mr_adamw_multi", d, [g, table], [p, m, v])

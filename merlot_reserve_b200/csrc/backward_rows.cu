@@ -503,6 +503,156 @@ adamw_kernel(const float* __restrict__ g, float* __restrict__ p, float* __restri
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Multi-tensor AdamW: ONE launch updates every parameter of the model.  Parameters, moments and gradients live in
+// flat arenas (same element order); a chunk table says, for every kChunk elements, where they start, how many
+// there are, whether weight decay applies (flax ndim > 1, optimization.py:182-184) and where the working copy the
+// GEMMs read lives.  Moments follow the reference's storage (pretrain/optimization.py:36-51,86-99):
+//   mu  bf16 (round to nearest even of the fp32 value),
+//   nu  the "unsigned bfloat16" code: bf16(nu^3), with the SIGN BIT as an extra mantissa bit -- a negative code c
+//       decodes to cbrt(|c| (1 + 2^-9)), a non-negative one to cbrt(c); the encoder picks whichever is closer.
+// The update uses the un-rounded fp32 moments of this step (optimization.py:101-111), optional bias correction,
+// then decoupled weight decay and the scheduled learning rate (optimization.py:179-195).
+// ---------------------------------------------------------------------------------------------
+constexpr int kAdamChunk = 2048;   // elements per block: 256 threads x 8
+static_assert(kAdamChunk == MR_ADAMW_CHUNK && sizeof(MrAdamWChunk) == 24, "chunk table layout is part of the ABI");
+
+struct AdamElem {
+  float p, m, v;
+};
+
+template <bool kBf16Moments>
+__device__ __forceinline__ float adam_decode_v(float code) {
+  if (!kBf16Moments) return code;
+  const float a = fabsf(code);
+  return cbrtf(code >= 0.f ? a : a * (1.0f + 1.0f / 512.0f));          // optimization.py:36-39
+}
+
+__device__ __forceinline__ bf16 adam_encode_v(float v) {
+  const float v_pow = v * v * v;                                         // optimization.py:42-50
+  const bf16 v_bf = __float2bfloat16(v_pow);
+  const float v_bf32 = __bfloat162float(v_bf);
+  const float err0 = fabsf(v_bf32 - v_pow);
+  const float err1 = fabsf(v_bf32 * (1.0f + 1.0f / 512.0f) - v_pow);
+  return err0 < err1 ? v_bf : __float2bfloat16(-v_bf32);
+}
+
+template <bool kBf16Moments, bool kBf16Grad>
+__global__ void __launch_bounds__(256)
+adamw_multi_kernel(const void* __restrict__ g_, const MrAdamWChunk* __restrict__ table, float* __restrict__ p_,
+                   void* __restrict__ m_, void* __restrict__ v_, MrAdamWMultiDesc d) {
+  const MrAdamWChunk ch = table[blockIdx.x];
+  const int i0 = threadIdx.x * 8;
+  if (i0 >= ch.count) return;
+  const int64_t base = ch.offset + i0;
+  const int n = min(8, ch.count - i0);
+  const float wd = (ch.flags & MR_ADAMW_DECAY) ? d.weight_decay : 0.f;
+  float g[8], p[8], m[8], v[8];
+  if (n == 8) {   // offsets are multiples of 8 elements: 16-byte (bf16) / 32-byte (fp32) vector accesses
+    if (kBf16Grad) {
+      const uint4 u = *reinterpret_cast<const uint4*>(static_cast<const bf16*>(g_) + base);
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) g[2 * k] = bf16_lo(w[k]), g[2 * k + 1] = bf16_hi(w[k]);
+    } else {
+      const float4 a = *reinterpret_cast<const float4*>(static_cast<const float*>(g_) + base);
+      const float4 b = *reinterpret_cast<const float4*>(static_cast<const float*>(g_) + base + 4);
+      g[0] = a.x, g[1] = a.y, g[2] = a.z, g[3] = a.w, g[4] = b.x, g[5] = b.y, g[6] = b.z, g[7] = b.w;
+    }
+    const float4 pa = *reinterpret_cast<const float4*>(p_ + base), pb = *reinterpret_cast<const float4*>(p_ + base + 4);
+    p[0] = pa.x, p[1] = pa.y, p[2] = pa.z, p[3] = pa.w, p[4] = pb.x, p[5] = pb.y, p[6] = pb.z, p[7] = pb.w;
+    if (kBf16Moments) {
+      const uint4 um = *reinterpret_cast<const uint4*>(static_cast<const bf16*>(m_) + base);
+      const uint4 uv = *reinterpret_cast<const uint4*>(static_cast<const bf16*>(v_) + base);
+      const uint32_t wm[4] = {um.x, um.y, um.z, um.w}, wv[4] = {uv.x, uv.y, uv.z, uv.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        m[2 * k] = bf16_lo(wm[k]), m[2 * k + 1] = bf16_hi(wm[k]);
+        v[2 * k] = bf16_lo(wv[k]), v[2 * k + 1] = bf16_hi(wv[k]);
+      }
+    } else {
+      const float* mf = static_cast<const float*>(m_) + base;
+      const float* vf = static_cast<const float*>(v_) + base;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) m[k] = mf[k], v[k] = vf[k];
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      if (k < n) {
+        g[k] = kBf16Grad ? __bfloat162float(static_cast<const bf16*>(g_)[base + k]) : static_cast<const float*>(g_)[base + k];
+        p[k] = p_[base + k];
+        m[k] = kBf16Moments ? __bfloat162float(static_cast<const bf16*>(m_)[base + k]) : static_cast<const float*>(m_)[base + k];
+        v[k] = kBf16Moments ? __bfloat162float(static_cast<const bf16*>(v_)[base + k]) : static_cast<const float*>(v_)[base + k];
+      } else {
+        g[k] = p[k] = m[k] = v[k] = 0.f;
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    float gi = g[k];
+    if (gi != gi) gi = 0.f;                                             // nan_to_num (pretrain_model.py:327)
+    gi = fminf(fmaxf(gi, -3.4028235e38f), 3.4028235e38f) * d.grad_scale;
+    // products and sum rounded separately (no FMA contraction), (1 - beta) rounded once from double, as the
+    // reference's XLA graph does: the bf16 rounding of mu sits on exact ties for bf16 inputs surprisingly often
+    const float mi = __fadd_rn(__fmul_rn(d.one_minus_beta1, gi), __fmul_rn(d.beta1, m[k]));       // optimization.py:86-90
+    const float vi = __fadd_rn(__fmul_rn(d.one_minus_beta2, __fmul_rn(gi, gi)),
+                               __fmul_rn(d.beta2, adam_decode_v<kBf16Moments>(v[k])));           // :92-95
+    const float upd = (mi / d.bias_corr1) / (sqrtf(vi / d.bias_corr2) + d.eps);                  // :101-111
+    p[k] -= d.lr * (upd + wd * p[k]);
+    m[k] = mi;
+    v[k] = vi;
+  }
+  bf16* w16 = (ch.flags & MR_ADAMW_W_F32) ? nullptr : static_cast<bf16*>(ch.w);
+  float* w32 = (ch.flags & MR_ADAMW_W_F32) ? static_cast<float*>(ch.w) : nullptr;
+  if (n == 8) {
+    *reinterpret_cast<float4*>(p_ + base) = make_float4(p[0], p[1], p[2], p[3]);
+    *reinterpret_cast<float4*>(p_ + base + 4) = make_float4(p[4], p[5], p[6], p[7]);
+    if (kBf16Moments) {
+      uint4 um, uv;
+      um.x = pack_bf16(m[0], m[1]), um.y = pack_bf16(m[2], m[3]), um.z = pack_bf16(m[4], m[5]), um.w = pack_bf16(m[6], m[7]);
+      bf16 c[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) c[k] = adam_encode_v(v[k]);
+      uv = *reinterpret_cast<const uint4*>(c);
+      *reinterpret_cast<uint4*>(static_cast<bf16*>(m_) + base) = um;
+      *reinterpret_cast<uint4*>(static_cast<bf16*>(v_) + base) = uv;
+    } else {
+      float* mf = static_cast<float*>(m_) + base;
+      float* vf = static_cast<float*>(v_) + base;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) mf[k] = m[k], vf[k] = v[k];
+    }
+    if (w16 != nullptr) {
+      uint4 uw;
+      uw.x = pack_bf16(p[0], p[1]), uw.y = pack_bf16(p[2], p[3]), uw.z = pack_bf16(p[4], p[5]), uw.w = pack_bf16(p[6], p[7]);
+      *reinterpret_cast<uint4*>(w16 + i0) = uw;
+    }
+    if (w32 != nullptr) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) w32[i0 + k] = p[k];
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      if (k < n) {
+        p_[base + k] = p[k];
+        if (kBf16Moments) {
+          static_cast<bf16*>(m_)[base + k] = __float2bfloat16(m[k]);
+          static_cast<bf16*>(v_)[base + k] = adam_encode_v(v[k]);
+        } else {
+          static_cast<float*>(m_)[base + k] = m[k];
+          static_cast<float*>(v_)[base + k] = v[k];
+        }
+        if (w16 != nullptr) w16[i0 + k] = __float2bfloat16(p[k]);
+        if (w32 != nullptr) w32[i0 + k] = p[k];
+      }
+    }
+  }
+}
+
 }  // namespace
 }  // namespace mr
 
@@ -796,5 +946,28 @@ extern "C" int32_t mr_adamw(mr_stream_t stream_, const MrAdamWDesc* d, const voi
   adamw_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
       static_cast<const float*>(in[0]), static_cast<float*>(out[0]), static_cast<float*>(out[1]),
       static_cast<float*>(out[2]), static_cast<bf16*>(out[3]), *d);
+  return after_launch();
+}
+
+extern "C" int32_t mr_adamw_multi(mr_stream_t stream_, const MrAdamWMultiDesc* d, const void* const* in, void* const* out,
+                                  void*, size_t) {
+  MR_REQUIRE(d && in && out && in[0] && in[1] && out[0] && out[1] && out[2], MR_ERR_NULL_POINTER);
+  MR_REQUIRE(d->n_chunks >= 0 && d->bias_corr1 > 0.f && d->bias_corr2 > 0.f, MR_ERR_BAD_SHAPE);
+  MR_REQUIRE(aligned16(in[0]) && aligned16(out[0]) && aligned16(out[1]) && aligned16(out[2]), MR_ERR_MISALIGNED);
+  if (d->n_chunks == 0) return MR_OK;
+  const MrAdamWChunk* table = static_cast<const MrAdamWChunk*>(in[1]);
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const unsigned grid = static_cast<unsigned>(d->n_chunks);
+  if (d->moments_bf16) {
+    if (d->grad_bf16)
+      adamw_multi_kernel<true, true><<<grid, 256, 0, stream>>>(in[0], table, static_cast<float*>(out[0]), out[1], out[2], *d);
+    else
+      adamw_multi_kernel<true, false><<<grid, 256, 0, stream>>>(in[0], table, static_cast<float*>(out[0]), out[1], out[2], *d);
+  } else {
+    if (d->grad_bf16)
+      adamw_multi_kernel<false, true><<<grid, 256, 0, stream>>>(in[0], table, static_cast<float*>(out[0]), out[1], out[2], *d);
+    else
+      adamw_multi_kernel<false, false><<<grid, 256, 0, stream>>>(in[0], table, static_cast<float*>(out[0]), out[1], out[2], *d);
+  }
   return after_launch();
 }

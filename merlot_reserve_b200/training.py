@@ -100,14 +100,38 @@ class PretrainStep:
         reg["head/kernel"], reg["head/bias"] = (p.head[0], True), (p.head[1], False)
         return reg
 
-    def _init_state(self):
-        # decay mask = flax ndim > 1 (optimization.py:182-184): the qkv / pool biases are [heads, 64] in flax
-        st = {}
-        for name, (t, decay) in self._registry().items():
-            master = t if t.dtype == torch.float32 else t.float()
-            st[name] = {"w": t if t.dtype != torch.float32 else None, "p": master,
-                        "m": torch.zeros_like(master), "v": torch.zeros_like(master), "decay": decay}
-        self._state = st
+    # default optimizer block = pretrain/configs/base.yaml:81-90
+    DEFAULT_OPT = {"learning_rate": 4e-4, "num_train_steps": 750000, "num_warmup_steps": 3750, "weight_decay_rate": 0.1,
+                   "beta_2": 0.98, "eps": 1e-6, "use_bfloat16_adam": True}
+
+    def _init_state(self, opt: Optional[Dict] = None):
+        """Optimizer state as flat arenas (mr_adamw_multi): fp32 master parameters, the two Adam moments in the
+        reference's storage (bf16 mu, sign-coded bf16 of nu^3; optimization.py:36-51,72) or fp32 when
+        `use_bfloat16_adam` is off, and the chunk table that maps arena elements to the tensors the kernels read.
+        Decay mask = flax ndim > 1 (optimization.py:182-184): the qkv / pool biases are [heads, 64] in flax."""
+        opt = opt or self.DEFAULT_OPT
+        reg = self._registry()
+        names = sorted(reg)
+        dev = next(iter(reg.values()))[0].device
+        offs, n = {}, 0
+        for name in names:
+            offs[name] = n
+            n += (reg[name][0].numel() + 7) // 8 * 8
+        n_total = (n + 1023) // 1024 * 1024                 # the gradient cast works on rows of 1024
+        mdt = BF16 if opt.get("use_bfloat16_adam", True) else torch.float32
+        p = torch.zeros(n_total, dtype=torch.float32, device=dev)
+        slots = []
+        for name in names:
+            t, decay = reg[name]
+            assert t.is_contiguous(), name
+            p[offs[name]:offs[name] + t.numel()].copy_(t.reshape(-1))
+            slots.append((offs[name], t.numel(), t, decay))
+        self._state = {"names": names, "offs": offs, "n": n_total, "p": p,
+                       "m": torch.zeros(n_total, dtype=mdt, device=dev), "v": torch.zeros(n_total, dtype=mdt, device=dev),
+                       "table": L.adamw_chunk_table(slots, dev),
+                       # gradient arena (+ 8 trailing slots: the 3 contrastive temperatures ride in the same all-reduce)
+                       "g": torch.zeros(n_total + 1024, dtype=torch.float32, device=dev),
+                       "g16": torch.empty(n_total + 1024, dtype=BF16, device=dev)}
         self._scale_state = {"m": np.zeros(3, np.float32), "v": np.zeros(3, np.float32)}
         self.step_count = 0
 
@@ -119,41 +143,49 @@ class PretrainStep:
         s = min((step - nw) / (nt - nw + 1.0), 1.0)
         return final + (1.0 - final) * (1.0 - (1.0 - math.cos(math.pi * s)) / 2.0)
 
+    def optimizer_state(self) -> Dict[str, Dict[str, torch.Tensor]]:
+        """Views of the arenas per flax parameter path (packed layout): {'p': .., 'm': .., 'v': ..}."""
+        st, reg = self._state, self._registry()
+        out = {}
+        for name in st["names"]:
+            o, k, shp = st["offs"][name], reg[name][0].numel(), reg[name][0].shape
+            out[name] = {key: st[key][o:o + k].view(shp) for key in ("p", "m", "v")}
+        return out
+
     def train_step(self, batch: Dict, opt: Optional[Dict] = None, group=None):
         """One optimisation step; returns (loss, loss_info) of this rank (0-d CUDA tensors)."""
         import torch.distributed as dist
-        opt = opt or {"learning_rate": 4e-4, "num_train_steps": 750000, "num_warmup_steps": 3750, "weight_decay_rate": 0.1,
-                      "beta_2": 0.98, "eps": 1e-6}
+        opt = opt or self.DEFAULT_OPT
         if self._state is None:
-            self._init_state()
+            self._init_state(opt)
+        st = self._state
         loss, info, grads = self.loss_and_grads(batch, group=group)
         world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
-        names = sorted(grads)
+        n, g = st["n"], st["g"]
+        for name in st["names"]:
+            t = grads[name]
+            g[st["offs"][name]:st["offs"][name] + t.numel()].copy_(t.reshape(-1))
+        g[n:n + 3].copy_(grads["contrastive_scales"].reshape(-1))
+        # The reference differentiates bf16 parameters, so its gradients ARE bf16, and averages them in bf16
+        # (pretrain_model.py:323-333): one flat bf16 bucket, one all-reduce, and the optimizer kernel reads it as is.
+        g16 = L.cast_pad(g.view(-1, 1024), (n + 1024) // 1024, 1024, 1024, out=st["g16"].view(-1, 1024)).view(-1)
         if world > 1:
-            # gradient all-reduce in bf16, one flat bucket (pretrain_model.py:323-333 casts to bf16 before the pmean)
-            flat = torch.cat([grads[n].reshape(-1) for n in names]).to(BF16)
-            dist.all_reduce(flat, group=group)
-            flat = flat.float()
-            off = 0
-            for n in names:
-                k = grads[n].numel()
-                grads[n] = flat[off:off + k].view(grads[n].shape)
-                off += k
+            dist.all_reduce(g16, group=group)
         lr = opt["learning_rate"] * self.lr_scale(self.step_count, opt)
         b1, b2, eps, wd = opt.get("beta_1", 0.9), opt.get("beta_2", 0.98), opt.get("eps", 1e-8), opt["weight_decay_rate"]
-        for n in names:
-            if n == "contrastive_scales":
-                continue
-            st = self._state[n]
-            g = grads[n].reshape(st["p"].shape)
-            L.adamw(g.contiguous() if not g.is_contiguous() else g, st["p"], st["m"], st["v"], st["w"], lr=lr, beta1=b1,
-                    beta2=b2, eps=eps, weight_decay=wd if st["decay"] else 0.0, grad_scale=1.0 / world)
-        # the three temperatures live on the host (they parameterise kernel launches)
-        gs = np.nan_to_num(grads["contrastive_scales"].cpu().numpy().astype(np.float32)) / world
+        # bias correction: off by default with the bf16 moments (optimization.py:165), always on for optax.scale_by_adam
+        corr = opt.get("do_bias_correction", False) if opt.get("use_bfloat16_adam", True) else True
+        t1 = self.step_count + 1
+        L.adamw_multi(g16, st["table"], st["p"], st["m"], st["v"], lr=lr, beta1=b1, beta2=b2, eps=eps, weight_decay=wd,
+                      grad_scale=1.0 / world, bias_corr1=(1 - b1 ** t1) if corr else 1.0,
+                      bias_corr2=(1 - b2 ** t1) if corr else 1.0)
+        # the three temperatures live on the host (they parameterise kernel launches); ndim 1: no decay
+        gs = np.nan_to_num(g16[n:n + 3].float().cpu().numpy()) / world
         ss, p = self._scale_state, self.model._p
         ss["m"] = b1 * ss["m"] + (1 - b1) * gs
         ss["v"] = b2 * ss["v"] + (1 - b2) * gs * gs
-        p.contrastive_scales = (p.contrastive_scales - lr * ss["m"] / (np.sqrt(ss["v"]) + eps)).astype(np.float32)
+        mh, vh = (ss["m"] / (1 - b1 ** t1), ss["v"] / (1 - b2 ** t1)) if corr else (ss["m"], ss["v"])
+        p.contrastive_scales = (p.contrastive_scales - lr * mh / (np.sqrt(vh) + eps)).astype(np.float32)
         self.step_count += 1
         return loss, info
 

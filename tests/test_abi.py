@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol(lib):
     assert len(names) >= 20
     for n in names:
         assert hasattr(cdll, n), f"{n} declared in the header but not exported"
-    assert cdll.mr_abi_version() == 10
+    assert cdll.mr_abi_version() == lib.ABI_VERSION == 11
     assert lib.launch_count() >= 0
 
 
@@ -39,7 +39,8 @@ def test_struct_sizes_match_c(lib, tmp_path):
                "MrAssembleDesc": lib.AssembleDesc, "MrRotaryDesc": lib.RotaryDesc, "MrNormalizeDesc": lib.NormalizeDesc,
                "MrSegmentPoolDesc": lib.SegmentPoolDesc, "MrContrastiveDesc": lib.ContrastiveDesc,
                "MrRowDotDesc": lib.RowDotDesc, "MrEncoderDesc": lib.EncoderDesc, "MrElementwiseDesc": lib.ElementwiseDesc,
-               "MrColsumDesc": lib.ColsumDesc, "MrRotaryBwdDesc": lib.RotaryBwdDesc, "MrAdamWDesc": lib.AdamWDesc}
+               "MrColsumDesc": lib.ColsumDesc, "MrRotaryBwdDesc": lib.RotaryBwdDesc, "MrAdamWDesc": lib.AdamWDesc,
+               "MrAdamWMultiDesc": lib.AdamWMultiDesc, "MrAdamWChunk": lib.AdamWChunk}
     src = tmp_path / "sz.c"
     body = "\n".join(f'  printf("{n} %zu\\n", sizeof({n}));' for n in structs)
     src.write_text(f'#include <stdio.h>\n#include "mreserve_b200.h"\nint main(void) {{\n{body}\n  return 0;\n}}\n')

@@ -27,6 +27,27 @@ from .pretrain_model import MerlotReservePretrainer, gather_contrastive_targets
 BF16 = torch.bfloat16
 
 
+def _np_dtype(dt):
+    if dt == BF16:
+        import ml_dtypes
+        return np.dtype(ml_dtypes.bfloat16)
+    return np.dtype(np.float32)
+
+
+def _nu_decode(code: np.ndarray) -> np.ndarray:
+    """Host twin of the device decoder (pretrain/optimization.py:36-39), for the three contrastive temperatures."""
+    a = np.abs(code.astype(np.float32))
+    return np.cbrt(np.where(code.astype(np.float32) >= 0, a, a * np.float32(1 + 1 / 512))).astype(np.float32)
+
+
+def _nu_encode(v: np.ndarray) -> np.ndarray:
+    """pretrain/optimization.py:42-50."""
+    bf = _np_dtype(BF16)
+    v_pow = (v * v * v).astype(np.float32)
+    c = v_pow.astype(bf).astype(np.float32)
+    return np.where(np.abs(c - v_pow) < np.abs(c * np.float32(1 + 1 / 512) - v_pow), c, -c).astype(bf)
+
+
 def _split_k(rows: int) -> int:
     """wgrad reduces over the token rows: enough K parts to occupy the SMs, at least ~2k rows per part."""
     return int(max(1, min(16, rows // 2048)))
@@ -132,7 +153,7 @@ class PretrainStep:
                        # gradient arena (+ 8 trailing slots: the 3 contrastive temperatures ride in the same all-reduce)
                        "g": torch.zeros(n_total + 1024, dtype=torch.float32, device=dev),
                        "g16": torch.empty(n_total + 1024, dtype=BF16, device=dev)}
-        self._scale_state = {"m": np.zeros(3, np.float32), "v": np.zeros(3, np.float32)}
+        self._scale_state = {"m": np.zeros(3, _np_dtype(mdt)), "v": np.zeros(3, _np_dtype(mdt))}
         self.step_count = 0
 
     def lr_scale(self, step: int, opt: Dict) -> float:
@@ -182,10 +203,14 @@ class PretrainStep:
         # the three temperatures live on the host (they parameterise kernel launches); ndim 1: no decay
         gs = np.nan_to_num(g16[n:n + 3].float().cpu().numpy()) / world
         ss, p = self._scale_state, self.model._p
-        ss["m"] = b1 * ss["m"] + (1 - b1) * gs
-        ss["v"] = b2 * ss["v"] + (1 - b2) * gs * gs
-        mh, vh = (ss["m"] / (1 - b1 ** t1), ss["v"] / (1 - b2 ** t1)) if corr else (ss["m"], ss["v"])
-        p.contrastive_scales = (p.contrastive_scales - lr * mh / (np.sqrt(vh) + eps)).astype(np.float32)
+        coded = ss["m"].dtype != np.float32
+        f32 = np.float32
+        mh = f32(1 - b1) * gs + f32(b1) * ss["m"].astype(f32)
+        vh = f32(1 - b2) * gs * gs + f32(b2) * (_nu_decode(ss["v"]) if coded else ss["v"])
+        ss["m"], ss["v"] = (mh.astype(ss["m"].dtype), _nu_encode(vh)) if coded else (mh, vh)
+        if corr:
+            mh, vh = mh / f32(1 - b1 ** t1), vh / f32(1 - b2 ** t1)
+        p.contrastive_scales = (p.contrastive_scales - f32(lr) * mh / (np.sqrt(vh) + f32(eps))).astype(np.float32)
         self.step_count += 1
         return loss, info
 
@@ -582,6 +607,92 @@ class PretrainStep:
         return loss, info, G.g
 
     # --------------------------------------------------------------------------------------------
+    # TrainState <-> checkpoint (mreserve/checkpoint.py:61-119): parameters and moments in the flax tree / layouts
+    # --------------------------------------------------------------------------------------------
+    def _flax_shape(self, path: str):
+        node = self.params
+        for part in path.split("/"):
+            node = node[part]
+        return np.asarray(node).shape
+
+    def _to_flax(self, name: str, t: torch.Tensor) -> np.ndarray:
+        """Packed layout (K-major [out, in(+pad)] kernels) -> the flax leaf; bf16 comes back as ml_dtypes.bfloat16."""
+        shp = self._flax_shape(name)
+        if name.endswith("kernel"):
+            t = t.t()
+            t = t[: int(np.prod(shp)) // t.shape[1]]         # drops the audio embedding's K padding rows
+        a = t.contiguous().reshape(shp).cpu()
+        return a.view(torch.int16).numpy().view(_np_dtype(BF16)) if a.dtype == BF16 else a.numpy()
+
+    def _from_flax(self, name: str, a: np.ndarray, like: torch.Tensor) -> torch.Tensor:
+        """The inverse of `_to_flax`: a tensor shaped and typed like the packed slot `like`."""
+        a = np.array(a, copy=True)                           # msgpack hands out read-only buffers
+        t = torch.from_numpy(a.view(np.int16)).view(BF16) if a.dtype == _np_dtype(BF16) else torch.from_numpy(a)
+        if name.endswith("kernel"):
+            out_f = like.shape[0]
+            t = t.reshape(-1, out_f).t()
+            if t.shape[1] < like.shape[1]:
+                t = torch.nn.functional.pad(t, (0, like.shape[1] - t.shape[1]))
+        return t.reshape(like.shape).to(dtype=like.dtype, device=like.device)
+
+    @staticmethod
+    def _nest(flat: Dict[str, np.ndarray]) -> Dict:
+        tree: Dict = {}
+        for k, v in flat.items():
+            node = tree
+            parts = k.split("/")
+            for part in parts[:-1]:
+                node = node.setdefault(part, {})
+            node[parts[-1]] = v
+        return tree
+
+    def state_dict(self) -> Dict:
+        """The reference's TrainState as `save_checkpoint` sees it (checkpoint.py:61-99): {'step', 'params',
+        'opt_state'} with fp32 parameters and the Adam moments in their stored form (bf16 mu, coded bf16 nu).
+        `opt_state` follows flax's state dict of the optax chain of optimization.py:173-193 -- a tuple becomes
+        {'0': ..} -- i.e. '0' = ScaleByAdamState{count, mu, nu}, '1' = MaskedState{inner_state: {}} of
+        add_decayed_weights, '2' = ScaleByScheduleState{count}, '3' = ScaleState {} (optax 0.0.9 layout restated
+        from library knowledge; not verifiable offline)."""
+        if self._state is None:
+            self._init_state()
+        views = self.optimizer_state()
+        trees = {key: {n: self._to_flax(n, d[key]) for n, d in views.items()} for key in ("p", "m", "v")}
+        trees["p"]["contrastive_scales"] = np.asarray(self.model._p.contrastive_scales, np.float32).copy()
+        trees["m"]["contrastive_scales"] = self._scale_state["m"].copy()
+        trees["v"]["contrastive_scales"] = self._scale_state["v"].copy()
+        count = np.int32(self.step_count)
+        return {"step": int(self.step_count), "params": self._nest(trees["p"]),
+                "opt_state": {"0": {"count": count, "mu": self._nest(trees["m"]), "nu": self._nest(trees["v"])},
+                              "1": {"inner_state": {}}, "2": {"count": count}, "3": {}}}
+
+    def load_state_dict(self, state: Dict, opt: Optional[Dict] = None) -> None:
+        """Restores parameters, moments and the step from `checkpoint.load_checkpoint(...)`; `opt_state` may be None
+        (checkpoints written with no_optimizer, checkpoint.py:84-90): the moments then restart from zero."""
+        from .checkpoint import flatten_dict
+        if self._state is None:
+            self._init_state(opt)
+        views, st = self.optimizer_state(), self._state
+        flat_p = flatten_dict(state["params"])
+        adam = (state.get("opt_state") or {}).get("0")
+        flat_m = flatten_dict(adam["mu"]) if adam else None
+        flat_v = flatten_dict(adam["nu"]) if adam else None
+        reg = self._registry()
+        for name, d in views.items():
+            d["p"].copy_(self._from_flax(name, np.asarray(flat_p[name], np.float32), d["p"]))
+            live = reg[name][0]
+            live.copy_(d["p"].to(live.dtype))
+            for key, flat in (("m", flat_m), ("v", flat_v)):
+                if flat is None:
+                    d[key].zero_()
+                else:
+                    d[key].copy_(self._from_flax(name, np.asarray(flat[name]), d[key]))
+        self.model._p.contrastive_scales = np.asarray(flat_p["contrastive_scales"], np.float32).copy()
+        sdt = self._scale_state["m"].dtype
+        self._scale_state = {"m": np.asarray(flat_m["contrastive_scales"]).astype(sdt) if flat_m else np.zeros(3, sdt),
+                             "v": np.asarray(flat_v["contrastive_scales"]).astype(sdt) if flat_v else np.zeros(3, sdt)}
+        self.step_count = int(np.asarray(state["step"]).reshape(-1)[0])
+        del st
+
     def grads_to_flax(self, g: Dict[str, torch.Tensor]) -> Dict[str, np.ndarray]:
         """Packed-layout gradients -> the flax shapes of the reference's parameter tree (numpy, fp32)."""
         out = {}

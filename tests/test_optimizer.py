@@ -171,3 +171,38 @@ def test_train_step_arenas_follow_the_reference_optimizer():
         live = reg[name][0]
         assert torch.equal(live.float().cpu(), after[name]["p"].to(live.dtype).float().cpu()), f"{name}: live tensor refreshed"
     assert step.step_count == 1
+
+
+@pytest.mark.gpu
+def test_train_state_round_trips_through_the_reference_checkpoint_format(tmp_path):
+    """train 2 steps -> state_dict -> save_checkpoint (fp16 params, bf16 moments) -> load -> a fresh PretrainStep:
+    parameters equal up to the fp16 storage, moments bit-identical, and the next step runs from the restored state."""
+    from merlot_reserve_b200 import checkpoint as ck
+    from merlot_reserve_b200.synthetic import synthetic_params, synthetic_pretrain_batch, tiny_config
+    from merlot_reserve_b200.training import PretrainStep
+    cfg = tiny_config()
+    params = synthetic_params(cfg, seed=0, weight_scale=4.0)
+    batch = synthetic_pretrain_batch(cfg, 2, seed=3)
+    opt = dict(PretrainStep.DEFAULT_OPT, num_warmup_steps=0, num_train_steps=100, learning_rate=1e-3)
+    a = PretrainStep(cfg, params)
+    for _ in range(2):
+        a.train_step(batch, opt)
+    sd = a.state_dict()
+    assert sd["step"] == 2 and set(sd["opt_state"]) == {"0", "1", "2", "3"}
+    assert sd["params"]["audio_encoder"]["embedding"]["kernel"].shape == (2, 65, cfg["model"]["hidden_size"])
+    assert sd["opt_state"]["0"]["mu"]["head"]["kernel"].dtype == BF16
+    ck.save_checkpoint(sd, str(tmp_path))
+    restored = ck.load_checkpoint(str(tmp_path))
+    b = PretrainStep(cfg, synthetic_params(cfg, seed=9, weight_scale=1.0))     # different weights: must be overwritten
+    b.load_state_dict(restored, opt)
+    sa, sb = a.optimizer_state(), b.optimizer_state()
+    for name in sa:
+        pa = sa[name]["p"].cpu()
+        assert torch.equal(sb[name]["p"].cpu(), pa.to(torch.float16).float()), name      # one fp16 rounding (checkpoint.py:29-36)
+        # value-identical codes (the K padding of the audio embedding comes back as +0 instead of the encoder's -0)
+        assert torch.equal(sb[name]["m"].float().cpu(), sa[name]["m"].float().cpu()), name
+        assert torch.equal(sb[name]["v"].float().cpu(), sa[name]["v"].float().cpu()), name
+    assert b.step_count == 2
+    assert np.allclose(b.model._p.contrastive_scales, a.model._p.contrastive_scales, rtol=1e-3)
+    la, lb = float(a.train_step(batch, opt)[0]), float(b.train_step(batch, opt)[0])
+    assert np.isfinite(lb) and abs(la - lb) < 0.05, (la, lb)

@@ -642,6 +642,57 @@ class MerlotReserve:
         rows = (torch.arange(B * n_cand, device=flat.device, dtype=torch.int32) * Ltok + pool_idx).contiguous()
         return _ret(L.row_dot(kept, proj, rows).view(B, n_cand), as_np)
 
+    def score_tvqa(self, batch, proj_kernel=None):
+        """TVQA-style multiple choice forward (MerlotReserveTVQA.__call__, finetune/tvqa/tvqa_finetune.py:163-258).
+        batch: 'images' [B, n_img, hw, 768]; 'audio_clips' [B, n_seg, n_sub, 60, 65]; 'textonly_seqs' and 'audio_seqs'
+        [B, n_ans, L, 2] = (token id, segment index).  Returns (logits_from_audio, logits_from_text), [B, n_ans] fp32.
+        Frames and audio are encoded once per example and shared by the n_ans candidates; the audio and the
+        text-only variants of every candidate run as ONE joint batch of 2 B n_ans sequences (:243-247).  The
+        reference's zero "frame 0" (:170-174) only exists to shift the segment coordinate of the real frames to
+        1..n_img; it is assembled and then its rows are dropped, as in :212-224."""
+        as_np = _is_np(batch["images"], batch["textonly_seqs"])
+        p, H = self._p, self.hidden_size
+        img = _dev(batch["images"], torch.float32)
+        B, n_img, hw, pp3 = img.shape
+        text = _dev(batch["textonly_seqs"], torch.int32)
+        aseq = _dev(batch["audio_seqs"], torch.int32)
+        _, n_ans, Ltok, _ = text.shape
+        proj = p.proj if proj_kernel is None else _f(proj_kernel)
+        per = hw // 4
+        enc = self._vision(img.reshape(B * n_img, hw, pp3))["seq_attnpool"].reshape(B, n_img * per, H)
+        enc = torch.cat([torch.zeros(B, per, H, dtype=enc.dtype, device=enc.device), enc], 1)
+        enc = enc.repeat_interleave(n_ans, dim=0).contiguous()
+        n_vis = (n_img + 1) * per
+        aud_in = _dev(batch["audio_clips"], torch.float32)
+        _, n_seg, n_sub, alen, mels = aud_in.shape
+        atl = self.config["audio_token_length"]
+        n_spans = n_seg * n_sub
+        aud = self._audio(aud_in.reshape(-1, alen, mels))["seq_attnpool"].reshape(B, n_spans, atl, H)
+        aud = aud.repeat_interleave(n_ans, dim=0).contiguous()
+        N = B * n_ans
+        a_tok = aseq[..., 0].reshape(N, Ltok).contiguous()
+        t_tok = text[..., 0].reshape(N, Ltok).contiguous()
+        ptr = (torch.div(torch.cumsum((a_tok == AUDIOSPAN).int(), -1) - 1, atl, rounding_mode="floor") % n_spans).to(torch.int32)
+        T0 = Ltok + n_vis
+        kw = dict(H=H, vision=enc, n_vis=n_vis, pool_h=self.output_grid_h // 2, pool_w=self.output_grid_w // 2, T=T0,
+                  audio_token_length=atl)
+        xa, ra, va = L.embed_assemble(a_tok, p.tok_emb, seg_idx=aseq[..., 1].reshape(N, Ltok).contiguous(), aud_ptr=ptr.contiguous(),
+                                      audio=aud, n_aud=n_spans, **kw)
+        xt, rt, vt = L.embed_assemble(t_tok, p.tok_emb, seg_idx=text[..., 1].reshape(N, Ltok).contiguous(), **kw)
+
+        def cut(a, b, width):      # [audio variant ; text variant] without the rows of the zero frame
+            z = torch.cat([a.view(N, T0, *width), b.view(N, T0, *width)], 0)
+            return torch.cat([z[:, :Ltok], z[:, Ltok + per:]], 1).contiguous()
+
+        T = T0 - per
+        x, rot, valid = cut(xa, xt, (H,)).view(-1, H), cut(ra, rt, (32,)).view(-1, 32), cut(va, vt, ()).view(-1)
+        kept = self._joint(x, rot, valid, 2 * N, T, Ltok)
+        toks = torch.cat([a_tok, t_tok], 0)
+        pool_idx = (toks == MASK).int().argmax(1).to(torch.int32)
+        rows = (torch.arange(2 * N, device=toks.device, dtype=torch.int32) * Ltok + pool_idx).contiguous()
+        logits = L.row_dot(kept, proj, rows)
+        return _ret(logits[:N].view(B, n_ans), as_np), _ret(logits[N:].view(B, n_ans), as_np)
+
     def __call__(self, batch):
         raise NotImplementedError()  # modeling.py:760-761
 

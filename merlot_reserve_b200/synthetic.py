@@ -314,3 +314,39 @@ def synthetic_pretrain_batch(config: Dict, batch: int, seed: int = 1) -> Dict:
     res["_rng/split_audio2text"], res["_rng/split_text2audio"] = split[0], split[1]
     res["_rng/gumbel_u"] = rng.random((batch, n_spans), dtype=np.float32) * np.float32(0.999) + np.float32(5e-4)
     return res
+
+
+def synthetic_tvqa_batch(config: Dict, batch: int, num_segments: int = 7, num_answers: int = 5, seq_len: int = 160,
+                         seed: int = 1) -> Dict:
+    """A batch in the layout `MerlotReserveTVQA.__call__` takes (finetune/tvqa/tvqa_finetune.py:163-258;
+    finetune/common_dataloader.py:140-230): per example `num_segments` frames, num_segments x 3 audio sub-segments,
+    and for each of `num_answers` candidates two token sequences of (token, segment) pairs -- subtitles as text
+    ('textonly_seqs') or as AUDIOSPAN placeholders ('audio_seqs') -- each = question + candidate ending in MASK,
+    followed by the per-segment material (segment indices 1..num_segments), padded with (0, -1)."""
+    m = config["model"]
+    gh, gw = m["output_grid"]
+    rng = np.random.default_rng(7000003 * seed + 11)
+    images = rng.random((batch, num_segments, gh * gw, 768), dtype=np.float32)
+    audio = np.abs(rng.standard_normal((batch, num_segments, 3, m["audio_seq_length"], 65), dtype=np.float32)) * np.float32(1.5)
+    audio[..., 64] = 1.0
+    text = np.zeros((batch, num_answers, seq_len, 2), np.int32)
+    aud = np.zeros((batch, num_answers, seq_len, 2), np.int32)
+    text[..., 1] = -1
+    aud[..., 1] = -1
+    for b in range(batch):
+        question = rng.integers(10, VOCAB, size=int(rng.integers(4, 9)))
+        subs = [rng.integers(10, VOCAB, size=int(rng.integers(2, 7))) for _ in range(num_segments)]
+        for a in range(num_answers):
+            head = list(question) + list(rng.integers(10, VOCAB, size=int(rng.integers(2, 6)))) + [MASK]
+            t_tok, t_seg = list(head), [0] * len(head)
+            a_tok, a_seg = list(head), [0] * len(head)
+            for i in range(num_segments):
+                t_tok += list(subs[i])
+                t_seg += [i + 1] * len(subs[i])
+                a_tok += [AUDIOSPAN] * 18          # 3 sub-segments x audio_token_length 6
+                a_seg += [i + 1] * 18
+            for arr, tok, seg in ((text, t_tok, t_seg), (aud, a_tok, a_seg)):
+                n = min(seq_len, len(tok))
+                arr[b, a, :n, 0] = tok[:n]
+                arr[b, a, :n, 1] = seg[:n]
+    return {"images": images, "audio_clips": audio, "textonly_seqs": text, "audio_seqs": aud}

@@ -486,6 +486,51 @@ class OracleMerlotReserve:
         return (pooled @ _t(proj_kernel).reshape(-1, 1)).reshape(B, n_cand)
 
 
+    def score_tvqa(self, batch, proj_kernel):
+        """MerlotReserveTVQA.__call__ (finetune/tvqa/tvqa_finetune.py:163-258), literally: a zero "frame 0" is put in
+        front of the encoded frames so the real frames get segment coordinates 1..n, both joint inputs are assembled,
+        and the rows (and mask columns) of that first frame are cut out again (:212-224).
+        batch: images [B, n_img, hw, 768]; audio_clips [B, n_seg, n_sub, 60, 65]; textonly_seqs / audio_seqs
+        [B, n_ans, L, 2] (token, segment).  Returns (logits_from_audio, logits_from_text), each [B, n_ans]."""
+        images = _t(batch["images"])
+        B, n_img, hw, pp3 = images.shape
+        H = self.hidden_size
+        imgs_enc = self.vision_encoder(images.reshape(B * n_img, hw, pp3))["seq_attnpool"].reshape(B, n_img, hw // 4, H)
+        imgs_enc = torch.cat([torch.zeros(B, 1, hw // 4, H), imgs_enc], 1)                       # :170-174
+        n_img += 1
+        text = torch.as_tensor(np.asarray(batch["textonly_seqs"])).long()
+        _, n_ans, L, _ = text.shape
+        imgs_enc = imgs_enc.reshape(B, n_img * hw // 4, H).repeat_interleave(n_ans, dim=0)       # :178-179
+        text_toks = text[..., 0].reshape(B * n_ans, L)
+        text_in = self.prepare_multimodal_inputs(tokens=text_toks, token_segment_idx=text[..., 1].reshape(B * n_ans, L),
+                                                 vision_input=imgs_enc)
+        audio_clips = _t(batch["audio_clips"])
+        _, n_seg, n_sub, alen, mels = audio_clips.shape
+        audio_enc = self.audio_encoder(audio_clips.reshape(-1, alen, mels))["seq_attnpool"]
+        atl = audio_enc.shape[1]
+        n_spans = n_seg * n_sub
+        audio_enc = audio_enc.reshape(B, n_spans, atl, H).repeat_interleave(n_ans, dim=0)       # :196-197
+        aseq = torch.as_tensor(np.asarray(batch["audio_seqs"])).long()
+        audio_toks = aseq[..., 0].reshape(B * n_ans, L)
+        ptr = torch.div(torch.cumsum((audio_toks == AUDIOSPAN).int(), -1) - 1, atl, rounding_mode="floor") % n_spans  # :200-201
+        audio_in = self.prepare_multimodal_inputs(tokens=audio_toks, token_segment_idx=aseq[..., 1].reshape(B * n_ans, L),
+                                                  vision_input=imgs_enc, audio_spans=audio_enc, audio_pointers=ptr)
+        start = L + hw // 4                                                                      # :212
+        for d in (text_in, audio_in):
+            for k in ("x", "rotary_coords", "attention_mask"):
+                d[k] = torch.cat([d[k][:, :L], d[k][:, start:]], 1)
+            d["attention_mask"] = torch.cat([d["attention_mask"][:, :, :L], d["attention_mask"][:, :, start:]], 2)
+        x = torch.cat([audio_in["x"], text_in["x"]], 0)                                          # :243-245
+        coords = torch.cat([audio_in["rotary_coords"], text_in["rotary_coords"]], 0)
+        mask = torch.cat([audio_in["attention_mask"], text_in["attention_mask"]], 0)
+        joint = self.joint_transformer(x, coords, mask)["seq"][:, :L]
+        toks = torch.cat([audio_toks, text_toks], 0)
+        pool_idx = (toks == MASK).float().argmax(1)                                              # :251
+        pooled = joint[torch.arange(2 * B * n_ans), pool_idx]
+        logits = (pooled @ _t(proj_kernel).reshape(-1, 1)).squeeze(-1)
+        la, lt = logits[: B * n_ans], logits[B * n_ans:]
+        return la.reshape(B, n_ans), lt.reshape(B, n_ans)
+
     # --- pretraining forward (pretrain/pretrain_model.py:38-259) ---
     @staticmethod
     def _augment_video_src_idx(video_src_idx, split_from_here):

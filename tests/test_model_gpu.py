@@ -187,3 +187,25 @@ def test_composite_encoder_call_equals_step_by_step(setup, lib):
         lib.PROFILE = None
     assert "mr_transformer_encode" not in names and "mr_gemm_epilogue" in names
     assert np.array_equal(a, b)
+
+
+def test_tvqa_forward_matches_oracle(setup):
+    """MerlotReserveTVQA.__call__ (finetune/tvqa/tvqa_finetune.py:163-258): 2 examples x 3 frames x 4 candidates, audio and
+    text-only variants in one joint batch, with the reference's zero "frame 0" trick.  Logits within the bf16
+    tolerance of the fp32 oracle and the same argmax wherever the oracle's top-2 margin exceeds it."""
+    from merlot_reserve_b200.synthetic import synthetic_tvqa_batch
+    cfg, params, model, orc = setup
+    H = cfg["model"]["hidden_size"]
+    batch = synthetic_tvqa_batch(cfg, 2, num_segments=3, num_answers=4, seq_len=96, seed=4)
+    proj = (np.random.default_rng(5).standard_normal((H, 1)) * 0.02).astype(np.float32)
+    got_a, got_t = model.apply({"params": params}, batch, proj, method=model.score_tvqa)
+    ref_a, ref_t = orc.score_tvqa(batch, proj)
+    for got, ref, name in ((got_a, ref_a, "audio"), (got_t, ref_t, "text")):
+        ref = ref.numpy()
+        assert got.shape == ref.shape == (2, 4)
+        tol = 2e-2 * np.abs(ref).max() + 2e-3
+        assert np.abs(got - ref).max() <= tol, (name, got, ref)
+        top2 = np.sort(ref, -1)[:, -2:]
+        clear = (top2[:, 1] - top2[:, 0]) > 2 * tol
+        assert (got.argmax(-1) == ref.argmax(-1))[clear].all()
+    assert np.abs(got_a - got_t).max() > 1e-4      # the two variants really are different sequences

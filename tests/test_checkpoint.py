@@ -138,3 +138,22 @@ def test_restored_checkpoint_runs_on_the_b200_path(tmp_path):
     got = PretrainedMerlotReserve.from_params(cfg, restored).embed_video(**clip)
     ref = PretrainedMerlotReserve.from_params(cfg, rounded).embed_video(**clip)
     assert np.array_equal(np.asarray(got), np.asarray(ref))
+
+
+def test_tokenizer_hook_loads_the_reference_vocabulary():
+    """get_encoder() + the padding protocol `get_label_space` relies on (modeling.py:1024-1032).  The vocabulary is a
+    data file of the reference: the test runs where that tree is mounted and is skipped elsewhere (GPU box)."""
+    from merlot_reserve_b200 import lowercase_encoder as le
+    fn = "/root/reference/mreserve/lowercase_encoder.json"
+    if not os.path.exists(fn):
+        with pytest.raises(FileNotFoundError):
+            le.get_encoder("/nonexistent/lowercase_encoder.json")
+        pytest.skip("reference vocabulary not available")
+    enc = le.get_encoder(fn)
+    for i, tok in enumerate(le.SPECIAL_TOKENS[:7]):
+        assert enc.token_to_id(tok) == i                      # lowercase_encoder.py:9-18
+    enc.enable_padding(pad_token="<|PAD|>", length=15)
+    ids = np.array([x.ids[:15] for x in enc.encode_batch(["cooking pasta", "playing the guitar on stage"])])
+    enc.no_padding()
+    assert ids.shape == (2, 15) and (ids[0] != le.PADDING).sum() < 15 and ids[0, -1] == le.PADDING
+    assert (ids >= 0).all() and ids.max() < 32768

@@ -32,7 +32,10 @@ __device__ __forceinline__ uint4 pack8b(const float (&f)[8]) {
 // Persistent blocks; every lane keeps the dgamma / dbeta partials of its own columns in registers, the 8 warps of a
 // block are combined through shared memory, blocks through `partial` + layernorm_bwd_reduce_kernel.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreadsRow)
+// NV = uint4 vectors per lane (H <= 256 NV): sized exactly so that two 256-thread blocks fit an SM (16 rows in
+// flight per SM; one row = 3 or 4 streams of H bf16, all requested before the first reduction).
+template <int NV>
+__global__ void __launch_bounds__(kThreadsRow, NV <= 3 ? 2 : 1)
 layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const float* __restrict__ gamma,
                      const bf16* __restrict__ dres, bf16* __restrict__ dx, float* __restrict__ partial, int rows, int H,
                      float eps) {
@@ -40,28 +43,33 @@ layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, co
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nvec = H / 8;
   const float inv_h = 1.0f / static_cast<float>(H);
-  float dg[kMaxVec][8], db[kMaxVec][8], gm[kMaxVec][8];
+  float dg[NV][8], db[NV][8];
 #pragma unroll
-  for (int i = 0; i < kMaxVec; ++i) {
-    const int v = lane + 32 * i;
+  for (int i = 0; i < NV; ++i) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      dg[i][j] = 0.f;
-      db[i][j] = 0.f;
-      gm[i][j] = v < nvec ? gamma[v * 8 + j] : 0.f;
-    }
+    for (int j = 0; j < 8; ++j) dg[i][j] = 0.f, db[i][j] = 0.f;
   }
   for (int row = blockIdx.x * kWarps + warp; row < rows; row += gridDim.x * kWarps) {
     const uint4* xs = reinterpret_cast<const uint4*>(x + static_cast<size_t>(row) * H);
     const uint4* ds = reinterpret_cast<const uint4*>(dy + static_cast<size_t>(row) * H);
-    float xv[kMaxVec][8], dv[kMaxVec][8];
-    float s = 0.f, s2 = 0.f;
+    const uint4* rs = reinterpret_cast<const uint4*>(dres + static_cast<size_t>(row) * H);
+    uint4 xu[NV], du[NV], ru[NV];
 #pragma unroll
-    for (int i = 0; i < kMaxVec; ++i) {
+    for (int i = 0; i < NV; ++i) {             // every load of the row is in flight before anything is consumed
       const int v = lane + 32 * i;
       if (v < nvec) {
-        unpack8b(__ldg(xs + v), xv[i]);
-        unpack8b(__ldg(ds + v), dv[i]);
+        xu[i] = __ldg(xs + v);
+        du[i] = __ldg(ds + v);
+        if (dres != nullptr) ru[i] = __ldg(rs + v);
+      }
+    }
+    float xv[NV][8], dv[NV][8];
+    float s = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      if (lane + 32 * i < nvec) {
+        unpack8b(xu[i], xv[i]);
+        unpack8b(du[i], dv[i]);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           s += xv[i][j];
@@ -75,12 +83,16 @@ layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, co
     const float rstd = rsqrtf(s2 * inv_h - mean * mean + eps);
     float sg = 0.f, sgx = 0.f;
 #pragma unroll
-    for (int i = 0; i < kMaxVec; ++i) {
-      if (lane + 32 * i < nvec) {
+    for (int i = 0; i < NV; ++i) {
+      const int v = lane + 32 * i;
+      if (v < nvec) {
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * v);       // L1-resident
+        const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * v + 1);
+        const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float xh = (xv[i][j] - mean) * rstd;
-          const float g = dv[i][j] * gm[i][j];
+          const float g = dv[i][j] * gm[j];
           dg[i][j] += dv[i][j] * xh;
           db[i][j] += dv[i][j];
           xv[i][j] = xh;
@@ -93,7 +105,7 @@ layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, co
     sg = wsum(sg) * inv_h;
     sgx = wsum(sgx) * inv_h;
 #pragma unroll
-    for (int i = 0; i < kMaxVec; ++i) {
+    for (int i = 0; i < NV; ++i) {
       const int v = lane + 32 * i;
       if (v < nvec) {
         float o[8];
@@ -101,7 +113,7 @@ layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, co
         for (int j = 0; j < 8; ++j) o[j] = rstd * (dv[i][j] - sg - xv[i][j] * sgx);
         if (dres != nullptr) {
           float r[8];
-          unpack8b(__ldg(reinterpret_cast<const uint4*>(dres + static_cast<size_t>(row) * H) + v), r);
+          unpack8b(ru[i], r);
 #pragma unroll
           for (int j = 0; j < 8; ++j) o[j] += r[j];
         }
@@ -111,7 +123,7 @@ layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, co
   }
   // block reduction of the parameter-gradient partials
 #pragma unroll
-  for (int i = 0; i < kMaxVec; ++i) {
+  for (int i = 0; i < NV; ++i) {
     const int v = lane + 32 * i;
     if (v < nvec) {
 #pragma unroll
@@ -676,15 +688,18 @@ extern "C" int32_t mr_layernorm_bwd(mr_stream_t stream_, const MrLayerNormDesc* 
   if (nblk > 148 * 2) nblk = 148 * 2;
   if (nblk < 1) nblk = 1;
   const size_t smem = static_cast<size_t>(kWarps) * 2 * d->H * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set && smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(layernorm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 2 * 1024 * 4);
+  const int nv = ceil_div(d->H / 8, 32);
+  auto launch = [&](auto kern) -> int32_t {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 2 * 1024 * 4);
     if (e != cudaSuccess) return cuda_status(e);
-    attr_set = true;
-  }
-  layernorm_bwd_kernel<<<nblk, kThreadsRow, smem, stream>>>(
-      static_cast<const bf16*>(in[0]), static_cast<const bf16*>(in[1]), static_cast<const float*>(in[2]),
-      static_cast<const bf16*>(in[3]), static_cast<bf16*>(out[0]), static_cast<float*>(workspace), d->rows, d->H, d->eps);
+    kern<<<nblk, kThreadsRow, smem, stream>>>(
+        static_cast<const bf16*>(in[0]), static_cast<const bf16*>(in[1]), static_cast<const float*>(in[2]),
+        static_cast<const bf16*>(in[3]), static_cast<bf16*>(out[0]), static_cast<float*>(workspace), d->rows, d->H, d->eps);
+    return MR_OK;
+  };
+  int32_t lst = nv <= 1 ? launch(layernorm_bwd_kernel<1>) : nv == 2 ? launch(layernorm_bwd_kernel<2>)
+              : nv == 3 ? launch(layernorm_bwd_kernel<3>) : launch(layernorm_bwd_kernel<4>);
+  if (lst != MR_OK) return lst;
   int32_t st = after_launch();
   if (st != MR_OK) return st;
   layernorm_bwd_reduce_kernel<<<ceil_div(2 * d->H, 256), 256, 0, stream>>>(

@@ -332,8 +332,8 @@ def attention(qkv: torch.Tensor, B: int, T: int, H: int, valid=None, group=None,
 
 
 def attention_bwd(qkv: torch.Tensor, dctx: torch.Tensor, ctx: torch.Tensor, lse: torch.Tensor, B: int, T: int, H: int,
-                  valid=None, group=None) -> torch.Tensor:
-    d = AttentionDesc(B=B, T=T, H=H)
+                  valid=None, group=None, algo=ATTN_AUTO) -> torch.Tensor:
+    d = AttentionDesc(B=B, T=T, H=H, algo=algo)
     dqkv = torch.empty_like(qkv)
     _call("mr_attention_bwd", d, [qkv, dctx, ctx, lse, valid, group], [dqkv],
           _ws("mr_attention_bwd_workspace_bytes", d, qkv.device))

@@ -323,6 +323,11 @@ constexpr int kBwdSmem = (2 + 2 + 2 + 2) * kTile * 2 + 4 * kBlk * 4 + 3 * kBlk *
 }  // namespace
 }  // namespace mr
 
+namespace mr {
+int32_t launch_attention_bwd_tc(cudaStream_t stream, const bf16* qkv, const bf16* dout, const float* lse, const float* Dsum,
+                                const uint8_t* valid, const int32_t* group, bf16* dqkv, float* dq_acc, int B, int T, int H);
+}
+
 extern "C" size_t mr_attention_bwd_workspace_bytes(const MrAttentionDesc* d) {
   if (!d || d->B <= 0 || d->T <= 0 || d->H <= 0) return 0;
   const size_t rows = static_cast<size_t>(d->B) * d->T;
@@ -349,6 +354,19 @@ extern "C" int32_t mr_attention_bwd(mr_stream_t stream_, const MrAttentionDesc* 
       static_cast<const bf16*>(in[1]), static_cast<const bf16*>(in[2]), Dsum, d->B, d->T, d->H);
   int32_t st = after_launch();
   if (st != MR_OK) return st;
+  // T > 64: tcgen05 / TMEM kernel (attention_bwd_tc.cu); short sequences (audio, span) and algo = MMA_SYNC: mma.sync
+  MR_REQUIRE(d->algo >= MR_ATTN_ALGO_AUTO && d->algo <= MR_ATTN_ALGO_TCGEN05, MR_ERR_BAD_SHAPE);
+  const bool use_tc = d->algo == MR_ATTN_ALGO_TCGEN05 || (d->algo == MR_ATTN_ALGO_AUTO && d->T > 64);
+  if (use_tc) {
+    st = launch_attention_bwd_tc(stream, static_cast<const bf16*>(in[0]), static_cast<const bf16*>(in[1]),
+                                 static_cast<const float*>(in[3]), Dsum, static_cast<const uint8_t*>(in[4]),
+                                 static_cast<const int32_t*>(in[5]), static_cast<bf16*>(out[0]), dq_acc, d->B, d->T, d->H);
+    if (st != MR_OK) return st;
+    int64_t cb = ceil_div64(rows * (d->H / 8), 256);
+    if (cb > 148 * 16) cb = 148 * 16;
+    dq_convert_kernel<<<static_cast<unsigned>(cb), 256, 0, stream>>>(dq_acc, static_cast<bf16*>(out[0]), rows, d->H);
+    return after_launch();
+  }
   static bool attr_set = false;
   if (!attr_set) {
     e = cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem);

@@ -145,9 +145,34 @@ def test_attention_bwd(cuda, lib, B, T, H, masked):
         _close(ctx, ref_ctx, 2e-2, 2e-2, f"ctx algo {algo}")
         ok = torch.ones(B, T, dtype=torch.bool) if valid is None else valid.bool()
         _close(lse.cpu().permute(0, 2, 1)[ok], ref_lse.permute(0, 2, 1)[ok], 2e-3, 1e-3, f"lse algo {algo}")
-        dqkv = lib.attention_bwd(qkv.to(cuda), dctx.to(cuda), ctx, lse, B, T, H, valid=dev(valid), group=dev(group))
         scale = ref_dqkv.abs().max().item()
-        _close(dqkv, ref_dqkv, 2e-2 * scale + 1e-3, 3e-2, f"dqkv algo {algo}")
+        for balgo in ([1, 2] if T > 64 else [1]):        # backward: mma.sync kernel and the tcgen05 / TMEM kernel
+            dqkv = lib.attention_bwd(qkv.to(cuda), dctx.to(cuda), ctx, lse, B, T, H, valid=dev(valid), group=dev(group),
+                                     algo=balgo)
+            _close(dqkv, ref_dqkv, 2e-2 * scale + 1e-3, 3e-2, f"dqkv fwd algo {algo} bwd algo {balgo}")
+
+
+def test_attention_bwd_tc_many_blocks_and_uniform_rows(cuda, lib):
+    """The tcgen05 backward on the training shapes' structure: several 128-key CTAs per sequence accumulating dQ
+    through global reductions, 12 heads, a padded tail, and invalid QUERY rows that carry a non-zero dctx (their
+    uniform attention still sends gradient to v, and dS = P (dP - D) to q and k, as in the mma.sync kernel)."""
+    B, T, H = 3, 300, 768
+    g = torch.Generator().manual_seed(17)
+    qkv = _bf(torch.randn(B * T, 3 * H, generator=g) * 0.8)
+    qkv[:, :H] *= 0.35
+    dctx = _bf(torch.randn(B * T, H, generator=g))
+    valid = torch.ones(B, T, dtype=torch.uint8)
+    valid[0, 40:90] = 0
+    valid[1, 250:] = 0
+    dev = lambda t: t.to(cuda).contiguous().view(-1)
+    lse = torch.empty(B, H // 64, T, device=cuda)
+    ctx = lib.attention(qkv.to(cuda), B, T, H, valid=dev(valid), lse=lse)
+    a = lib.attention_bwd(qkv.to(cuda), dctx.to(cuda), ctx, lse, B, T, H, valid=dev(valid), algo=1)
+    b = lib.attention_bwd(qkv.to(cuda), dctx.to(cuda), ctx, lse, B, T, H, valid=dev(valid), algo=2)
+    scale = a.float().abs().max().item()
+    _close(b, a.float().cpu(), 2e-2 * scale + 1e-3, 3e-2, "tcgen05 vs mma.sync backward")
+    _, ref_dqkv, _ = _attn_ref_autograd(qkv, dctx, B, T, H, valid, None)
+    _close(b, ref_dqkv, 2e-2 * ref_dqkv.abs().max().item() + 1e-3, 3e-2, "tcgen05 backward vs autograd")
 
 
 def test_transformer_layer_backward_composition(cuda, lib):

@@ -142,16 +142,28 @@ layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, co
   }
 }
 
-__global__ void layernorm_bwd_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dgamma,
-                                            float* __restrict__ dbeta, int nblk, int H) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= 2 * H) return;
+// Sums the per-block partials [nblk][2H]: 32 columns x 8 row groups per block, so a launch is ~50 blocks of coalesced
+// 128-byte row reads instead of 2H threads walking nblk rows one after the other.
+__global__ void __launch_bounds__(256)
+layernorm_bwd_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                            int nblk, int H) {
+  __shared__ float red[8][33];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx;
   float a = 0.f;
-  for (int b = 0; b < nblk; ++b) a += partial[static_cast<size_t>(b) * 2 * H + c];
-  if (c < H)
-    dgamma[c] = a;
-  else
-    dbeta[c - H] = a;
+  if (c < 2 * H)
+    for (int b = ry; b < nblk; b += 8) a += partial[static_cast<size_t>(b) * 2 * H + c];
+  red[ry][cx] = a;
+  __syncthreads();
+  if (ry == 0 && c < 2 * H) {
+    float t = 0.f;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) t += red[r][cx];   // fixed order: deterministic
+    if (c < H)
+      dgamma[c] = t;
+    else
+      dbeta[c - H] = t;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -702,7 +714,7 @@ extern "C" int32_t mr_layernorm_bwd(mr_stream_t stream_, const MrLayerNormDesc* 
   if (lst != MR_OK) return lst;
   int32_t st = after_launch();
   if (st != MR_OK) return st;
-  layernorm_bwd_reduce_kernel<<<ceil_div(2 * d->H, 256), 256, 0, stream>>>(
+  layernorm_bwd_reduce_kernel<<<ceil_div(2 * d->H, 32), 256, 0, stream>>>(
       static_cast<const float*>(workspace), static_cast<float*>(out[1]), static_cast<float*>(out[2]), nblk, d->H);
   return after_launch();
 }

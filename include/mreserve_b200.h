@@ -92,7 +92,11 @@ enum {
   MR_EPI_ROTARY_QKV = 8,
   MR_EPI_OUT_F32 = 16,
   MR_EPI_LN_IN = 32,     /* A is the UN-normalised residual stream; LayerNorm is folded into the GEMM (below) */
-  MR_EPI_STATS_OUT = 64  /* also emit per-row (sum, sum of squares) partials of the bf16 output (below) */
+  MR_EPI_STATS_OUT = 64, /* also emit per-row (sum, sum of squares) partials of the bf16 output (below) */
+  MR_EPI_DGELU = 128     /* backward of my_gelu fused into the dgrad that produces its input gradient:
+                            D = acc * gelu'(in[3]), in[3] = the forward's PRE-activation, bf16, indexed like D
+                            (gelu'(p) = s (1 + 1.702 p (1 - s)), s = sigmoid(1.702 p)).  bf16 staged output with
+                            trans_b = 1, trans_a = 0 only; excludes every other epilogue flag. */
 };
 
 enum { MR_GEMM_ALGO_TCGEN05 = 0, MR_GEMM_ALGO_SIMT_DEBUG = 1 };
@@ -121,6 +125,9 @@ typedef struct MrGemmDesc {
   int32_t trans_a, trans_b;
   int32_t ldb;       /* row pitch of in[1] in elements; 0 = dense (K, or N when trans_b) */
   int32_t split_k;
+  int32_t tile_n;    /* 0 = auto (256 columns unless that leaves SMs without a tile), 128 or 256 = force the tile
+                        width (256 needs N % 256 == 0).  The auto rule counts output tiles only; a split-K caller
+                        that knows tiles x split_k fills the SMs asks for 256 here. */
 } MrGemmDesc;
 
 int32_t mr_gemm_epilogue(mr_stream_t stream, const MrGemmDesc* d, const void* const* in, void* const* out,

@@ -8,13 +8,13 @@ from __future__ import annotations
 
 import ctypes as C
 from pathlib import Path
-from typing import Optional, Sequence
+from typing import Optional, Sequence, Tuple
 
 import torch
 
 _LIB_PATH = Path(__file__).resolve().parent / "lib" / "libmreserve_b200.so"
 
-EPI_BIAS, EPI_GELU, EPI_RESIDUAL, EPI_ROTARY_QKV, EPI_OUT_F32, EPI_LN_IN, EPI_STATS_OUT = 1, 2, 4, 8, 16, 32, 64
+EPI_BIAS, EPI_GELU, EPI_RESIDUAL, EPI_ROTARY_QKV, EPI_OUT_F32, EPI_LN_IN, EPI_STATS_OUT, EPI_DGELU = 1, 2, 4, 8, 16, 32, 64, 128
 ALGO_TCGEN05, ALGO_SIMT_DEBUG = 0, 1
 
 
@@ -27,7 +27,8 @@ class GemmDesc(C.Structure):
                 ("epilogue", C.c_int32), ("seq_in", C.c_int32), ("seq_out", C.c_int32), ("row_off", C.c_int32),
                 ("rot_rows", C.c_int32), ("hidden", C.c_int32), ("algo", C.c_int32), ("q_scale", C.c_float),
                 ("num_sms", C.c_int32), ("ln_eps", C.c_float), ("algo_pair", C.c_int32),
-                ("trans_a", C.c_int32), ("trans_b", C.c_int32), ("ldb", C.c_int32), ("split_k", C.c_int32)]
+                ("trans_a", C.c_int32), ("trans_b", C.c_int32), ("ldb", C.c_int32), ("split_k", C.c_int32),
+                ("tile_n", C.c_int32)]
 
 
 class AttentionDesc(C.Structure):
@@ -166,7 +167,7 @@ MISC_FNS = ["mr_check_device", "mr_abi_version", "mr_status_string", "mr_launch_
 import os as _os
 GEMM_PAIR_DEFAULT = int(_os.environ.get("MR_GEMM_PAIR", "0"))
 
-ABI_VERSION = 11  # must equal mr_abi_version() of the loaded library (struct layouts above)
+ABI_VERSION = 12  # must equal mr_abi_version() of the loaded library (struct layouts above)
 
 _lib = None
 
@@ -455,25 +456,60 @@ def contrastive_reduce(lse: torch.Tensor, numer: torch.Tensor, sources=None) -> 
 
 
 def gemm_bwd(a: torch.Tensor, b: torch.Tensor, *, trans_a=False, trans_b=False, out_f32=True, split_k=0, out=None,
-             bias=None) -> torch.Tensor:
+             bias=None, tile_n=0, dgelu_pre=None) -> torch.Tensor:
     """Backward GEMMs on transposed (MN-major) operands, D [M, N] = op(a) . op(b):
        trans_a: a is [K, M] (else [M, K]);  trans_b: b is [K, N] (else [N, K]).
-    dgrad: gemm_bwd(dY, W_packed, trans_b=True);  wgrad (packed layout): gemm_bwd(dY, X, trans_a=True, trans_b=True)."""
+    dgrad: gemm_bwd(dY, W_packed, trans_b=True);  wgrad (packed layout): gemm_bwd(dY, X, trans_a=True, trans_b=True).
+    dgelu_pre: bf16 [M, N] pre-activation of my_gelu; the result is D * gelu'(dgelu_pre) (MR_EPI_DGELU, bf16 dgrad).
+    tile_n: 0 = the library's rule, 128 / 256 = force the tile width (wgrad plans, `wgrad_plan`)."""
     assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16 and a.is_contiguous() and b.is_contiguous()
     K, M = a.shape if trans_a else (a.shape[1], a.shape[0])
     Kb, N = b.shape if trans_b else (b.shape[1], b.shape[0])
     assert K == Kb, (a.shape, b.shape)
+    if dgelu_pre is not None:
+        assert trans_b and not trans_a and not out_f32 and bias is None and split_k <= 1
+        assert dgelu_pre.dtype == torch.bfloat16 and dgelu_pre.is_contiguous() and tuple(dgelu_pre.shape) == (M, N)
     if out is None:
         out = torch.empty((M, N), dtype=torch.float32 if out_f32 else torch.bfloat16, device=a.device)
     epi = (EPI_OUT_F32 if out.dtype == torch.float32 else 0) | (EPI_BIAS if bias is not None else 0)
+    if dgelu_pre is not None:
+        epi = EPI_DGELU
     d = GemmDesc(M=M, N=N, K=K, lda=a.shape[1], ldd=out.shape[-1], epilogue=epi, algo=ALGO_TCGEN05, q_scale=1.0,
-                 trans_a=int(trans_a), trans_b=int(trans_b), ldb=b.shape[1], split_k=split_k)
+                 trans_a=int(trans_a), trans_b=int(trans_b), ldb=b.shape[1], split_k=split_k, tile_n=tile_n)
     ws = None
     if split_k > 1:
         nbytes = load().mr_gemm_epilogue_workspace_bytes(C.byref(d))
         ws = torch.empty((nbytes,), dtype=torch.uint8, device=a.device)
-    _call("mr_gemm_epilogue", d, [a, b, bias, None, None, None, None], [out, None], ws)
+    _call("mr_gemm_epilogue", d, [a, b, bias, dgelu_pre, None, None, None], [out, None], ws)
     return out
+
+
+def wgrad_plan(out_features: int, in_features: int, rows: int, sms: int = 148) -> Tuple[int, int]:
+    """(tile_n, split_k) for dW [out, in] = dY^T . X reduced over `rows` token rows.
+
+    The kernel walks tiles x splits round-robin over one persistent CTA per SM, so the time is
+    waves x (k-blocks per part x t_kb + t_epilogue) + the second-stage sum over the fp32 partials.  Constants (us, a
+    B200 at ~1.8 GHz): one 64-row k-block of a 128 x 256 tile = 4 MMAs of 128 clocks; a 128 x 128 tile runs at the
+    shared-memory read limit (8 KB per 64 clocks), hence a little more than half of that; the epilogue stores the
+    fp32 tile from registers; the reduce streams split_k + 1 fp32 copies of dW at HBM rate plus a launch."""
+    kb_total = -(-rows // 64)
+    m_tiles = -(-out_features // 128)
+    best = None
+    for bn in (256, 128):
+        if bn == 256 and in_features % 256 != 0:
+            continue
+        tiles = m_tiles * -(-in_features // bn)
+        t_kb, t_epi = (0.29, 1.6) if bn == 256 else (0.17, 0.9)
+        for s in range(1, 17):
+            if s > kb_total:
+                break
+            waves = -(-(tiles * s) // sms)
+            t = waves * (-(-kb_total // s) * t_kb + t_epi)
+            if s > 1:
+                t += 3.0 + (s + 1) * out_features * in_features * 4 / 5.0e6
+            if best is None or t < best[0] - 1e-9:
+                best = (t, bn, s)
+    return best[1], (best[2] if best[2] > 1 else 0)
 
 
 def row_dot(x: torch.Tensor, w: torch.Tensor, row_idx=None, rows=None) -> torch.Tensor:

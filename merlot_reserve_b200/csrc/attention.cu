@@ -7,28 +7,32 @@
 //
 // v1 data path: cp.async double-buffered K/V tiles (XOR-swizzled, conflict-free ldmatrix), mma.sync
 // m16n8k16 bf16 with fp32 accumulation, online softmax in fp32 (base-2), P kept in registers.
+//
+// Two instantiations.  <64, 2>: 64-query x 64-key tiles, 4 warps, double-buffered keys (any T).  <32, 1>: the
+// audio (T = 31) and span (T = 16) sequences fit ONE 32 x 32 tile, so the CTA is 2 warps with 12 KB of shared
+// memory (no second key buffer) instead of 4 warps (two of them idle) with 40 KB: ~3.5x more (sequence, head)
+// items in flight per SM for a kernel whose time is the load -> mma -> softmax -> mma -> store latency chain.
 #include "common.cuh"
 #include "ptx.cuh"
 
 namespace mr {
 namespace {
 
-constexpr int kBlockM = 64;
-constexpr int kBlockN = 64;
 constexpr int kD = 64;
-constexpr int kAttnThreads = 128;
 constexpr int kInfoOob = static_cast<int>(0x80000000u);      // key index >= T
 constexpr int kInfoInvalid = static_cast<int>(0x80000001u);  // padding key
 constexpr float kLog2e = 1.4426950408889634f;
 
 __device__ __forceinline__ int swz(int row, int chunk) { return row * kD + ((chunk ^ (row & 7)) << 3); }
 
-// Loads a [64 x 64] bf16 tile (rows row0.. of sequence b, column offset col0 in the qkv matrix).
+// Loads a [kTile x 64] bf16 tile (rows row0.. of sequence b, column offset col0 in the qkv matrix); the CTA has
+// 2 * kTile threads, so every thread moves four 16-byte chunks.
+template <int kTile>
 __device__ __forceinline__ void load_tile(bf16* s, const bf16* __restrict__ qkv, size_t seq_base, int row0, int T,
                                           int ld, int col0, int tid) {
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    const int i = tid + kAttnThreads * k;
+    const int i = tid + 2 * kTile * k;
     const int row = i >> 3, ch = i & 7;
     const int t = row0 + row;
     const bool ok = t < T;
@@ -37,13 +41,17 @@ __device__ __forceinline__ void load_tile(bf16* s, const bf16* __restrict__ qkv,
   }
 }
 
-__global__ void __launch_bounds__(kAttnThreads)
+template <int kTile, int kBufs>
+__global__ void __launch_bounds__(2 * kTile, kTile == 32 ? 10 : 1)
 attention_fwd_kernel(const bf16* __restrict__ qkv, const uint8_t* __restrict__ valid, const int32_t* __restrict__ group,
                      bf16* __restrict__ out, float* __restrict__ lse_out, int B, int T, int H) {
+  constexpr int kBlockM = kTile, kBlockN = kTile;
+  static_assert(kTile == 64 || kTile == 32, "tile = 16 rows per warp x (2 or 4) warps");
+  static_assert(kBufs == 1 || kBufs == 2, "kBufs == 1 requires T <= kTile (a single key block)");
   __shared__ __align__(128) bf16 sQ[kBlockM * kD];
-  __shared__ __align__(128) bf16 sK[2][kBlockN * kD];
-  __shared__ __align__(128) bf16 sV[2][kBlockN * kD];
-  __shared__ int sInfo[2][kBlockN];
+  __shared__ __align__(128) bf16 sK[kBufs][kBlockN * kD];
+  __shared__ __align__(128) bf16 sV[kBufs][kBlockN * kD];
+  __shared__ int sInfo[kBufs][kBlockN];
 
   const int nh = H / kD;
   const int nqb = (T + kBlockM - 1) / kBlockM;
@@ -68,9 +76,9 @@ attention_fwd_kernel(const bf16* __restrict__ qkv, const uint8_t* __restrict__ v
     }
   };
 
-  load_tile(sQ, qkv, seq_base, q0, T, ld, h * kD, tid);
-  load_tile(sK[0], qkv, seq_base, 0, T, ld, H + h * kD, tid);
-  load_tile(sV[0], qkv, seq_base, 0, T, ld, 2 * H + h * kD, tid);
+  load_tile<kTile>(sQ, qkv, seq_base, q0, T, ld, h * kD, tid);
+  load_tile<kTile>(sK[0], qkv, seq_base, 0, T, ld, H + h * kD, tid);
+  load_tile<kTile>(sV[0], qkv, seq_base, 0, T, ld, 2 * H + h * kD, tid);
   write_info(0, 0);
   cp_async_commit();
 
@@ -98,11 +106,12 @@ attention_fwd_kernel(const bf16* __restrict__ qkv, const uint8_t* __restrict__ v
   float l_run[2] = {0.f, 0.f};
 
   for (int kb = 0; kb < nkb; ++kb) {
-    const int buf = kb & 1;
-    if (kb + 1 < nkb) {
-      load_tile(sK[buf ^ 1], qkv, seq_base, (kb + 1) * kBlockN, T, ld, H + h * kD, tid);
-      load_tile(sV[buf ^ 1], qkv, seq_base, (kb + 1) * kBlockN, T, ld, 2 * H + h * kD, tid);
-      write_info(buf ^ 1, kb + 1);
+    const int buf = kb & (kBufs - 1);
+    if (kBufs == 2 && kb + 1 < nkb) {
+      const int nxt = (kb + 1) & (kBufs - 1);
+      load_tile<kTile>(sK[nxt], qkv, seq_base, (kb + 1) * kBlockN, T, ld, H + h * kD, tid);
+      load_tile<kTile>(sV[nxt], qkv, seq_base, (kb + 1) * kBlockN, T, ld, 2 * H + h * kD, tid);
+      write_info(nxt, kb + 1);
       cp_async_commit();
       cp_async_wait<1>();
     } else {
@@ -120,15 +129,15 @@ attention_fwd_kernel(const bf16* __restrict__ qkv, const uint8_t* __restrict__ v
         }
       }
       // ---- S = Q K^T (16 x 64 per warp) ----
-      float s[8][4];
+      float s[kBlockN / 8][4];
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
+      for (int i = 0; i < kBlockN / 8; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) s[i][j] = 0.f;
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks) {
 #pragma unroll
-        for (int n16 = 0; n16 < 4; ++n16) {
+        for (int n16 = 0; n16 < kBlockN / 16; ++n16) {
           const int mat = lane >> 3;
           const int row = n16 * 16 + (mat >> 1) * 8 + (lane & 7);
           const int ch = 2 * ks + (mat & 1);
@@ -141,7 +150,7 @@ attention_fwd_kernel(const bf16* __restrict__ qkv, const uint8_t* __restrict__ v
       // ---- mask + online softmax ----
       float blk_max[2] = {-INFINITY, -INFINITY};
 #pragma unroll
-      for (int nt = 0; nt < 8; ++nt) {
+      for (int nt = 0; nt < kBlockN / 8; ++nt) {
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const int r = e >> 1;
@@ -169,7 +178,7 @@ attention_fwd_kernel(const bf16* __restrict__ qkv, const uint8_t* __restrict__ v
       }
       float blk_sum[2] = {0.f, 0.f};
 #pragma unroll
-      for (int nt = 0; nt < 8; ++nt) {
+      for (int nt = 0; nt < kBlockN / 8; ++nt) {
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const int r = e >> 1;
@@ -189,7 +198,7 @@ attention_fwd_kernel(const bf16* __restrict__ qkv, const uint8_t* __restrict__ v
       }
       // ---- O += P V ----
 #pragma unroll
-      for (int kk = 0; kk < 4; ++kk) {
+      for (int kk = 0; kk < kBlockN / 16; ++kk) {
         uint32_t pa[4];
         pa[0] = pack_bf16(s[2 * kk][0], s[2 * kk][1]);
         pa[1] = pack_bf16(s[2 * kk][2], s[2 * kk][3]);
@@ -270,11 +279,19 @@ extern "C" int32_t mr_attention_fwd(mr_stream_t stream_, const MrAttentionDesc* 
                                static_cast<bf16*>(out[0]), lse, d->B, d->T, d->H);
   }
   const int nh = d->H / 64;
-  const int nqb = ceil_div(d->T, kBlockM);
+  // T <= 32 (audio T = 31, span T = 16): one 32 x 32 tile per (sequence, head), 2-warp CTAs, 12 KB smem
+  const bool small = d->T <= 32 && d->algo == MR_ATTN_ALGO_AUTO;   // MR_ATTN_ALGO_MMA_SYNC keeps the 64 x 64 tiles
+  const int tile = small ? 32 : 64;
+  const int nqb = ceil_div(d->T, tile);
   const int64_t blocks = static_cast<int64_t>(d->B) * nh * nqb;
   MR_REQUIRE(blocks < (int64_t(1) << 31), MR_ERR_BAD_SHAPE);
-  attention_fwd_kernel<<<static_cast<unsigned>(blocks), kAttnThreads, 0, static_cast<cudaStream_t>(stream_)>>>(
-      static_cast<const bf16*>(in[0]), static_cast<const uint8_t*>(in[1]), static_cast<const int32_t*>(in[2]),
-      static_cast<bf16*>(out[0]), lse, d->B, d->T, d->H);
+  if (small)
+    attention_fwd_kernel<32, 1><<<static_cast<unsigned>(blocks), 64, 0, static_cast<cudaStream_t>(stream_)>>>(
+        static_cast<const bf16*>(in[0]), static_cast<const uint8_t*>(in[1]), static_cast<const int32_t*>(in[2]),
+        static_cast<bf16*>(out[0]), lse, d->B, d->T, d->H);
+  else
+    attention_fwd_kernel<64, 2><<<static_cast<unsigned>(blocks), 128, 0, static_cast<cudaStream_t>(stream_)>>>(
+        static_cast<const bf16*>(in[0]), static_cast<const uint8_t*>(in[1]), static_cast<const int32_t*>(in[2]),
+        static_cast<bf16*>(out[0]), lse, d->B, d->T, d->H);
   return after_launch();
 }

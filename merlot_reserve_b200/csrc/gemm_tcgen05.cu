@@ -88,6 +88,14 @@ __device__ __forceinline__ float gelu_sigmoid(float x) {
   return fmaf(h, t, h);
 }
 
+__device__ __forceinline__ float gelu_sigmoid_grad(float x) {
+  // d/dx [x sigmoid(1.702 x)] = s (1 + 1.702 x (1 - s)), s = sigmoid(1.702 x) = 0.5 (1 + tanh(0.851 x))
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.851f * x));
+  const float sg = fmaf(0.5f, t, 0.5f);
+  return sg * fmaf(1.702f * x, 1.0f - sg, 1.0f);
+}
+
 __device__ __forceinline__ int map_row(int r, int seq_in, int seq_out, int row_off) {
   return seq_in == 0 ? r : (r / seq_in) * seq_out + (r % seq_in) + row_off;
 }
@@ -124,6 +132,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   // An MN-major operand is staged as 64-column slabs of [64 k-rows x 128 B] (one TMA box each, 128B swizzle):
   // slab stride = LBO = 8 KB, 8-row groups inside a slab = SBO = 1 KB, one K=16 MMA step = 2 KB further.
   constexpr bool kAmn = (kTrans & 1) != 0, kBmn = (kTrans & 2) != 0;
+  // MR_EPI_DGELU (the dgrad of the MLP "out" projection): the "residual" box carries the forward's pre-activation
+  // and the accumulator is MULTIPLIED by gelu'(box) instead of added to it.  Spelled gelu + residual on kTrans == 2.
+  constexpr bool kDGelu = kGelu && kResidual && kTrans == 2;
+  static_assert(!kDGelu || !kDirect, "the fused GELU backward lives on the staged path");
   static_assert(!(kPair && kTrans != 0), "MN-major operands: single-CTA tiles only");
   const uint32_t cta_rank = kPair ? cluster_ctarank() : 0u;   // 0 = leader (issues the MMAs of the pair)
   extern __shared__ uint8_t smem_raw[];
@@ -447,12 +459,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                   for (int q = 0; q < 8; ++q) f[q] *= p.q_scale;
                 }
               }
-              if constexpr (kGelu) {
+              if constexpr (kGelu && !kDGelu) {
 #pragma unroll
                 for (int q = 0; q < 8; ++q) f[q] = gelu_sigmoid(f[q]);
               }
               uint4* cell = reinterpret_cast<uint4*>(my_row + ((j ^ sw) << 4));
-              if constexpr (kResidual) {
+              if constexpr (kDGelu) {
+                const uint4 rr = *cell;
+                const float pre[8] = {bf16_lo(rr.x), bf16_hi(rr.x), bf16_lo(rr.y), bf16_hi(rr.y),
+                                      bf16_lo(rr.z), bf16_hi(rr.z), bf16_lo(rr.w), bf16_hi(rr.w)};
+#pragma unroll
+                for (int q = 0; q < 8; ++q) f[q] *= gelu_sigmoid_grad(pre[q]);
+              } else if constexpr (kResidual) {
                 const uint4 rr = *cell;
                 f[0] += bf16_lo(rr.x); f[1] += bf16_hi(rr.x);
                 f[2] += bf16_lo(rr.y); f[3] += bf16_hi(rr.y);
@@ -839,6 +857,13 @@ extern "C" int32_t mr_gemm_epilogue(mr_stream_t stream_, const MrGemmDesc* d, co
   MR_REQUIRE(aligned16(A) && aligned16(W) && aligned16(out[0]), MR_ERR_MISALIGNED);
   const bool bias = d->epilogue & MR_EPI_BIAS, gelu = d->epilogue & MR_EPI_GELU;
   const bool residual = d->epilogue & MR_EPI_RESIDUAL, rotary = d->epilogue & MR_EPI_ROTARY_QKV;
+  const bool dgelu = d->epilogue & MR_EPI_DGELU;
+  if (dgelu) {
+    // D = acc * gelu'(pre-activation): the dgrad of the MLP "out" projection, staged bf16 path
+    MR_REQUIRE(d->epilogue == MR_EPI_DGELU && d->trans_b && !d->trans_a && d->seq_in == 0 && d->split_k <= 1 &&
+                   d->algo == MR_GEMM_ALGO_TCGEN05, MR_ERR_BAD_SHAPE);
+    MR_REQUIRE(in[3] && aligned16(in[3]), in[3] ? MR_ERR_MISALIGNED : MR_ERR_NULL_POINTER);
+  }
   if (bias) MR_REQUIRE(in[2] && aligned16(in[2]), in[2] ? MR_ERR_MISALIGNED : MR_ERR_NULL_POINTER);
   if (residual) MR_REQUIRE(in[3] && aligned16(in[3]), in[3] ? MR_ERR_MISALIGNED : MR_ERR_NULL_POINTER);
   if (rotary) {
@@ -897,6 +922,10 @@ extern "C" int32_t mr_gemm_epilogue(mr_stream_t stream_, const MrGemmDesc* d, co
   const int m_tiles = ceil_div(d->M, kBM);
   int bn = 256;
   if (d->N % 256 != 0 || static_cast<int64_t>(m_tiles) * ceil_div(d->N, 256) < sms) bn = 128;
+  if (d->tile_n != 0) {
+    MR_REQUIRE(d->tile_n == 128 || (d->tile_n == 256 && d->N % 256 == 0), MR_ERR_BAD_SHAPE);
+    bn = d->tile_n;
+  }
   p.num_n_tiles = ceil_div(d->N, bn);
   p.num_tiles = m_tiles * p.num_n_tiles;
   p.num_k_blocks = ceil_div(d->K, kBK);
@@ -926,6 +955,7 @@ extern "C" int32_t mr_gemm_epilogue(mr_stream_t stream_, const MrGemmDesc* d, co
     MR_REQUIRE(make_tmap_2d(&m.b, W, d->K, d->N, ldb, 64, 64), MR_ERR_DRIVER);
   else
     MR_REQUIRE(make_tmap_2d(&m.b, W, d->N, d->K, ldb, bn, kBK), MR_ERR_DRIVER);
+  MR_REQUIRE(!dgelu || (trans == 2 && !direct_path), MR_ERR_BAD_SHAPE);
   if (trans != 0) {
     MR_REQUIRE(!(gelu || residual || rotary || ln_in || stats_out) && (direct_path || !bias), MR_ERR_BAD_SHAPE);
     int32_t st;
@@ -936,6 +966,11 @@ extern "C" int32_t mr_gemm_epilogue(mr_stream_t stream_, const MrGemmDesc* d, co
     } else {
       MR_REQUIRE(make_tmap_2d(&m.out, out[0], d->M, d->N, d->ldd, 32, 64), MR_ERR_DRIVER);
       m.res = m.out;
+      if (dgelu) {
+        MR_REQUIRE(make_tmap_2d(&m.res, in[3], d->M, d->N, d->ldd, 32, 64), MR_ERR_DRIVER);
+        return bn == 256 ? launch_one<256, true, true, false, false, false, false, false, 1, 2>(stream, m, p, grid)
+                         : launch_one<128, true, true, false, false, false, false, false, 1, 2>(stream, m, p, grid);
+      }
       st = bn == 256 ? launch_trans<256>(stream, m, p, grid, trans, false) : launch_trans<128>(stream, m, p, grid, trans, false);
     }
     if (st != MR_OK || splits == 1) return st;

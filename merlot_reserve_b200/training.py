@@ -15,6 +15,7 @@ gamma / beta and would have to be re-packed every step).
 from __future__ import annotations
 
 import math
+import os
 from typing import Dict, List, Optional, Tuple
 
 import numpy as np
@@ -49,13 +50,21 @@ def _nu_encode(v: np.ndarray) -> np.ndarray:
 
 
 def _split_k(rows: int) -> int:
-    """wgrad reduces over the token rows: enough K parts to occupy the SMs, at least ~2k rows per part."""
+    """The round-1 rule (kept for A/B, MR_WGRAD_PLAN=legacy): enough K parts to occupy the SMs, ~2k rows per part."""
     return int(max(1, min(16, rows // 2048)))
 
 
+_LEGACY_WGRAD = os.environ.get("MR_WGRAD_PLAN", "") == "legacy"
+_FUSED_DGELU = os.environ.get("MR_FUSED_DGELU", "1") != "0"
+
+
 def _wgrad(dy: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
-    """dW in the packed [out, in] layout = dy^T [out, rows] . x [rows, in]."""
-    return L.gemm_bwd(dy, x, trans_a=True, trans_b=True, split_k=_split_k(dy.shape[0]))
+    """dW in the packed [out, in] layout = dy^T [out, rows] . x [rows, in]; tile width and split-K from the
+    wave model of `_lib.wgrad_plan` (tiles x splits a multiple of the SM count, few fp32 partials)."""
+    if _LEGACY_WGRAD:
+        return L.gemm_bwd(dy, x, trans_a=True, trans_b=True, split_k=_split_k(dy.shape[0]))
+    tile_n, split_k = L.wgrad_plan(dy.shape[1], x.shape[1], dy.shape[0])
+    return L.gemm_bwd(dy, x, trans_a=True, trans_b=True, split_k=split_k, tile_n=tile_n)
 
 
 def _dgrad(dy: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
@@ -241,9 +250,11 @@ class PretrainStep:
             lw = enc.layers[i]
             x, h1, qkv, lse, ctx, xm, h2, up, u = tape["layers"][i]
             p = f"{prefix}/layer_{i:02d}"
-            du = _dgrad(dx, lw["w2"])
             G.add(f"{p}/mlp_layer/out/kernel", _wgrad(dx, u))
-            dup = L.gelu(up, du)
+            if _FUSED_DGELU:          # d(up) = (dx . W2) * gelu'(up) in the dgrad's epilogue (MR_EPI_DGELU)
+                dup = L.gemm_bwd(dx, lw["w2"], trans_b=True, out_f32=False, dgelu_pre=up)
+            else:
+                dup = L.gelu(up, _dgrad(dx, lw["w2"]))
             dh2 = _dgrad(dup, lw["w1"])
             G.add(f"{p}/mlp_layer/intermediate/kernel", _wgrad(dup, h2))
             G.add(f"{p}/mlp_layer/intermediate/bias", L.colsum(dup))

@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol(lib):
     assert len(names) >= 20
     for n in names:
         assert hasattr(cdll, n), f"{n} declared in the header but not exported"
-    assert cdll.mr_abi_version() == lib.ABI_VERSION == 11
+    assert cdll.mr_abi_version() == lib.ABI_VERSION == 12
     assert lib.launch_count() >= 0
 
 
@@ -85,3 +85,15 @@ def test_product_never_imports_oracle():
     pat = re.compile(r"^\s*(from|import)\s+[\w.]*oracle", re.M)
     for f in (ROOT / "merlot_reserve_b200").rglob("*.py"):
         assert not pat.search(f.read_text()), f
+
+
+def test_wgrad_plan_fills_the_sms(lib):
+    """Host logic only: every plan keeps tiles x splits within a whole number of waves that is >= 85 % full, or is
+    a single partial wave of a small problem."""
+    for o, i, rows in [(3072, 768, 30848), (768, 3072, 30848), (2304, 768, 30848), (768, 768, 30848), (3072, 768, 11904),
+                       (768, 768, 6144), (768, 192, 11520), (1024, 4096, 73856), (4096, 1024, 73856), (3072, 1024, 73856)]:
+        bn, s = lib.wgrad_plan(o, i, rows)
+        assert bn in (128, 256) and (bn == 128 or i % 256 == 0) and 0 <= s <= 16 and s != 1
+        items = -(-o // 128) * -(-i // bn) * max(s, 1)
+        waves = -(-items // 148)
+        assert items / (waves * 148) >= 0.85 or waves == 1, (o, i, rows, bn, s, items)

@@ -543,3 +543,67 @@ def test_gemm_transposed_a_only(cuda, lib):
     w = _bf(torch.randn(N, K, generator=g) * 0.05).to(cuda)
     b = torch.randn(N, generator=g).to(cuda)
     _close(lib.gemm_bwd(at, w, trans_a=True, bias=b), at.float().t() @ w.float().t() + b, 2e-3, 1e-3, "A^T . W^T + b")
+
+
+@pytest.mark.parametrize("M,N,K,tile_n,split", [(3072, 768, 30848, 256, 2), (768, 3072, 30848, 256, 2), (2304, 768, 30848, 256, 5),
+                                                (768, 768, 30720, 256, 8), (768, 768, 11904, 128, 4), (520, 512, 1000, 256, 3),
+                                                (520, 512, 1000, 256, 0), (520, 512, 1000, 128, 0)])
+def test_gemm_wgrad_forced_tile(cuda, lib, M, N, K, tile_n, split):
+    """MrGemmDesc.tile_n: the wgrad plans of `wgrad_plan` (256-wide tiles with few K parts) against fp32 matmul and
+    against the library's own tile choice (same partial order per element => same bits when the split is equal)."""
+    g = torch.Generator().manual_seed(M + K + split + tile_n)
+    at = _bf(torch.randn(K, M, generator=g)).to(cuda)
+    bt = _bf(torch.randn(K, N, generator=g) * 0.05).to(cuda)
+    ref = at.float().t() @ bt.float()
+    got = lib.gemm_bwd(at, bt, trans_a=True, trans_b=True, split_k=split, tile_n=tile_n)
+    _close(got, ref, 5e-3 * math.sqrt(K / 64), 2e-3, f"wgrad tile_n={tile_n} split={split}")
+    assert torch.equal(got, lib.gemm_bwd(at, bt, trans_a=True, trans_b=True, split_k=split, tile_n=tile_n))
+    auto = lib.gemm_bwd(at, bt, trans_a=True, trans_b=True, split_k=split)
+    _close(got, auto, 1e-3 * math.sqrt(K / 64), 1e-3, "forced tile vs auto tile")
+
+
+def test_gemm_tile_n_rejects_bad_width(cuda, lib):
+    a = _bf(torch.randn(64, 128)).to(cuda)
+    b = _bf(torch.randn(64, 200)).to(cuda)
+    with pytest.raises(lib.MrError):
+        lib.gemm_bwd(a, b, trans_a=True, trans_b=True, tile_n=256)      # N % 256 != 0
+    with pytest.raises(lib.MrError):
+        lib.gemm_bwd(a, b, trans_a=True, trans_b=True, tile_n=64)
+
+
+@pytest.mark.parametrize("M,N,K", [(1000, 3072, 768), (333, 264, 136), (4096, 3072, 768), (30848, 3072, 768)])
+def test_gemm_dgrad_fused_gelu_backward(cuda, lib, M, N, K):
+    """MR_EPI_DGELU: d(pre) = (dY . W) * gelu'(pre) in the dgrad epilogue == dgrad followed by mr_gelu(mode 1),
+    and == autograd of x * sigmoid(1.702 x) (modeling.py:240)."""
+    g = torch.Generator().manual_seed(M + N)
+    dy = _bf(torch.randn(M, K, generator=g)).to(cuda)
+    wt = _bf(torch.randn(K, N, generator=g) * 0.05).to(cuda)            # packed [out = K_f, in = N_f] weight
+    pre = _bf(torch.randn(M, N, generator=g) * 2.0).to(cuda)
+    fused = lib.gemm_bwd(dy, wt, trans_b=True, out_f32=False, dgelu_pre=pre)
+    two_pass = lib.gelu(pre, lib.gemm_bwd(dy, wt, trans_b=True, out_f32=False))
+    p = pre.float().requires_grad_(True)
+    (p * torch.sigmoid(1.702 * p)).backward(dy.float() @ wt.float())
+    _close(fused, p.grad, 3e-2, 2e-2, "fused dgelu vs autograd")
+    _close(fused, two_pass.float(), 3e-2, 2e-2, "fused dgelu vs dgrad + gelu kernel")
+
+
+@pytest.mark.parametrize("B,T,H", [(5, 31, 768), (7, 16, 128), (3, 32, 256), (4, 17, 128), (2, 1, 128), (300, 31, 768)])
+def test_attention_short_sequences_single_tile(cuda, lib, B, T, H):
+    """T <= 32 under MR_ATTN_ALGO_AUTO runs the one-tile, two-warp instantiation (audio T = 31, span T = 16):
+    against the fp32 reference, with validity + group masks, and its log-sum-exp against the 64 x 64 kernel's."""
+    g = torch.Generator().manual_seed(T * 7 + B)
+    qkv = _bf(torch.randn(B * T, 3 * H, generator=g)).to(cuda)
+    qkv.view(B * T, 3, H)[:, 0] *= 0.35
+    _close(lib.attention(qkv, B, T, H, algo=0), _attn_ref(qkv, B, T, H), 2e-2, 2e-2, f"short T={T}")
+    valid = (torch.rand(B, T, generator=g) > 0.3).to(torch.uint8)
+    valid[:, 0] = 1
+    valid[0, T // 2 + 1:] = 0
+    group = torch.randint(0, 3, (B, T), generator=g).to(torch.int32)
+    valid, group = valid.to(cuda).contiguous(), group.to(cuda).contiguous()
+    lse0 = torch.empty((B, H // 64, T), dtype=torch.float32, device=cuda)
+    lse1 = torch.empty_like(lse0)
+    o0 = lib.attention(qkv, B, T, H, valid=valid.view(-1), group=group.view(-1), algo=0, lse=lse0)
+    o1 = lib.attention(qkv, B, T, H, valid=valid.view(-1), group=group.view(-1), algo=1, lse=lse1)
+    _close(o0, _attn_ref(qkv, B, T, H, valid, group), 2e-2, 2e-2, "short valid+group")
+    _close(o0, o1.float(), 1e-2, 1e-2, "one-tile vs 64 x 64 kernel")
+    _close(lse0, lse1, 1e-4, 1e-5, "lse")

@@ -488,10 +488,12 @@ def wgrad_plan(out_features: int, in_features: int, rows: int, sms: int = 148) -
     """(tile_n, split_k) for dW [out, in] = dY^T . X reduced over `rows` token rows.
 
     The kernel walks tiles x splits round-robin over one persistent CTA per SM, so the time is
-    waves x (k-blocks per part x t_kb + t_epilogue) + the second-stage sum over the fp32 partials.  Constants (us, a
-    B200 at ~1.8 GHz): one 64-row k-block of a 128 x 256 tile = 4 MMAs of 128 clocks; a 128 x 128 tile runs at the
-    shared-memory read limit (8 KB per 64 clocks), hence a little more than half of that; the epilogue stores the
-    fp32 tile from registers; the reduce streams split_k + 1 fp32 copies of dW at HBM rate plus a launch."""
+    waves x (k-blocks per part x t_kb + t_epilogue) + the second-stage sum over the fp32 partials.  Constants in us,
+    fitted to same-box timings on a B200 (profiles/r01q_probe.jsonl): a 64-row k-block of a 128 x 256 tile costs
+    0.40 (1.55 PFLOP/s over 148 SMs); a 128 x 128 tile with both operands MN-major costs 0.32, i.e. 1.6x more per
+    FLOP (two 8 KB slab boxes per operand and k-block, shared-memory read limit), so the wide tile wins whenever
+    in_features % 256 == 0; the epilogue stores the fp32 tile from registers (4 / 2.5); the reduce streams
+    split_k + 1 fp32 copies of dW at ~5 TB/s plus a launch."""
     kb_total = -(-rows // 64)
     m_tiles = -(-out_features // 128)
     best = None
@@ -499,7 +501,7 @@ def wgrad_plan(out_features: int, in_features: int, rows: int, sms: int = 148) -
         if bn == 256 and in_features % 256 != 0:
             continue
         tiles = m_tiles * -(-in_features // bn)
-        t_kb, t_epi = (0.29, 1.6) if bn == 256 else (0.17, 0.9)
+        t_kb, t_epi = (0.40, 4.0) if bn == 256 else (0.32, 2.5)
         for s in range(1, 17):
             if s > kb_total:
                 break

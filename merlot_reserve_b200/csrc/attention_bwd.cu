@@ -18,20 +18,19 @@
 namespace mr {
 namespace {
 
-constexpr int kBlk = 64;
 constexpr int kD = 64;
-constexpr int kThreadsB = 128;
-constexpr int kTile = kBlk * kD;   // elements
 constexpr int kInfoOob = static_cast<int>(0x80000000u);
 constexpr int kInfoInvalid = static_cast<int>(0x80000001u);
 
 __device__ __forceinline__ int swz(int row, int chunk) { return row * kD + ((chunk ^ (row & 7)) << 3); }
 
+// [kBlk x 64] bf16 tile; the CTA has 2 * kBlk threads, four 16-byte chunks each.
+template <int kBlk>
 __device__ __forceinline__ void load_tile(bf16* s, const bf16* __restrict__ src, size_t seq_base, int row0, int T, int ld,
                                           int col0, int tid) {
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    const int i = tid + kThreadsB * k;
+    const int i = tid + 2 * kBlk * k;
     const int row = i >> 3, ch = i & 7;
     const int t = row0 + row;
     const bool ok = t < T;
@@ -39,42 +38,56 @@ __device__ __forceinline__ void load_tile(bf16* s, const bf16* __restrict__ src,
   }
 }
 
+// D[b, h, t] = sum_d dO . O.  One warp per token row: a lane owns 8 consecutive features (one 16-byte load of dO and
+// of O), 8 lanes cover one head, so a warp step covers 4 heads and a three-step shuffle finishes each of them.
 __global__ void __launch_bounds__(256)
 attn_bwd_prep_kernel(const bf16* __restrict__ dout, const bf16* __restrict__ out, float* __restrict__ Dsum, int B, int T,
                      int H) {
   const int nh = H / kD;
-  const int64_t gw = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);   // b * T + t
   const int lane = threadIdx.x & 31;
-  if (gw >= static_cast<int64_t>(B) * T * nh) return;
-  const int h = static_cast<int>(gw % nh);
-  const int64_t row = gw / nh;   // b * T + t
-  const size_t off = static_cast<size_t>(row) * H + h * kD;
-  const uint32_t a = reinterpret_cast<const uint32_t*>(dout + off)[lane];
-  const uint32_t b = reinterpret_cast<const uint32_t*>(out + off)[lane];
-  float v = bf16_lo(a) * bf16_lo(b) + bf16_hi(a) * bf16_hi(b);
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  if (lane == 0) {
-    const int b_ = static_cast<int>(row / T), t = static_cast<int>(row % T);
-    Dsum[(static_cast<size_t>(b_) * nh + h) * T + t] = v;
+  if (row >= static_cast<int64_t>(B) * T) return;
+  const int b_ = static_cast<int>(row / T), t = static_cast<int>(row % T);
+  const uint4* a4 = reinterpret_cast<const uint4*>(dout + static_cast<size_t>(row) * H);
+  const uint4* b4 = reinterpret_cast<const uint4*>(out + static_cast<size_t>(row) * H);
+  for (int c = lane; c < H / 8; c += 32) {          // H % 64 == 0: whole groups of 8 lanes are in range together
+    const uint4 a = __ldg(a4 + c), b = __ldg(b4 + c);
+    float v = bf16_lo(a.x) * bf16_lo(b.x) + bf16_hi(a.x) * bf16_hi(b.x);
+    v = fmaf(bf16_lo(a.y), bf16_lo(b.y), fmaf(bf16_hi(a.y), bf16_hi(b.y), v));
+    v = fmaf(bf16_lo(a.z), bf16_lo(b.z), fmaf(bf16_hi(a.z), bf16_hi(b.z), v));
+    v = fmaf(bf16_lo(a.w), bf16_lo(b.w), fmaf(bf16_hi(a.w), bf16_hi(b.w), v));
+    const unsigned grp = 0xffu << (lane & 24);      // the 8 lanes of this head
+    v += __shfl_xor_sync(grp, v, 4);
+    v += __shfl_xor_sync(grp, v, 2);
+    v += __shfl_xor_sync(grp, v, 1);
+    if ((lane & 7) == 0) Dsum[(static_cast<size_t>(b_) * nh + (c >> 3)) * T + t] = v;
   }
 }
 
-__global__ void __launch_bounds__(kThreadsB)
+// kBlk = 64: 4 warps, any T (the key blocks of a sequence live in different CTAs: dQ through fp32 atomics).
+// kBlk = 32: T <= 32 (audio T = 31, span T = 16): the whole (sequence, head) is ONE 32 x 32 block, so the CTA is
+// 2 warps with 24 KB of shared memory (64 KB before: ~3x more items in flight per SM), and dQ is complete inside
+// the CTA: written as bf16 straight into the q columns of d(qkv), no memset / atomics / convert pass.
+template <int kBlk>
+__global__ void __launch_bounds__(2 * kBlk)
 attention_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dout, const float* __restrict__ lse,
                      const float* __restrict__ Dsum, const uint8_t* __restrict__ valid, const int32_t* __restrict__ group,
                      bf16* __restrict__ dqkv, float* __restrict__ dq_acc, int B, int T, int H) {
+  static_assert(kBlk == 64 || kBlk == 32, "16 rows per warp x (2 or 4) warps");
+  constexpr int kTile = kBlk * kD;            // elements
+  constexpr int kQBufs = kBlk == 64 ? 2 : 1;  // the one-block kernel has nothing to prefetch
+  constexpr bool kDirectDQ = kBlk == 32;
   extern __shared__ __align__(128) uint8_t smem_raw[];
   bf16* sK = reinterpret_cast<bf16*>(smem_raw);
   bf16* sV = sK + kTile;
-  bf16* sQ = sV + kTile;          // [2]
-  bf16* sdO = sQ + 2 * kTile;     // [2]
-  bf16* sP = sdO + 2 * kTile;
+  bf16* sQ = sV + kTile;               // [kQBufs]
+  bf16* sdO = sQ + kQBufs * kTile;     // [kQBufs]
+  bf16* sP = sdO + kQBufs * kTile;
   bf16* sdS = sP + kTile;
-  float* sLse = reinterpret_cast<float*>(sdS + kTile);   // [2][64]
-  float* sD = sLse + 2 * kBlk;                           // [2][64]
-  int* sKInfo = reinterpret_cast<int*>(sD + 2 * kBlk);   // [64]
-  int* sQInfo = sKInfo + kBlk;                           // [2][64]: group id, or kInfoInvalid / kInfoOob
+  float* sLse = reinterpret_cast<float*>(sdS + kTile);   // [2][kBlk]
+  float* sD = sLse + 2 * kBlk;                           // [2][kBlk]
+  int* sKInfo = reinterpret_cast<int*>(sD + 2 * kBlk);   // [kBlk]
+  int* sQInfo = sKInfo + kBlk;                           // [2][kBlk]: group id, or kInfoInvalid / kInfoOob
 
   const int nh = H / kD;
   const int nkb = (T + kBlk - 1) / kBlk;
@@ -89,8 +102,8 @@ attention_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dout
   const size_t stat_base = (static_cast<size_t>(b) * nh + h) * T;
 
   auto load_q_side = [&](int buf, int qb) {
-    load_tile(sQ + buf * kTile, qkv, seq_base, qb * kBlk, T, ld, h * kD, tid);
-    load_tile(sdO + buf * kTile, dout, seq_base, qb * kBlk, T, H, h * kD, tid);
+    load_tile<kBlk>(sQ + buf * kTile, qkv, seq_base, qb * kBlk, T, ld, h * kD, tid);
+    load_tile<kBlk>(sdO + buf * kTile, dout, seq_base, qb * kBlk, T, H, h * kD, tid);
     if (tid < kBlk) {
       const int t = qb * kBlk + tid;
       float l = 0.f, dsum = 0.f;
@@ -107,8 +120,8 @@ attention_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dout
     }
   };
 
-  load_tile(sK, qkv, seq_base, k0, T, ld, H + h * kD, tid);
-  load_tile(sV, qkv, seq_base, k0, T, ld, 2 * H + h * kD, tid);
+  load_tile<kBlk>(sK, qkv, seq_base, k0, T, ld, H + h * kD, tid);
+  load_tile<kBlk>(sV, qkv, seq_base, k0, T, ld, 2 * H + h * kD, tid);
   if (tid < kBlk) {
     const int kidx = k0 + tid;
     int info = kInfoOob;
@@ -132,8 +145,8 @@ attention_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dout
 
   const int nqb = nkb;
   for (int qb = 0; qb < nqb; ++qb) {
-    const int buf = qb & 1;
-    if (qb + 1 < nqb) {
+    const int buf = qb & (kQBufs - 1);
+    if (kQBufs == 2 && qb + 1 < nqb) {
       load_q_side(buf ^ 1, qb + 1);
       cp_async_commit();
       cp_async_wait<1>();
@@ -145,9 +158,9 @@ attention_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dout
     const bf16* do_s = sdO + buf * kTile;
 
     // ---- S = Q K^T and dP = dO V^T for this warp's 16 query rows ----
-    float s[8][4], dp[8][4];
+    float s[kBlk / 8][4], dp[kBlk / 8][4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < kBlk / 8; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         s[i][j] = 0.f;
@@ -163,7 +176,7 @@ attention_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dout
         ldmatrix_x4(smem_u32(do_s + swz(row, ch)), of[0], of[1], of[2], of[3]);
       }
 #pragma unroll
-      for (int n16 = 0; n16 < 4; ++n16) {
+      for (int n16 = 0; n16 < kBlk / 16; ++n16) {
         const int mat = lane >> 3;
         const int row = n16 * 16 + (mat >> 1) * 8 + (lane & 7);
         const int ch = 2 * ks + (mat & 1);
@@ -188,7 +201,7 @@ attention_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dout
         qinfo[r] = sQInfo[buf * kBlk + rl[r]];
       }
 #pragma unroll
-      for (int nt = 0; nt < 8; ++nt) {
+      for (int nt = 0; nt < kBlk / 8; ++nt) {
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const int r = e >> 1;
@@ -219,7 +232,7 @@ attention_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dout
 #pragma unroll
         for (int j = 0; j < 4; ++j) dq[i][j] = 0.f;
 #pragma unroll
-      for (int kk = 0; kk < 4; ++kk) {
+      for (int kk = 0; kk < kBlk / 16; ++kk) {
         uint32_t pa[4];
         pa[0] = pack_bf16(dp[2 * kk][0], dp[2 * kk][1]);
         pa[1] = pack_bf16(dp[2 * kk][2], dp[2 * kk][3]);
@@ -240,6 +253,11 @@ attention_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dout
 #pragma unroll
       for (int dt = 0; dt < 8; ++dt) {
         const int col = h * kD + dt * 8 + tq * 2;
+        if constexpr (kDirectDQ) {
+          // the only key block of the sequence: dQ is final
+          if (t0 < T) *reinterpret_cast<uint32_t*>(dqkv + (seq_base + t0) * ld + col) = pack_bf16(dq[dt][0], dq[dt][1]);
+          if (t1 < T) *reinterpret_cast<uint32_t*>(dqkv + (seq_base + t1) * ld + col) = pack_bf16(dq[dt][2], dq[dt][3]);
+        } else {
         if (t0 < T) {
           float* dst = dq_acc + (seq_base + t0) * H + col;
           atomicAdd(dst, dq[dt][0]);
@@ -250,12 +268,13 @@ attention_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dout
           atomicAdd(dst, dq[dt][2]);
           atomicAdd(dst + 1, dq[dt][3]);
         }
+        }
       }
     }
-    __syncthreads();   // P / dS of all 64 query rows are in shared memory
+    __syncthreads();   // P / dS of all kBlk query rows are in shared memory
     // ---- dV_j += P^T dO_i ; dK_j += dS^T Q_i  (this warp's 16 keys; A = transposed load of [q][key]) ----
 #pragma unroll
-    for (int ks = 0; ks < 4; ++ks) {   // 16 query rows per step
+    for (int ks = 0; ks < kBlk / 16; ++ks) {   // 16 query rows per step
       uint32_t pa[4], sa[4];
       {
         const int mat = lane >> 3;
@@ -318,7 +337,10 @@ dq_convert_kernel(const float* __restrict__ dq_acc, bf16* __restrict__ dqkv, int
   }
 }
 
-constexpr int kBwdSmem = (2 + 2 + 2 + 2) * kTile * 2 + 4 * kBlk * 4 + 3 * kBlk * 4;
+template <int kBlk>
+constexpr int bwd_smem_bytes() {
+  return (4 + 2 * (kBlk == 64 ? 2 : 1)) * kBlk * kD * 2 + 4 * kBlk * 4 + 3 * kBlk * 4;
+}
 
 }  // namespace
 }  // namespace mr
@@ -348,15 +370,18 @@ extern "C" int32_t mr_attention_bwd(mr_stream_t stream_, const MrAttentionDesc* 
   const int64_t rows = static_cast<int64_t>(d->B) * d->T;
   float* dq_acc = static_cast<float*>(workspace);
   float* Dsum = dq_acc + rows * d->H;
-  cudaError_t e = cudaMemsetAsync(dq_acc, 0, static_cast<size_t>(rows) * d->H * sizeof(float), stream);
+  MR_REQUIRE(d->algo >= MR_ATTN_ALGO_AUTO && d->algo <= MR_ATTN_ALGO_TCGEN05, MR_ERR_BAD_SHAPE);
+  const bool use_tc = d->algo == MR_ATTN_ALGO_TCGEN05 || (d->algo == MR_ATTN_ALGO_AUTO && d->T > 64);
+  // T <= 32 under AUTO: the one-block kernel, dQ written in place (no fp32 accumulator to clear or convert)
+  const bool one_block = !use_tc && d->T <= 32 && d->algo == MR_ATTN_ALGO_AUTO;
+  cudaError_t e = cudaSuccess;
+  if (!one_block) e = cudaMemsetAsync(dq_acc, 0, static_cast<size_t>(rows) * d->H * sizeof(float), stream);
   if (e != cudaSuccess) return cuda_status(e);
-  attn_bwd_prep_kernel<<<static_cast<unsigned>(ceil_div64(rows * nh, 8)), 256, 0, stream>>>(
+  attn_bwd_prep_kernel<<<static_cast<unsigned>(ceil_div64(rows, 8)), 256, 0, stream>>>(
       static_cast<const bf16*>(in[1]), static_cast<const bf16*>(in[2]), Dsum, d->B, d->T, d->H);
   int32_t st = after_launch();
   if (st != MR_OK) return st;
   // T > 64: tcgen05 / TMEM kernel (attention_bwd_tc.cu); short sequences (audio, span) and algo = MMA_SYNC: mma.sync
-  MR_REQUIRE(d->algo >= MR_ATTN_ALGO_AUTO && d->algo <= MR_ATTN_ALGO_TCGEN05, MR_ERR_BAD_SHAPE);
-  const bool use_tc = d->algo == MR_ATTN_ALGO_TCGEN05 || (d->algo == MR_ATTN_ALGO_AUTO && d->T > 64);
   if (use_tc) {
     st = launch_attention_bwd_tc(stream, static_cast<const bf16*>(in[0]), static_cast<const bf16*>(in[1]),
                                  static_cast<const float*>(in[3]), Dsum, static_cast<const uint8_t*>(in[4]),
@@ -367,16 +392,25 @@ extern "C" int32_t mr_attention_bwd(mr_stream_t stream_, const MrAttentionDesc* 
     dq_convert_kernel<<<static_cast<unsigned>(cb), 256, 0, stream>>>(dq_acc, static_cast<bf16*>(out[0]), rows, d->H);
     return after_launch();
   }
+  if (one_block) {
+    const int64_t blocks = static_cast<int64_t>(d->B) * nh;
+    MR_REQUIRE(blocks < (int64_t(1) << 31), MR_ERR_BAD_SHAPE);
+    attention_bwd_kernel<32><<<static_cast<unsigned>(blocks), 64, bwd_smem_bytes<32>(), stream>>>(
+        static_cast<const bf16*>(in[0]), static_cast<const bf16*>(in[1]), static_cast<const float*>(in[3]), Dsum,
+        static_cast<const uint8_t*>(in[4]), static_cast<const int32_t*>(in[5]), static_cast<bf16*>(out[0]), dq_acc, d->B,
+        d->T, d->H);
+    return after_launch();
+  }
   static bool attr_set = false;
   if (!attr_set) {
-    e = cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem);
+    e = cudaFuncSetAttribute(attention_bwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd_smem_bytes<64>());
     if (e != cudaSuccess) return cuda_status(e);
     attr_set = true;
   }
-  const int nkb = ceil_div(d->T, kBlk);
+  const int nkb = ceil_div(d->T, 64);
   const int64_t blocks = static_cast<int64_t>(d->B) * nh * nkb;
   MR_REQUIRE(blocks < (int64_t(1) << 31), MR_ERR_BAD_SHAPE);
-  attention_bwd_kernel<<<static_cast<unsigned>(blocks), kThreadsB, kBwdSmem, stream>>>(
+  attention_bwd_kernel<64><<<static_cast<unsigned>(blocks), 128, bwd_smem_bytes<64>(), stream>>>(
       static_cast<const bf16*>(in[0]), static_cast<const bf16*>(in[1]), static_cast<const float*>(in[3]), Dsum,
       static_cast<const uint8_t*>(in[4]), static_cast<const int32_t*>(in[5]), static_cast<bf16*>(out[0]), dq_acc, d->B,
       d->T, d->H);

@@ -237,29 +237,36 @@ __global__ void colsum_reduce_kernel(const float* __restrict__ partial, float* _
 
 // ---------------------------------------------------------------------------------------------
 // Backward of the qkv epilogue (rotary scale on the first 32 dims of every q / k head, 1/sqrt(d) on q): the same
-// element-wise factors applied to d(qkv), in place.  One thread per 8 columns.
+// element-wise factors applied to d(qkv), in place.  Only the vectors that change are visited -- all of q and the
+// lower half of every k head, (H/8 + H/16) 16-byte vectors per row -- so every lane of every warp has a load in
+// flight (the first version walked all 3H/8 vectors and idled on v and the upper k halves: 2.4 TB/s).
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 rotary_bwd_kernel(bf16* __restrict__ dqkv, const float* __restrict__ rot, int64_t rows, int hidden, int rot_rows,
                   float q_scale) {
-  const int vec_per_row = 3 * hidden / 8;
-  const int64_t total = rows * vec_per_row;
+  const int q_vecs = hidden / 8;
+  const int per_row = q_vecs + hidden / 16;
+  const int64_t total = rows * per_row;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int64_t r = i / vec_per_row;
-    const int c = static_cast<int>(i % vec_per_row) * 8;
-    if (c >= 2 * hidden) continue;              // v columns: untouched
-    const bool is_q = c < hidden;
+    const int64_t r = i / per_row;
+    const int v = static_cast<int>(i - r * per_row);
+    const bool is_q = v < q_vecs;
+    // k: vector kv of the row's active k vectors = head kv / 4, 8-column group kv % 4 of its lower half
+    const int c = is_q ? v * 8 : hidden + ((v - q_vecs) >> 2) * 64 + ((v - q_vecs) & 3) * 8;
     const int in_head = c & 63;
-    if (!is_q && in_head >= 32) continue;       // k, upper half of the head: factor 1
     uint4* cell = reinterpret_cast<uint4*>(dqkv + r * 3 * hidden + c);
     float f[8];
     unpack8b(*cell, f);
+    const float base = is_q ? q_scale : 1.0f;
+    if (in_head < 32) {
+      const float4* rp = reinterpret_cast<const float4*>(rot + static_cast<size_t>(r % rot_rows) * 32 + in_head);
+      const float4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
+      f[0] *= base * r0.x; f[1] *= base * r0.y; f[2] *= base * r0.z; f[3] *= base * r0.w;
+      f[4] *= base * r1.x; f[5] *= base * r1.y; f[6] *= base * r1.z; f[7] *= base * r1.w;
+    } else {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float s = is_q ? q_scale : 1.0f;
-      if (in_head < 32) s *= rot[static_cast<size_t>(r % rot_rows) * 32 + in_head + j];
-      f[j] *= s;
+      for (int j = 0; j < 8; ++j) f[j] *= base;
     }
     *cell = pack8b(f);
   }
@@ -761,9 +768,9 @@ extern "C" int32_t mr_rotary_bwd(mr_stream_t stream_, const MrRotaryBwdDesc* d, 
                                  void*, size_t) {
   MR_REQUIRE(d && in && out && in[0] && out[0], MR_ERR_NULL_POINTER);
   MR_REQUIRE(d->rows >= 0 && d->hidden > 0 && d->hidden % 64 == 0 && d->rot_rows > 0, MR_ERR_BAD_SHAPE);
-  MR_REQUIRE(aligned16(out[0]), MR_ERR_MISALIGNED);
+  MR_REQUIRE(aligned16(out[0]) && aligned16(in[0]), MR_ERR_MISALIGNED);
   if (d->rows == 0) return MR_OK;
-  const int64_t total = static_cast<int64_t>(d->rows) * (3 * d->hidden / 8);
+  const int64_t total = static_cast<int64_t>(d->rows) * (d->hidden / 8 + d->hidden / 16);
   int64_t blocks = ceil_div64(total, 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
   rotary_bwd_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream_)>>>(

@@ -123,7 +123,8 @@ def _attn_ref_autograd(qkv, dctx, B, T, H, valid=None, group=None):
 
 
 @pytest.mark.parametrize("B,T,H,masked", [(3, 241, 128, False), (5, 31, 128, False), (4, 16, 128, True), (2, 640, 128, True),
-                                          (2, 200, 256, True), (1, 64, 64, False)])
+                                          (2, 200, 256, True), (1, 64, 64, False), (6, 31, 768, True), (3, 32, 256, True),
+                                          (400, 31, 768, False), (2, 17, 64, False)])
 def test_attention_bwd(cuda, lib, B, T, H, masked):
     g = torch.Generator().manual_seed(B * 1000 + T)
     qkv = _bf(torch.randn(B * T, 3 * H, generator=g) * 0.8)
@@ -139,14 +140,15 @@ def test_attention_bwd(cuda, lib, B, T, H, masked):
         dctx.view(B, T, H)[valid == 0] = 0               # outputs of padded rows are never used downstream
     ref_ctx, ref_dqkv, ref_lse = _attn_ref_autograd(qkv, dctx, B, T, H, valid, group)
     dev = lambda t: None if t is None else t.to(cuda).contiguous().view(-1)
-    for algo in ([1, 2] if T > 64 else [1]):
+    # algo 0 (AUTO) at T <= 32 = the one-block two-warp kernels (forward and backward); 1 = the 64 x 64 mma.sync kernels
+    for algo in ([1, 2] if T > 64 else ([0, 1] if T <= 32 else [1])):
         lse = torch.empty(B, H // 64, T, device=cuda)
         ctx = lib.attention(qkv.to(cuda), B, T, H, valid=dev(valid), group=dev(group), algo=algo, lse=lse)
         _close(ctx, ref_ctx, 2e-2, 2e-2, f"ctx algo {algo}")
         ok = torch.ones(B, T, dtype=torch.bool) if valid is None else valid.bool()
         _close(lse.cpu().permute(0, 2, 1)[ok], ref_lse.permute(0, 2, 1)[ok], 2e-3, 1e-3, f"lse algo {algo}")
         scale = ref_dqkv.abs().max().item()
-        for balgo in ([1, 2] if T > 64 else [1]):        # backward: mma.sync kernel and the tcgen05 / TMEM kernel
+        for balgo in ([1, 2] if T > 64 else ([0, 1] if T <= 32 else [1])):   # mma.sync kernels / tcgen05 + TMEM kernel
             dqkv = lib.attention_bwd(qkv.to(cuda), dctx.to(cuda), ctx, lse, B, T, H, valid=dev(valid), group=dev(group),
                                      algo=balgo)
             _close(dqkv, ref_dqkv, 2e-2 * scale + 1e-3, 3e-2, f"dqkv fwd algo {algo} bwd algo {balgo}")

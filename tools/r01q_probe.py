@@ -70,6 +70,27 @@ def main():
                           "tflops_legacy": round(flops / res["legacy"][0] / 1e6, 1)}), flush=True)
         del dys, xs
 
+    # attention backward: short sequences (one-block kernel, algo AUTO, against the 64 x 64 kernel, algo MMA_SYNC) and the
+    # tcgen05 shapes (whole entry: memset + D = rowsum(dO . O) prep + main kernel + dQ convert)
+    for name, B, T, H, algos in [("pretrain_audio_b8", 384, 31, 768, (0, 1, 0)), ("pretrain_span_b8", 384, 16, 768, (0, 1, 0)),
+                                 ("pretrain_vision_b8", 128, 241, 768, (0,)), ("pretrain_joint_b8", 48, 640, 768, (0,))]:
+        nbuf = 3
+        qkvs = [torch.randn(B * T, 3 * H, device=dev, dtype=BF) * 0.5 for _ in range(nbuf)]
+        dctx = torch.randn(B * T, H, device=dev, dtype=BF)
+        lse = torch.empty(B, H // 64, T, device=dev)
+        ctxs = [L.attention(q, B, T, H, lse=lse) for q in qkvs]
+        res = {}
+        for n, algo in enumerate(algos):
+            res[f"algo{algo}_{n}"] = timed(lambda i: L.attention_bwd(qkvs[i], dctx, ctxs[i], lse, B, T, H, algo=algo), args.reps, nbuf)
+        print(json.dumps({"probe": "attention_bwd", "shape": name, "B": B, "T": T, "H": H, "us_median_min": res}), flush=True)
+
+    for name, rows, H, rr in [("rotary_bwd_vision_b8", 30848, 768, 241), ("rotary_bwd_joint_b8", 30720, 768, 30720)]:
+        dq = [torch.randn(rows, 3 * H, device=dev, dtype=BF) for _ in range(3)]
+        rot = torch.randn(rr, 32, device=dev)
+        t = timed(lambda i: L.rotary_bwd(dq[i], rot, H), args.reps, 3)
+        print(json.dumps({"probe": "rotary_bwd", "shape": name, "rows": rows, "us_median_min": t,
+                          "touched_bytes": rows * (H + H // 2) * 2 * 2}), flush=True)
+
     for name, rows, H in [("base_b8_vision", 30848, 768), ("base_b8_audio", 11904, 768)]:
         nbuf = 3
         dxs = [torch.randn(rows, H, device=dev, dtype=BF) for _ in range(nbuf)]

@@ -56,6 +56,7 @@ def _split_k(rows: int) -> int:
 
 _LEGACY_WGRAD = os.environ.get("MR_WGRAD_PLAN", "") == "legacy"
 _FUSED_DGELU = os.environ.get("MR_FUSED_DGELU", "1") != "0"
+_OVERLAP_ALLREDUCE = os.environ.get("MR_OVERLAP_ALLREDUCE", "1") != "0"
 
 
 def _wgrad(dy: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
@@ -143,8 +144,11 @@ class PretrainStep:
         reg = self._registry()
         names = sorted(reg)
         dev = next(iter(reg.values()))[0].device
-        offs, n = {}, 0
+        offs, n, top = {}, 0, None
         for name in names:
+            if name.split("/")[0] != top:                   # a top-level module starts on a 1024-element boundary:
+                top = name.split("/")[0]                    # the buckets of the overlapped all-reduce are whole rows
+                n = (n + 1023) // 1024 * 1024               # of the bf16 cast (rows of 1024)
             offs[name] = n
             n += (reg[name][0].numel() + 7) // 8 * 8
         n_total = (n + 1023) // 1024 * 1024                 # the gradient cast works on rows of 1024
@@ -189,18 +193,57 @@ class PretrainStep:
         if self._state is None:
             self._init_state(opt)
         st = self._state
-        loss, info, grads = self.loss_and_grads(batch, group=group)
         world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
         n, g = st["n"], st["g"]
-        for name in st["names"]:
-            t = grads[name]
-            g[st["offs"][name]:st["offs"][name] + t.numel()].copy_(t.reshape(-1))
-        g[n:n + 3].copy_(grads["contrastive_scales"].reshape(-1))
         # The reference differentiates bf16 parameters, so its gradients ARE bf16, and averages them in bf16
-        # (pretrain_model.py:323-333): one flat bf16 bucket, one all-reduce, and the optimizer kernel reads it as is.
-        g16 = L.cast_pad(g.view(-1, 1024), (n + 1024) // 1024, 1024, 1024, out=st["g16"].view(-1, 1024)).view(-1)
-        if world > 1:
-            dist.all_reduce(g16, group=group)
+        # (pretrain_model.py:323-333): one flat bf16 arena that the optimizer kernel reads as is.  With more than one
+        # rank the arena is reduced in three buckets AS THE BACKWARD PASS FINISHES THEM (the order of
+        # `loss_and_grads`: heads + span + joint + token table, then the audio encoder, then the vision encoder), each
+        # an asynchronous NCCL all-reduce that runs under the rest of the backward pass; MR_OVERLAP_ALLREDUCE=0 keeps
+        # the single blocking all-reduce of round 1p.
+        pending, done = [], set()
+
+        def flush(names, reduce_now):
+            """Copy finished gradients into the arena, cast their 1024-element rows to bf16, start their all-reduce."""
+            names = [k for k in names if k not in done]
+            if not names:
+                return
+            done.update(names)
+            lo = min(st["offs"][k] for k in names) // 1024
+            hi = -(-max(st["offs"][k] + grads_ref[k].numel() for k in names) // 1024)
+            for k in names:
+                t = grads_ref[k]
+                g[st["offs"][k]:st["offs"][k] + t.numel()].copy_(t.reshape(-1))
+            L.cast_pad(g.view(-1, 1024)[lo:hi], hi - lo, 1024, 1024, out=st["g16"].view(-1, 1024)[lo:hi])
+            if reduce_now:
+                pending.append(dist.all_reduce(st["g16"][lo * 1024:hi * 1024], group=group, async_op=True))
+
+        overlap = world > 1 and _OVERLAP_ALLREDUCE
+        grads_ref: Dict[str, torch.Tensor] = {}
+
+        def on_ready(grads_so_far, prefixes):
+            grads_ref.update(grads_so_far)
+            flush([k for k in st["names"] if k.split("/")[0] in prefixes and k in grads_so_far], True)
+
+        loss, info, grads = self.loss_and_grads(batch, group=group, on_ready=on_ready if overlap else None)
+        grads_ref.update(grads)
+        if overlap:
+            g[n:n + 3].copy_(grads["contrastive_scales"].reshape(-1))
+            L.cast_pad(g.view(-1, 1024)[n // 1024:], 1, 1024, 1024, out=st["g16"].view(-1, 1024)[n // 1024:])
+            pending.append(dist.all_reduce(st["g16"][n:], group=group, async_op=True))
+            left = [k for k in st["names"] if k not in done]
+            assert not left, f"gradients outside the all-reduce buckets: {left[:4]}"
+            for w in pending:
+                w.wait()                                     # the current stream waits for NCCL's stream
+            g16 = st["g16"]
+        else:
+            for name in st["names"]:
+                t = grads[name]
+                g[st["offs"][name]:st["offs"][name] + t.numel()].copy_(t.reshape(-1))
+            g[n:n + 3].copy_(grads["contrastive_scales"].reshape(-1))
+            g16 = L.cast_pad(g.view(-1, 1024), (n + 1024) // 1024, 1024, 1024, out=st["g16"].view(-1, 1024)).view(-1)
+            if world > 1:
+                dist.all_reduce(g16, group=group)
         lr = opt["learning_rate"] * self.lr_scale(self.step_count, opt)
         b1, b2, eps, wd = opt.get("beta_1", 0.9), opt.get("beta_2", 0.98), opt.get("eps", 1e-8), opt["weight_decay_rate"]
         # bias correction: off by default with the bf16 moments (optimization.py:165), always on for optax.scale_by_adam
@@ -338,7 +381,9 @@ class PretrainStep:
         G.add(f"{prefix}/embedding/bias", L.colsum(dxe))
 
     # --------------------------------------------------------------------------------------------
-    def loss_and_grads(self, batch: Dict, group=None):
+    def loss_and_grads(self, batch: Dict, group=None, on_ready=None):
+        """on_ready(grads, prefixes): called during the backward pass each time every gradient under the given
+        top-level parameter prefixes is final (train_step starts their all-reduce under the remaining backward)."""
         import torch.distributed as dist
         m, p, H = self.model, self.model._p, self.H
         cfg, data = self.cfg, self.cfg["data"]
@@ -599,6 +644,8 @@ class PretrainStep:
                                  d_audio=d_audio_seq if kw.get("n_aud", 0) else None,
                                  d_vision=d_imgs_seq if kw.get("n_vis", 0) else None, **kw)
         G.add("token_encoder/Embed_0/embedding", d_tok_emb)
+        if on_ready is not None:
+            on_ready(G.g, ("head", "span_encoder", "joint_transformer", "token_encoder"))
 
         # ---- audio encoder ----
         dxaf = self._pool_bwd(d_audio_seq.view(-1, H).to(BF16), xaf, a_pool_saved, p.aud_pool, Ba, Ta, geom_a, G,
@@ -606,6 +653,8 @@ class PretrainStep:
         dxa_last = self._final_bwd(dxaf, d_acls.to(BF16), xa_last, a_cls_rows, p.aud, Ba, Ta, G, "audio_encoder/transformer")
         dxa0 = self._enc_bwd(dxa_last, tape_a, p.aud, G, "audio_encoder/transformer")
         self._embed_rows_bwd(dxa0, aa, Ba, Ta, G, "audio_encoder")
+        if on_ready is not None:
+            on_ready(G.g, ("audio_encoder",))
 
         # ---- vision encoder ----
         dxvf = self._pool_bwd(d_imgs_seq.view(-1, H).to(BF16), xvf, v_pool_saved, p.vis_pool, Bv, Tv, geom_v, G,
@@ -613,6 +662,8 @@ class PretrainStep:
         dxv_last = self._final_bwd(dxvf, d_vcls.to(BF16), xv_last, v_cls_rows, p.vis, Bv, Tv, G, "vision_encoder/transformer")
         dxv0 = self._enc_bwd(dxv_last, tape_v, p.vis, G, "vision_encoder/transformer")
         self._embed_rows_bwd(dxv0, av, Bv, Tv, G, "vision_encoder")
+        if on_ready is not None:
+            on_ready(G.g, ("vision_encoder",))
         if getattr(self, "_keep_locals", False):
             self._dbg = dict(locals())
         return loss, info, G.g

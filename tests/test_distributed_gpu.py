@@ -64,3 +64,53 @@ def test_nccl_packed_allgather_loss_world2(cuda):
     for k in ("imgs_to_audio", "text_to_audio", "stuff_to_span"):
         m = sum(info[k] for _, _, info in res) / world
         assert abs(m - float(ref_info[k])) < 3e-3, k
+
+
+def _train_worker(rank, world, port, q):
+    """Two train_steps per mode on a rank-specific batch: bucketed all-reduce started during the backward pass
+    against the single blocking all-reduce after it (MR_OVERLAP_ALLREDUCE=0)."""
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(f"cuda:{rank}"))
+    from merlot_reserve_b200 import training
+    from merlot_reserve_b200.synthetic import synthetic_params, synthetic_pretrain_batch, tiny_config
+    cfg = tiny_config()
+    batch = synthetic_pretrain_batch(cfg, 2, seed=30 + rank)
+    opt = {"learning_rate": 2e-4, "num_train_steps": 100, "num_warmup_steps": 0, "weight_decay_rate": 0.1, "beta_2": 0.98,
+           "eps": 1e-6, "final_lr_scale": 1.0}
+    out = {}
+    for mode in (True, False):
+        training._OVERLAP_ALLREDUCE = mode
+        step = training.PretrainStep(cfg, synthetic_params(cfg, seed=0, weight_scale=4.0))
+        losses = [float(step.train_step(batch, opt)[0]) for _ in range(2)]
+        torch.cuda.synchronize()
+        st = step._state
+        out[mode] = (losses, st["p"].cpu(), st["g16"].float().cpu(), step.model._p.contrastive_scales.copy())
+    (la, pa, ga, sa), (lb, pb, gb, sb) = out[True], out[False]
+    same = bool(torch.equal(pa, pb) and torch.equal(ga, gb) and (sa == sb).all() and la == lb)
+    q.put((rank, same, float((pa - pb).abs().max()), pa.double().sum().item(), la))
+    dist.destroy_process_group()
+
+
+def test_nccl_overlapped_gradient_allreduce_world2(cuda):
+    """train_step on two GPUs: the three-bucket all-reduce that overlaps the backward pass leaves exactly the same
+    master parameters, reduced gradient arena and temperatures as the single blocking all-reduce (with two ranks the
+    bf16 sum a + b has one order), and both ranks end with identical parameters."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import torch.multiprocessing as mp
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_train_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=600) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, same, maxdiff, psum, losses in res:
+        assert same, f"rank {rank}: overlapped and blocking all-reduce differ (max |dp| {maxdiff})"
+        assert all(l == l for l in losses)
+    assert res[0][3] == res[1][3], "ranks diverged"

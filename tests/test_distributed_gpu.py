@@ -4,6 +4,7 @@ per-rank loss must equal the oracle's single-device loss on the global batch."""
 import os
 import socket
 
+import numpy as np
 import pytest
 import torch
 
@@ -88,15 +89,18 @@ def _train_worker(rank, world, port, q):
         st = step._state
         out[mode] = (losses, st["p"].cpu(), st["g16"].float().cpu(), step.model._p.contrastive_scales.copy())
     (la, pa, ga, sa), (lb, pb, gb, sb) = out[True], out[False]
-    same = bool(torch.equal(pa, pb) and torch.equal(ga, gb) and (sa == sb).all() and la == lb)
-    q.put((rank, same, float((pa - pb).abs().max()), pa.double().sum().item(), la))
+    dp = (pa - pb).abs()
+    q.put((rank, float(dp.max()), float(dp.mean()), float((ga - gb).abs().sum() / gb.abs().sum()),
+           float(np.abs(sa - sb).max()), pa.double().sum().item(), la + lb))
     dist.destroy_process_group()
 
 
 def test_nccl_overlapped_gradient_allreduce_world2(cuda):
-    """train_step on two GPUs: the three-bucket all-reduce that overlaps the backward pass leaves exactly the same
-    master parameters, reduced gradient arena and temperatures as the single blocking all-reduce (with two ranks the
-    bf16 sum a + b has one order), and both ranks end with identical parameters."""
+    """train_step on two GPUs: the three-bucket all-reduce that overlaps the backward pass leaves the same master
+    parameters, reduced gradient arena and temperatures as the single blocking all-reduce, and both ranks end with
+    identical parameters.  The two modes are two separate runs of a backward pass that accumulates dQ and the
+    embedding-table gradient with fp32 atomics, so they agree to rounding, not bit for bit: a bucket that was
+    skipped, reduced twice or reduced before it was final would move whole tensors by ~lr = 2e-4 per step."""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
     import torch.multiprocessing as mp
@@ -110,7 +114,9 @@ def test_nccl_overlapped_gradient_allreduce_world2(cuda):
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    for rank, same, maxdiff, psum, losses in res:
-        assert same, f"rank {rank}: overlapped and blocking all-reduce differ (max |dp| {maxdiff})"
+    for rank, dp_max, dp_mean, g_rel, ds_max, psum, losses in res:
+        assert dp_max < 2e-5 and dp_mean < 2e-8, f"rank {rank}: parameters differ, max {dp_max} mean {dp_mean}"
+        assert g_rel < 2e-3, f"rank {rank}: reduced gradient arenas differ, relative L1 {g_rel}"
+        assert ds_max < 1e-5, f"rank {rank}: temperatures differ by {ds_max}"
         assert all(l == l for l in losses)
-    assert res[0][3] == res[1][3], "ranks diverged"
+    assert res[0][5] == res[1][5], "ranks diverged"

@@ -115,7 +115,7 @@ def test_nccl_overlapped_gradient_allreduce_world2(cuda):
         p.join(timeout=60)
         assert p.exitcode == 0
     for rank, dp_max, dp_mean, g_rel, ds_max, psum, losses in res:
-        assert dp_max < 2e-5 and dp_mean < 2e-8, f"rank {rank}: parameters differ, max {dp_max} mean {dp_mean}"
+        assert dp_max < 2e-5 and dp_mean < 5e-8, f"rank {rank}: parameters differ, max {dp_max} mean {dp_mean}"
         assert g_rel < 2e-3, f"rank {rank}: reduced gradient arenas differ, relative L1 {g_rel}"
         assert ds_max < 1e-5, f"rank {rank}: temperatures differ by {ds_max}"
         assert all(l == l for l in losses)

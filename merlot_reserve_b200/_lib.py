@@ -417,6 +417,8 @@ def unit_normalize(x: torch.Tensor, scale: float = 1.0, out_f32: bool = True, ro
     rows = x.shape[0] if row_idx is None else row_idx.numel()
     if out is None:
         out = torch.empty((rows, H), dtype=torch.float32 if out_f32 else torch.bfloat16, device=x.device)
+    if rows == 0:
+        return out
     d = NormalizeDesc(rows=rows, H=H, in_f32=int(x.dtype == torch.float32), out_f32=int(out.dtype == torch.float32),
                       scale=scale)
     _call("mr_unit_normalize", d, [x, row_idx], [out])

@@ -314,6 +314,9 @@ class MerlotReserve:
         if r != 2:
             raise ValueError("vit_pooling_ratio must be 2")
         T = hw + 1
+        if B == 0:      # empty batch: what vmap / jit over a zero-length axis returns (no kernel is launched)
+            z = lambda *shp: torch.zeros(shp, dtype=torch.bfloat16, device=images.device)
+            return {"seq_attnpool": z(0, (gh // 2) * (gw // 2), H), "_xf": z(0, H), "cls": z(0, H)}
         a = L.cast_pad(images.reshape(B * hw, pp3), B * hw, pp3, pp3)
         x = torch.empty((B * T, H), dtype=torch.bfloat16, device=images.device)
         L.gemm(a, p.vis_emb[0], bias=p.vis_emb[1], out=x, seq_in=hw, seq_out=T, row_off=1)
@@ -335,6 +338,9 @@ class MerlotReserve:
             raise ValueError(f"audio_clips must be [*, L, 65] with L % {ps} == 0")
         n = raw_len // ps
         T = n + 1
+        if B == 0:
+            z = lambda *shp: torch.zeros(shp, dtype=torch.bfloat16, device=audio.device)
+            return {"seq_attnpool": z(0, n // self.audio_pooling_ratio, H), "cls": z(0, H)}
         a = L.cast_pad(audio.reshape(B * n, ps * nm), B * n, ps * nm, _AUDIO_K_PAD)
         x = torch.empty((B * T, H), dtype=torch.bfloat16, device=audio.device)
         L.gemm(a, p.aud_emb[0], bias=p.aud_emb[1], out=x, seq_in=n, seq_out=T, row_off=1)
@@ -354,6 +360,8 @@ class MerlotReserve:
         if n != self.config["text_span_length"]:
             raise ValueError(f"text_spans must be [B, {self.config['text_span_length']}]")
         T = n + 1
+        if B == 0:
+            return torch.zeros((0, H), dtype=torch.float32 if out_f32 else torch.bfloat16, device=text_spans.device)
         x, _, valid = L.embed_assemble(text_spans, p.tok_emb, H=H, cls_offset=1)
         L.fill_cls(x, p.span.cls, B, T, H)
         x = self._encoder(x, p.span, B, T, self._table("span"), valid=valid)
@@ -537,6 +545,8 @@ class MerlotReserve:
         if tok.shape != sub.shape or tok.dim() != 2 or tok.shape[0] != B:
             raise ValueError("tokens and subseg_idxs must both be [B, L] (modeling.py:824-826)")
         H = self.hidden_size
+        if B == 0:
+            return _ret(torch.zeros((0, tok.shape[1], H), dtype=torch.float32, device=img.device), as_np)
         imgs_enc = self._vision(img.reshape(B * nseg, hw, pp3))["seq_attnpool"].reshape(B, nseg * hw // 4, H)
         audio_enc = self._audio(aud.reshape(B * 3 * nseg, aud.shape[2], 65))["seq_attnpool"]
         audio_enc = audio_enc.reshape(B, 3 * nseg, self.config["audio_token_length"], H)

@@ -113,9 +113,8 @@ typedef struct MrGemmDesc {
   float q_scale;
   int32_t num_sms;  /* 0 = use every SM of the current device */
   float ln_eps;     /* MR_EPI_LN_IN */
-  int32_t algo_pair; /* 0 = auto, 1 = force CTA pairs (cta_group::2, 256 x 256 tiles), 2 = never, 3 = clusters of two
-                        pairs that multicast the W tile (512 x 256 super-tiles); pairs need the staged bf16 output
-                        path and a 256-wide tile, otherwise the field is ignored */
+  int32_t algo_pair; /* 0 = auto, 1 = force CTA pairs (cta_group::2, 256 x 256 tiles), 2 = never; pairs need the
+                        staged bf16 output path and a 256-wide tile, otherwise the field is ignored */
   /* Backward GEMMs: operands given TRANSPOSED (MN-major for the tensor core, no transposed copies in HBM):
        trans_a: in[0] is A^T, bf16 [K, lda >= M]        trans_b: in[1] is W^T, bf16 [K, ldb >= N]
      dgrad  dX[M, K_f] = dY[M, N_f] . W[N_f, K_f]:  A = dY, in[1] = the forward's packed W with trans_b = 1;

@@ -21,7 +21,6 @@
 //
 // The arithmetic this replaces is flax Dense/DenseGeneral (+ the elementwise ops around it) at the
 // reference call sites listed in include/mreserve_b200.h.
-#include <cstdlib>
 #include <type_traits>
 
 #include "common.cuh"
@@ -67,15 +66,11 @@ constexpr int kBoxBytes = 32 * 128;  // one epilogue staging box: 32 rows x 64 b
 // HALF of the W tile (BN / 2 rows); the leader issues 256 x BN x 16 MMAs that read both CTAs' shared memory and
 // write each CTA's half of the accumulator into its own TMEM.  Per CTA and k-block that is 32 KB of L2 -> SMEM
 // traffic instead of 48 KB, and the smaller stages allow a 6-deep ring.
-// kCtas = 4: a cluster of TWO pairs stacked along M (512 x BN super-tile).  Both pairs need the same W tile, so each
-// CTA fetches only a QUARTER of it (BN / 4 rows) and TMA-multicasts the box into its own shared memory and into the
-// CTA of the other pair that holds the same half: 24 KB of L2 reads per CTA and k-block instead of 32 KB.  A ring
-// slot is now written by two producers, so its `empty` barrier collects the commits of BOTH pairs' MMA issuers.
 template <int BN, int kCtas = 1>
 struct Cfg {
   static constexpr int kStages = (BN == 256 && kCtas == 1) ? 4 : 6;
   static constexpr int kABytes = kBM * kBK * 2;
-  static constexpr int kBBytes = (BN / (kCtas >= 2 ? 2 : 1)) * kBK * 2;   // a CTA of a pair HOLDS half of the W tile
+  static constexpr int kBBytes = (BN / kCtas) * kBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTmemCols = 2 * BN;  // two accumulator stages
   static constexpr int kOutBytes = kEpiWarps * kBoxBytes;
@@ -131,9 +126,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res,
                     const GemmParams p) {
   using C = Cfg<BN, kCtas>;
-  constexpr bool kPair = kCtas >= 2;      // cta_group::2 MMAs (kCtas = 4: two pairs per cluster)
-  constexpr bool kQuad = kCtas == 4;
-  static_assert(kCtas == 1 || kCtas == 2 || kCtas == 4, "1 CTA, a CTA pair, or two pairs sharing the W tile");
+  constexpr bool kPair = kCtas == 2;
   static_assert(!(kPair && kDirect) && (!kPair || BN == 256), "CTA pairs: staged 256-wide tiles only");
   // kTrans bit 0: A is MN-major (given as [K, M], the backward's "A^T"); bit 1: B is MN-major (given as [K, N]).
   // An MN-major operand is staged as 64-column slabs of [64 k-rows x 128 B] (one TMA box each, 128B swizzle):
@@ -144,9 +137,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   constexpr bool kDGelu = kGelu && kResidual && kTrans == 2;
   static_assert(!kDGelu || !kDirect, "the fused GELU backward lives on the staged path");
   static_assert(!(kPair && kTrans != 0), "MN-major operands: single-CTA tiles only");
-  const uint32_t cta_rank = kPair ? cluster_ctarank() : 0u;   // even = leader (issues the MMAs of its pair)
-  const uint32_t pair_rank = cta_rank & 1u;                   // position inside the pair: which W half this CTA holds
-  const uint32_t leader_rank = cta_rank & ~1u;
+  const uint32_t cta_rank = kPair ? cluster_ctarank() : 0u;   // 0 = leader (issues the MMAs of the pair)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
@@ -172,11 +163,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   if (warp_idx == 1 && lane == 0) {
     for (int s = 0; s < C::kStages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], kQuad ? 2 : 1);   // quad: the slot is also written by the other pair's producer
+      mbar_init(&empty_bar[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full_bar[a], 1);
-      mbar_init(&tmem_empty_bar[a], kEpiWarps * (kPair ? 2 : 1));   // pair: the leader's barrier collects both CTAs' epilogues
+      mbar_init(&tmem_empty_bar[a], kEpiWarps * kCtas);   // pair: the leader's barrier collects both CTAs' epilogues
     }
     for (int w = 0; w < kEpiWarps; ++w) mbar_init(&res_bar[w], 1);
     fence_mbar_init();
@@ -238,19 +229,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           // activations are streamed once per N-sweep; weights are re-read by every M block
           if constexpr (kPair) {
             // both CTAs load into their own ring slot; all bytes are credited to the leader's barrier
-            if (pair_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * C::kStageBytes);
+            if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * C::kStageBytes);
             tma_load_2d_pair(&tmap_a, &full_bar[stage], sa, kb * kBK, m_blk * kBM, kEvictNormal);
-            if constexpr (kQuad) {
-              // quarter `pair` of W half `pair_rank`, delivered to this CTA and to the CTA of the other pair that holds
-              // the same half (ranks pair_rank and 2 + pair_rank); every receiver credits ITS pair leader's barrier
-              const int pair = static_cast<int>(cta_rank >> 1);
-              tma_load_2d_pair_mc(&tmap_b, &full_bar[stage], sb + pair * (C::kBBytes / 2), kb * kBK,
-                                  n_blk * BN + static_cast<int>(pair_rank) * (BN / 2) + pair * (BN / 4),
-                                  static_cast<uint16_t>(5u << pair_rank), kEvictLast);
-            } else {
-              tma_load_2d_pair(&tmap_b, &full_bar[stage], sb, kb * kBK, n_blk * BN + static_cast<int>(pair_rank) * (BN / 2),
-                               kEvictLast);
-            }
+            tma_load_2d_pair(&tmap_b, &full_bar[stage], sb, kb * kBK, n_blk * BN + static_cast<int>(cta_rank) * (BN / 2),
+                             kEvictLast);
           } else {
           mbar_arrive_expect_tx(&full_bar[stage], C::kStageBytes);
           if constexpr (kAmn) {
@@ -277,10 +259,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
   } else if (warp_idx == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0 && pair_rank == 0) {
-      const uint16_t pair_mask = static_cast<uint16_t>(3u << leader_rank);          // both CTAs of this pair
-      const uint16_t ring_mask = kQuad ? static_cast<uint16_t>(0xF) : pair_mask;     // every CTA that writes these slots
-      constexpr uint32_t idesc = umma_idesc_bf16_f32(kBM * (kPair ? 2 : 1), BN) | (kAmn ? (1u << 15) : 0u) | (kBmn ? (1u << 16) : 0u);
+    if (lane == 0 && cta_rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16_f32(kBM * kCtas, BN) | (kAmn ? (1u << 15) : 0u) | (kBmn ? (1u << 16) : 0u);
       constexpr uint64_t kLboMn = static_cast<uint64_t>((8192 >> 4) - 1) << 16;   // LBO field holds 1 for K-major
       int stage = 0;
       uint32_t phase = 0;
@@ -311,14 +291,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
               umma_bf16_ss(d_tmem, ad, bd, idesc, accum);
           }
           // frees the ring slot (in both CTAs of a pair) once these MMAs have read it
-          if constexpr (kPair) umma_commit_pair(&empty_bar[stage], ring_mask); else umma_commit(&empty_bar[stage]);
+          if constexpr (kPair) umma_commit_pair(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
           if (++stage == C::kStages) {
             stage = 0;
             phase ^= 1;
           }
         }
         // accumulator complete (each CTA's epilogue reads its own half from its own TMEM)
-        if constexpr (kPair) umma_commit_pair(&tmem_full_bar[acc], pair_mask); else umma_commit(&tmem_full_bar[acc]);
+        if constexpr (kPair) umma_commit_pair(&tmem_full_bar[acc]); else umma_commit(&tmem_full_bar[acc]);
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1;
@@ -435,7 +415,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             __syncwarp();
             if (lane == 0) {
               if constexpr (kPair)
-                mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty_bar[acc]), leader_rank));
+                mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty_bar[acc]), 0));
               else
                 mbar_arrive(&tmem_empty_bar[acc]);
             }
@@ -739,7 +719,7 @@ int32_t launch_one(cudaStream_t stream, const Maps& m, const GemmParams& p, int 
     if (e != cudaSuccess) return cuda_status(e);
     attr_set = true;
   }
-  if constexpr (P >= 2) {
+  if constexpr (P == 2) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(static_cast<unsigned>(grid));
     cfg.blockDim = dim3(kThreads);
@@ -747,27 +727,11 @@ int32_t launch_one(cudaStream_t stream, const Maps& m, const GemmParams& p, int 
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = P;
+    attr[0].val.clusterDim.x = 2;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    if constexpr (P == 4) {
-      // persistent clusters of 4: never launch more than can be co-resident (GPC sizes decide), or the surplus
-      // cluster would run as a second wave behind all the others
-      static int max_clusters = 0;   // benign race: idempotent
-      if (max_clusters == 0) {
-        int n = 0;
-        cfg.gridDim = dim3(4 * 37);
-        if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n <= 0) {
-          (void)cudaGetLastError();
-          n = 32;
-        }
-        max_clusters = n;
-      }
-      if (grid > 4 * max_clusters) grid = 4 * max_clusters;
-      cfg.gridDim = dim3(static_cast<unsigned>(grid));
-    }
     cudaError_t e = cudaLaunchKernelEx(&cfg, kern, m.a, m.b, m.out, m.res, p);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return cuda_status(e != cudaSuccess ? e : cudaGetLastError());
@@ -1034,26 +998,9 @@ extern "C" int32_t mr_gemm_epilogue(mr_stream_t stream_, const MrGemmDesc* d, co
   MR_REQUIRE(make_tmap_2d(&m.out, out[0], d->M, d->N, d->ldd, 32, 64), MR_ERR_DRIVER);
   m.res = m.out;
   if (residual) MR_REQUIRE(make_tmap_2d(&m.res, in[3], d->M, d->N, d->ldd, 32, 64), MR_ERR_DRIVER);
-  // algo_pair = 3: clusters of two CTA pairs that share (multicast) the W tile, 512 x 256 super-tiles.  A call that
-  // leaves the field at 0 (the composite encoder entry) can be steered by MR_GEMM_PAIR for same-box A/B runs.
-  int algo_pair = d->algo_pair;
-  if (algo_pair == 0) {
-    static const int env_pair = [] {
-      const char* e = std::getenv("MR_GEMM_PAIR");
-      return e ? std::atoi(e) : 0;
-    }();
-    algo_pair = env_pair;
-  }
-  if (bn == 256 && trans == 0 && algo_pair == 3 && sms >= 4) {
-    const int quad_tiles = ceil_div(d->M, 4 * kBM) * p.num_n_tiles;
-    p.num_tiles = quad_tiles;
-    const int clusters = quad_tiles < sms / 4 ? quad_tiles : sms / 4;
-    MR_REQUIRE(make_tmap_2d(&m.b, W, d->N, d->K, d->K, bn / 4, kBK), MR_ERR_DRIVER);
-    return launch_staged<256, 4>(stream, m, p, 4 * clusters, epi);
-  }
   // CTA pairs (cta_group::2, 256 x 256 pair tiles) whenever every pair of SMs gets at least one pair tile
   const int pair_tiles = ceil_div(d->M, 2 * kBM) * p.num_n_tiles;
-  if (bn == 256 && trans == 0 && algo_pair != 2 && sms >= 2 && (algo_pair == 1 || pair_tiles >= sms / 2)) {
+  if (bn == 256 && trans == 0 && d->algo_pair != 2 && sms >= 2 && (d->algo_pair == 1 || pair_tiles >= sms / 2)) {
     p.num_tiles = pair_tiles;
     const int pairs = pair_tiles < sms / 2 ? pair_tiles : sms / 2;
     MR_REQUIRE(make_tmap_2d(&m.b, W, d->N, d->K, d->K, bn / 2, kBK), MR_ERR_DRIVER);

@@ -431,19 +431,6 @@ __device__ __forceinline__ void tma_load_2d_pair(const void* desc, uint64_t* bar
       : "memory");
 }
 
-// The same, multicast: the box lands at the same shared-memory offset in every CTA of `mask`, and each receiving CTA
-// credits the bytes to the mbarrier at this offset in the leader of ITS OWN pair (peer bit cleared).
-__device__ __forceinline__ void tma_load_2d_pair_mc(const void* desc, uint64_t* bar, void* smem_dst, int32_t c0,
-                                                    int32_t c1, uint16_t mask, uint64_t hint) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
-      ".L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5, %6;"
-      :
-      : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(desc)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0),
-        "r"(c1), "h"(mask), "l"(hint)
-      : "memory");
-}
-
 __device__ __forceinline__ void tmem_alloc_pair(uint32_t* dst_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
                "r"(ncols)
@@ -471,13 +458,11 @@ __device__ __forceinline__ void umma_bf16_ss_pair(uint32_t tmem_d, uint64_t desc
 }
 
 // Arrive on the mbarrier at this offset in BOTH CTAs of the pair once the MMAs issued so far have retired.
-// `mask`: the cluster ranks whose barrier (same offset) receives the arrive -- the two CTAs of the issuing pair,
-// or all four CTAs of a two-pair cluster for the ring slots that both pairs' producers write.
-__device__ __forceinline__ void umma_commit_pair(uint64_t* bar, uint16_t mask = 3) {
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
   asm volatile(
       "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
           smem_u32(bar)),
-      "h"(mask)
+      "h"(static_cast<uint16_t>(3))
       : "memory");
 }
 

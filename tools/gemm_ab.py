@@ -11,9 +11,8 @@ from merlot_reserve_b200 import _lib as L  # noqa: E402
 
 L.require_b200(0)
 dev = torch.device("cuda:0")
-_pos = [a for a in sys.argv[1:] if not a.startswith("--")]
-H = int(_pos[0]) if len(_pos) > 0 else 768
-M = int(_pos[1]) if len(_pos) > 1 else 246784
+H = int(sys.argv[1]) if len(sys.argv) > 1 else 768
+M = int(sys.argv[2]) if len(sys.argv) > 2 else 246784
 x = torch.randn(M, H, device=dev).to(torch.bfloat16)
 qkv = torch.empty(M, 3 * H, device=dev, dtype=torch.bfloat16)
 ctx = torch.randn(M, H, device=dev).to(torch.bfloat16)
@@ -51,26 +50,18 @@ def block(fn, n=12):
     return e0, e1, n
 
 
-QUAD = "--quad" in sys.argv
 for _ in range(3):
     layer(1), layer(2), cublas()
-    if QUAD:
-        layer(3)
-res = {"pair": [], "single": [], "cublas": [], "quad": []}
+res = {"pair": [], "single": [], "cublas": []}
 blocks = []
 for r in range(6):
     blocks.append(("pair", block(lambda: layer(1))))
-    if QUAD:
-        blocks.append(("quad", block(lambda: layer(3))))
-    else:
-        blocks.append(("single", block(lambda: layer(2))))
+    blocks.append(("single", block(lambda: layer(2))))
     blocks.append(("cublas", block(cublas)))
 torch.cuda.synchronize()
 for k, (e0, e1, n) in blocks:
     res[k].append(flops * n / e0.elapsed_time(e1) / 1e9)
 for k, v in res.items():
-    if not v:
-        continue
     print(f"{k:7s} TFLOP/s per block: " + " ".join(f"{t:7.1f}" for t in v) + f"   median {sorted(v)[len(v) // 2]:.1f}")
 # per-GEMM timings
 def one(fn, n=20):
@@ -79,7 +70,7 @@ def one(fn, n=20):
     e0, e1, _ = block(fn, n)
     torch.cuda.synchronize()
     return e0.elapsed_time(e1) / n
-for pair in ((1, 3) if QUAD else (1, 2)):
+for pair in (1, 2):
     t = [one(lambda: L.gemm(x, wqkv, bias=bq, rot=rot, hidden=H, q_scale=0.125, out=qkv, ln_stats=stats, ln_colsum=sq, pair=pair)),
          one(lambda: L.gemm(ctx, wo, residual=x, out=x, stats_out=stats, pair=pair)),
          one(lambda: L.gemm(x, w1, bias=b1, gelu=True, out=u, ln_stats=stats, ln_colsum=s1, pair=pair)),

@@ -20,6 +20,8 @@ SHAPES = [
     ("large_vision_18x32_x16", 256, 577, 1024, False),
     ("large_joint_18x32_x16", 16, 2464, 1024, True),
     ("pretrain_joint_b8", 48, 640, 768, True),
+    ("large_mc_joint_b128", 512, 288, 1024, True),     # cfg 5: 128 examples x 4 candidates, T = 144 + 144
+    ("large_mc_vision_b128", 128, 577, 1024, False),
 ]
 
 

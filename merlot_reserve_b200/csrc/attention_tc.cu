@@ -437,26 +437,19 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
         if (!fast) {
           if (kMasked) {
             cs = kLog2e;
-            if (p.group == nullptr && !any_uniform) {
-              // additive per-key bias (0 / -inf), broadcast smem reads: one FADD per score
+            if (p.group == nullptr) {
+              // additive per-key bias (0 / -inf) folded into one FFMA per score.  A valid query row reads the
+              // "key valid and in range" vector with scale 1; an invalid query row (it attends uniformly to every
+              // existing key, modeling.py:343-358) reads the "key in range" vector with scale 0.  The choice is per
+              // THREAD (a pointer), not per score: at most two broadcast addresses per warp and no selects.
+              const float* myBias = q_uniform ? myBiasE : myBiasV;
 #pragma unroll
               for (int c4 = 0; c4 < kKV / 4; ++c4) {
-                const float4 b = *reinterpret_cast<const float4*>(myBiasV + 4 * c4);
-                sc[4 * c4 + 0] += b.x;
-                sc[4 * c4 + 1] += b.y;
-                sc[4 * c4 + 2] += b.z;
-                sc[4 * c4 + 3] += b.w;
-              }
-            } else if (p.group == nullptr) {
-              // some rows of this warp are invalid queries: they see score 0 on every existing key
-#pragma unroll
-              for (int c4 = 0; c4 < kKV / 4; ++c4) {
-                const float4 bvv = *reinterpret_cast<const float4*>(myBiasV + 4 * c4);
-                const float4 bee = *reinterpret_cast<const float4*>(myBiasE + 4 * c4);
-                sc[4 * c4 + 0] = fmaf(sc[4 * c4 + 0], qs, q_uniform ? bee.x : bvv.x);
-                sc[4 * c4 + 1] = fmaf(sc[4 * c4 + 1], qs, q_uniform ? bee.y : bvv.y);
-                sc[4 * c4 + 2] = fmaf(sc[4 * c4 + 2], qs, q_uniform ? bee.z : bvv.z);
-                sc[4 * c4 + 3] = fmaf(sc[4 * c4 + 3], qs, q_uniform ? bee.w : bvv.w);
+                const float4 b = *reinterpret_cast<const float4*>(myBias + 4 * c4);
+                sc[4 * c4 + 0] = fmaf(sc[4 * c4 + 0], qs, b.x);
+                sc[4 * c4 + 1] = fmaf(sc[4 * c4 + 1], qs, b.y);
+                sc[4 * c4 + 2] = fmaf(sc[4 * c4 + 2], qs, b.z);
+                sc[4 * c4 + 3] = fmaf(sc[4 * c4 + 3], qs, b.w);
               }
             } else {
               // group ids (video_src): per-thread comparison against the query's own group

@@ -151,8 +151,10 @@ enum { MR_ATTN_ALGO_AUTO = 0, MR_ATTN_ALGO_MMA_SYNC = 1, MR_ATTN_ALGO_TCGEN05 = 
 
 typedef struct MrAttentionDesc {
   int32_t B, T, H; /* H = hidden = 64 * heads */
-  int32_t algo;    /* AUTO: tcgen05/TMEM kernel (128-query tiles) when T > 64, else the small-sequence
-                      mma.sync kernel (64-query tiles; audio T=31, span T=16) */
+  int32_t algo;    /* AUTO: tcgen05/TMEM kernel (128-query tiles) when T > 64; mma.sync kernels below that: one
+                      32 x 32 tile per (sequence, head) in a two-warp CTA when T <= 32 (audio T=31, span T=16),
+                      64-query tiles otherwise.  MMA_SYNC forces the 64-tile mma.sync kernel, TCGEN05 the
+                      tensor-memory kernel (both directions). */
   int32_t emit_lse; /* fwd: 1 = also write out[1] = lse f32 [B, H/64, T], the natural-log row log-sum-exp of the
                        masked scores (what mr_attention_bwd needs to recompute the probabilities) */
 } MrAttentionDesc;
@@ -165,7 +167,8 @@ size_t mr_attention_fwd_workspace_bytes(const MrAttentionDesc* d);
  *   in[0] qkv bf16 [B*T, 3H] (the forward's input); in[1] dctx bf16 [B*T, H]; in[2] ctx bf16 [B*T, H] (the forward's
  *   output); in[3] lse f32 [B, H/64, T] (emit_lse); in[4] valid u8 optional; in[5] group i32 optional
  *   out[0] dqkv bf16 [B*T, 3H] (dq | dk | dv, same layout as qkv); apply mr_rotary_bwd next, then the qkv dgrad/wgrad.
- *   workspace: mr_attention_bwd_workspace_bytes (fp32 dq accumulator + row sums of dctx . ctx). */
+ *   workspace: mr_attention_bwd_workspace_bytes (fp32 dq accumulator + row sums of dctx . ctx).  AUTO with T <= 32
+ *   runs the one-block kernel, which writes dq in place and leaves the accumulator part of the workspace untouched. */
 int32_t mr_attention_bwd(mr_stream_t stream, const MrAttentionDesc* d, const void* const* in, void* const* out,
                          void* workspace, size_t workspace_bytes);
 size_t mr_attention_bwd_workspace_bytes(const MrAttentionDesc* d);

@@ -73,6 +73,27 @@ def _dgrad(dy: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
     return L.gemm_bwd(dy, w, trans_b=True, out_f32=False)
 
 
+def arena_layout(names: List[str], numel: Dict[str, int]) -> Tuple[Dict[str, int], int]:
+    """Element offsets of the flat optimizer / gradient arenas: tensors in sorted-name order, 8-element (16-byte bf16)
+    alignment, and every top-level module ('audio_encoder', 'head', 'joint_transformer', ...) starting on a
+    1024-element boundary, so that the buckets of the overlapped gradient all-reduce are whole rows of the bf16
+    cast (rows of 1024) and never share a row with a module that is still differentiating.  -> (offsets, total)."""
+    assert list(names) == sorted(names)
+    offs, n, top = {}, 0, None
+    for name in names:
+        if name.split("/")[0] != top:
+            top = name.split("/")[0]
+            n = (n + 1023) // 1024 * 1024
+        offs[name] = n
+        n += (numel[name] + 7) // 8 * 8
+    return offs, (n + 1023) // 1024 * 1024
+
+
+# The groups of top-level modules whose gradients become final together during `loss_and_grads`' backward pass, in
+# that order; train_step starts one asynchronous all-reduce per group (`on_ready`).
+ALLREDUCE_BUCKETS = (("head", "span_encoder", "joint_transformer", "token_encoder"), ("audio_encoder",), ("vision_encoder",))
+
+
 class _Grads:
     """Accumulates parameter gradients (fp32, packed layout) under flax-style path names."""
 
@@ -144,14 +165,7 @@ class PretrainStep:
         reg = self._registry()
         names = sorted(reg)
         dev = next(iter(reg.values()))[0].device
-        offs, n, top = {}, 0, None
-        for name in names:
-            if name.split("/")[0] != top:                   # a top-level module starts on a 1024-element boundary:
-                top = name.split("/")[0]                    # the buckets of the overlapped all-reduce are whole rows
-                n = (n + 1023) // 1024 * 1024               # of the bf16 cast (rows of 1024)
-            offs[name] = n
-            n += (reg[name][0].numel() + 7) // 8 * 8
-        n_total = (n + 1023) // 1024 * 1024                 # the gradient cast works on rows of 1024
+        offs, n_total = arena_layout(names, {k: reg[k][0].numel() for k in names})
         mdt = BF16 if opt.get("use_bfloat16_adam", True) else torch.float32
         p = torch.zeros(n_total, dtype=torch.float32, device=dev)
         slots = []
@@ -645,7 +659,7 @@ class PretrainStep:
                                  d_vision=d_imgs_seq if kw.get("n_vis", 0) else None, **kw)
         G.add("token_encoder/Embed_0/embedding", d_tok_emb)
         if on_ready is not None:
-            on_ready(G.g, ("head", "span_encoder", "joint_transformer", "token_encoder"))
+            on_ready(G.g, ALLREDUCE_BUCKETS[0])
 
         # ---- audio encoder ----
         dxaf = self._pool_bwd(d_audio_seq.view(-1, H).to(BF16), xaf, a_pool_saved, p.aud_pool, Ba, Ta, geom_a, G,
@@ -654,7 +668,7 @@ class PretrainStep:
         dxa0 = self._enc_bwd(dxa_last, tape_a, p.aud, G, "audio_encoder/transformer")
         self._embed_rows_bwd(dxa0, aa, Ba, Ta, G, "audio_encoder")
         if on_ready is not None:
-            on_ready(G.g, ("audio_encoder",))
+            on_ready(G.g, ALLREDUCE_BUCKETS[1])
 
         # ---- vision encoder ----
         dxvf = self._pool_bwd(d_imgs_seq.view(-1, H).to(BF16), xvf, v_pool_saved, p.vis_pool, Bv, Tv, geom_v, G,
@@ -663,7 +677,7 @@ class PretrainStep:
         dxv0 = self._enc_bwd(dxv_last, tape_v, p.vis, G, "vision_encoder/transformer")
         self._embed_rows_bwd(dxv0, av, Bv, Tv, G, "vision_encoder")
         if on_ready is not None:
-            on_ready(G.g, ("vision_encoder",))
+            on_ready(G.g, ALLREDUCE_BUCKETS[2])
         if getattr(self, "_keep_locals", False):
             self._dbg = dict(locals())
         return loss, info, G.g

@@ -206,3 +206,31 @@ def test_train_state_round_trips_through_the_reference_checkpoint_format(tmp_pat
     assert np.allclose(b.model._p.contrastive_scales, a.model._p.contrastive_scales, rtol=1e-3)
     la, lb = float(a.train_step(batch, opt)[0]), float(b.train_step(batch, opt)[0])
     assert np.isfinite(lb) and abs(la - lb) < 0.05, (la, lb)
+
+
+def test_gradient_arena_layout_keeps_allreduce_buckets_apart():
+    """Host logic of the overlapped gradient all-reduce (training.arena_layout / ALLREDUCE_BUCKETS): every top-level
+    module starts on a row of the bf16 cast, the modules of a bucket are adjacent in the arena, and no 1024-element
+    row is shared by two buckets -- so a bucket can be cast and reduced while later ones are still being written."""
+    from merlot_reserve_b200.training import ALLREDUCE_BUCKETS, arena_layout
+    rng = np.random.default_rng(0)
+    tops = ["audio_encoder", "head", "joint_transformer", "span_encoder", "token_encoder", "vision_encoder"]
+    names = sorted(f"{t}/{sub}/p{i}" for t in tops for sub in ("a", "transformer/layer_00") for i in range(5))
+    numel = {k: int(rng.integers(1, 5000)) for k in names}
+    offs, total = arena_layout(names, numel)
+    assert total % 1024 == 0 and all(o % 8 == 0 for o in offs.values())
+    spans = []
+    for k in names:                                              # no overlap, sorted order
+        spans.append((offs[k], offs[k] + numel[k]))
+    assert all(a[1] <= b[0] for a, b in zip(spans, spans[1:]))
+    assert {t for b in ALLREDUCE_BUCKETS for t in b} == set(tops)
+    rows = []
+    for bucket in ALLREDUCE_BUCKETS:
+        mine = [k for k in names if k.split("/")[0] in bucket]
+        lo = min(offs[k] for k in mine) // 1024
+        hi = -(-max(offs[k] + numel[k] for k in mine) // 1024)
+        inside = [k for k in names if lo * 1024 <= offs[k] < hi * 1024]
+        assert inside == mine, "a bucket's row range covers exactly its own tensors"
+        rows.append((lo, hi))
+    rows.sort()
+    assert all(a[1] <= b[0] for a, b in zip(rows, rows[1:])), "buckets share no row of the cast"

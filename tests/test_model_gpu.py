@@ -209,3 +209,22 @@ def test_tvqa_forward_matches_oracle(setup):
         clear = (top2[:, 1] - top2[:, 0]) > 2 * tol
         assert (got.argmax(-1) == ref.argmax(-1))[clear].all()
     assert np.abs(got_a - got_t).max() > 1e-4      # the two variants really are different sequences
+
+
+def test_product_against_the_reference_bf16_noise_floor(setup):
+    """Distance of the B200 path from the fp32 oracle next to the distance of the reference's OWN bf16 graph
+    (oracle bf16_graph mode, rounding at every op as the dtype=bfloat16 flax modules do) from the same fp32 result:
+    the fused epilogues round once per GEMM, so the product must not be further away than that floor (factor 2 of
+    slack on the mean, and the worst row no worse than the floor's worst row by more than 1e-3)."""
+    from oracle.reserve_oracle import bf16_graph
+    cfg, params, model, orc = setup
+    clip = synthetic_clip(cfg, nseg=4, seed=5)
+    ref = orc.embed_video(**clip)
+    with bf16_graph():
+        floor = orc.embed_video(**clip)
+    got = model.apply({"params": params}, **clip, method=model.embed_video)
+    d_floor, d_got = 1.0 - _cos(floor, ref), 1.0 - _cos(got, ref)
+    assert d_got.mean() <= 2.0 * d_floor.mean() + 1e-6, (float(d_got.mean()), float(d_floor.mean()))
+    assert d_got.max() <= d_floor.max() + 1e-3, (float(d_got.max()), float(d_floor.max()))
+    print(f"1 - cosine vs fp32: product mean {float(d_got.mean()):.2e} max {float(d_got.max()):.2e}; "
+          f"reference bf16 graph mean {float(d_floor.mean()):.2e} max {float(d_floor.max()):.2e}")

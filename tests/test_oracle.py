@@ -217,3 +217,23 @@ def test_pretrain_batch_layout():
         for g in range(2):
             ptr = b["text2audio/audio_ptr"][i, g][t2a[g] == 4]
             assert ((ptr >= 24 * g) & (ptr < 24 * (g + 1))).all()
+
+
+@pytest.mark.parametrize("scale,min_cos,mean_cos", [(1.0, 0.9999, 0.99995), (4.0, 0.998, 0.9999)])
+def test_bf16_graph_noise_floor(scale, min_cos, mean_cos):
+    """The oracle's bf16-graph mode (rounding at the points where the reference's dtype=bfloat16 modules round,
+    SURVEY.md Appendix A) against its own fp32 mode: the noise floor of the reference's bf16 execution, which is what
+    the north_star tolerance (cosine >= 0.999 vs fp32) has to be read against.  With the weight_scale = 4 parameters
+    single rows of the bf16 graph already fall to ~0.9987."""
+    from oracle.reserve_oracle import bf16_graph
+    cfg = tiny_config()
+    orc = O.OracleMerlotReserve(cfg, synthetic_params(cfg, seed=0, weight_scale=scale))
+    clip = synthetic_clip(cfg, nseg=4, seed=5)
+    ref = orc.embed_video(**clip)
+    with bf16_graph():
+        low = orc.embed_video(**clip)
+    again = orc.embed_video(**clip)
+    assert torch.equal(ref, again), "the bf16 mode must not leak out of its context"
+    cos = torch.nn.functional.cosine_similarity(ref, low, dim=-1)
+    assert not torch.equal(ref, low)
+    assert cos.min() >= min_cos and cos.mean() >= mean_cos, (float(cos.min()), float(cos.mean()))

@@ -237,3 +237,27 @@ def test_bf16_graph_noise_floor(scale, min_cos, mean_cos):
     cos = torch.nn.functional.cosine_similarity(ref, low, dim=-1)
     assert not torch.equal(ref, low)
     assert cos.min() >= min_cos and cos.mean() >= mean_cos, (float(cos.min()), float(cos.mean()))
+
+
+@pytest.mark.parametrize("scale", [1.0, 4.0])
+def test_bf16_graph_noise_floor_of_contrastive_logits(scale):
+    """Same yardstick for the pretraining head: logits x . y^T (temperature 20, |logit| <= 20) of the bf16-graph
+    forward against the fp32 forward.  The stated tolerance for the CUDA path, 2e-2 * scale + 2e-2 * |ref| (0.4 at the
+    extremes), is ~8x this floor; the loss moves by less than 5e-3."""
+    from merlot_reserve_b200.synthetic import synthetic_pretrain_batch
+    from oracle.reserve_oracle import bf16_graph, contrastive_loss
+    cfg = tiny_config()
+    orc = O.OracleMerlotReserve(cfg, synthetic_params(cfg, seed=0, weight_scale=scale))
+    batch = synthetic_pretrain_batch(cfg, 2, seed=3)
+    p32 = orc.pretrain_forward(batch)
+    with bf16_graph():
+        p16 = orc.pretrain_forward(batch)
+    l32, _ = contrastive_loss(p32)
+    l16, _ = contrastive_loss(p16)
+    assert abs(float(l32) - float(l16)) < 5e-3
+    for head in p32:
+        lg32 = p32[head]["x"].float() @ p32[head]["y"].float().T
+        lg16 = p16[head]["x"].float() @ p16[head]["y"].float().T
+        d = (lg32 - lg16).abs()
+        assert float(d.max()) < 0.1, (head, float(d.max()))
+        assert bool((d <= 2e-2 * 20.0 + 2e-2 * lg32.abs()).all())

@@ -1,6 +1,7 @@
 """CPU oracle for the MERLOT Reserve encoder + contrastive hot path.  TEST INFRASTRUCTURE ONLY.
 
-This file restates, in plain torch fp32 on the CPU, the arithmetic that the reference
+This file restates, in plain torch fp32 on the CPU (plus an emulation of the reference's bf16 graph, `bf16_graph()`,
+used to measure that graph's own rounding noise), the arithmetic that the reference
 (`/root/reference/mreserve/modeling.py`, `pretrain/pretrain_model.py`) asks XLA to perform through
 flax.linen.  It is the checker for the CUDA path: only `tests/`, `__graft_entry__.smoke()` and the
 `cpu_baseline` / `--impl reference` legs of `bench.py` may import it.  The product package

@@ -32,7 +32,25 @@ import torch
 PADDING, START, END, MASK, MASKAUDIO, AUDIOSPAN, LTOVPOOL = 0, 1, 2, 3, 4, 5, 6
 
 
-def _t(x, dtype=torch.float32):
+_FLOAT = torch.float32      # working precision; `with fp64():` re-runs the same restatement in double precision
+
+
+class fp64:
+    """Spot-check mode: activations and parameters in float64 (coordinates / sinusoid tables stay fp32 constants).
+    Shows how much of any oracle-vs-kernel distance is the oracle's own fp32 rounding (it is ~1e-7 in cosine)."""
+
+    def __enter__(self):
+        global _FLOAT
+        self._prev, _FLOAT = _FLOAT, torch.float64
+        return self
+
+    def __exit__(self, *exc):
+        global _FLOAT
+        _FLOAT = self._prev
+
+
+def _t(x, dtype=None):
+    dtype = dtype or _FLOAT
     if isinstance(x, torch.Tensor):
         return x.to(dtype)
     return torch.as_tensor(np.asarray(x)).to(dtype)
@@ -62,7 +80,7 @@ class bf16_graph:
 
 def _r(x: torch.Tensor) -> torch.Tensor:
     """A rounding point of the bf16 graph (identity in fp32 mode)."""
-    return x.to(torch.bfloat16).float() if _BF16_GRAPH else x
+    return x.to(torch.bfloat16).to(x.dtype) if _BF16_GRAPH else x
 
 
 def _w(x) -> torch.Tensor:
@@ -154,7 +172,7 @@ def dense(x, p):
 
 def layer_norm(x, p, eps=1e-5):
     """flax LayerNorm: fp32 stats, var = E[x^2] - E[x]^2, (x - mean) * (rsqrt(var + eps) * scale) + bias."""
-    x = x.float()
+    x = x.to(_FLOAT)
     mean = x.mean(-1, keepdim=True)
     mean2 = (x * x).mean(-1, keepdim=True)
     var = mean2 - mean * mean
@@ -686,7 +704,7 @@ class OracleMerlotReserve:
 
 def unit_normalize(x):
     """modeling.py:570-578."""
-    x = x.float()
+    x = x.to(_FLOAT)
     return x / torch.sqrt((x * x).sum(-1, keepdim=True) + 1e-5)
 
 

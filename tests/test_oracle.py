@@ -261,3 +261,24 @@ def test_bf16_graph_noise_floor_of_contrastive_logits(scale):
         d = (lg32 - lg16).abs()
         assert float(d.max()) < 0.1, (head, float(d.max()))
         assert bool((d <= 2e-2 * 20.0 + 2e-2 * lg32.abs()).all())
+
+
+@pytest.mark.parametrize("scale", [1.0, 4.0])
+def test_fp64_spot_check_of_the_fp32_oracle(scale):
+    """The same restatement in float64 (`fp64()`): on every real token row the fp32 oracle is at 1 - cosine < 1e-10
+    of it, so none of the oracle-vs-kernel distance is the oracle's own rounding.  Padding rows are the exception
+    that proves a reference behaviour: their queries are fully masked, and only because fp32 (and bf16) absorb the
+    scores into the -1e10 bias do they attend UNIFORMLY (modeling.py:343-358) -- in float64 the scores survive next to
+    -1e10 and those rows come out differently.  The CUDA path reproduces the fp32 / bf16 behaviour."""
+    from oracle.reserve_oracle import fp64
+    cfg = tiny_config()
+    orc = O.OracleMerlotReserve(cfg, synthetic_params(cfg, seed=0, weight_scale=scale))
+    clip = synthetic_clip(cfg, nseg=4, seed=5)
+    ref = orc.embed_video(**clip)
+    with fp64():
+        hi = orc.embed_video(**clip)
+    assert ref.dtype == torch.float32 and hi.dtype == torch.float64
+    d = 1.0 - torch.nn.functional.cosine_similarity(ref.double(), hi, dim=-1)
+    real = torch.from_numpy(clip["tokens"] != 0)
+    assert float(d[real].max()) < 1e-10
+    assert torch.equal(orc.embed_video(**clip), ref), "fp64 mode must not leak out of its context"

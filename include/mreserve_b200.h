@@ -237,6 +237,24 @@ int32_t mr_cast_pad(mr_stream_t stream, const MrCastDesc* d, const void* const* 
                     void* workspace, size_t workspace_bytes);
 
 /* ------------------------------------------------------------------------------------------
+ * mr_patchify_u8: uint8 frames, already at the model's resolution -> bf16 patch rows, i.e. the tail of
+ * preprocess_image_to_patches (mreserve/preprocess.py:464-481) on the device:
+ *   tf.image.convert_image_dtype(uint8 -> float32)   = float32(u8) * float32(1/255)              (:471)
+ *   tf.nn.space_to_depth(img, 16, NHWC) + reshape    = patch (by, bx) row-major, features (py, px, c)   (:478-479)
+ * followed by the cast to the module dtype that modeling.py:402 applies (bf16, round to nearest even), so the
+ * output is bit-identical to mr_cast_pad of the reference's fp32 patches.  Host-to-device traffic per frame is
+ * 1 byte per sample instead of 4.  (The bilinear resize + pad in front of it, preprocess.py:474-477, is TensorFlow
+ * code with no restatement here: frames must arrive at grid_h*16 x grid_w*16.)
+ *   in[0] frames u8 [B, grid_h*patch, grid_w*patch, 3] (NHWC); out[0] patches bf16 [B*grid_h*grid_w, patch*patch*3]
+ * patch must be 16 (768 features); pointers 16-byte aligned.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct MrPatchifyDesc {
+  int32_t B, grid_h, grid_w, patch;
+} MrPatchifyDesc;
+int32_t mr_patchify_u8(mr_stream_t stream, const MrPatchifyDesc* d, const void* const* in, void* const* out,
+                       void* workspace, size_t workspace_bytes);
+
+/* ------------------------------------------------------------------------------------------
  * mr_fill_cls: writes the CLS parameter into row 0 of every sequence of x [B, T, H]
  * (modeling.py:316-320).   in[0] cls f32 [H]; out[0] x bf16 [B*T, H]
  * ------------------------------------------------------------------------------------------ */

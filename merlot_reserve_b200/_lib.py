@@ -49,6 +49,10 @@ class CastDesc(C.Structure):
     _fields_ = [("rows", C.c_int64), ("cols", C.c_int32), ("ld_out", C.c_int32)]
 
 
+class PatchifyDesc(C.Structure):
+    _fields_ = [("B", C.c_int32), ("grid_h", C.c_int32), ("grid_w", C.c_int32), ("patch", C.c_int32)]
+
+
 class FillClsDesc(C.Structure):
     _fields_ = [("B", C.c_int32), ("T", C.c_int32), ("H", C.c_int32)]
 
@@ -127,6 +131,7 @@ ENTRY_POINTS = {
     "mr_layernorm_fwd": LayerNormDesc,
     "mr_transformer_encode": EncoderDesc,
     "mr_cast_pad": CastDesc,
+    "mr_patchify_u8": PatchifyDesc,
     "mr_fill_cls": FillClsDesc,
     "mr_window_mean": WindowDesc,
     "mr_window_attention": WindowDesc,
@@ -359,6 +364,20 @@ def cast_pad(x: torch.Tensor, rows: int, cols: int, ld_out: int, out=None) -> to
     if out is None:
         out = torch.empty((rows, ld_out), dtype=torch.bfloat16, device=x.device)
     _call("mr_cast_pad", CastDesc(rows=rows, cols=cols, ld_out=ld_out), [x], [out])
+    return out
+
+
+def patchify_u8(frames: torch.Tensor, grid_h: int, grid_w: int, out=None) -> torch.Tensor:
+    """uint8 NHWC frames [B, grid_h*16, grid_w*16, 3] -> bf16 patches [B*grid_h*grid_w, 768] (preprocess.py:464-481
+    without the resize: convert_image_dtype, space_to_depth(16), cast to bf16)."""
+    assert frames.dtype == torch.uint8 and frames.dim() == 4 and frames.is_contiguous()
+    B = frames.shape[0]
+    if tuple(frames.shape[1:]) != (grid_h * 16, grid_w * 16, 3):
+        raise MrError(f"frames must be [B, {grid_h * 16}, {grid_w * 16}, 3] uint8, got {tuple(frames.shape)}")
+    if out is None:
+        out = torch.empty((B * grid_h * grid_w, 768), dtype=torch.bfloat16, device=frames.device)
+    if B:
+        _call("mr_patchify_u8", PatchifyDesc(B=B, grid_h=grid_h, grid_w=grid_w, patch=16), [frames], [out])
     return out
 
 

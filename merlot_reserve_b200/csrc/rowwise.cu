@@ -179,6 +179,38 @@ cast_pad_kernel(const float* __restrict__ x, bf16* __restrict__ y, int64_t rows,
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// uint8 NHWC frames -> bf16 patch rows (convert_image_dtype + space_to_depth + cast, preprocess.py:471,478-479).
+// One thread per 8 output features: for a 16 x 16 patch the 48 features of one patch row (px, c) are 48 contiguous
+// bytes of the image row, so every thread reads one aligned 8-byte word and writes one 16-byte vector.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+patchify_u8_kernel(const uint8_t* __restrict__ frames, bf16* __restrict__ y, int64_t n_patches, int grid_h, int grid_w) {
+  constexpr int kP = 16, kFeat = kP * kP * 3, kVec = kFeat / 8;   // 768 features, 96 vectors per patch
+  const int64_t total = n_patches * kVec;
+  const int img_w3 = grid_w * kP * 3;                             // bytes per image row
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t patch = i / kVec;
+    const int f0 = static_cast<int>(i - patch * kVec) * 8;        // first feature of this vector
+    const int py = f0 / (kP * 3), rest = f0 - py * (kP * 3);      // rest = px * 3 + c, a multiple of 8
+    const int bx = static_cast<int>(patch % grid_w);
+    const int64_t t = patch / grid_w;
+    const int by = static_cast<int>(t % grid_h);
+    const int64_t b = t / grid_h;
+    const uint8_t* src = frames + ((b * grid_h + by) * kP + py) * static_cast<int64_t>(img_w3) + bx * (kP * 3) + rest;
+    const uint2 w = __ldg(reinterpret_cast<const uint2*>(src));
+    float f[8];
+    const float s = 1.0f / 255.0f;                                // float32(1/255), as TF's convert_image_dtype
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      f[j] = static_cast<float>((w.x >> (8 * j)) & 0xffu) * s;
+      f[4 + j] = static_cast<float>((w.y >> (8 * j)) & 0xffu) * s;
+    }
+    *reinterpret_cast<uint4*>(y + patch * kFeat + f0) = pack8(f);
+  }
+}
+
 __global__ void fill_cls_kernel(const float* __restrict__ cls, bf16* __restrict__ x, int B, int T, int H) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= B * H) return;
@@ -536,6 +568,21 @@ extern "C" int32_t mr_cast_pad(mr_stream_t stream_, const MrCastDesc* d, const v
   if (blocks > 148 * 64) blocks = 148 * 64;
   cast_pad_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
       static_cast<const float*>(in[0]), static_cast<bf16*>(out[0]), d->rows, d->cols, d->ld_out);
+  return after_launch();
+}
+
+extern "C" int32_t mr_patchify_u8(mr_stream_t stream_, const MrPatchifyDesc* d, const void* const* in, void* const* out,
+                                  void*, size_t) {
+  MR_REQUIRE(d && in && out, MR_ERR_NULL_POINTER);
+  MR_REQUIRE(d->B >= 0 && d->grid_h > 0 && d->grid_w > 0 && d->patch == 16, MR_ERR_BAD_SHAPE);
+  if (d->B == 0) return MR_OK;
+  MR_REQUIRE(in[0] && out[0], MR_ERR_NULL_POINTER);
+  MR_REQUIRE(aligned16(in[0]) && aligned16(out[0]), MR_ERR_MISALIGNED);
+  const int64_t n_patches = static_cast<int64_t>(d->B) * d->grid_h * d->grid_w;
+  int64_t blocks = ceil_div64(n_patches * 96, 256);
+  if (blocks > 148 * 64) blocks = 148 * 64;
+  patchify_u8_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
+      static_cast<const uint8_t*>(in[0]), static_cast<bf16*>(out[0]), n_patches, d->grid_h, d->grid_w);
   return after_launch();
 }
 

@@ -317,7 +317,10 @@ class MerlotReserve:
         if B == 0:      # empty batch: what vmap / jit over a zero-length axis returns (no kernel is launched)
             z = lambda *shp: torch.zeros(shp, dtype=torch.bfloat16, device=images.device)
             return {"seq_attnpool": z(0, (gh // 2) * (gw // 2), H), "_xf": z(0, H), "cls": z(0, H)}
-        a = L.cast_pad(images.reshape(B * hw, pp3), B * hw, pp3, pp3)
+        if images.dtype == torch.bfloat16:      # patches made on the device by `patchify` (already in the module dtype)
+            a = images.reshape(B * hw, pp3).contiguous()
+        else:
+            a = L.cast_pad(images.reshape(B * hw, pp3), B * hw, pp3, pp3)
         x = torch.empty((B * T, H), dtype=torch.bfloat16, device=images.device)
         L.gemm(a, p.vis_emb[0], bias=p.vis_emb[1], out=x, seq_in=hw, seq_out=T, row_off=1)
         L.fill_cls(x, p.vis.cls, B, T, H)
@@ -449,10 +452,24 @@ class MerlotReserve:
         cls = self._audio(a.reshape(-1, self.config["audio_seq_length"], 65), want_cls=True)["cls"]
         return _ret(L.unit_normalize(cls).view(*lead, self.hidden_size), as_np)
 
+    def patchify(self, frames):
+        """uint8 frames [*, grid_h*16, grid_w*16, 3] at the model's resolution -> bf16 patches [*, hw, 768] ON THE
+        DEVICE: the tail of `preprocess_image_to_patches` (mreserve/preprocess.py:464-481; convert_image_dtype,
+        space_to_depth, cast to the module dtype) as one kernel, 1 byte per sample over PCIe instead of 4.  The
+        result feeds `get_imgseq_only` / `get_imgs_enc` (bit-identical to passing the reference's fp32 patches)."""
+        f = frames if isinstance(frames, torch.Tensor) else torch.as_tensor(np.asarray(frames))
+        if f.dtype != torch.uint8 or f.dim() < 3 or f.shape[-1] != 3:
+            raise ValueError("frames must be uint8 [*, H, W, 3]")
+        gh, gw = self.output_grid_h, self.output_grid_w
+        if tuple(f.shape[-3:-1]) != (gh * 16, gw * 16):
+            raise ValueError(f"frames must be {gh * 16} x {gw * 16} (resize_and_pad, preprocess.py:474-477, stays on the host)")
+        lead = f.shape[:-3]
+        return L.patchify_u8(_dev(f.reshape(-1, gh * 16, gw * 16, 3)), gh, gw).view(*lead, gh * gw, 768)
+
     def get_imgseq_only(self, imgs):
         """modeling.py:787-795."""
         as_np = _is_np(imgs)
-        x = _dev(imgs, torch.float32)
+        x = imgs if (isinstance(imgs, torch.Tensor) and imgs.dtype == torch.bfloat16 and imgs.is_cuda) else _dev(imgs, torch.float32)
         lead, n, pp3 = x.shape[:-2], x.shape[-2], x.shape[-1]
         enc = self._vision(x.reshape(-1, n, pp3))["seq_attnpool"]
         return _ret(enc.reshape(*lead, n // 4, self.hidden_size), as_np)

@@ -702,6 +702,23 @@ class OracleMerlotReserve:
         return out
 
 
+def frames_to_patches(frames_u8: np.ndarray, grid_h: int, grid_w: int, patch: int = 16) -> np.ndarray:
+    """The tail of preprocess_image_to_patches (mreserve/preprocess.py:464-481) for frames that already have the
+    model's resolution: tf.image.convert_image_dtype(uint8 -> float32) = float32(x) * float32(1/255) (:471),
+    tf.nn.space_to_depth(img[None], P, 'NHWC') -- output channel (py * P + px) * 3 + c of block (by, bx) -- and the
+    reshape to [h1 * w1, P * P * 3] (:478-479).  frames [B, grid_h*P, grid_w*P, 3] uint8 -> [B, h1*w1, P*P*3] fp32."""
+    f = np.asarray(frames_u8)
+    assert f.dtype == np.uint8 and f.shape[1:] == (grid_h * patch, grid_w * patch, 3)
+    x = f.astype(np.float32) * np.float32(1.0 / 255.0)
+    B = x.shape[0]
+    out = np.empty((B, grid_h * grid_w, patch * patch * 3), np.float32)
+    for by in range(grid_h):
+        for bx in range(grid_w):
+            blk = x[:, by * patch:(by + 1) * patch, bx * patch:(bx + 1) * patch, :]      # [B, py, px, c]
+            out[:, by * grid_w + bx] = blk.reshape(B, -1)
+    return out
+
+
 def unit_normalize(x):
     """modeling.py:570-578."""
     x = x.to(_FLOAT)

@@ -40,7 +40,7 @@ def test_struct_sizes_match_c(lib, tmp_path):
                "MrSegmentPoolDesc": lib.SegmentPoolDesc, "MrContrastiveDesc": lib.ContrastiveDesc,
                "MrRowDotDesc": lib.RowDotDesc, "MrEncoderDesc": lib.EncoderDesc, "MrElementwiseDesc": lib.ElementwiseDesc,
                "MrColsumDesc": lib.ColsumDesc, "MrRotaryBwdDesc": lib.RotaryBwdDesc, "MrAdamWDesc": lib.AdamWDesc,
-               "MrAdamWMultiDesc": lib.AdamWMultiDesc, "MrAdamWChunk": lib.AdamWChunk}
+               "MrAdamWMultiDesc": lib.AdamWMultiDesc, "MrAdamWChunk": lib.AdamWChunk, "MrPatchifyDesc": lib.PatchifyDesc}
     src = tmp_path / "sz.c"
     body = "\n".join(f'  printf("{n} %zu\\n", sizeof({n}));' for n in structs)
     src.write_text(f'#include <stdio.h>\n#include "mreserve_b200.h"\nint main(void) {{\n{body}\n  return 0;\n}}\n')

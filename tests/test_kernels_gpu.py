@@ -607,3 +607,21 @@ def test_attention_short_sequences_single_tile(cuda, lib, B, T, H):
     _close(o0, _attn_ref(qkv, B, T, H, valid, group), 2e-2, 2e-2, "short valid+group")
     _close(o0, o1.float(), 1e-2, 1e-2, "one-tile vs 64 x 64 kernel")
     _close(lse0, lse1, 1e-4, 1e-5, "lse")
+
+
+@pytest.mark.parametrize("B,gh,gw", [(3, 12, 20), (1, 18, 32), (2, 2, 2), (0, 12, 20)])
+def test_patchify_u8_is_bit_exact(cuda, lib, B, gh, gw):
+    """mr_patchify_u8 (convert_image_dtype + space_to_depth(16) + cast to bf16 on the device) against the numpy
+    restatement of preprocess.py:464-481 followed by the fp32 -> bf16 cast the model applies: identical bits."""
+    from oracle.reserve_oracle import frames_to_patches
+    rng = np.random.default_rng(B * 100 + gh)
+    frames = rng.integers(0, 256, size=(B, gh * 16, gw * 16, 3), dtype=np.uint8)
+    got = lib.patchify_u8(torch.from_numpy(frames).to(cuda), gh, gw)
+    assert got.shape == (B * gh * gw, 768) and got.dtype == torch.bfloat16
+    if B == 0:
+        return
+    ref32 = torch.from_numpy(frames_to_patches(frames, gh, gw)).reshape(B * gh * gw, 768)
+    assert torch.equal(got.cpu(), ref32.to(torch.bfloat16))
+    # and identical to the existing path: fp32 patches through mr_cast_pad
+    via_cast = lib.cast_pad(ref32.to(cuda), B * gh * gw, 768, 768)
+    assert torch.equal(got, via_cast)

@@ -228,3 +228,18 @@ def test_product_against_the_reference_bf16_noise_floor(setup):
     assert d_got.max() <= d_floor.max() + 1e-3, (float(d_got.max()), float(d_floor.max()))
     print(f"1 - cosine vs fp32: product mean {float(d_got.mean()):.2e} max {float(d_got.max()):.2e}; "
           f"reference bf16 graph mean {float(d_floor.mean()):.2e} max {float(d_floor.max()):.2e}")
+
+
+def test_device_patchify_feeds_the_vision_encoder(setup):
+    """uint8 frames -> `patchify` (device) -> get_imgs_enc equals the reference route: fp32 patches made on the host
+    by the restatement of preprocess_image_to_patches -> get_imgs_enc.  Bit for bit (same bf16 operand)."""
+    from oracle.reserve_oracle import frames_to_patches
+    cfg, params, model, orc = setup
+    model.bind(params)
+    gh, gw = cfg["model"]["output_grid"]
+    frames = np.random.default_rng(8).integers(0, 256, size=(3, gh * 16, gw * 16, 3), dtype=np.uint8)
+    on_device = model.get_imgs_enc(model.patchify(frames))
+    on_host = model.get_imgs_enc(frames_to_patches(frames, gh, gw))
+    assert tuple(on_device.shape) == (3, gh * gw // 4, cfg["model"]["hidden_size"])
+    assert np.array_equal(np.asarray(on_device.float().cpu()), np.asarray(torch.as_tensor(np.asarray(on_host)).float()))
+    assert _cos(on_device.float().cpu(), orc.get_imgseq_only(frames_to_patches(frames, gh, gw))).min() >= COS_MIN

@@ -282,3 +282,16 @@ def test_fp64_spot_check_of_the_fp32_oracle(scale):
     real = torch.from_numpy(clip["tokens"] != 0)
     assert float(d[real].max()) < 1e-10
     assert torch.equal(orc.embed_video(**clip), ref), "fp64 mode must not leak out of its context"
+
+
+def test_frames_to_patches_is_space_to_depth():
+    """oracle.frames_to_patches (preprocess.py:464-481 without the resize) against an independent formulation of
+    tf.nn.space_to_depth(NHWC, block 16) + reshape: [B, h1, P, w1, P, 3] -> transpose -> [B, h1*w1, P*P*3]."""
+    rng = np.random.default_rng(0)
+    gh, gw, P = 3, 5, 16
+    f = rng.integers(0, 256, size=(2, gh * P, gw * P, 3), dtype=np.uint8)
+    got = O.frames_to_patches(f, gh, gw)
+    x = f.astype(np.float32) * np.float32(1.0 / 255.0)
+    ref = x.reshape(2, gh, P, gw, P, 3).transpose(0, 1, 3, 2, 4, 5).reshape(2, gh * gw, P * P * 3)
+    assert got.dtype == np.float32 and np.array_equal(got, ref)
+    assert got.min() >= 0.0 and got.max() <= 1.0 and got[0, 1, 0] == x[0, 0, P, 0]      # patch 1 = block (0, 1)

@@ -81,17 +81,24 @@ def _train_worker(rank, world, port, q):
     opt = {"learning_rate": 2e-4, "num_train_steps": 100, "num_warmup_steps": 0, "weight_decay_rate": 0.1, "beta_2": 0.98,
            "eps": 1e-6, "final_lr_scale": 1.0}
     out = {}
-    for mode in (True, False):
+    # "same" = a second run of the overlapped mode: the run-to-run spread of one mode is the noise floor the
+    # cross-mode difference is judged against (fp32 atomics in dQ / embedding-table accumulation).
+    for tag, mode in (("overlap", True), ("same", True), ("blocking", False)):
         training._OVERLAP_ALLREDUCE = mode
         step = training.PretrainStep(cfg, synthetic_params(cfg, seed=0, weight_scale=4.0))
         losses = [float(step.train_step(batch, opt)[0]) for _ in range(2)]
         torch.cuda.synchronize()
         st = step._state
-        out[mode] = (losses, st["p"].cpu(), st["g16"].float().cpu(), step.model._p.contrastive_scales.copy())
-    (la, pa, ga, sa), (lb, pb, gb, sb) = out[True], out[False]
-    dp = (pa - pb).abs()
-    q.put((rank, float(dp.max()), float(dp.mean()), float((ga - gb).abs().sum() / gb.abs().sum()),
-           float(np.abs(sa - sb).max()), pa.double().sum().item(), la + lb))
+        out[tag] = (losses, st["p"].cpu(), st["g16"].float().cpu(), step.model._p.contrastive_scales.copy())
+
+    def diff(a, b):
+        (_, pa, ga, sa), (_, pb, gb, sb) = out[a], out[b]
+        dp = (pa - pb).abs()
+        return (float(dp.max()), float(dp.mean()), float((ga - gb).abs().sum() / gb.abs().sum()),
+                float(np.abs(sa - sb).max()))
+
+    q.put((rank, diff("overlap", "blocking"), diff("overlap", "same"), out["overlap"][1].double().sum().item(),
+           out["overlap"][0] + out["blocking"][0]))
     dist.destroy_process_group()
 
 
@@ -100,7 +107,9 @@ def test_nccl_overlapped_gradient_allreduce_world2(cuda):
     parameters, reduced gradient arena and temperatures as the single blocking all-reduce, and both ranks end with
     identical parameters.  The two modes are two separate runs of a backward pass that accumulates dQ and the
     embedding-table gradient with fp32 atomics, so they agree to rounding, not bit for bit: a bucket that was
-    skipped, reduced twice or reduced before it was final would move whole tensors by ~lr = 2e-4 per step."""
+    skipped, reduced twice or reduced before it was final would move whole tensors by ~lr = 2e-4 per step.  The
+    noise floor is measured in the same test: the overlapped mode is run twice and the cross-mode difference must
+    be within 4x of that same-mode run-to-run spread (printed; the 2-GPU log is committed under profiles/)."""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
     import torch.multiprocessing as mp
@@ -114,9 +123,16 @@ def test_nccl_overlapped_gradient_allreduce_world2(cuda):
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    for rank, dp_max, dp_mean, g_rel, ds_max, psum, losses in res:
+    for rank, cross, same, psum, losses in res:
+        print(f"rank {rank}: overlap-vs-blocking (dp_max, dp_mean, g_relL1, dscale) = {cross}; "
+              f"same-mode run-to-run = {same}")
+        (dp_max, dp_mean, g_rel, ds_max), (s_max, s_mean, s_rel, s_ds) = cross, same
+        # absolute ceilings (a wrong bucket moves tensors by ~lr = 2e-4) ...
         assert dp_max < 2e-5 and dp_mean < 5e-8, f"rank {rank}: parameters differ, max {dp_max} mean {dp_mean}"
         assert g_rel < 2e-3, f"rank {rank}: reduced gradient arenas differ, relative L1 {g_rel}"
         assert ds_max < 1e-5, f"rank {rank}: temperatures differ by {ds_max}"
+        # ... and the cross-mode difference is of the size of the same-mode run-to-run spread measured here
+        assert dp_mean <= 4 * s_mean + 1e-9, f"rank {rank}: cross-mode mean |dp| {dp_mean} vs same-mode {s_mean}"
+        assert g_rel <= 4 * s_rel + 1e-5, f"rank {rank}: cross-mode grad L1 {g_rel} vs same-mode {s_rel}"
         assert all(l == l for l in losses)
-    assert res[0][5] == res[1][5], "ranks diverged"
+    assert res[0][3] == res[1][3], "ranks diverged"

@@ -1,0 +1,61 @@
+"""jax.lax subset: select, top_k, rsqrt, square, and the named-axis collectives (thread rendezvous under pmap)."""
+import threading
+
+import numpy as np
+
+_tls = threading.local()
+_tls.ctx = None
+
+
+class _AxisCtx:
+    def __init__(self, name, n):
+        self.name, self.n = name, n
+        self.barrier = threading.Barrier(n)
+        self.slots = [None] * n
+
+
+def select(pred, on_true, on_false):
+    return np.where(pred, on_true, on_false)
+
+
+def top_k(x, k):
+    """Largest k along the last axis, ties -> lower index first (stable), as XLA's TopK."""
+    idx = np.argsort(-np.asarray(x), axis=-1, kind="stable")[..., :k]
+    return np.take_along_axis(np.asarray(x), idx, -1), idx.astype(np.int32)
+
+
+def rsqrt(x):
+    return 1.0 / np.sqrt(x)
+
+
+def square(x):
+    return np.square(x)
+
+
+def stop_gradient(x):
+    return x
+
+
+def _exchange(x):
+    ctx = getattr(_tls, "ctx", None)
+    if ctx is None:
+        return [np.asarray(x)]
+    ctx.slots[_tls.rank] = np.asarray(x)
+    ctx.barrier.wait()
+    out = list(ctx.slots)
+    ctx.barrier.wait()
+    return out
+
+
+def all_gather(x, axis_name, **kw):
+    return np.stack(_exchange(x), 0)
+
+
+def pmean(x, axis_name):
+    from .tree_util import tree_map
+    return tree_map(lambda a: np.mean(np.stack(_exchange(a), 0), 0).astype(np.asarray(a).dtype), x)
+
+
+def psum(x, axis_name):
+    from .tree_util import tree_map
+    return tree_map(lambda a: np.sum(np.stack(_exchange(a), 0), 0).astype(np.asarray(a).dtype), x)

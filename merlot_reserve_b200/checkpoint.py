@@ -88,7 +88,8 @@ def _ext_unpack(code: int, data: bytes):
 def _chunk(arr: np.ndarray, max_bytes: int) -> Dict:
     per = max(1, int(max_bytes // arr.dtype.itemsize))
     flat = arr.reshape(-1)
-    return {_CHUNK_KEY: True, "shape": [int(s) for s in arr.shape],
+    # flax.serialization._chunk stores the shape through _tuple_to_dict: {'0': d0, '1': d1, ...}
+    return {_CHUNK_KEY: True, "shape": {str(i): int(s) for i, s in enumerate(arr.shape)},
             "chunks": {str(i): flat[o:o + per] for i, o in enumerate(range(0, flat.size, per))}}
 
 
@@ -107,7 +108,10 @@ def _unchunk_leaves(tree):
         if tree.get(_CHUNK_KEY):
             n = len(tree["chunks"])
             flat = np.concatenate([np.asarray(tree["chunks"][str(i)]).reshape(-1) for i in range(n)])
-            return flat.reshape(tuple(tree["shape"]))
+            shape = tree["shape"]
+            if isinstance(shape, dict):          # flax's layout; a plain list (files written by round-1 code) also reads
+                shape = [shape[str(i)] for i in range(len(shape))]
+            return flat.reshape(tuple(int(x) for x in shape))
         return {k: _unchunk_leaves(v) for k, v in tree.items()}
     return tree
 

@@ -112,6 +112,7 @@ class _PackedEncoder:
         if add_cls:
             self.cls = _f(p["cls"])
             self.cls_proj = (_w(p["cls_proj"]["kernel"], H), _f(p["cls_proj"]["bias"]))
+        self.pe = _f(p["pe"]) if "pe" in p else None       # learned positions of the no-rotary branch (modeling.py:338)
         self.layers = []
         for i in range(num_layers):
             lp = p[f"layer_{i:02d}"]
@@ -399,9 +400,10 @@ class MerlotReserve:
     # --------------------------------------------------------------------------------------------
     def prepare_multimodal_inputs(self, tokens, token_segment_idx=None, token_embs=None, vision_input=None,
                                   audio_spans=None, audio_pointers=None, padding_len=None, video_src_idx=None):
-        """modeling.py:651-758.  Returns x [B, T, H] (bf16), and -- instead of the reference's O(T^2)
-        boolean `attention_mask` and raw `rotary_coords` -- the equivalent compact forms the kernels
-        consume: `rotary_scale` [B, T, 32], `is_valid` [B, T] and `video_src` [B, T] (or None)."""
+        """modeling.py:651-758.  Returns the reference's schema -- `x` [B, T, H] (bf16), `rotary_coords` [B, T, 4]
+        (fp32) and `attention_mask` [B, T, T] (bool) -- plus the compact forms the kernels consume in place of the
+        O(T^2) mask and the raw coordinates: `rotary_scale` [B, T, 32], `is_valid` [B, T], `video_src` [B, T] or
+        None.  `joint_transformer(**mm_inputs)` takes the whole dict, like the reference's call at :841."""
         as_np = _is_np(tokens)
         p, H = self._p, self.hidden_size
         tok = _dev(tokens, torch.int32)
@@ -413,30 +415,140 @@ class MerlotReserve:
         emb = None if token_embs is None else _dev(token_embs, torch.bfloat16)
         if aud is None or ptr is None:
             aud, ptr = None, None
+        elif aud.shape[2] != self.config["audio_token_length"] or aud.shape[0] != B or ptr.shape != tok.shape:
+            raise ValueError("audio_spans must be [B, n, audio_token_length, H] and audio_pointers shaped like tokens")
         n_vis = 0 if vis is None else vis.shape[1]
         T = Ltok + n_vis
         if padding_len is not None:
             if padding_len < T:
                 raise ValueError("padding_len smaller than the assembled sequence")
             T = padding_len
+        hp, wp = self.output_grid_h // 2, self.output_grid_w // 2
         x, rot, valid = L.embed_assemble(tok, p.tok_emb, H=H, seg_idx=seg, aud_ptr=ptr, audio=aud, vision=vis,
                                          tok_emb=emb, n_aud=0 if aud is None else aud.shape[1], n_vis=n_vis,
-                                         pool_h=self.output_grid_h // 2, pool_w=self.output_grid_w // 2, T=T,
+                                         pool_h=hp, pool_w=wp, T=T,
                                          audio_token_length=self.config["audio_token_length"])
+        per = hp * wp
+        vseg = None
+        if n_vis:
+            vseg = torch.arange(n_vis // per, device=tok.device).repeat_interleave(per)[None].expand(B, -1)
         video_src = None
         if video_src_idx is not None and seg is not None:
             vsi = _dev(video_src_idx, torch.int64)
             parts = [torch.gather(vsi, 1, seg.long())]
             if n_vis:
-                per = (self.output_grid_h // 2) * (self.output_grid_w // 2)
-                vseg = torch.arange(n_vis // per, device=tok.device).repeat_interleave(per)[None].expand(B, -1)
                 parts.append(torch.gather(vsi, 1, vseg))
             if T > Ltok + n_vis:
                 parts.append(torch.full((B, T - Ltok - n_vis), -1, dtype=torch.int64, device=tok.device))
             video_src = torch.cat(parts, 1).to(torch.int32).contiguous()
-        out = {"x": x.view(B, T, H), "rotary_scale": rot.view(B, T, 32), "is_valid": valid.view(B, T),
-               "video_src": video_src}
+        # the reference's own outputs (index arithmetic only; :697-719 and :743-756)
+        coords = torch.zeros((B, T, 4), dtype=torch.float32, device=tok.device)
+        if seg is not None:
+            coords[:, :Ltok, 2] = seg.float() / 16.0
+        coords[:, :Ltok, 3] = (1.0 + torch.arange(Ltok, dtype=torch.float32, device=tok.device)) / 1024.0
+        if n_vis:
+            c2 = _dev(get_rotary_coordinates_2d(hp, wp), torch.float32).repeat(n_vis // per, 1)
+            coords[:, Ltok:Ltok + n_vis, :2] = c2
+            coords[:, Ltok:Ltok + n_vis, 2] = vseg.float() / 16.0
+        v = valid.view(B, T).bool()
+        mask = v[:, None, :] & v[:, :, None]
+        if video_src is not None:
+            mask = mask & (video_src[:, None, :] == video_src[:, :, None])
+        out = {"x": x.view(B, T, H), "rotary_coords": coords, "attention_mask": mask,
+               "rotary_scale": rot.view(B, T, 32), "is_valid": valid.view(B, T), "video_src": video_src}
         return {k: (_ret(v, True) if (as_np and v is not None and k != "x") else v) for k, v in out.items()}
+
+    # --------------------------------------------------------------------------------------------
+    # the reference's sub-modules as callables (modeling.py:600-632), reference argument names and return schemas;
+    # tensors in, tensors out (device, bf16 activations)
+    # --------------------------------------------------------------------------------------------
+    def vision_encoder(self, x):
+        """VisionTransformer.__call__ (modeling.py:391-430): [B, hw, 768] -> {'seq' [B, hw, H], 'cls' [B, H],
+        'seq_attnpool' [B, hw/4, H]}."""
+        img = _dev(x, None)
+        if img.dtype not in (torch.float32, torch.bfloat16):
+            img = img.float()
+        out = self._vision(img, want_cls=True)
+        B, T = img.shape[0], img.shape[1] + 1
+        return {"seq": out["_xf"].view(B, T, self.hidden_size)[:, 1:], "cls": out["cls"], "seq_attnpool": out["seq_attnpool"]}
+
+    def audio_encoder(self, x):
+        """AudioTransformer.__call__ (modeling.py:443-476): [B, 60, 65] -> {'cls' [B, H], 'seq_attnpool' [B, 6, H]}."""
+        return self._audio(_dev(x, torch.float32), want_cls=True)
+
+    def token_encoder(self, token_dict):
+        """TokenEmbedder.__call__ (modeling.py:516-538): dict of int tensors -> dict of [..., H] embeddings."""
+        p, H = self._p, self.hidden_size
+        out = {}
+        for k in sorted(token_dict.keys()):
+            t = _dev(token_dict[k], torch.int32)
+            flat = t.reshape(1, -1).contiguous()
+            x, _, _ = L.embed_assemble(flat, p.tok_emb, H=H)
+            out[k] = x.view(*t.shape, H)
+        return out
+
+    def span_encoder(self, x, x_isvalid):
+        """SpanTransformer.__call__ (modeling.py:488-504) on EMBEDDED spans: x [B, L, H], x_isvalid [B, L] -> cls [B, H]."""
+        p, H = self._p, self.hidden_size
+        emb = _dev(x, torch.bfloat16)
+        B, n, _ = emb.shape
+        if n >= 16:
+            raise ValueError("span length must be < max_len = 16 (modeling.py:495)")
+        if n != self.config["text_span_length"]:
+            raise ValueError(f"spans must be [B, {self.config['text_span_length']}, H]")
+        T = n + 1
+        pseudo = _dev(x_isvalid).to(torch.int32).contiguous()             # token != PADDING <=> valid
+        xs, _, valid = L.embed_assemble(pseudo, p.tok_emb, H=H, tok_emb=emb.contiguous(), cls_offset=1)
+        L.fill_cls(xs, p.span.cls, B, T, H)
+        xs = self._encoder(xs, p.span, B, T, self._table("span"), valid=valid)
+        cls_ln = L.layernorm(xs, *p.span.final_ln, rows=B, seq_in=T, seq_out=1, row_off=0)
+        return L.gemm(cls_ln, p.span.cls_proj[0], bias=p.span.cls_proj[1], out_f32=True)
+
+    def joint_proj(self, x):
+        """`head` Dense (modeling.py:631-632): [..., H] -> [..., H] fp32."""
+        p, H = self._p, self.hidden_size
+        t = _dev(x, torch.bfloat16)
+        return L.gemm(t.reshape(-1, H).contiguous(), p.head[0], bias=p.head[1], out_f32=True).view(*t.shape)
+
+    def joint_transformer(self, x, rotary_coords=None, attention_mask=None, is_valid=None, rotary_scale=None,
+                          video_src=None):
+        """TransformerEncoder.__call__ of the joint model (modeling.py:297-376, no CLS): x [B, T, H] -> {'seq'}.
+        Takes the dict `prepare_multimodal_inputs` returns (`**mm_inputs`), or the reference's three arguments alone:
+        then the scale table is built from `rotary_coords` and the [B, T, T] mask must have the only structure the
+        reference ever builds (:743-756) -- valid_q & valid_k & same-source -- which is what the kernels take
+        (per-key validity + group ids); any other mask is refused."""
+        p, H = self._p, self.hidden_size
+        xs = _dev(x, torch.bfloat16)
+        B, T, _ = xs.shape
+        if rotary_scale is None and rotary_coords is None:
+            # learned-`pe` branch (modeling.py:335-341): x += pe[T, H], q / k untouched (scale table of ones)
+            if p.joint.pe is None or tuple(p.joint.pe.shape) != (T, H):
+                raise ValueError(f"no rotary_coords given and the tree has no joint_transformer/pe of shape [{T}, {H}]")
+            xs = L.add(xs.contiguous(), p.joint.pe[None].expand(B, T, H).contiguous())
+            rotary_scale = torch.ones((B * T, 32), dtype=torch.float32, device=xs.device)
+        if rotary_scale is None:
+            rc = _dev(rotary_coords, torch.float32)
+            if rc.dim() == 2:
+                rc = rc[None].expand(B, -1, -1)
+            rotary_scale = L.rotary_table(rc.reshape(B * T, rc.shape[-1]).contiguous())
+        rot = _dev(rotary_scale, torch.float32).reshape(B * T, 32).contiguous()
+        group = None
+        if is_valid is not None:
+            valid = _dev(is_valid).to(torch.uint8).reshape(B * T).contiguous()
+            group = None if video_src is None else _dev(video_src, torch.int32).reshape(B * T).contiguous()
+        elif attention_mask is not None:
+            m = _dev(attention_mask).bool()
+            v = torch.diagonal(m, dim1=1, dim2=2)
+            first = m.int().argmax(-1).to(torch.int32)                 # rows of one group are identical: first key = id
+            g = torch.where(v, first, torch.full_like(first, -1))
+            rebuilt = v[:, None, :] & v[:, :, None] & (g[:, None, :] == g[:, :, None])
+            if not torch.equal(rebuilt, m):
+                raise ValueError("attention_mask is not of the form valid_q & valid_k & same_source (modeling.py:743-756)")
+            valid, group = v.to(torch.uint8).reshape(B * T).contiguous(), g.reshape(B * T).contiguous()
+        else:
+            valid = None
+        xs = self._encoder(xs.reshape(B * T, H).contiguous().clone(), p.joint, B, T, rot, valid=valid, group=group)
+        return {"seq": L.layernorm(xs, *p.joint.final_ln).view(B, T, H)}
 
     def embed_text_spans_only(self, text_spans):
         """modeling.py:767-774: [B, 15] token ids -> [B, H] unit vectors."""
@@ -801,7 +913,8 @@ def unit_normalize(x):
 
 
 def one_hot_pool(do_pool, idx, v, num_segments, real_bsize=None):
-    """modeling.py:541-567 as a segment gather; returns {'x': [b, S, H] fp32, 'count': [b, S]}."""
+    """modeling.py:541-567 as a segment gather; returns {'x': [b, S, H] fp32, 'idx_oh': [b, L, S] (the reference's
+    one-hot, index arithmetic only), 'count': [b, S] = idx_oh.sum(1) (what pretrain_model.py:179,205 takes from it)}."""
     as_np = _is_np(do_pool, idx, v)
     dp = _dev(do_pool).to(torch.uint8)
     ix = _dev(idx, torch.int32)
@@ -811,4 +924,6 @@ def one_hot_pool(do_pool, idx, v, num_segments, real_bsize=None):
         l2 = (Ls * B) // real_bsize
         dp, ix, vv = dp.reshape(real_bsize, l2), ix.reshape(real_bsize, l2), vv.reshape(real_bsize, l2, H)
     pooled, count = L.segment_pool(dp.contiguous(), ix.contiguous(), vv.contiguous(), num_segments)
-    return {"x": _ret(pooled, as_np), "count": _ret(count, as_np)}
+    pointer = torch.where(dp.bool(), ix, torch.full_like(ix, -1))
+    idx_oh = (pointer[..., None] == torch.arange(num_segments, device=ix.device, dtype=ix.dtype)).to(pooled.dtype)
+    return {"x": _ret(pooled, as_np), "idx_oh": _ret(idx_oh, as_np), "count": _ret(count, as_np)}

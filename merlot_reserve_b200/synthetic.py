@@ -134,6 +134,43 @@ def synthetic_params(config: Dict, seed: int = 0, weight_scale: float = 1.0) -> 
     }
 
 
+class _ShapeOnly:
+    """Stands in for an array in `param_shapes`."""
+
+    def __init__(self, shape):
+        self.shape = tuple(int(x) for x in shape)
+
+    def astype(self, _):
+        return self
+
+    def __radd__(self, _):
+        return self
+
+
+def param_shapes(config: Dict) -> Dict[str, list]:
+    """'a/b/c' -> shape of every leaf `synthetic_params(config)` would create, without drawing the values
+    (the tree layout of SURVEY.md 8b; compared with the reference's own Module.init in tests/test_reference_goldens.py)."""
+    g = globals()
+    saved = {k: g[k] for k in ("_kernel_init", "_lecun", "_small")}
+    g["_kernel_init"] = lambda rng, shape, scale=1.0: _ShapeOnly(shape)
+    g["_lecun"] = lambda rng, shape, fan_in, scale=1.0: _ShapeOnly(shape)
+    g["_small"] = lambda rng, shape: _ShapeOnly(shape)
+    try:
+        tree = synthetic_params(config)
+    finally:
+        g.update(saved)
+
+    def flat(t, prefix=""):
+        out = {}
+        for k, v in t.items():
+            if isinstance(v, dict):
+                out.update(flat(v, f"{prefix}{k}/"))
+            else:
+                out[prefix + k] = [int(x) for x in v.shape]
+        return out
+    return flat(tree)
+
+
 def synthetic_clip(config: Dict, nseg: int = 16, seed: int = 1, token_length: int = 160, text_len: int = 12) -> Dict:
     """One clip in the layout `MerlotReserve.embed_video` takes (modeling.py:806-826)."""
     m = config["model"]

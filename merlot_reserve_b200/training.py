@@ -169,10 +169,15 @@ class PretrainStep:
         mdt = BF16 if opt.get("use_bfloat16_adam", True) else torch.float32
         p = torch.zeros(n_total, dtype=torch.float32, device=dev)
         slots = []
+        from .checkpoint import flatten_dict
+        flat_src = flatten_dict(self.params)
         for name in names:
             t, decay = reg[name]
             assert t.is_contiguous(), name
-            p[offs[name]:offs[name] + t.numel()].copy_(t.reshape(-1))
+            dst = p[offs[name]:offs[name] + t.numel()].view(t.shape)
+            # fp32 masters come from the caller's fp32 tree (pretrain_model.py:321-323 keeps fp32 TrainState.params and
+            # casts only a copy to bf16), not from the bf16 working copies the kernels read
+            dst.copy_(self._from_flax(name, np.asarray(flat_src[name], np.float32), dst))
             slots.append((offs[name], t.numel(), t, decay))
         self._state = {"names": names, "offs": offs, "n": n_total, "p": p,
                        "m": torch.zeros(n_total, dtype=mdt, device=dev), "v": torch.zeros(n_total, dtype=mdt, device=dev),

@@ -126,13 +126,13 @@ class Module:
     def param(self, name, init_fn, *init_args):
         self._require_bound()
         if name in self._scope:
-            return np.asarray(self._scope[name])
+            return jnp.asarray(self._scope[name])
         if self._mode != "init":
             raise KeyError("parameter '" + "/".join(self._path + (name,)) + "' is missing from the supplied tree")
         key = self._rng
         for part in self._path + (name,):
             key = jax.random.fold_in(key, sum(part.encode()) * 131 + len(part))
-        val = np.asarray(init_fn(key, *init_args))
+        val = jnp.asarray(init_fn(key, *init_args))
         self._scope[name] = val
         return val
 
@@ -312,9 +312,9 @@ class Embed(Module):
 
     def __call__(self, inputs):
         self._require_bound()
-        inputs = np.asarray(inputs)
+        inputs = jnp.asarray(inputs)
         assert inputs.dtype.kind in "iu", "Input type must be an integer or unsigned integer."
-        return np.asarray(self.embedding)[inputs]
+        return jnp.asarray(self.embedding)[inputs]
 
 
 class MultiHeadDotProductAttention(Module):

@@ -59,3 +59,19 @@ def pmean(x, axis_name):
 def psum(x, axis_name):
     from .tree_util import tree_map
     return tree_map(lambda a: np.sum(np.stack(_exchange(a), 0), 0).astype(np.asarray(a).dtype), x)
+
+
+def _wrap_public(ns, names):
+    import functools
+    from ._array import unwrap, wrap
+
+    def deco(fn):
+        @functools.wraps(fn)
+        def f(*a, **k):
+            return wrap(fn(*unwrap(a), **unwrap(k)))
+        return f
+    for n in names:
+        ns[n] = deco(ns[n])
+
+
+_wrap_public(globals(), ["select", "top_k", "rsqrt", "square", "all_gather", "pmean", "psum"])

@@ -46,3 +46,19 @@ def gelu(x, approximate=True):
     x0 = np.asarray(x)
     xf = _f(x0)
     return (0.5 * xf * (1 + np.tanh(np.sqrt(2 / np.pi) * (xf + 0.044715 * xf ** 3)))).astype(x0.dtype)
+
+
+def _wrap_public(ns, names):
+    import functools
+    from .._array import unwrap, wrap
+
+    def deco(fn):
+        @functools.wraps(fn)
+        def f(*a, **k):
+            return wrap(fn(*unwrap(a), **unwrap(k)))
+        return f
+    for n in names:
+        ns[n] = deco(ns[n])
+
+
+_wrap_public(globals(), ["one_hot", "softmax", "logsumexp", "log_softmax", "sigmoid", "gelu"])

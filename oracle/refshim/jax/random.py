@@ -25,18 +25,18 @@ def PRNGKey(seed):
 
 
 def _gen(key):
-    return np.random.default_rng([int(v) for v in np.asarray(key).reshape(-1)])
+    return np.random.default_rng([int(v) & 0xFFFFFFFFFFFFFFFF for v in np.asarray(key).reshape(-1)])
 
 
 def split(key, num=2):
     k = np.asarray(key).reshape(-1)
-    return np.stack([np.array([zlib.crc32(bytes(k.tobytes()) + bytes([i & 255, i >> 8])) & 0xFFFFFFFF, int(k[-1]) + i + 1],
+    return np.stack([np.array([zlib.crc32(bytes(k.tobytes()) + bytes([i & 255, i >> 8])) & 0xFFFFFFFF, (int(k[-1]) + i + 1) & 0xFFFFFFFF],
                               np.uint32) for i in range(num)], 0)
 
 
 def fold_in(key, data):
     k = np.asarray(key).reshape(-1)
-    return np.array([zlib.crc32(k.tobytes() + int(data).to_bytes(8, "little", signed=True)) & 0xFFFFFFFF, int(k[-1])],
+    return np.array([zlib.crc32(k.tobytes() + int(data).to_bytes(8, "little", signed=True)) & 0xFFFFFFFF, int(k[-1]) & 0xFFFFFFFF],
                     np.uint32)
 
 
@@ -74,3 +74,19 @@ def randint(key, shape, minval, maxval, dtype=np.int32):
 
 def bernoulli(key, p=0.5, shape=()):
     return _gen(key).random(shape) < p
+
+
+def _wrap_public(ns, names):
+    import functools
+    from ._array import unwrap, wrap
+
+    def deco(fn):
+        @functools.wraps(fn)
+        def f(*a, **k):
+            return wrap(fn(*unwrap(a), **unwrap(k)))
+        return f
+    for n in names:
+        ns[n] = deco(ns[n])
+
+
+_wrap_public(globals(), ["PRNGKey", "split", "fold_in", "normal", "uniform", "truncated_normal", "choice", "randint", "bernoulli"])

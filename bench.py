@@ -314,11 +314,106 @@ def build_workload(args, rank, dev):
                  metric="examples/sec (train step: forward + backward + all-reduce + AdamW)", unit="examples/s",
                  workload=f"reserve-{args.config} contrastive pretraining train_step (pretrain_model.py:306-340): {b} examples "
                           f"per GPU (16 frames {gh}x{gw}, 48 audio sub-segments, 6 joint sequences x 640), targets "
-                          f"all-gathered and gradients all-reduced (bf16) over the ranks, fp32-moment AdamW",
+                          f"all-gathered and gradients all-reduced (bf16) over the ranks, AdamW with bf16-coded moments",
                  extra={"examples_per_gpu": b})
     else:
         raise ValueError(args.workload)
     return w
+
+
+def train_step_leg(cfg, params, rank, world, dev, timed, steps=8, warmup=3, b=8):
+    """BASELINE configs[2] inside the default line: Reserve-Base contrastive train_step (pretrain_model.py:306-340),
+    b examples per GPU, the packed all-gather of the contrastive targets, the packed reduce-scatter of their
+    gradients and the bucketed bf16 gradient all-reduce over the `world` ranks.  This is the leg of the N = 1/2/4/8
+    curve that moves data between GPUs.  Collective costs are reported three ways: each collective timed alone on its
+    real buffers, the step with the gradient all-reduce skipped (timing probe; the difference to the full step is the
+    EXPOSED all-reduce), and the step with the single blocking all-reduce after the backward pass."""
+    import torch.distributed as dist
+    from merlot_reserve_b200 import training
+    from merlot_reserve_b200.synthetic import synthetic_pretrain_batch
+    H = cfg["model"]["hidden_size"]
+    stepper = training.PretrainStep(cfg, params)
+    batch = {k: torch.from_numpy(np.ascontiguousarray(v)).to(dev) for k, v in
+             synthetic_pretrain_batch(cfg, b, seed=1 + 1000 * rank).items()}
+    for _ in range(warmup):
+        stepper.train_step(batch)
+    ms = timed(lambda: stepper.train_step(batch), steps) / steps
+    out = {"workload": f"reserve-base train_step, {b} examples per GPU (16 frames 12x20, 48 audio sub-segments, 6 joint "
+                       f"sequences x 640, 48 spans), bf16, bf16-coded AdamW moments",
+           "n_gpus": world, "steps": steps, "warmup": warmup, "examples_per_s": world * b / (ms * 1e-3), "ms_per_step": ms,
+           "tflops_per_gpu": 3.0 * flops_pretrain_example(cfg) * b / (ms * 1e-3) / 1e12,
+           "bucket_bytes": list(getattr(stepper, "last_bucket_bytes", [])),
+           "grad_allreduce_bytes": int(stepper._state["g16"].numel() * 2)}
+    if world > 1:
+        training._SKIP_GRAD_ALLREDUCE = True                 # timing probe: same kernels, no gradient all-reduce
+        for _ in range(2):
+            stepper.train_step(batch)
+        ms_skip = timed(lambda: stepper.train_step(batch), steps) / steps
+        training._SKIP_GRAD_ALLREDUCE = False
+        training._OVERLAP_ALLREDUCE = False                  # the single blocking all-reduce after the backward pass
+        for _ in range(2):
+            stepper.train_step(batch)
+        ms_block = timed(lambda: stepper.train_step(batch), steps) / steps
+        training._OVERLAP_ALLREDUCE = True
+        g16 = stepper._state["g16"]
+        rows = 188 * b                                       # the six packed target sets (SURVEY 8e): 188 b rows of H bf16
+        src = torch.zeros((rows, H), dtype=torch.bfloat16, device=dev)
+        dst = torch.empty((world * rows, H), dtype=torch.bfloat16, device=dev)
+        rs_in = torch.zeros((world, rows, H), dtype=torch.float32, device=dev)
+        rs_out = torch.empty((rows, H), dtype=torch.float32, device=dev)
+        alone = {}
+        for name, fn in (("allgather_ms", lambda: dist.all_gather_into_tensor(dst, src)),
+                         ("reduce_scatter_ms", lambda: dist.reduce_scatter_tensor(rs_out, rs_in)),
+                         ("allreduce_standalone_ms", lambda: dist.all_reduce(g16))):
+            for _ in range(3):
+                fn()
+            alone[name] = timed(fn, 10) / 10
+        g16.zero_()
+        out.update(alone)
+        out.update({"ms_per_step_no_grad_allreduce": ms_skip, "allreduce_exposed_ms": max(ms - ms_skip, 0.0),
+                    "ms_per_step_blocking_allreduce": ms_block,
+                    "allreduce_busbw_gbs": 2.0 * (world - 1) / world * g16.numel() * 2 / (alone["allreduce_standalone_ms"] * 1e-3) / 1e9,
+                    "limiting_collective": "bf16 gradient all-reduce (633 MB) against the tail of the backward pass: the "
+                                           "vision-encoder bucket is final only when the backward pass ends"})
+    del stepper, batch
+    return out
+
+
+def large_legs(rank, world, dev, timed, steps=5, warmup=3):
+    """BASELINE configs[3] and [4] inside the default line (short legs, replicas only -- no data-path collective):
+    Reserve-Large 18x32 embed_video on the metric's 16-frame clip, and VCR-style multiple-choice scoring, batch 128."""
+    from merlot_reserve_b200 import MerlotReserve
+    from merlot_reserve_b200.synthetic import load_config, synthetic_batch, synthetic_params
+    cfg = load_config("large", (18, 32))
+    H = cfg["model"]["hidden_size"]
+    model = MerlotReserve.from_config(cfg).bind(synthetic_params(cfg, seed=0))
+    out = {}
+    clips = 8
+    batch = {k: torch.from_numpy(np.ascontiguousarray(v)).to(dev) for k, v in
+             synthetic_batch(cfg, clips, nseg=NSEG, seed=1 + 1000 * rank).items()}
+    for _ in range(warmup):
+        model.batch_embed_video(**batch)
+    ms = timed(lambda: model.batch_embed_video(**batch), steps) / steps
+    out["large_embed_video"] = {
+        "workload": f"reserve-large resadapt embed_video, {clips} clips x 16 segments (18x32 patches, joint T = 2464) per GPU",
+        "n_gpus": world, "steps": steps, "warmup": warmup, "segments_per_s": world * clips * NSEG / (ms * 1e-3),
+        "ms_per_step": ms, "tflops_per_gpu": flops_per_clip(cfg) * clips / (ms * 1e-3) / 1e12}
+    del batch
+    B, n_cand, Ltok = 128, 4, 144
+    rng = np.random.default_rng(5 + rank)
+    toks = rng.integers(10, 32768, size=(B, n_cand, Ltok)).astype(np.int32)
+    toks[:, :, -1] = 3
+    images = torch.from_numpy(rng.random((B, 18 * 32, 768), dtype=np.float32)).to(dev)
+    tokens = torch.from_numpy(toks).to(dev)
+    proj = (rng.standard_normal(H) * 0.05).astype(np.float32)
+    for _ in range(warmup):
+        model.score_multiple_choice(images, tokens, proj)
+    ms = timed(lambda: model.score_multiple_choice(images, tokens, proj), steps) / steps
+    out["mc_scoring"] = {
+        "workload": f"reserve-large VCR-style multiple-choice scoring, batch {B}, 1 frame (18x32) x {n_cand} candidates, L = {Ltok}, per GPU",
+        "n_gpus": world, "steps": steps, "warmup": warmup, "examples_per_s": world * B / (ms * 1e-3), "ms_per_step": ms,
+        "tflops_per_gpu": flops_mc_example(cfg, n_cand, Ltok) * B / (ms * 1e-3) / 1e12}
+    return out
 
 
 def run_b200(args):
@@ -414,6 +509,23 @@ def run_b200(args):
                 "avg_launch_ms": gemm["ms"] / gemm["launches"], "flops_per_launch": gemm["flops"] / gemm["launches"],
                 "share_of_step": gemm["ms"] / prof_ms, "traffic": traffic, "traffic_note": traffic_note}
     whole = w["flops"] / (ms_step * 1e-3) / 1e12
+    w_metric, w_unit, w_h2d, w_d2h = w["metric"], w["unit"], w["h2d"], w["d2h"]
+    w_workload, w_extra = w.get("workload"), w.get("extra", {})
+
+    # the other BASELINE configs as short legs of the same line (headline metric / config above are unchanged)
+    legs = {}
+    if args.workload == "embed_video" and args.config == "base" and not args.grid and not args.no_extra_legs:
+        import gc
+        w.clear()
+        del step_resident, step_e2e
+        gc.collect()
+        torch.cuda.empty_cache()
+        legs["train_step"] = train_step_leg(cfg, params, rank, world, dev, timed)
+        gc.collect()
+        torch.cuda.empty_cache()
+        legs.update(large_legs(rank, world, dev, timed))
+        gc.collect()
+        torch.cuda.empty_cache()
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline and args.workload == "embed_video":
@@ -423,15 +535,15 @@ def run_b200(args):
                          f"1 clip x {NSEG} segments, 2 timed passes, {dt:.2f} s each"}
     if rank == 0:
         line = {
-            "metric": w["metric"], "value": value, "unit": w["unit"], "n_gpus": world, "steps": args.steps,
+            "metric": w_metric, "value": value, "unit": w_unit, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": workload_config(args, world) if args.workload == "embed_video" else
-                      {"workload": w["workload"], **w["extra"], "parallelism": f"replicas x{world}",
+                      {"workload": w_workload, **w_extra, "parallelism": f"replicas x{world}",
                        "l2": "inputs and activations of a step exceed the 126 MB L2 many times over"},
             "clocks": clk.summary(),
-            "e2e": {"value": e2e_value, "unit": w["unit"], "ms_per_step": e2e_ms, "h2d_bytes_per_step": w["h2d"],
-                    "d2h_bytes_per_step": w["d2h"]},
+            "e2e": {"value": e2e_value, "unit": w_unit, "ms_per_step": e2e_ms, "h2d_bytes_per_step": w_h2d,
+                    "d2h_bytes_per_step": w_d2h},
             "gpu_launches": int(launches),
             "roofline": roofline,
             "whole_step_tflops": whole, "whole_step_frac_of_sustained_peak": whole / peak,
@@ -439,6 +551,7 @@ def run_b200(args):
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        line.update(legs)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -457,6 +570,8 @@ def main():
                          "mc_scoring = configs[4]; pretrain_fwd = the forward half of configs[2]")
     ap.add_argument("--grid", type=int, nargs=2, default=None, help="output_grid override, e.g. 18 32")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra-legs", action="store_true",
+                    help="skip the train_step / large_embed_video / mc_scoring legs of the default line")
     args = ap.parse_args()
     if args.clips is None:
         args.clips = {"embed_video": 64 if args.config == "base" else 16, "mc_scoring": 128, "pretrain_fwd": 8, "pretrain_step": 8}[args.workload]

@@ -232,6 +232,9 @@ typedef struct MrCastDesc {
   int64_t rows;
   int32_t cols;
   int32_t ld_out;
+  int32_t sanitize; /* 1: jnp.nan_to_num before the cast (NaN -> 0, +-inf -> +-largest finite bf16): the gradient arena,
+                       sanitised per replica BEFORE the all-reduce as pretrain_model.py:327-329 orders it */
+  int32_t reserved_;
 } MrCastDesc;
 int32_t mr_cast_pad(mr_stream_t stream, const MrCastDesc* d, const void* const* in, void* const* out,
                     void* workspace, size_t workspace_bytes);
@@ -369,17 +372,23 @@ int32_t mr_segment_pool(mr_stream_t stream, const MrSegmentPoolDesc* d, const vo
                         void* workspace, size_t workspace_bytes);
 
 /* ------------------------------------------------------------------------------------------
- * mr_contrastive_lse_fwd: one direction of loss_fn_given_preds (pretrain_model.py:276,293-295):
- *   numer[i] = sum_h x[i,h] * y[i,h]            (the positive logit)
- *   lse[i]   = logsumexp_j( x[i] . y_all[j] )   in fp32, [n, n_all] never materialised
- *   in[0] x bf16 [n, H]; in[1] y_all bf16 [n_all, H] (rank-major all-gather of y);
- *   in[2] y_pos bf16 [n, H] (this rank's positives)
+ * mr_contrastive_lse_fwd: one direction of loss_fn_given_preds (pretrain_model.py:276,288-295) in ONE kernel
+ * (csrc/contrastive_tc.cu): tcgen05 logit tiles in TMEM, online row log-sum-exp, positive logit from the diagonal
+ * block, column tiles spread over a thread-block cluster whose partial (max, sum) pairs are merged through
+ * distributed shared memory.  The [n, n_all] logit matrix is never written to memory; no workspace.
+ *   numer[i] = x[i] . y_all[pos_off + i]        (= sum_h x[i,h] * y[i,h], the positive logit, :276)
+ *   lse[i]   = logsumexp_j( x[i] . y_all[j] )   in fp32 (:293-294)
+ *   in[0] x bf16 [n, H]; in[1] y_all bf16 [n_all, H] (rank-major all-gather of cat(y, y_extra), :288-290)
  *   out[0] lse f32 [n]; out[1] numer f32 [n]
  * ------------------------------------------------------------------------------------------ */
 typedef struct MrContrastiveDesc {
   int32_t n, n_all, H;
-  int32_t pos_off;   /* _bwd: column of y_all holding row 0's positive (rank * n for the rank-major all-gather) */
+  int32_t pos_off;   /* column of y_all holding row 0's positive (rank * rows-per-rank of the rank-major all-gather) */
   float grad_scale;  /* _bwd: upstream gradient times 1 / (2 n) (pretrain_model.py:295) */
+  /* _bwd: row remap of out[1] = dy_all so that the six directions of a step land in ONE rank-major buffer that a
+   * single reduce-scatter returns to the owners: row r -> (r / dy_seq_in) * dy_seq_out + r % dy_seq_in + dy_row_off
+   * (dy_seq_in = rows per rank of this direction; 0 = plain [n_all, H]) */
+  int32_t dy_seq_in, dy_seq_out, dy_row_off;
 } MrContrastiveDesc;
 int32_t mr_contrastive_lse_fwd(mr_stream_t stream, const MrContrastiveDesc* d, const void* const* in,
                                void* const* out, void* workspace, size_t workspace_bytes);

@@ -46,7 +46,8 @@ class EncoderDesc(C.Structure):
 
 
 class CastDesc(C.Structure):
-    _fields_ = [("rows", C.c_int64), ("cols", C.c_int32), ("ld_out", C.c_int32)]
+    _fields_ = [("rows", C.c_int64), ("cols", C.c_int32), ("ld_out", C.c_int32), ("sanitize", C.c_int32),
+                ("reserved_", C.c_int32)]
 
 
 class PatchifyDesc(C.Structure):
@@ -85,7 +86,7 @@ class SegmentPoolDesc(C.Structure):
 
 class ContrastiveDesc(C.Structure):
     _fields_ = [("n", C.c_int32), ("n_all", C.c_int32), ("H", C.c_int32), ("pos_off", C.c_int32),
-                ("grad_scale", C.c_float)]
+                ("grad_scale", C.c_float), ("dy_seq_in", C.c_int32), ("dy_seq_out", C.c_int32), ("dy_row_off", C.c_int32)]
 
 
 class ElementwiseDesc(C.Structure):
@@ -172,7 +173,7 @@ MISC_FNS = ["mr_check_device", "mr_abi_version", "mr_status_string", "mr_launch_
 import os as _os
 GEMM_PAIR_DEFAULT = int(_os.environ.get("MR_GEMM_PAIR", "0"))
 
-ABI_VERSION = 12  # must equal mr_abi_version() of the loaded library (struct layouts above)
+ABI_VERSION = 13  # must equal mr_abi_version() of the loaded library (struct layouts above)
 
 _lib = None
 
@@ -359,11 +360,11 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, rows=
     return out
 
 
-def cast_pad(x: torch.Tensor, rows: int, cols: int, ld_out: int, out=None) -> torch.Tensor:
+def cast_pad(x: torch.Tensor, rows: int, cols: int, ld_out: int, out=None, sanitize: bool = False) -> torch.Tensor:
     assert x.dtype == torch.float32
     if out is None:
         out = torch.empty((rows, ld_out), dtype=torch.bfloat16, device=x.device)
-    _call("mr_cast_pad", CastDesc(rows=rows, cols=cols, ld_out=ld_out), [x], [out])
+    _call("mr_cast_pad", CastDesc(rows=rows, cols=cols, ld_out=ld_out, sanitize=int(sanitize)), [x], [out])
     return out
 
 
@@ -458,14 +459,13 @@ def segment_pool(do_pool: torch.Tensor, idx: torch.Tensor, v: torch.Tensor, S: i
     return pooled, count
 
 
-def contrastive_lse(x: torch.Tensor, y_all: torch.Tensor, y_pos: torch.Tensor):
+def contrastive_lse(x: torch.Tensor, y_all: torch.Tensor, pos_off: int = 0):
+    """(lse [n], numer [n]) of one loss direction; row i's positive is row pos_off + i of y_all.  One fused kernel."""
     n, H = x.shape
-    d = ContrastiveDesc(n=n, n_all=y_all.shape[0], H=H)
-    nbytes = load().mr_contrastive_lse_fwd_workspace_bytes(C.byref(d))
-    ws = torch.empty((max(nbytes, 16),), dtype=torch.uint8, device=x.device)
+    d = ContrastiveDesc(n=n, n_all=y_all.shape[0], H=H, pos_off=pos_off)
     lse = torch.empty((n,), dtype=torch.float32, device=x.device)
     numer = torch.empty((n,), dtype=torch.float32, device=x.device)
-    _call("mr_contrastive_lse_fwd", d, [x, y_all, y_pos], [lse, numer], ws)
+    _call("mr_contrastive_lse_fwd", d, [x, y_all], [lse, numer])
     return lse, numer
 
 
@@ -583,11 +583,15 @@ def rotary_bwd(dqkv: torch.Tensor, rot: torch.Tensor, hidden: int, q_scale: floa
     return dqkv
 
 
-def contrastive_lse_bwd(x: torch.Tensor, y_all: torch.Tensor, lse: torch.Tensor, pos_off: int, grad_scale: float):
+def contrastive_lse_bwd(x: torch.Tensor, y_all: torch.Tensor, lse: torch.Tensor, pos_off: int, grad_scale: float,
+                        dy_out=None, dy_seq_in: int = 0, dy_seq_out: int = 0, dy_row_off: int = 0):
+    """dx [n, H], dy_all.  With `dy_out` (a [world, S, H] fp32 buffer shared by the six directions of a step) the rows
+    of dy_all are written rank-major at (rank, dy_row_off + i): the layout one reduce-scatter returns to the owners."""
     n, H = x.shape
-    d = ContrastiveDesc(n=n, n_all=y_all.shape[0], H=H, pos_off=pos_off, grad_scale=grad_scale)
+    d = ContrastiveDesc(n=n, n_all=y_all.shape[0], H=H, pos_off=pos_off, grad_scale=grad_scale,
+                        dy_seq_in=dy_seq_in, dy_seq_out=dy_seq_out, dy_row_off=dy_row_off)
     dx = torch.empty((n, H), dtype=torch.float32, device=x.device)
-    dy = torch.empty((y_all.shape[0], H), dtype=torch.float32, device=x.device)
+    dy = torch.empty((y_all.shape[0], H), dtype=torch.float32, device=x.device) if dy_out is None else dy_out
     _call("mr_contrastive_lse_bwd", d, [x, y_all, lse], [dx, dy], _ws("mr_contrastive_lse_bwd_workspace_bytes", d, x.device))
     return dx, dy
 

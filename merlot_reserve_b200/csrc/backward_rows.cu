@@ -872,6 +872,13 @@ extern "C" int32_t mr_contrastive_lse_bwd(mr_stream_t stream_, const MrContrasti
   gy.trans_a = 1;
   gy.trans_b = 1;
   gy.epilogue = MR_EPI_OUT_F32;
+  if (d->dy_seq_in > 0) {   // rows go straight into the step's packed rank-major reduce-scatter buffer
+    MR_REQUIRE(d->n_all % d->dy_seq_in == 0 && d->dy_seq_out >= d->dy_seq_in + d->dy_row_off && d->dy_row_off >= 0,
+               MR_ERR_BAD_SHAPE);
+    gy.seq_in = d->dy_seq_in;
+    gy.seq_out = d->dy_seq_out;
+    gy.row_off = d->dy_row_off;
+  }
   const void* gin[7] = {dl_b, x2, nullptr, nullptr, nullptr, nullptr, nullptr};
   void* gout[2] = {out[1], nullptr};
   return mr_gemm_epilogue(stream_, &gy, gin, gout, nullptr, 0);

@@ -156,7 +156,7 @@ layernorm_kernel(const bf16* __restrict__ x, const float* __restrict__ gamma, co
 // fp32 -> bf16 cast with zero column padding.  One thread per 8 output columns.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-cast_pad_kernel(const float* __restrict__ x, bf16* __restrict__ y, int64_t rows, int cols, int ld_out) {
+cast_pad_kernel(const float* __restrict__ x, bf16* __restrict__ y, int64_t rows, int cols, int ld_out, int sanitize) {
   const int vec_per_row = ld_out / 8;
   const int64_t total = rows * vec_per_row;
   const bool fast = (cols % 4) == 0;
@@ -174,6 +174,10 @@ cast_pad_kernel(const float* __restrict__ x, bf16* __restrict__ y, int64_t rows,
     } else {
 #pragma unroll
       for (int j = 0; j < 8; ++j) f[j] = (c + j < cols) ? __ldg(src + j) : 0.f;
+    }
+    if (sanitize) {   // jnp.nan_to_num: NaN -> 0, +-inf -> +-largest finite value of the target type (bf16)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = (f[j] != f[j]) ? 0.f : fminf(fmaxf(f[j], -3.3895314e38f), 3.3895314e38f);
     }
     *reinterpret_cast<uint4*>(y + r * ld_out + c) = pack8(f);
   }
@@ -456,29 +460,6 @@ segment_pool_kernel(const uint8_t* __restrict__ do_pool, const int32_t* __restri
 // ---------------------------------------------------------------------------------------------
 // Row log-sum-exp over fp32 logits + positive logit: one warp per row
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kRowThreads)
-row_lse_kernel(const float* __restrict__ logits, const bf16* __restrict__ x, const bf16* __restrict__ ypos,
-               float* __restrict__ lse, float* __restrict__ numer, int n, int n_all, int ld, int H) {
-  const int row = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (row >= n) return;
-  const float* lr = logits + static_cast<size_t>(row) * ld;
-  float m = -INFINITY;
-  for (int c = lane; c < n_all; c += 32) m = fmaxf(m, lr[c]);
-  m = warp_max(m);
-  float s = 0.f;
-  for (int c = lane; c < n_all; c += 32) s += expf(lr[c] - m);
-  s = warp_sum(s);
-  float dot = 0.f;
-  for (int c = lane; c < H; c += 32)
-    dot += __bfloat162float(x[static_cast<size_t>(row) * H + c]) * __bfloat162float(ypos[static_cast<size_t>(row) * H + c]);
-  dot = warp_sum(dot);
-  if (lane == 0) {
-    lse[row] = m + logf(s);
-    numer[row] = dot;
-  }
-}
-
 // One block: out[0] = mean(lse - numer); out[1 + s] = sum((lse - numer) [src == s]) / (count_s + 1e-5).
 __global__ void __launch_bounds__(256)
 contrastive_reduce_kernel(const float* __restrict__ lse, const float* __restrict__ numer,
@@ -567,7 +548,7 @@ extern "C" int32_t mr_cast_pad(mr_stream_t stream_, const MrCastDesc* d, const v
   int64_t blocks = ceil_div64(total, 256);
   if (blocks > 148 * 64) blocks = 148 * 64;
   cast_pad_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
-      static_cast<const float*>(in[0]), static_cast<bf16*>(out[0]), d->rows, d->cols, d->ld_out);
+      static_cast<const float*>(in[0]), static_cast<bf16*>(out[0]), d->rows, d->cols, d->ld_out, d->sanitize);
   return after_launch();
 }
 
@@ -707,34 +688,6 @@ extern "C" int32_t mr_segment_pool(mr_stream_t stream_, const MrSegmentPoolDesc*
     segment_pool_kernel<false><<<grid, kRowThreads, 0, stream>>>(
         static_cast<const uint8_t*>(in[0]), static_cast<const int32_t*>(in[1]), in[2], static_cast<float*>(out[0]),
         static_cast<float*>(out[1]), *d);
-  return after_launch();
-}
-
-extern "C" size_t mr_contrastive_lse_fwd_workspace_bytes(const MrContrastiveDesc* d) {
-  return static_cast<size_t>(d->n) * static_cast<size_t>((d->n_all + 7) / 8 * 8) * sizeof(float);
-}
-
-extern "C" int32_t mr_contrastive_lse_fwd(mr_stream_t stream_, const MrContrastiveDesc* d, const void* const* in,
-                                          void* const* out, void* workspace, size_t workspace_bytes) {
-  MR_REQUIRE(d && in && out && in[0] && in[1] && in[2] && out[0] && out[1], MR_ERR_NULL_POINTER);
-  MR_REQUIRE(d->n >= 0 && d->n_all > 0 && d->H > 0 && d->H % 8 == 0, MR_ERR_BAD_SHAPE);
-  if (d->n == 0) return MR_OK;
-  MR_REQUIRE(workspace && workspace_bytes >= mr_contrastive_lse_fwd_workspace_bytes(d), MR_ERR_WORKSPACE);
-  // logits[n, n_all] = x . y_all^T on the tensor cores (fp32 out), then a row LSE.
-  MrGemmDesc g{};
-  g.M = d->n;
-  g.N = d->n_all;
-  g.K = d->H;
-  g.lda = d->H;
-  g.ldd = (d->n_all + 7) / 8 * 8;
-  g.epilogue = MR_EPI_OUT_F32;
-  const void* gin[5] = {in[0], in[1], nullptr, nullptr, nullptr};
-  void* gout[1] = {workspace};
-  int32_t st = mr_gemm_epilogue(stream_, &g, gin, gout, nullptr, 0);
-  if (st != MR_OK) return st;
-  row_lse_kernel<<<ceil_div(d->n, kWarpsPerBlock), kRowThreads, 0, static_cast<cudaStream_t>(stream_)>>>(
-      static_cast<const float*>(workspace), static_cast<const bf16*>(in[0]), static_cast<const bf16*>(in[2]),
-      static_cast<float*>(out[0]), static_cast<float*>(out[1]), d->n, d->n_all, g.ldd, d->H);
   return after_launch();
 }
 

@@ -209,9 +209,11 @@ def gather_contrastive_targets(preds: Dict[str, Dict[str, torch.Tensor]], group=
     """The exchange step of the path (pretrain_model.py:284-290): for every (head, direction) pair the targets
     `y` (+ `y_extra`) of ALL data-parallel ranks.  The six target sets of a rank are packed into one buffer and
     moved by ONE all-gather; each returned `y_all` is rank-major, i.e. `all_gather(y, 'batch').reshape(-1, H)`.
-    Pure tensor plumbing (works on any device / backend).  Returns [(head, x, y_pos, y_all)]."""
+    Pure tensor plumbing (works on any device / backend).  Returns [(head, x, pos_off, y_all)]: row i of x has its
+    positive at row pos_off + i of y_all (this rank's block of the rank-major gather)."""
     import torch.distributed as dist
     world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+    rank = dist.get_rank(group) if world > 1 else 0
     jobs = []
     for name, d in preds.items():
         for k1, k2 in _PAIRS:
@@ -226,8 +228,8 @@ def gather_contrastive_targets(preds: Dict[str, Dict[str, torch.Tensor]], group=
     else:
         gathered = packed[None]
     out, off = [], 0
-    for (name, x, y_pos, _), n in zip(jobs, sizes):
-        out.append((name, x, y_pos, gathered[:, off:off + n].reshape(world * n, H)))
+    for (name, x, _, _), n in zip(jobs, sizes):
+        out.append((name, x, rank * n, gathered[:, off:off + n].reshape(world * n, H)))
         off += n
     return out
 
@@ -237,8 +239,8 @@ def loss_fn_given_preds(preds: Dict[str, Dict[str, torch.Tensor]], group=None):
     `mean(logsumexp(x . y_all^T) - sum(x * y)) / 2` plus the per-source breakdown of `stuff_to_span`.
     Returns (loss, loss_info) as 0-d CUDA tensors (this rank's loss; the reference pmean()s metrics later)."""
     info = {}
-    for name, x, y_pos, y_all in gather_contrastive_targets(preds, group):
-        lse, numer = L.contrastive_lse(x, y_all, y_pos)
+    for name, x, pos_off, y_all in gather_contrastive_targets(preds, group):
+        lse, numer = L.contrastive_lse(x, y_all, pos_off)
         red = L.contrastive_reduce(lse, numer, preds[name].get("_sources"))
         info[name] = info.get(name, 0.0) + red[0] / 2.0
         if "_sources" in preds[name]:

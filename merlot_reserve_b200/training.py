@@ -57,6 +57,9 @@ def _split_k(rows: int) -> int:
 _LEGACY_WGRAD = os.environ.get("MR_WGRAD_PLAN", "") == "legacy"
 _FUSED_DGELU = os.environ.get("MR_FUSED_DGELU", "1") != "0"
 _OVERLAP_ALLREDUCE = os.environ.get("MR_OVERLAP_ALLREDUCE", "1") != "0"
+# Timing probe of bench.py only: run the step WITHOUT the gradient all-reduce (the result is then not a training
+# step); the difference to the full step is the all-reduce time that the backward pass does not hide.
+_SKIP_GRAD_ALLREDUCE = False
 
 
 def _wgrad(dy: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
@@ -221,6 +224,7 @@ class PretrainStep:
         # an asynchronous NCCL all-reduce that runs under the rest of the backward pass; MR_OVERLAP_ALLREDUCE=0 keeps
         # the single blocking all-reduce of round 1p.
         pending, done = [], set()
+        self.last_bucket_bytes = []
 
         def flush(names, reduce_now):
             """Copy finished gradients into the arena, cast their 1024-element rows to bf16, start their all-reduce."""
@@ -233,9 +237,11 @@ class PretrainStep:
             for k in names:
                 t = grads_ref[k]
                 g[st["offs"][k]:st["offs"][k] + t.numel()].copy_(t.reshape(-1))
-            L.cast_pad(g.view(-1, 1024)[lo:hi], hi - lo, 1024, 1024, out=st["g16"].view(-1, 1024)[lo:hi])
+            L.cast_pad(g.view(-1, 1024)[lo:hi], hi - lo, 1024, 1024, out=st["g16"].view(-1, 1024)[lo:hi], sanitize=True)
             if reduce_now:
-                pending.append(dist.all_reduce(st["g16"][lo * 1024:hi * 1024], group=group, async_op=True))
+                self.last_bucket_bytes.append((hi - lo) * 2048)
+                if not _SKIP_GRAD_ALLREDUCE:
+                    pending.append(dist.all_reduce(st["g16"][lo * 1024:hi * 1024], group=group, async_op=True))
 
         overlap = world > 1 and _OVERLAP_ALLREDUCE
         grads_ref: Dict[str, torch.Tensor] = {}
@@ -248,8 +254,9 @@ class PretrainStep:
         grads_ref.update(grads)
         if overlap:
             g[n:n + 3].copy_(grads["contrastive_scales"].reshape(-1))
-            L.cast_pad(g.view(-1, 1024)[n // 1024:], 1, 1024, 1024, out=st["g16"].view(-1, 1024)[n // 1024:])
-            pending.append(dist.all_reduce(st["g16"][n:], group=group, async_op=True))
+            L.cast_pad(g.view(-1, 1024)[n // 1024:], 1, 1024, 1024, out=st["g16"].view(-1, 1024)[n // 1024:], sanitize=True)
+            if not _SKIP_GRAD_ALLREDUCE:
+                pending.append(dist.all_reduce(st["g16"][n:], group=group, async_op=True))
             left = [k for k in st["names"] if k not in done]
             assert not left, f"gradients outside the all-reduce buckets: {left[:4]}"
             for w in pending:
@@ -260,8 +267,8 @@ class PretrainStep:
                 t = grads[name]
                 g[st["offs"][name]:st["offs"][name] + t.numel()].copy_(t.reshape(-1))
             g[n:n + 3].copy_(grads["contrastive_scales"].reshape(-1))
-            g16 = L.cast_pad(g.view(-1, 1024), (n + 1024) // 1024, 1024, 1024, out=st["g16"].view(-1, 1024)).view(-1)
-            if world > 1:
+            g16 = L.cast_pad(g.view(-1, 1024), (n + 1024) // 1024, 1024, 1024, out=st["g16"].view(-1, 1024), sanitize=True).view(-1)
+            if world > 1 and not _SKIP_GRAD_ALLREDUCE:
                 dist.all_reduce(g16, group=group)
         lr = opt["learning_rate"] * self.lr_scale(self.step_count, opt)
         b1, b2, eps, wd = opt.get("beta_1", 0.9), opt.get("beta_2", 0.98), opt.get("eps", 1e-8), opt["weight_decay_rate"]
@@ -580,8 +587,8 @@ class PretrainStep:
         rank = dist.get_rank(group) if world > 1 else 0
         jobs = gather_contrastive_targets(preds, group)
         info, lses = {}, []
-        for name, x, y_pos, y_all in jobs:
-            lse, numer = L.contrastive_lse(x, y_all, y_pos)
+        for name, x, pos_off, y_all in jobs:
+            lse, numer = L.contrastive_lse(x, y_all, pos_off)
             lses.append(lse)
             red = L.contrastive_reduce(lse, numer, preds[name].get("_sources"))
             info[name] = info.get(name, 0.0) + red[0] / 2.0
@@ -592,28 +599,31 @@ class PretrainStep:
         loss = sum(v for k, v in info.items() if not k.startswith("_"))
 
         # ================================ backward ================================
-        # ---- loss: d(preds) (fp32); the gradients w.r.t. gathered targets go back to the ranks that own the rows ----
+        # ---- loss: d(preds) (fp32).  The gradients w.r.t. the gathered targets go back to the ranks that own the rows
+        # by ONE packed reduce-scatter, the transpose of the packed all-gather (pretrain_model.py:290): every
+        # direction's dy_all GEMM writes its rows rank-major into one [world, S, H] buffer (row remap in the epilogue).
         dpred = {name: {f: torch.zeros(t.shape, dtype=torch.float32, device=dev) for f, t in d.items() if f != "_sources"}
                  for name, d in preds.items()}
-        dy_alls = []
-        for (name, x, y_pos, y_all), lse in zip(jobs, lses):
-            n = x.shape[0]
-            n_own = y_all.shape[0] // world
-            dx, dy_all = L.contrastive_lse_bwd(x, y_all, lse, rank * n_own, 1.0 / (2.0 * n))
-            dy_alls.append((name, x, dx, dy_all, n_own))
+        n_owns = [y_all.shape[0] // world for _, _, _, y_all in jobs]
+        S = sum(n_owns)
+        packed = torch.empty((world, S, H), dtype=torch.float32, device=dev)
+        dxs, off = [], 0
+        for (name, x, pos_off, y_all), lse, n_own in zip(jobs, lses, n_owns):
+            dx, _ = L.contrastive_lse_bwd(x, y_all, lse, pos_off, 1.0 / (2.0 * x.shape[0]), dy_out=packed,
+                                          dy_seq_in=n_own, dy_seq_out=S, dy_row_off=off)
+            dxs.append(dx)
+            off += n_own
         if world > 1:
-            flat = torch.cat([d[3].reshape(-1) for d in dy_alls])
-            dist.all_reduce(flat, group=group)               # every rank contributed to every rank's targets
-            off = 0
-            new = []
-            for name, x, dx, dy_all, n_own in dy_alls:
-                new.append((name, x, dx, flat[off:off + dy_all.numel()].view_as(dy_all), n_own))
-                off += dy_all.numel()
-            dy_alls = new
-        for ji, (name, x, dx, dy_all, n_own) in enumerate(dy_alls):
+            own_all = torch.empty((S, H), dtype=torch.float32, device=dev)
+            dist.reduce_scatter_tensor(own_all, packed, group=group)
+        else:
+            own_all = packed[0]
+        off = 0
+        for ji, ((name, x, pos_off, y_all), dx, n_own) in enumerate(zip(jobs, dxs, n_owns)):
             k1, k2 = ("x", "y") if ji % 2 == 0 else ("y", "x")
             dpred[name][k1] += dx
-            own = dy_all[rank * n_own:(rank + 1) * n_own]
+            own = own_all[off:off + n_own]
+            off += n_own
             n2 = preds[name][k2].shape[0]
             dpred[name][k2] += own[:n2]
             if (k2 + "_extra") in preds[name]:

@@ -75,10 +75,18 @@ def test_contrastive_lse_bwd(cuda, lib, n, n_all, pos_off):
     numer = (xr * yr[pos_off:pos_off + n]).sum(-1)
     loss = (torch.logsumexp(logits, -1) - numer).mean() / 2.0
     loss.backward()
-    lse, _ = lib.contrastive_lse(x.to(cuda), y.to(cuda), y[pos_off:pos_off + n].contiguous().to(cuda))
+    lse, _ = lib.contrastive_lse(x.to(cuda), y.to(cuda), pos_off)
     dx, dy = lib.contrastive_lse_bwd(x.to(cuda), y.to(cuda), lse, pos_off, 1.0 / (2 * n))
     _close(dx, xr.grad, 2e-3, 2e-2, "dx")
     _close(dy, yr.grad, 2e-3, 2e-2, "dy_all")
+    # rows written rank-major into a packed [world, S, H] buffer (the layout of the step's single reduce-scatter)
+    if n_all % n == 0:
+        world, S, off = n_all // n, n + 16, 8
+        packed = torch.full((world, S, H), 7.0, device=cuda)
+        lib.contrastive_lse_bwd(x.to(cuda), y.to(cuda), lse, pos_off, 1.0 / (2 * n), dy_out=packed, dy_seq_in=n,
+                                dy_seq_out=S, dy_row_off=off)
+        assert torch.equal(packed[:, off:off + n].reshape(n_all, H), dy)
+        assert (packed[:, :off] == 7.0).all() and (packed[:, off + n:] == 7.0).all()
 
 
 def test_unit_normalize_bwd(cuda, lib):

@@ -285,15 +285,24 @@ def test_unit_normalize_segment_pool_rowdot(cuda, lib):
     _close(lib.row_dot(xb, w, rows), xb.float()[rows.long()] @ w, 1e-4, 1e-4, "row dot")
 
 
-def test_contrastive_lse(cuda, lib):
-    g = torch.Generator().manual_seed(10)
-    n, n_all, H = 96, 384, 768
+@pytest.mark.parametrize("n,n_all,H,pos_off", [
+    (96, 384, 768, 0),        # one row tile, 3 column tiles (cluster of 3)
+    (128, 128, 768, 0),       # single tile, cluster of 1
+    (384, 3072, 768, 1152),   # cfg 3 stuff_to_span on 8 ranks: 3 row tiles x 24 column tiles over a cluster of 8
+    (96, 776, 1024, 680),     # ragged: n_all not a multiple of 128 (and of 8), Large hidden size, diagonal in the tail tile
+    (1, 1, 64, 0),            # the smallest legal problem
+    (130, 1100, 264, 3),      # ragged rows, K not a multiple of 64, diagonal crossing a tile boundary
+])
+def test_contrastive_lse(cuda, lib, n, n_all, H, pos_off):
+    """mr_contrastive_lse_fwd (fused tcgen05 logits + online LSE + diagonal positive) against fp32 torch."""
+    g = torch.Generator().manual_seed(10 + n)
     x = _bf(torch.nn.functional.normalize(torch.randn(n, H, generator=g), dim=-1) * 4.4).to(cuda)
     y = _bf(torch.nn.functional.normalize(torch.randn(n_all, H, generator=g), dim=-1) * 4.4).to(cuda)
-    lse, numer = lib.contrastive_lse(x, y, y[:n].contiguous())
+    y[pos_off:pos_off + n] = _bf(0.7 * x.float() + 0.3 * y[pos_off:pos_off + n].float())     # positives that stand out
+    lse, numer = lib.contrastive_lse(x, y, pos_off)
     logits = x.float() @ y.float().t()
     _close(lse, torch.logsumexp(logits, -1), 1e-3, 1e-4, "lse")
-    _close(numer, (x.float() * y[:n].float()).sum(-1), 1e-3, 1e-4, "numer")
+    _close(numer, (x.float() * y[pos_off:pos_off + n].float()).sum(-1), 1e-3, 1e-4, "numer")
 
 
 def test_rotary_table_and_assemble(cuda, lib):

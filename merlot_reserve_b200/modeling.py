@@ -112,7 +112,8 @@ class _PackedEncoder:
         if add_cls:
             self.cls = _f(p["cls"])
             self.cls_proj = (_w(p["cls_proj"]["kernel"], H), _f(p["cls_proj"]["bias"]))
-        self.pe = _f(p["pe"]) if "pe" in p else None       # learned positions of the no-rotary branch (modeling.py:338)
+        # learned positions of the no-rotary branch (modeling.py:338), [T, H]
+        self.pe = torch.as_tensor(np.asarray(p["pe"]), dtype=torch.float32).cuda().contiguous() if "pe" in p else None
         self.layers = []
         for i in range(num_layers):
             lp = p[f"layer_{i:02d}"]

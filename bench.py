@@ -379,6 +379,35 @@ def train_step_leg(cfg, params, rank, world, dev, timed, steps=8, warmup=3, b=8)
     return out
 
 
+def latency_leg(cfg, params, rank, world, dev, timed, iters=20):
+    """BASELINE configs[0] on the B200 path: ONE Reserve-Base clip (16 segments), latency in ms.  Three host paths over
+    the same kernels: per-op ctypes calls composed in Python (with the profiling events of that mode), the single
+    mr_embed_video_batched C call, and its CUDA-graph replay (one graph launch per forward)."""
+    from merlot_reserve_b200 import MerlotReserve, _lib
+    from merlot_reserve_b200.synthetic import synthetic_batch
+    model = MerlotReserve.from_config(cfg).bind(params)
+    batch = {k: torch.from_numpy(np.ascontiguousarray(v)).to(dev) for k, v in synthetic_batch(cfg, 1, nseg=NSEG, seed=7 + rank).items()}
+    out = {"workload": "reserve-base embed_video, 1 clip x 16 segments (12x20 patches) + 48 audio sub-segments, L=160",
+           "n_gpus": world, "iters": iters}
+    for _ in range(3):
+        model.batch_embed_video(**batch)
+    out["composite_call_ms"] = timed(lambda: model.batch_embed_video(**batch), iters) / iters
+    run = model.capture_embed_video(1, nseg=NSEG)
+    args = (batch["images"], batch["audio_clips"], batch["tokens"], batch["subseg_idxs"])
+    for _ in range(3):
+        run(*args)
+    out["cuda_graph_ms"] = timed(lambda: run(*args), iters) / iters
+    _lib.PROFILE = []
+    for _ in range(3):
+        model.batch_embed_video(**batch)
+    out["per_op_calls_ms"] = timed(lambda: model.batch_embed_video(**batch), iters) / iters
+    out["kernel_launches_per_forward"] = len(_lib.PROFILE) // (iters + 3)
+    _lib.PROFILE = None
+    out["flops_per_clip"] = flops_per_clip(cfg)
+    out["tflops_graph"] = flops_per_clip(cfg) / (out["cuda_graph_ms"] * 1e-3) / 1e12
+    return out
+
+
 def large_legs(rank, world, dev, timed, steps=5, warmup=3):
     """BASELINE configs[3] and [4] inside the default line (short legs, replicas only -- no data-path collective):
     Reserve-Large 18x32 embed_video on the metric's 16-frame clip, and VCR-style multiple-choice scoring, batch 128."""
@@ -518,6 +547,9 @@ def run_b200(args):
         import gc
         w.clear()
         del step_resident, step_e2e
+        gc.collect()
+        torch.cuda.empty_cache()
+        legs["latency_1clip"] = latency_leg(cfg, params, rank, world, dev, timed)
         gc.collect()
         torch.cuda.empty_cache()
         legs["train_step"] = train_step_leg(cfg, params, rank, world, dev, timed)

@@ -223,6 +223,117 @@ int32_t mr_transformer_encode(mr_stream_t stream, const MrEncoderDesc* d, const 
 size_t mr_transformer_encode_workspace_bytes(const MrEncoderDesc* d);
 
 /* ------------------------------------------------------------------------------------------
+ * Composite entries: one call per sub-module of the reference model, and one for the whole zero-shot forward
+ * (what `jax.jit(model.apply(..., method=embed_video))` is in the reference: ONE call, modeling.py:1017-1019).
+ * Host code only: each enqueues the kernels behind the per-op entries on the caller's stream and carves its
+ * temporaries out of the caller's workspace; nothing is allocated, nothing synchronises, every call is CUDA-graph
+ * capturable.  Weights are DEVICE pointers in the packed layouts of the per-op entries, grouped in the POD structs
+ * below (owned by the caller; `layers` is a HOST array of device pointers).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct MrEncoderWeights {
+  const void* pre_ln_g;   const void* pre_ln_b;    /* f32 [H]   modeling.py:360 */
+  const void* final_ln_g; const void* final_ln_b;  /* f32 [H]   modeling.py:366 */
+  const void* cls;                                  /* f32 [H]   modeling.py:316; NULL for the joint encoder */
+  const void* cls_proj_w; const void* cls_proj_b;   /* bf16 [H, H], f32 [H]   modeling.py:371; NULL likewise */
+  const void* const* layers; /* host array of 8 * num_layers device pointers, in mr_transformer_encode's order */
+  int32_t num_layers;
+  int32_t reserved_;
+} MrEncoderWeights;
+
+typedef struct MrPoolWeights {   /* seq_attnpool (flax MultiHeadDotProductAttention), modeling.py:424,468 */
+  const void* wq;  const void* bq;    /* bf16 [H, H], f32 [H] */
+  const void* wkv; const void* bkv;   /* bf16 [2H, H] (key rows, then value rows), f32 [2H] */
+  const void* wo;  const void* bo;    /* bf16 [H, H], f32 [H] */
+} MrPoolWeights;
+
+/* mr_vision_encode: VisionTransformer.__call__ (modeling.py:391-430): cast, patch embed into rows 1.. of
+ * [B, 1 + hw, H], CLS, layer stack, final_ln, 2x2 attention pool, optional cls_proj.
+ *   in[0] images f32 (or bf16 when in_bf16) [B, hw, 768]
+ *   out[0] seq_attnpool bf16 [B, hw/4, H]; out[1] cls bf16 [B, H] optional; out[2] seq incl. CLS row, after
+ *   final_ln, bf16 [B*(1+hw), H] optional */
+typedef struct MrVisionDesc {
+  int32_t B, grid_h, grid_w, H;
+  int32_t in_bf16;
+  float ln_eps;
+  MrEncoderWeights enc;
+  MrPoolWeights pool;
+  const void* emb_w; const void* emb_b;   /* bf16 [H, 768], f32 [H]   modeling.py:402 */
+  const void* rot;                        /* f32 [1 + hw, 32] scale table of get_rotary_coordinates_2d, CLS row first */
+} MrVisionDesc;
+int32_t mr_vision_encode(mr_stream_t stream, const MrVisionDesc* d, const void* const* in, void* const* out,
+                         void* workspace, size_t workspace_bytes);
+size_t mr_vision_encode_workspace_bytes(const MrVisionDesc* d);
+
+/* mr_audio_encode: AudioTransformer.__call__ (modeling.py:443-476).
+ *   in[0] audio f32 [B, seq_len, 65]; out[0] seq_attnpool bf16 [B, seq_len/patch/pool_ratio, H]; out[1] cls bf16 [B, H] optional */
+typedef struct MrAudioDesc {
+  int32_t B, seq_len, patch, pool_ratio, H;
+  float ln_eps;
+  MrEncoderWeights enc;
+  MrPoolWeights pool;
+  const void* emb_w; const void* emb_b;   /* bf16 [H, 192] (K = patch * 65 = 130 zero padded to 192), f32 [H]   :453 */
+  const void* rot;                        /* f32 [1 + seq_len/patch, 32] */
+} MrAudioDesc;
+int32_t mr_audio_encode(mr_stream_t stream, const MrAudioDesc* d, const void* const* in, void* const* out,
+                        void* workspace, size_t workspace_bytes);
+size_t mr_audio_encode_workspace_bytes(const MrAudioDesc* d);
+
+/* mr_span_encode: TokenEmbedder + SpanTransformer (modeling.py:488-504, 516-538); with `normalize` also the
+ * unit_normalize of embed_text_spans_only (:767-774).
+ *   in[0] tokens i32 [B, L] (0 = padding); in[1] embedded spans bf16 [B, L, H] optional (replaces the table lookup;
+ *   in[0] then only carries validity); out[0] f32 [B, H] */
+typedef struct MrSpanDesc {
+  int32_t B, L, H, vocab;
+  int32_t normalize;
+  float ln_eps;
+  MrEncoderWeights enc;
+  const void* tok_emb;                    /* bf16 [vocab, H] */
+  const void* rot;                        /* f32 [1 + L, 32] */
+} MrSpanDesc;
+int32_t mr_span_encode(mr_stream_t stream, const MrSpanDesc* d, const void* const* in, void* const* out,
+                       void* workspace, size_t workspace_bytes);
+size_t mr_span_encode_workspace_bytes(const MrSpanDesc* d);
+
+/* mr_joint_encode: prepare_multimodal_inputs (modeling.py:651-758) + joint_transformer (:297-376) + final_ln on the
+ * first n_keep rows of every sequence; with `head` also joint_proj + unit_normalize (:842).
+ *   in[0] tokens i32 [B, L]; in[1] seg_idx i32 [B, L] optional; in[2] aud_ptr i32 [B, L] optional;
+ *   in[3] audio bf16 [B', n_aud, audio_token_length, H] optional; in[4] vision bf16 [B', n_vis, H] optional;
+ *   in[5] group i32 [B*T] optional video_src ids (:746-756); in[6] token_embs bf16 [B, L, H] optional
+ *   out[0] head ? f32 [B*n_keep, H] unit rows : bf16 [B*n_keep, H] final_ln rows
+ * Field meanings as in MrAssembleDesc. */
+typedef struct MrJointDesc {
+  int32_t B, L, H;
+  int32_t n_aud, n_vis, pool_h, pool_w, T, vocab, audio_token_length;
+  int32_t aud_div, vis_group, vis_tile, seg_div;
+  int32_t n_keep;
+  int32_t head;
+  float ln_eps;
+  int32_t reserved_;
+  MrEncoderWeights enc;
+  const void* tok_emb;                    /* bf16 [vocab, H] */
+  const void* head_w; const void* head_b; /* bf16 [H, H], f32 [H]   modeling.py:631 */
+} MrJointDesc;
+int32_t mr_joint_encode(mr_stream_t stream, const MrJointDesc* d, const void* const* in, void* const* out,
+                        void* workspace, size_t workspace_bytes);
+size_t mr_joint_encode_workspace_bytes(const MrJointDesc* d);
+
+/* mr_embed_video_batched: batch_embed_video (modeling.py:806-846) for B clips of nseg segments in ONE call.
+ *   in[0] images f32 [B*nseg, hw, 768]; in[1] audio_clips f32 [B*3*nseg, seq_len, 65]; in[2] tokens i32 [B, L];
+ *   in[3] subseg_idxs i32 [B, L];  out[0] f32 [B, L, H] unit rows
+ * The three sub-descriptors must describe exactly this composition (vision.B = B nseg, audio.B = 3 B nseg,
+ * joint: B, L, n_vis = nseg hw/4, n_aud = 3 nseg, T = L + n_vis, n_keep = L, head = 1, seg_div = 3). */
+typedef struct MrEmbedVideoDesc {
+  int32_t B, nseg, L;
+  int32_t reserved_;
+  MrVisionDesc vision;
+  MrAudioDesc audio;
+  MrJointDesc joint;
+} MrEmbedVideoDesc;
+int32_t mr_embed_video_batched(mr_stream_t stream, const MrEmbedVideoDesc* d, const void* const* in, void* const* out,
+                               void* workspace, size_t workspace_bytes);
+size_t mr_embed_video_batched_workspace_bytes(const MrEmbedVideoDesc* d);
+
+/* ------------------------------------------------------------------------------------------
  * mr_cast_pad: f32 [rows, cols] -> bf16 [rows, ld_out] (zero padded columns).  Stages the
  * fp32 pixel patches (modeling.py:402 casts to module dtype) and the [B,30,130] audio patches
  * (:453; K=130 is padded to a TMA-legal pitch).
@@ -327,6 +438,8 @@ typedef struct MrAssembleDesc {
      0 in aud_div / vis_tile means identity (row b). */
   int32_t aud_div;
   int32_t vis_group, vis_tile;
+  int32_t seg_div;        /* > 1: in[1] holds raw sub-segment indices and token_segment_idx = floor(in[1] / seg_div)
+                             (`subseg_idxs // 3`, modeling.py:836); 0 / 1: in[1] is used as given */
 } MrAssembleDesc;
 int32_t mr_embed_assemble(mr_stream_t stream, const MrAssembleDesc* d, const void* const* in, void* const* out,
                           void* workspace, size_t workspace_bytes);

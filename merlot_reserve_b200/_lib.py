@@ -67,7 +67,49 @@ class AssembleDesc(C.Structure):
     _fields_ = [("B", C.c_int32), ("L", C.c_int32), ("H", C.c_int32), ("n_aud", C.c_int32), ("n_vis", C.c_int32),
                 ("pool_h", C.c_int32), ("pool_w", C.c_int32), ("T", C.c_int32), ("vocab", C.c_int32),
                 ("audio_token_length", C.c_int32), ("cls_offset", C.c_int32), ("aud_div", C.c_int32),
-                ("vis_group", C.c_int32), ("vis_tile", C.c_int32)]
+                ("vis_group", C.c_int32), ("vis_tile", C.c_int32), ("seg_div", C.c_int32)]
+
+
+class EncoderWeights(C.Structure):
+    _fields_ = [("pre_ln_g", C.c_void_p), ("pre_ln_b", C.c_void_p), ("final_ln_g", C.c_void_p), ("final_ln_b", C.c_void_p),
+                ("cls", C.c_void_p), ("cls_proj_w", C.c_void_p), ("cls_proj_b", C.c_void_p),
+                ("layers", C.POINTER(C.c_void_p)), ("num_layers", C.c_int32), ("reserved_", C.c_int32)]
+
+
+class PoolWeights(C.Structure):
+    _fields_ = [("wq", C.c_void_p), ("bq", C.c_void_p), ("wkv", C.c_void_p), ("bkv", C.c_void_p), ("wo", C.c_void_p),
+                ("bo", C.c_void_p)]
+
+
+class VisionDesc(C.Structure):
+    _fields_ = [("B", C.c_int32), ("grid_h", C.c_int32), ("grid_w", C.c_int32), ("H", C.c_int32), ("in_bf16", C.c_int32),
+                ("ln_eps", C.c_float), ("enc", EncoderWeights), ("pool", PoolWeights), ("emb_w", C.c_void_p),
+                ("emb_b", C.c_void_p), ("rot", C.c_void_p)]
+
+
+class AudioDesc(C.Structure):
+    _fields_ = [("B", C.c_int32), ("seq_len", C.c_int32), ("patch", C.c_int32), ("pool_ratio", C.c_int32), ("H", C.c_int32),
+                ("ln_eps", C.c_float), ("enc", EncoderWeights), ("pool", PoolWeights), ("emb_w", C.c_void_p),
+                ("emb_b", C.c_void_p), ("rot", C.c_void_p)]
+
+
+class SpanDesc(C.Structure):
+    _fields_ = [("B", C.c_int32), ("L", C.c_int32), ("H", C.c_int32), ("vocab", C.c_int32), ("normalize", C.c_int32),
+                ("ln_eps", C.c_float), ("enc", EncoderWeights), ("tok_emb", C.c_void_p), ("rot", C.c_void_p)]
+
+
+class JointDesc(C.Structure):
+    _fields_ = [("B", C.c_int32), ("L", C.c_int32), ("H", C.c_int32), ("n_aud", C.c_int32), ("n_vis", C.c_int32),
+                ("pool_h", C.c_int32), ("pool_w", C.c_int32), ("T", C.c_int32), ("vocab", C.c_int32),
+                ("audio_token_length", C.c_int32), ("aud_div", C.c_int32), ("vis_group", C.c_int32),
+                ("vis_tile", C.c_int32), ("seg_div", C.c_int32), ("n_keep", C.c_int32), ("head", C.c_int32),
+                ("ln_eps", C.c_float), ("reserved_", C.c_int32), ("enc", EncoderWeights), ("tok_emb", C.c_void_p),
+                ("head_w", C.c_void_p), ("head_b", C.c_void_p)]
+
+
+class EmbedVideoDesc(C.Structure):
+    _fields_ = [("B", C.c_int32), ("nseg", C.c_int32), ("L", C.c_int32), ("reserved_", C.c_int32),
+                ("vision", VisionDesc), ("audio", AudioDesc), ("joint", JointDesc)]
 
 
 class RotaryDesc(C.Structure):
@@ -131,6 +173,11 @@ ENTRY_POINTS = {
     "mr_attention_bwd": AttentionDesc,
     "mr_layernorm_fwd": LayerNormDesc,
     "mr_transformer_encode": EncoderDesc,
+    "mr_vision_encode": VisionDesc,
+    "mr_audio_encode": AudioDesc,
+    "mr_span_encode": SpanDesc,
+    "mr_joint_encode": JointDesc,
+    "mr_embed_video_batched": EmbedVideoDesc,
     "mr_cast_pad": CastDesc,
     "mr_patchify_u8": PatchifyDesc,
     "mr_fill_cls": FillClsDesc,
@@ -162,6 +209,11 @@ WORKSPACE_FNS = {
     "mr_attention_fwd_workspace_bytes": AttentionDesc,
     "mr_attention_bwd_workspace_bytes": AttentionDesc,
     "mr_transformer_encode_workspace_bytes": EncoderDesc,
+    "mr_vision_encode_workspace_bytes": VisionDesc,
+    "mr_audio_encode_workspace_bytes": AudioDesc,
+    "mr_span_encode_workspace_bytes": SpanDesc,
+    "mr_joint_encode_workspace_bytes": JointDesc,
+    "mr_embed_video_batched_workspace_bytes": EmbedVideoDesc,
     "mr_layernorm_bwd_workspace_bytes": LayerNormDesc,
     "mr_colsum_workspace_bytes": ColsumDesc,
     "mr_contrastive_lse_bwd_workspace_bytes": ContrastiveDesc,
@@ -173,7 +225,7 @@ MISC_FNS = ["mr_check_device", "mr_abi_version", "mr_status_string", "mr_launch_
 import os as _os
 GEMM_PAIR_DEFAULT = int(_os.environ.get("MR_GEMM_PAIR", "0"))
 
-ABI_VERSION = 13  # must equal mr_abi_version() of the loaded library (struct layouts above)
+ABI_VERSION = 14  # must equal mr_abi_version() of the loaded library (struct layouts above)
 
 _lib = None
 
@@ -324,6 +376,52 @@ def transformer_encode(x: torch.Tensor, rot: torch.Tensor, pre_ln, layer_ptrs: S
     ws = torch.empty((nbytes,), dtype=torch.uint8, device=x.device)
     _call("mr_transformer_encode", d, [x, rot, valid, group, pre_ln[0], pre_ln[1], *layer_ptrs], [x], ws)
     return x
+
+
+def encoder_weights(enc) -> EncoderWeights:
+    """`MrEncoderWeights` over a packed encoder (modeling._PackedEncoder with the LayerNorms folded in).  The returned
+    struct references `enc`'s tensors by address: keep `enc` alive as long as the struct is used."""
+    n = len(enc.layer_ptrs)
+    arr = (C.c_void_p * max(n, 1))(*[t.data_ptr() for t in enc.layer_ptrs])
+    w = EncoderWeights(pre_ln_g=enc.pre_ln[0].data_ptr(), pre_ln_b=enc.pre_ln[1].data_ptr(),
+                       final_ln_g=enc.final_ln[0].data_ptr(), final_ln_b=enc.final_ln[1].data_ptr(),
+                       cls=enc.cls.data_ptr() if enc.add_cls else None,
+                       cls_proj_w=enc.cls_proj[0].data_ptr() if enc.add_cls else None,
+                       cls_proj_b=enc.cls_proj[1].data_ptr() if enc.add_cls else None,
+                       layers=C.cast(arr, C.POINTER(C.c_void_p)), num_layers=n // 8)
+    w._keep = arr          # the host pointer array must outlive the struct
+    return w
+
+
+def pool_weights(p) -> PoolWeights:
+    return PoolWeights(wq=p.wq.data_ptr(), bq=p.bq.data_ptr(), wkv=p.wkv.data_ptr(), bkv=p.bkv.data_ptr(),
+                       wo=p.wo.data_ptr(), bo=p.bo.data_ptr())
+
+
+_WS_CACHE = {}
+
+
+def workspace(nbytes: int, device) -> torch.Tensor:
+    """A per-device scratch buffer that only grows (composite entries: the caller owns the workspace)."""
+    key = torch.device(device).index
+    buf = _WS_CACHE.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty((max(nbytes, 256),), dtype=torch.uint8, device=device)
+        _WS_CACHE[key] = buf
+    return buf
+
+
+def composite_workspace_bytes(name: str, desc) -> int:
+    return int(getattr(load(), name + "_workspace_bytes")(C.byref(desc)))
+
+
+def composite(name: str, desc, ins, outs, device, ws=None) -> None:
+    """One composite entry (mr_vision_encode / mr_audio_encode / mr_span_encode / mr_joint_encode /
+    mr_embed_video_batched).  `ws` = caller-owned workspace (CUDA-graph captures own theirs); default = the growing
+    per-device scratch buffer."""
+    if ws is None:
+        ws = workspace(composite_workspace_bytes(name, desc), device)
+    _call(name, desc, ins, outs, ws)
 
 
 ATTN_AUTO, ATTN_MMA_SYNC, ATTN_TCGEN05 = 0, 1, 2

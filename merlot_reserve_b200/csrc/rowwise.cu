@@ -371,7 +371,11 @@ embed_assemble_kernel(const int32_t* __restrict__ tokens, const int32_t* __restr
       else
         src = reinterpret_cast<const uint4*>(emb + static_cast<size_t>(min(max(tok, 0), d.vocab - 1)) * d.H);
     }
-    c[2] = seg_idx ? static_cast<float>(seg_idx[static_cast<size_t>(b) * d.L + t]) / 16.0f : 0.f;
+    if (seg_idx) {
+      int sv = seg_idx[static_cast<size_t>(b) * d.L + t];
+      if (d.seg_div > 1) sv = sv >= 0 ? sv / d.seg_div : -((-sv + d.seg_div - 1) / d.seg_div);   // floor division
+      c[2] = static_cast<float>(sv) / 16.0f;
+    }
     c[3] = static_cast<float>(1 + t) / 1024.0f;
   } else if (t < d.L + d.n_vis) {
     const int v = t - d.L;

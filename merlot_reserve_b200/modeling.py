@@ -168,6 +168,15 @@ class _Packed:
         if "proj" in params:  # finetune heads (finetune/vcr/qa_qar_joint_finetune.py:147)
             self.proj = _f(params["proj"]["kernel"])
         self.contrastive_scales = np.asarray(params.get("contrastive_scales", np.zeros(3)), dtype=np.float32)
+        self.fuse_ln = fuse_ln
+        self._cw: Dict[str, Any] = {}
+
+    def cw(self, which: str):
+        """ctypes weight structs of the composite entries (MrEncoderWeights / MrPoolWeights), built once."""
+        if which not in self._cw:
+            enc = {"vis": "vis", "aud": "aud", "span": "span", "joint": "joint"}.get(which)
+            self._cw[which] = L.encoder_weights(getattr(self, enc)) if enc else L.pool_weights(getattr(self, which))
+        return self._cw[which]
 
 
 # ------------------------------------------------------------------------------------------------
@@ -307,7 +316,7 @@ class MerlotReserve:
         return L.gemm(xf, enc.cls_proj[0], bias=enc.cls_proj[1], M=B, lda=T * enc.H, out_f32=out_f32)
 
     # --- VisionTransformer.__call__ (modeling.py:391-430) ---
-    def _vision(self, images: torch.Tensor, want_cls: bool = False) -> Dict[str, torch.Tensor]:
+    def _vision(self, images: torch.Tensor, want_cls: bool = False, want_seq: bool = False) -> Dict[str, torch.Tensor]:
         p, H = self._p, self.hidden_size
         gh, gw, r = self.output_grid_h, self.output_grid_w, self.config["vit_pooling_ratio"]
         B, hw, pp3 = images.shape
@@ -319,6 +328,24 @@ class MerlotReserve:
         if B == 0:      # empty batch: what vmap / jit over a zero-length axis returns (no kernel is launched)
             z = lambda *shp: torch.zeros(shp, dtype=torch.bfloat16, device=images.device)
             return {"seq_attnpool": z(0, (gh // 2) * (gw // 2), H), "_xf": z(0, H), "cls": z(0, H)}
+        if p.fuse_ln and L.PROFILE is None:
+            # ONE C-ABI call (mr_vision_encode); the step-by-step composition below enqueues the same kernels and is
+            # kept for per-launch timing (bench.py) and for bisecting with fuse_layernorm = False
+            n_win = (gh // 2) * (gw // 2)
+            img = images.contiguous()
+            d = L.VisionDesc(B=B, grid_h=gh, grid_w=gw, H=H, in_bf16=int(img.dtype == torch.bfloat16), ln_eps=1e-5,
+                             enc=p.cw("vis"), pool=p.cw("vis_pool"), emb_w=p.vis_emb[0].data_ptr(),
+                             emb_b=p.vis_emb[1].data_ptr(), rot=self._table("vision").data_ptr())
+            pooled = torch.empty((B, n_win, H), dtype=torch.bfloat16, device=img.device)
+            cls = torch.empty((B, H), dtype=torch.bfloat16, device=img.device) if want_cls else None
+            xf = torch.empty((B * T, H), dtype=torch.bfloat16, device=img.device) if want_seq else None
+            L.composite("mr_vision_encode", d, [img], [pooled, cls, xf], img.device)
+            out = {"seq_attnpool": pooled}
+            if want_cls:
+                out["cls"] = cls
+            if want_seq:
+                out["_xf"] = xf
+            return out
         if images.dtype == torch.bfloat16:      # patches made on the device by `patchify` (already in the module dtype)
             a = images.reshape(B * hw, pp3).contiguous()
         else:
@@ -346,6 +373,16 @@ class MerlotReserve:
         if B == 0:
             z = lambda *shp: torch.zeros(shp, dtype=torch.bfloat16, device=audio.device)
             return {"seq_attnpool": z(0, n // self.audio_pooling_ratio, H), "cls": z(0, H)}
+        if p.fuse_ln and L.PROFILE is None:      # ONE C-ABI call (mr_audio_encode)
+            r = self.audio_pooling_ratio
+            aud = audio.contiguous()
+            d = L.AudioDesc(B=B, seq_len=raw_len, patch=ps, pool_ratio=r, H=H, ln_eps=1e-5, enc=p.cw("aud"),
+                            pool=p.cw("aud_pool"), emb_w=p.aud_emb[0].data_ptr(), emb_b=p.aud_emb[1].data_ptr(),
+                            rot=self._table("audio").data_ptr())
+            pooled = torch.empty((B, n // r, H), dtype=torch.bfloat16, device=aud.device)
+            cls = torch.empty((B, H), dtype=torch.bfloat16, device=aud.device) if want_cls else None
+            L.composite("mr_audio_encode", d, [aud], [pooled, cls], aud.device)
+            return {"seq_attnpool": pooled, "cls": cls} if want_cls else {"seq_attnpool": pooled}
         a = L.cast_pad(audio.reshape(B * n, ps * nm), B * n, ps * nm, _AUDIO_K_PAD)
         x = torch.empty((B * T, H), dtype=torch.bfloat16, device=audio.device)
         L.gemm(a, p.aud_emb[0], bias=p.aud_emb[1], out=x, seq_in=n, seq_out=T, row_off=1)
@@ -359,7 +396,7 @@ class MerlotReserve:
         return out
 
     # --- SpanTransformer.__call__ (modeling.py:488-504) on token ids ---
-    def _span(self, text_spans: torch.Tensor, out_f32: bool = True) -> torch.Tensor:
+    def _span(self, text_spans: torch.Tensor, out_f32: bool = True, normalize: bool = False, embs=None) -> torch.Tensor:
         p, H = self._p, self.hidden_size
         B, n = text_spans.shape
         if n != self.config["text_span_length"]:
@@ -367,6 +404,17 @@ class MerlotReserve:
         T = n + 1
         if B == 0:
             return torch.zeros((0, H), dtype=torch.float32 if out_f32 else torch.bfloat16, device=text_spans.device)
+        if p.fuse_ln and L.PROFILE is None and out_f32:      # ONE C-ABI call (mr_span_encode)
+            tok = text_spans.contiguous()
+            d = L.SpanDesc(B=B, L=n, H=H, vocab=p.tok_emb.shape[0], normalize=int(normalize), ln_eps=1e-5, enc=p.cw("span"),
+                           tok_emb=p.tok_emb.data_ptr(), rot=self._table("span").data_ptr())
+            out = torch.empty((B, H), dtype=torch.float32, device=tok.device)
+            L.composite("mr_span_encode", d, [tok, embs], [out], tok.device)
+            return out
+        if embs is not None:
+            raise L.MrError("embedded spans need the composite span path (fuse_layernorm, no PROFILE)")
+        if normalize:
+            return L.unit_normalize(self._span(text_spans, out_f32=True))
         x, _, valid = L.embed_assemble(text_spans, p.tok_emb, H=H, cls_offset=1)
         L.fill_cls(x, p.span.cls, B, T, H)
         x = self._encoder(x, p.span, B, T, self._table("span"), valid=valid)
@@ -380,6 +428,14 @@ class MerlotReserve:
         x = self._encoder(x, p.joint, B, T, rot, valid=valid, group=group)
         return L.layernorm(x, *p.joint.final_ln, rows=B * n_keep, seq_in=T, seq_out=n_keep, row_off=0)
 
+    def _joint_desc(self, B, Ltok, n_vis, n_aud, T, n_keep, head, seg_div=0):
+        p = self._p
+        return L.JointDesc(B=B, L=Ltok, H=self.hidden_size, n_aud=n_aud, n_vis=n_vis, pool_h=self.output_grid_h // 2,
+                           pool_w=self.output_grid_w // 2, T=T, vocab=p.tok_emb.shape[0],
+                           audio_token_length=self.config["audio_token_length"], seg_div=seg_div, n_keep=n_keep,
+                           head=int(head), ln_eps=1e-5, enc=p.cw("joint"), tok_emb=p.tok_emb.data_ptr(),
+                           head_w=p.head[0].data_ptr() if head else None, head_b=p.head[1].data_ptr() if head else None)
+
     def _joint_embed(self, tokens, seg_idx, *, vision=None, audio=None, aud_ptr=None) -> torch.Tensor:
         """prepare_multimodal_inputs -> joint_transformer -> head -> unit_normalize: [B, L, H] fp32
         (the tail of every embed_* method, modeling.py:834-843)."""
@@ -389,6 +445,11 @@ class MerlotReserve:
         n_vis = 0 if vision is None else vision.shape[1]
         n_aud = 0 if audio is None else audio.shape[1]
         T = Ltok + n_vis
+        if p.fuse_ln and L.PROFILE is None:      # ONE C-ABI call (mr_joint_encode with the head)
+            d = self._joint_desc(B, Ltok, n_vis, n_aud, T, Ltok, True)
+            out = torch.empty((B, Ltok, H), dtype=torch.float32, device=tokens.device)
+            L.composite("mr_joint_encode", d, [tokens, seg_idx, aud_ptr, audio, vision, None, None], [out], tokens.device)
+            return out
         x, rot, valid = L.embed_assemble(tokens, p.tok_emb, H=H, seg_idx=seg_idx, aud_ptr=aud_ptr, audio=audio,
                                          vision=vision, n_aud=n_aud, n_vis=n_vis, pool_h=hp, pool_w=wp, T=T,
                                          audio_token_length=self.config["audio_token_length"])
@@ -469,7 +530,7 @@ class MerlotReserve:
         img = _dev(x, None)
         if img.dtype not in (torch.float32, torch.bfloat16):
             img = img.float()
-        out = self._vision(img, want_cls=True)
+        out = self._vision(img, want_cls=True, want_seq=True)
         B, T = img.shape[0], img.shape[1] + 1
         return {"seq": out["_xf"].view(B, T, self.hidden_size)[:, 1:], "cls": out["cls"], "seq_attnpool": out["seq_attnpool"]}
 
@@ -554,8 +615,7 @@ class MerlotReserve:
     def embed_text_spans_only(self, text_spans):
         """modeling.py:767-774: [B, 15] token ids -> [B, H] unit vectors."""
         as_np = _is_np(text_spans)
-        cls = self._span(_dev(text_spans, torch.int32))
-        return _ret(L.unit_normalize(cls), as_np)
+        return _ret(self._span(_dev(text_spans, torch.int32), normalize=True), as_np)
 
     def embed_audio_only(self, audio_clips):
         """modeling.py:776-785."""
@@ -677,12 +737,75 @@ class MerlotReserve:
         H = self.hidden_size
         if B == 0:
             return _ret(torch.zeros((0, tok.shape[1], H), dtype=torch.float32, device=img.device), as_np)
+        if self._p.fuse_ln and L.PROFILE is None:
+            return _ret(self._embed_video_call(img, aud, tok, sub), as_np)
         imgs_enc = self._vision(img.reshape(B * nseg, hw, pp3))["seq_attnpool"].reshape(B, nseg * hw // 4, H)
         audio_enc = self._audio(aud.reshape(B * 3 * nseg, aud.shape[2], 65))["seq_attnpool"]
         audio_enc = audio_enc.reshape(B, 3 * nseg, self.config["audio_token_length"], H)
         seg = torch.div(sub, 3, rounding_mode="floor").to(torch.int32)
         out = self._joint_embed(tok, seg, vision=imgs_enc, audio=audio_enc, aud_ptr=sub)
         return _ret(out, as_np)
+
+    def _embed_video_desc(self, B: int, nseg: int, Ltok: int):
+        """MrEmbedVideoDesc of batch_embed_video on B clips of nseg segments with Ltok token positions."""
+        p, H = self._p, self.hidden_size
+        gh, gw = self.output_grid_h, self.output_grid_w
+        hw, ps, alen = gh * gw, self.config["audio_patch_size"], self.config["audio_seq_length"]
+        vis = L.VisionDesc(B=B * nseg, grid_h=gh, grid_w=gw, H=H, in_bf16=0, ln_eps=1e-5, enc=p.cw("vis"),
+                           pool=p.cw("vis_pool"), emb_w=p.vis_emb[0].data_ptr(), emb_b=p.vis_emb[1].data_ptr(),
+                           rot=self._table("vision").data_ptr())
+        aud = L.AudioDesc(B=B * 3 * nseg, seq_len=alen, patch=ps, pool_ratio=self.audio_pooling_ratio, H=H, ln_eps=1e-5,
+                          enc=p.cw("aud"), pool=p.cw("aud_pool"), emb_w=p.aud_emb[0].data_ptr(),
+                          emb_b=p.aud_emb[1].data_ptr(), rot=self._table("audio").data_ptr())
+        n_vis = nseg * hw // 4
+        joint = self._joint_desc(B, Ltok, n_vis, 3 * nseg, Ltok + n_vis, Ltok, True, seg_div=3)
+        return L.EmbedVideoDesc(B=B, nseg=nseg, L=Ltok, vision=vis, audio=aud, joint=joint)
+
+    def _embed_video_call(self, img, aud, tok, sub, out=None, ws=None) -> torch.Tensor:
+        """batch_embed_video as ONE C-ABI call (mr_embed_video_batched) on device-resident inputs."""
+        B, nseg = img.shape[0], img.shape[1]
+        d = self._embed_video_desc(B, nseg, tok.shape[1])
+        if out is None:
+            out = torch.empty((B, tok.shape[1], self.hidden_size), dtype=torch.float32, device=img.device)
+        L.composite("mr_embed_video_batched", d, [img, aud, tok, sub], [out], img.device, ws=ws)
+        return out
+
+    def capture_embed_video(self, batch: int, nseg: int = 16, token_length: int = 160):
+        """CUDA-graph form of batch_embed_video for a fixed shape: the ~200 kernel launches of one
+        forward are captured once and replayed with one graph launch -- what matters at batch 1 (BASELINE configs[0],
+        latency), where the step is launch-bound.  Returns a callable `run(images, audio_clips, tokens, subseg_idxs)
+        -> [batch, L, H] fp32 CUDA tensor` (inputs: numpy or tensors of the captured shapes; they are copied into the
+        graph's static buffers; the returned tensor is the graph's static output, valid until the next call)."""
+        p, H = self._p, self.hidden_size
+        dev = torch.device("cuda", torch.cuda.current_device())
+        hw, alen = self.output_grid_h * self.output_grid_w, self.config["audio_seq_length"]
+        img = torch.zeros((batch, nseg, hw, 768), dtype=torch.float32, device=dev)
+        aud = torch.zeros((batch, 3 * nseg, alen, 65), dtype=torch.float32, device=dev)
+        tok = torch.zeros((batch, token_length), dtype=torch.int32, device=dev)
+        sub = torch.zeros((batch, token_length), dtype=torch.int32, device=dev)
+        out = torch.empty((batch, token_length, H), dtype=torch.float32, device=dev)
+        nbytes = L.composite_workspace_bytes("mr_embed_video_batched", self._embed_video_desc(batch, nseg, token_length))
+        ws = torch.empty((max(nbytes, 256),), dtype=torch.uint8, device=dev)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):                      # warm-up outside the capture (lazy kernel attributes)
+            self._embed_video_call(img, aud, tok, sub, out=out, ws=ws)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            self._embed_video_call(img, aud, tok, sub, out=out, ws=ws)
+
+        def run(images, audio_clips, tokens, subseg_idxs):
+            for dst, src, dt in ((img, images, torch.float32), (aud, audio_clips, torch.float32), (tok, tokens, torch.int32),
+                                 (sub, subseg_idxs, torch.int32)):
+                t = src if isinstance(src, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(src))
+                dst.copy_(t.reshape(dst.shape).to(dt), non_blocking=True)
+            graph.replay()
+            return out
+
+        run.graph, run.buffers, run._keep = graph, (img, aud, tok, sub, out, ws), p
+        return run
 
     def _batch_embed_video_pinned(self, images, audio_clips, tokens, subseg_idxs):
         """batch_embed_video for pinned host inputs: same arithmetic, H2D of the patches overlapped with compute."""
@@ -771,13 +894,21 @@ class MerlotReserve:
         proj = p.proj if proj_kernel is None else _f(proj_kernel)
         enc = self._vision(img)["seq_attnpool"]
         n_vis = enc.shape[1]
-        enc = enc.repeat_interleave(n_cand, dim=0).contiguous()
         flat = tok.reshape(B * n_cand, Ltok).contiguous()
-        seg = torch.zeros_like(flat)
         T = Ltok + n_vis
-        x, rot, valid = L.embed_assemble(flat, p.tok_emb, H=H, seg_idx=seg, vision=enc, n_vis=n_vis,
-                                         pool_h=self.output_grid_h // 2, pool_w=self.output_grid_w // 2, T=T)
-        kept = self._joint(x, rot, valid, B * n_cand, T, Ltok)
+        if p.fuse_ln and L.PROFILE is None:
+            # ONE C-ABI call for the joint side (mr_joint_encode, no head): every candidate reads its example's frame
+            # through the vision row map (b -> b // n_cand) instead of a repeat() copy (:155); segment index 0 (:158)
+            d = self._joint_desc(B * n_cand, Ltok, n_vis, 0, T, Ltok, False)
+            d.vis_group, d.vis_tile = 1, n_cand
+            kept = torch.empty((B * n_cand * Ltok, H), dtype=torch.bfloat16, device=flat.device)
+            L.composite("mr_joint_encode", d, [flat, None, None, None, enc.contiguous(), None, None], [kept], flat.device)
+        else:
+            enc = enc.repeat_interleave(n_cand, dim=0).contiguous()
+            seg = torch.zeros_like(flat)
+            x, rot, valid = L.embed_assemble(flat, p.tok_emb, H=H, seg_idx=seg, vision=enc, n_vis=n_vis,
+                                             pool_h=self.output_grid_h // 2, pool_w=self.output_grid_w // 2, T=T)
+            kept = self._joint(x, rot, valid, B * n_cand, T, Ltok)
         pool_idx = (flat == MASK).int().argmax(1).to(torch.int32)
         rows = (torch.arange(B * n_cand, device=flat.device, dtype=torch.int32) * Ltok + pool_idx).contiguous()
         return _ret(L.row_dot(kept, proj, rows).view(B, n_cand), as_np)

@@ -25,14 +25,15 @@ COS_MIN = 0.999
 MASK, AUDIOSPAN = 3, 5
 
 
-def _cos(a, b):
-    a = torch.as_tensor(np.asarray(a)).float().reshape(-1, np.asarray(a).shape[-1])
-    b = torch.as_tensor(np.asarray(b)).float().reshape(-1, np.asarray(b).shape[-1])
-    return torch.nn.functional.cosine_similarity(a, b, dim=-1)
-
-
 def _np(x):
     return x.float().cpu().numpy() if isinstance(x, torch.Tensor) else np.asarray(x)
+
+
+def _cos(a, b):
+    a, b = _np(a), _np(b)
+    a = torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).reshape(-1, a.shape[-1])
+    b = torch.from_numpy(np.ascontiguousarray(b, dtype=np.float32)).reshape(-1, b.shape[-1])
+    return torch.nn.functional.cosine_similarity(a, b, dim=-1)
 
 
 @pytest.fixture(scope="module", params=["tiny_init", "tiny_scale4"])

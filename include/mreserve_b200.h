@@ -369,6 +369,44 @@ int32_t mr_patchify_u8(mr_stream_t stream, const MrPatchifyDesc* d, const void* 
                        void* workspace, size_t workspace_bytes);
 
 /* ------------------------------------------------------------------------------------------
+ * mr_logmel: make_spectrogram (mreserve/preprocess.py:121-156) on the device: librosa.feature.melspectrogram
+ * (sr 22050, n_fft 1536, hop 588, 64 Slaney mels 20..11025 Hz, symmetric Hann, centred / reflect padded, power 2),
+ * log(mel + 0.1) - log(0.1), the playback-speed column.  The STFT is one tcgen05 GEMM against the windowed DFT
+ * matrix with hi / lo split bf16 operands (three products along K, fp32 accumulate).
+ *   in[0] waveform f32 [B, n_samples]
+ *   in[1] tables   persistent device buffer of mr_logmel_tables_bytes() (DFT matrix + mel basis); written when
+ *                  build_tables = 1 (first call), only read afterwards
+ *   out[0] split = 0: f32 [B, n_frames, 65], n_frames = 1 + n_samples / 588
+ *          split = 1: f32 [B, 3, 60, 65], the three sub-clips with `pad_size` gap frames (:151-155); needs
+ *                     n_frames == 180 + 4 * pad_size (n_samples = 110250 = 5 s for pad_size 2)
+ * ------------------------------------------------------------------------------------------ */
+typedef struct MrLogmelDesc {
+  int32_t B, n_samples;
+  int32_t playback_speed; /* 1 (the only value the reference's callers pass, preprocess.py:424,448) */
+  int32_t pad_size, split;
+  int32_t build_tables;
+} MrLogmelDesc;
+int32_t mr_logmel(mr_stream_t stream, const MrLogmelDesc* d, const void* const* in, void* const* out,
+                  void* workspace, size_t workspace_bytes);
+size_t mr_logmel_workspace_bytes(const MrLogmelDesc* d);
+size_t mr_logmel_tables_bytes(void);
+
+/* ------------------------------------------------------------------------------------------
+ * mr_resize_patchify: preprocess_image_to_patches (mreserve/preprocess.py:464-481) for uint8 frames of ANY size:
+ * convert_image_dtype, resize_and_pad (pretrain/data_utils.py:42-147 with do_random_scale = False,
+ * do_flip_if_vertical = False: aspect-preserving scale = min(dw / w, dh / h), tf.image.resize BILINEAR with
+ * antialias = True, clip to [0, 1], zero pad bottom / right), space_to_depth(16), cast to the module dtype.
+ *   in[0] frames u8 [B, in_h, in_w, 3];  out[0] patches bf16 (f32 when out_f32) [B, grid_h * grid_w, 768]
+ * ------------------------------------------------------------------------------------------ */
+typedef struct MrResizePatchifyDesc {
+  int32_t B, in_h, in_w, grid_h, grid_w;
+  int32_t out_f32;
+} MrResizePatchifyDesc;
+int32_t mr_resize_patchify(mr_stream_t stream, const MrResizePatchifyDesc* d, const void* const* in, void* const* out,
+                           void* workspace, size_t workspace_bytes);
+size_t mr_resize_patchify_workspace_bytes(const MrResizePatchifyDesc* d);
+
+/* ------------------------------------------------------------------------------------------
  * mr_fill_cls: writes the CLS parameter into row 0 of every sequence of x [B, T, H]
  * (modeling.py:316-320).   in[0] cls f32 [H]; out[0] x bf16 [B*T, H]
  * ------------------------------------------------------------------------------------------ */

@@ -54,6 +54,16 @@ class PatchifyDesc(C.Structure):
     _fields_ = [("B", C.c_int32), ("grid_h", C.c_int32), ("grid_w", C.c_int32), ("patch", C.c_int32)]
 
 
+class LogmelDesc(C.Structure):
+    _fields_ = [("B", C.c_int32), ("n_samples", C.c_int32), ("playback_speed", C.c_int32), ("pad_size", C.c_int32),
+                ("split", C.c_int32), ("build_tables", C.c_int32)]
+
+
+class ResizePatchifyDesc(C.Structure):
+    _fields_ = [("B", C.c_int32), ("in_h", C.c_int32), ("in_w", C.c_int32), ("grid_h", C.c_int32), ("grid_w", C.c_int32),
+                ("out_f32", C.c_int32)]
+
+
 class FillClsDesc(C.Structure):
     _fields_ = [("B", C.c_int32), ("T", C.c_int32), ("H", C.c_int32)]
 
@@ -180,6 +190,8 @@ ENTRY_POINTS = {
     "mr_embed_video_batched": EmbedVideoDesc,
     "mr_cast_pad": CastDesc,
     "mr_patchify_u8": PatchifyDesc,
+    "mr_logmel": LogmelDesc,
+    "mr_resize_patchify": ResizePatchifyDesc,
     "mr_fill_cls": FillClsDesc,
     "mr_window_mean": WindowDesc,
     "mr_window_attention": WindowDesc,
@@ -209,6 +221,8 @@ WORKSPACE_FNS = {
     "mr_attention_fwd_workspace_bytes": AttentionDesc,
     "mr_attention_bwd_workspace_bytes": AttentionDesc,
     "mr_transformer_encode_workspace_bytes": EncoderDesc,
+    "mr_logmel_workspace_bytes": LogmelDesc,
+    "mr_resize_patchify_workspace_bytes": ResizePatchifyDesc,
     "mr_vision_encode_workspace_bytes": VisionDesc,
     "mr_audio_encode_workspace_bytes": AudioDesc,
     "mr_span_encode_workspace_bytes": SpanDesc,
@@ -219,13 +233,14 @@ WORKSPACE_FNS = {
     "mr_contrastive_lse_bwd_workspace_bytes": ContrastiveDesc,
     "mr_contrastive_lse_fwd_workspace_bytes": ContrastiveDesc,
 }
-MISC_FNS = ["mr_check_device", "mr_abi_version", "mr_status_string", "mr_launch_count", "mr_debug_attention_trace"]
+MISC_FNS = ["mr_check_device", "mr_abi_version", "mr_status_string", "mr_launch_count", "mr_debug_attention_trace",
+            "mr_logmel_tables_bytes"]
 
 # MrGemmDesc.algo_pair used when a call does not say: 0 auto, 1 force CTA pairs, 2 never (MR_GEMM_PAIR overrides)
 import os as _os
 GEMM_PAIR_DEFAULT = int(_os.environ.get("MR_GEMM_PAIR", "0"))
 
-ABI_VERSION = 14  # must equal mr_abi_version() of the loaded library (struct layouts above)
+ABI_VERSION = 15  # must equal mr_abi_version() of the loaded library (struct layouts above)
 
 _lib = None
 
@@ -253,6 +268,8 @@ def load() -> C.CDLL:
     lib.mr_status_string.restype = C.c_char_p
     lib.mr_status_string.argtypes = [C.c_int32]
     lib.mr_launch_count.restype = C.c_int64
+    lib.mr_logmel_tables_bytes.restype = C.c_size_t
+    lib.mr_logmel_tables_bytes.argtypes = []
     if lib.mr_abi_version() != ABI_VERSION:
         raise MrError(f"{_LIB_PATH} has ABI version {lib.mr_abi_version()}, this package needs {ABI_VERSION}: "
                       f"rebuild with `python -m merlot_reserve_b200.build --force`")
@@ -477,6 +494,35 @@ def patchify_u8(frames: torch.Tensor, grid_h: int, grid_w: int, out=None) -> tor
         out = torch.empty((B * grid_h * grid_w, 768), dtype=torch.bfloat16, device=frames.device)
     if B:
         _call("mr_patchify_u8", PatchifyDesc(B=B, grid_h=grid_h, grid_w=grid_w, patch=16), [frames], [out])
+    return out
+
+
+_LOGMEL_TABLES = {}
+
+
+def logmel(waveform: torch.Tensor, pad_size: int = 2, split: bool = True) -> torch.Tensor:
+    """make_spectrogram on the device: f32 [B, n_samples] -> [B, 3, 60, 65] (split) or [B, n_frames, 65]."""
+    assert waveform.dtype == torch.float32 and waveform.dim() == 2
+    B, n = waveform.shape
+    dev = waveform.device
+    key = dev.index
+    build = key not in _LOGMEL_TABLES
+    if build:
+        _LOGMEL_TABLES[key] = torch.empty((int(load().mr_logmel_tables_bytes()),), dtype=torch.uint8, device=dev)
+    d = LogmelDesc(B=B, n_samples=n, playback_speed=1, pad_size=pad_size, split=int(split), build_tables=int(build))
+    n_frames = 1 + n // 588
+    out = torch.empty((B, 3, 60, 65) if split else (B, n_frames, 65), dtype=torch.float32, device=dev)
+    _call("mr_logmel", d, [waveform.contiguous(), _LOGMEL_TABLES[key]], [out], _ws("mr_logmel_workspace_bytes", d, dev))
+    return out
+
+
+def resize_patchify(frames: torch.Tensor, grid_h: int, grid_w: int, out_f32: bool = False) -> torch.Tensor:
+    """preprocess_image_to_patches on the device: uint8 [B, h, w, 3] (any size) -> [B, grid_h * grid_w, 768]."""
+    assert frames.dtype == torch.uint8 and frames.dim() == 4 and frames.shape[-1] == 3
+    B, h, w, _ = frames.shape
+    d = ResizePatchifyDesc(B=B, in_h=h, in_w=w, grid_h=grid_h, grid_w=grid_w, out_f32=int(out_f32))
+    out = torch.empty((B, grid_h * grid_w, 768), dtype=torch.float32 if out_f32 else torch.bfloat16, device=frames.device)
+    _call("mr_resize_patchify", d, [frames.contiguous()], [out], _ws("mr_resize_patchify_workspace_bytes", d, frames.device))
     return out
 
 

@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol(lib):
     assert len(names) >= 20
     for n in names:
         assert hasattr(cdll, n), f"{n} declared in the header but not exported"
-    assert cdll.mr_abi_version() == lib.ABI_VERSION == 14
+    assert cdll.mr_abi_version() == lib.ABI_VERSION == 15
     assert lib.launch_count() >= 0
 
 
@@ -43,7 +43,8 @@ def test_struct_sizes_match_c(lib, tmp_path):
                "MrAdamWMultiDesc": lib.AdamWMultiDesc, "MrAdamWChunk": lib.AdamWChunk, "MrPatchifyDesc": lib.PatchifyDesc,
                "MrEncoderWeights": lib.EncoderWeights, "MrPoolWeights": lib.PoolWeights, "MrVisionDesc": lib.VisionDesc,
                "MrAudioDesc": lib.AudioDesc, "MrSpanDesc": lib.SpanDesc, "MrJointDesc": lib.JointDesc,
-               "MrEmbedVideoDesc": lib.EmbedVideoDesc}
+               "MrEmbedVideoDesc": lib.EmbedVideoDesc, "MrLogmelDesc": lib.LogmelDesc,
+               "MrResizePatchifyDesc": lib.ResizePatchifyDesc}
     src = tmp_path / "sz.c"
     body = "\n".join(f'  printf("{n} %zu\\n", sizeof({n}));' for n in structs)
     src.write_text(f'#include <stdio.h>\n#include "mreserve_b200.h"\nint main(void) {{\n{body}\n  return 0;\n}}\n')

@@ -504,6 +504,8 @@ typedef struct MrNormalizeDesc {
   int32_t rows, H;
   int32_t in_f32, out_f32;
   float scale;
+  int32_t scale_from_device; /* 1: the scale is desc.scale * *(const float*)in[2] (forward) / in[3] (backward), read on
+                                the device at run time -- the learned temperature of a CUDA-graph-captured train step */
 } MrNormalizeDesc;
 int32_t mr_unit_normalize(mr_stream_t stream, const MrNormalizeDesc* d, const void* const* in, void* const* out,
                           void* workspace, size_t workspace_bytes);
@@ -664,6 +666,8 @@ typedef struct MrAdamWMultiDesc {
   int32_t grad_bf16;    /* dtype of in[0] */
   float lr, beta1, beta2, eps, weight_decay, grad_scale, bias_corr1, bias_corr2;
   float one_minus_beta1, one_minus_beta2; /* (float)(1.0 - (double)beta): rounded once, as a traced python constant is */
+  int32_t hyper_from_device; /* 1: in[2] = f32 [3] {lr, bias_corr1, bias_corr2} in device memory replaces the three
+                                fields above at run time (the step-dependent scalars of a CUDA-graph-captured step) */
 } MrAdamWMultiDesc;
 int32_t mr_adamw_multi(mr_stream_t stream, const MrAdamWMultiDesc* d, const void* const* in, void* const* out,
                        void* workspace, size_t workspace_bytes);

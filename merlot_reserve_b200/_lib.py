@@ -128,7 +128,7 @@ class RotaryDesc(C.Structure):
 
 class NormalizeDesc(C.Structure):
     _fields_ = [("rows", C.c_int32), ("H", C.c_int32), ("in_f32", C.c_int32), ("out_f32", C.c_int32),
-                ("scale", C.c_float)]
+                ("scale", C.c_float), ("scale_from_device", C.c_int32)]
 
 
 class SegmentPoolDesc(C.Structure):
@@ -162,7 +162,7 @@ class AdamWMultiDesc(C.Structure):
     _fields_ = [("n_chunks", C.c_int32), ("moments_bf16", C.c_int32), ("grad_bf16", C.c_int32), ("lr", C.c_float),
                 ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float), ("weight_decay", C.c_float),
                 ("grad_scale", C.c_float), ("bias_corr1", C.c_float), ("bias_corr2", C.c_float),
-                ("one_minus_beta1", C.c_float), ("one_minus_beta2", C.c_float)]
+                ("one_minus_beta1", C.c_float), ("one_minus_beta2", C.c_float), ("hyper_from_device", C.c_int32)]
 
 
 ADAMW_DECAY, ADAMW_W_F32, ADAMW_CHUNK = 1, 2, 2048
@@ -240,7 +240,7 @@ MISC_FNS = ["mr_check_device", "mr_abi_version", "mr_status_string", "mr_launch_
 import os as _os
 GEMM_PAIR_DEFAULT = int(_os.environ.get("MR_GEMM_PAIR", "0"))
 
-ABI_VERSION = 15  # must equal mr_abi_version() of the loaded library (struct layouts above)
+ABI_VERSION = 16  # must equal mr_abi_version() of the loaded library (struct layouts above)
 
 _lib = None
 
@@ -575,8 +575,9 @@ def rotary_table(coords: torch.Tensor) -> torch.Tensor:
     return out
 
 
-def unit_normalize(x: torch.Tensor, scale: float = 1.0, out_f32: bool = True, row_idx=None, out=None) -> torch.Tensor:
-    """y[r] = x[row_idx[r]] / sqrt(|x[row_idx[r]]|^2 + 1e-5) * scale (row_idx None: identity)."""
+def unit_normalize(x: torch.Tensor, scale: float = 1.0, out_f32: bool = True, row_idx=None, out=None, scale_dev=None) -> torch.Tensor:
+    """y[r] = x[row_idx[r]] / sqrt(|x[row_idx[r]]|^2 + 1e-5) * scale (row_idx None: identity); `scale_dev`: optional
+    f32 [1] device tensor multiplied into `scale` at run time."""
     H = x.shape[-1]
     rows = x.shape[0] if row_idx is None else row_idx.numel()
     if out is None:
@@ -584,8 +585,8 @@ def unit_normalize(x: torch.Tensor, scale: float = 1.0, out_f32: bool = True, ro
     if rows == 0:
         return out
     d = NormalizeDesc(rows=rows, H=H, in_f32=int(x.dtype == torch.float32), out_f32=int(out.dtype == torch.float32),
-                      scale=scale)
-    _call("mr_unit_normalize", d, [x, row_idx], [out])
+                      scale=scale, scale_from_device=int(scale_dev is not None))
+    _call("mr_unit_normalize", d, [x, row_idx, scale_dev], [out])
     return out
 
 
@@ -740,12 +741,14 @@ def contrastive_lse_bwd(x: torch.Tensor, y_all: torch.Tensor, lse: torch.Tensor,
     return dx, dy
 
 
-def unit_normalize_bwd(x: torch.Tensor, dy: torch.Tensor, scale: float = 1.0, row_idx=None) -> torch.Tensor:
+def unit_normalize_bwd(x: torch.Tensor, dy: torch.Tensor, scale: float = 1.0, row_idx=None, scale_dev=None) -> torch.Tensor:
+    """`scale_dev`: optional f32 [1] device tensor multiplied into `scale` at run time (CUDA-graph-safe temperature)."""
     H = x.shape[-1]
     rows = dy.shape[0]
     dx = torch.zeros((x.shape[0], H), dtype=torch.float32, device=x.device)
-    d = NormalizeDesc(rows=rows, H=H, in_f32=int(x.dtype == torch.float32), out_f32=int(dy.dtype == torch.float32), scale=scale)
-    _call("mr_unit_normalize_bwd", d, [x, dy, row_idx], [dx])
+    d = NormalizeDesc(rows=rows, H=H, in_f32=int(x.dtype == torch.float32), out_f32=int(dy.dtype == torch.float32), scale=scale,
+                      scale_from_device=int(scale_dev is not None))
+    _call("mr_unit_normalize_bwd", d, [x, dy, row_idx, scale_dev], [dx])
     return dx
 
 
@@ -810,7 +813,7 @@ def adamw_chunk_table(slots, device) -> torch.Tensor:
 
 
 def adamw_multi(g, table, p, m, v, *, lr, beta1=0.9, beta2=0.98, eps=1e-8, weight_decay=0.0, grad_scale=1.0,
-                bias_corr1=1.0, bias_corr2=1.0) -> None:
+                bias_corr1=1.0, bias_corr2=1.0, hyper_dev=None) -> None:
     """One launch for all parameters (include/mreserve_b200.h: mr_adamw_multi).  Moment dtype selects the storage:
     bf16 = the reference's compressed moments (pretrain/optimization.py:36-51), fp32 = plain Adam."""
     assert m.dtype == v.dtype and m.dtype in (torch.bfloat16, torch.float32) and p.dtype == torch.float32
@@ -818,5 +821,5 @@ def adamw_multi(g, table, p, m, v, *, lr, beta1=0.9, beta2=0.98, eps=1e-8, weigh
     d = AdamWMultiDesc(n_chunks=table.numel() // C.sizeof(AdamWChunk), moments_bf16=int(m.dtype == torch.bfloat16),
                        grad_bf16=int(g.dtype == torch.bfloat16), lr=lr, beta1=beta1, beta2=beta2, eps=eps,
                        weight_decay=weight_decay, grad_scale=grad_scale, bias_corr1=bias_corr1, bias_corr2=bias_corr2,
-                       one_minus_beta1=1.0 - beta1, one_minus_beta2=1.0 - beta2)
-    _call("mr_adamw_multi", d, [g, table], [p, m, v])
+                       one_minus_beta1=1.0 - beta1, one_minus_beta2=1.0 - beta2, hyper_from_device=int(hyper_dev is not None))
+    _call("mr_adamw_multi", d, [g, table, hyper_dev], [p, m, v])

@@ -64,7 +64,7 @@ bool make_tmap_3d(CUtensorMap* m, const void* base, int cols, int rows, int batc
 
 }  // namespace mr
 
-extern "C" int32_t mr_abi_version(void) { return 15; }
+extern "C" int32_t mr_abi_version(void) { return 16; }
 
 extern "C" int64_t mr_launch_count(void) { return mr::g_launches.load(std::memory_order_relaxed); }
 

@@ -313,10 +313,11 @@ contrastive_dlogits_kernel(const float* __restrict__ logits, const float* __rest
 template <bool kXF32, bool kDyF32>
 __global__ void __launch_bounds__(kThreadsRow)
 unit_normalize_bwd_kernel(const void* __restrict__ x_, const void* __restrict__ dy_, const int32_t* __restrict__ row_idx,
-                          float* __restrict__ dx, int rows, int H, float scale) {
+                          float* __restrict__ dx, int rows, int H, float scale, const float* __restrict__ scale_dev) {
   const int row = blockIdx.x * kWarps + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
+  if (scale_dev != nullptr) scale *= __ldg(scale_dev);
   const size_t xr = row_idx ? static_cast<size_t>(row_idx[row]) : static_cast<size_t>(row);
   auto X = [&](int c) {
     return kXF32 ? static_cast<const float*>(x_)[xr * H + c] : __bfloat162float(static_cast<const bf16*>(x_)[xr * H + c]);
@@ -572,7 +573,12 @@ __device__ __forceinline__ bf16 adam_encode_v(float v) {
 template <bool kBf16Moments, bool kBf16Grad>
 __global__ void __launch_bounds__(256)
 adamw_multi_kernel(const void* __restrict__ g_, const MrAdamWChunk* __restrict__ table, float* __restrict__ p_,
-                   void* __restrict__ m_, void* __restrict__ v_, MrAdamWMultiDesc d) {
+                   void* __restrict__ m_, void* __restrict__ v_, MrAdamWMultiDesc d, const float* __restrict__ hyper) {
+  if (hyper != nullptr) {   // step-dependent scalars from device memory: the launch can sit in a CUDA graph
+    d.lr = __ldg(hyper);
+    d.bias_corr1 = __ldg(hyper + 1);
+    d.bias_corr2 = __ldg(hyper + 2);
+  }
   const MrAdamWChunk ch = table[blockIdx.x];
   const int i0 = threadIdx.x * 8;
   if (i0 >= ch.count) return;
@@ -893,15 +899,17 @@ extern "C" int32_t mr_unit_normalize_bwd(mr_stream_t stream_, const MrNormalizeD
   const int grid = ceil_div(d->rows, kWarps);
   const int32_t* ridx = static_cast<const int32_t*>(in[2]);
   float* dx = static_cast<float*>(out[0]);
+  const float* sdev = d->scale_from_device ? static_cast<const float*>(in[3]) : nullptr;
+  MR_REQUIRE(!d->scale_from_device || sdev, MR_ERR_NULL_POINTER);
   // in_f32: dtype of x (the forward's input); out_f32: dtype of dy (the forward's output)
   if (d->in_f32 && d->out_f32)
-    unit_normalize_bwd_kernel<true, true><<<grid, kThreadsRow, 0, stream>>>(in[0], in[1], ridx, dx, d->rows, d->H, d->scale);
+    unit_normalize_bwd_kernel<true, true><<<grid, kThreadsRow, 0, stream>>>(in[0], in[1], ridx, dx, d->rows, d->H, d->scale, sdev);
   else if (d->in_f32)
-    unit_normalize_bwd_kernel<true, false><<<grid, kThreadsRow, 0, stream>>>(in[0], in[1], ridx, dx, d->rows, d->H, d->scale);
+    unit_normalize_bwd_kernel<true, false><<<grid, kThreadsRow, 0, stream>>>(in[0], in[1], ridx, dx, d->rows, d->H, d->scale, sdev);
   else if (d->out_f32)
-    unit_normalize_bwd_kernel<false, true><<<grid, kThreadsRow, 0, stream>>>(in[0], in[1], ridx, dx, d->rows, d->H, d->scale);
+    unit_normalize_bwd_kernel<false, true><<<grid, kThreadsRow, 0, stream>>>(in[0], in[1], ridx, dx, d->rows, d->H, d->scale, sdev);
   else
-    unit_normalize_bwd_kernel<false, false><<<grid, kThreadsRow, 0, stream>>>(in[0], in[1], ridx, dx, d->rows, d->H, d->scale);
+    unit_normalize_bwd_kernel<false, false><<<grid, kThreadsRow, 0, stream>>>(in[0], in[1], ridx, dx, d->rows, d->H, d->scale, sdev);
   return after_launch();
 }
 
@@ -997,18 +1005,20 @@ extern "C" int32_t mr_adamw_multi(mr_stream_t stream_, const MrAdamWMultiDesc* d
   MR_REQUIRE(aligned16(in[0]) && aligned16(out[0]) && aligned16(out[1]) && aligned16(out[2]), MR_ERR_MISALIGNED);
   if (d->n_chunks == 0) return MR_OK;
   const MrAdamWChunk* table = static_cast<const MrAdamWChunk*>(in[1]);
+  const float* hyper = d->hyper_from_device ? static_cast<const float*>(in[2]) : nullptr;
+  MR_REQUIRE(!d->hyper_from_device || hyper, MR_ERR_NULL_POINTER);
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const unsigned grid = static_cast<unsigned>(d->n_chunks);
   if (d->moments_bf16) {
     if (d->grad_bf16)
-      adamw_multi_kernel<true, true><<<grid, 256, 0, stream>>>(in[0], table, static_cast<float*>(out[0]), out[1], out[2], *d);
+      adamw_multi_kernel<true, true><<<grid, 256, 0, stream>>>(in[0], table, static_cast<float*>(out[0]), out[1], out[2], *d, hyper);
     else
-      adamw_multi_kernel<true, false><<<grid, 256, 0, stream>>>(in[0], table, static_cast<float*>(out[0]), out[1], out[2], *d);
+      adamw_multi_kernel<true, false><<<grid, 256, 0, stream>>>(in[0], table, static_cast<float*>(out[0]), out[1], out[2], *d, hyper);
   } else {
     if (d->grad_bf16)
-      adamw_multi_kernel<false, true><<<grid, 256, 0, stream>>>(in[0], table, static_cast<float*>(out[0]), out[1], out[2], *d);
+      adamw_multi_kernel<false, true><<<grid, 256, 0, stream>>>(in[0], table, static_cast<float*>(out[0]), out[1], out[2], *d, hyper);
     else
-      adamw_multi_kernel<false, false><<<grid, 256, 0, stream>>>(in[0], table, static_cast<float*>(out[0]), out[1], out[2], *d);
+      adamw_multi_kernel<false, false><<<grid, 256, 0, stream>>>(in[0], table, static_cast<float*>(out[0]), out[1], out[2], *d, hyper);
   }
   return after_launch();
 }

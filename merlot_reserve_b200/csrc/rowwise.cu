@@ -407,10 +407,11 @@ embed_assemble_kernel(const int32_t* __restrict__ tokens, const int32_t* __restr
 template <bool kInF32, bool kOutF32>
 __global__ void __launch_bounds__(kRowThreads)
 unit_normalize_kernel(const void* __restrict__ x_, const int32_t* __restrict__ row_idx, void* __restrict__ y_,
-                      int rows, int H, float scale) {
+                      int rows, int H, float scale, const float* __restrict__ scale_dev) {
   const int row = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
+  if (scale_dev != nullptr) scale *= __ldg(scale_dev);
   const size_t in_row = row_idx ? static_cast<size_t>(row_idx[row]) : static_cast<size_t>(row);
   float ss = 0.f;
   for (int c = lane; c < H; c += 32) {
@@ -666,14 +667,16 @@ extern "C" int32_t mr_unit_normalize(mr_stream_t stream_, const MrNormalizeDesc*
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const int grid = ceil_div(d->rows, kWarpsPerBlock);
   const int32_t* ridx = static_cast<const int32_t*>(in[1]);
+  const float* sdev = d->scale_from_device ? static_cast<const float*>(in[2]) : nullptr;
+  MR_REQUIRE(!d->scale_from_device || sdev, MR_ERR_NULL_POINTER);
   if (d->in_f32 && d->out_f32)
-    unit_normalize_kernel<true, true><<<grid, kRowThreads, 0, stream>>>(in[0], ridx, out[0], d->rows, d->H, d->scale);
+    unit_normalize_kernel<true, true><<<grid, kRowThreads, 0, stream>>>(in[0], ridx, out[0], d->rows, d->H, d->scale, sdev);
   else if (d->in_f32)
-    unit_normalize_kernel<true, false><<<grid, kRowThreads, 0, stream>>>(in[0], ridx, out[0], d->rows, d->H, d->scale);
+    unit_normalize_kernel<true, false><<<grid, kRowThreads, 0, stream>>>(in[0], ridx, out[0], d->rows, d->H, d->scale, sdev);
   else if (d->out_f32)
-    unit_normalize_kernel<false, true><<<grid, kRowThreads, 0, stream>>>(in[0], ridx, out[0], d->rows, d->H, d->scale);
+    unit_normalize_kernel<false, true><<<grid, kRowThreads, 0, stream>>>(in[0], ridx, out[0], d->rows, d->H, d->scale, sdev);
   else
-    unit_normalize_kernel<false, false><<<grid, kRowThreads, 0, stream>>>(in[0], ridx, out[0], d->rows, d->H, d->scale);
+    unit_normalize_kernel<false, false><<<grid, kRowThreads, 0, stream>>>(in[0], ridx, out[0], d->rows, d->H, d->scale, sdev);
   return after_launch();
 }
 

@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol(lib):
     assert len(names) >= 20
     for n in names:
         assert hasattr(cdll, n), f"{n} declared in the header but not exported"
-    assert cdll.mr_abi_version() == lib.ABI_VERSION == 15
+    assert cdll.mr_abi_version() == lib.ABI_VERSION == 16
     assert lib.launch_count() >= 0
 
 

@@ -191,6 +191,107 @@ class PretrainStep:
         self._scale_state = {"m": np.zeros(3, _np_dtype(mdt)), "v": np.zeros(3, _np_dtype(mdt))}
         self.step_count = 0
 
+    def _step_scalars(self, opt: Dict):
+        """(lr, bias correction on?, t) of the step about to be taken."""
+        lr = opt["learning_rate"] * self.lr_scale(self.step_count, opt)
+        # bias correction: off by default with the bf16 moments (optimization.py:165), always on for optax.scale_by_adam
+        corr = opt.get("do_bias_correction", False) if opt.get("use_bfloat16_adam", True) else True
+        return lr, corr, self.step_count + 1
+
+    def _update_temperatures(self, g_scales: np.ndarray, opt: Dict, world: int) -> None:
+        """Adam on the three contrastive temperatures.  They live on the host (they parameterise kernel launches);
+        ndim 1: no weight decay (optimization.py:182-184)."""
+        b1, b2, eps = opt.get("beta_1", 0.9), opt.get("beta_2", 0.98), opt.get("eps", 1e-8)
+        lr, corr, t1 = self._step_scalars(opt)
+        gs = np.nan_to_num(g_scales) / world
+        ss, p = self._scale_state, self.model._p
+        coded = ss["m"].dtype != np.float32
+        f32 = np.float32
+        mh = f32(1 - b1) * gs + f32(b1) * ss["m"].astype(f32)
+        vh = f32(1 - b2) * gs * gs + f32(b2) * (_nu_decode(ss["v"]) if coded else ss["v"])
+        ss["m"], ss["v"] = (mh.astype(ss["m"].dtype), _nu_encode(vh)) if coded else (mh, vh)
+        if corr:
+            mh, vh = mh / f32(1 - b1 ** t1), vh / f32(1 - b2 ** t1)
+        p.contrastive_scales = (p.contrastive_scales - f32(lr) * mh / (np.sqrt(vh) + f32(eps))).astype(np.float32)
+        self.step_count += 1
+
+    # --------------------------------------------------------------------------------------------
+    # CUDA-graph form of train_step: the ~1 700 kernel launches and the index glue of one step are captured once and
+    # replayed with one graph launch.  Everything that changes from step to step enters through device memory:
+    # the batch (static input buffers), the learning rate / bias corrections (mr_adamw_multi reads f32 [3]) and the
+    # three temperatures (mr_unit_normalize(_bwd) read exp(min(s, log 100) / 2) from a device scalar).  The Adam
+    # update of the three temperatures stays on the host, between replays.
+    # --------------------------------------------------------------------------------------------
+    def capture_train_step(self, batch: Dict, opt: Optional[Dict] = None, group=None):
+        """Captures train_step for batches shaped like `batch` (which must carry the '_rng/*' draws: the numpy draw of
+        the eager path cannot be captured).  Returns `run(batch) -> (loss, loss_info)` (0-d CUDA tensors, valid until
+        the next call).  With more than one rank the NCCL collectives of the step are captured too."""
+        import torch.distributed as dist
+        opt = opt or self.DEFAULT_OPT
+        if self._state is None:
+            self._init_state(opt)
+        for k in ("_rng/split_audio2text", "_rng/split_text2audio", "_rng/gumbel_u"):
+            if k not in batch:
+                raise ValueError(f"capture_train_step needs the random draws as inputs: '{k}' is missing from the batch")
+        dev = next(iter(self._registry().values()))[0].device
+        static = {k: _dev(v).clone() for k, v in batch.items()}
+        self._graph_scalars = {"temp": torch.ones(3, dtype=torch.float32, device=dev),
+                               "unclipped": torch.ones(3, dtype=torch.float32, device=dev),
+                               "hyper": torch.ones(3, dtype=torch.float32, device=dev)}
+        host = torch.empty(9, dtype=torch.float32).pin_memory()
+        out_host = torch.empty(3, dtype=torch.float32).pin_memory()
+        world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+
+        def set_scalars():
+            ls_raw = self.model._p.contrastive_scales.astype(np.float32)
+            b1, b2 = opt.get("beta_1", 0.9), opt.get("beta_2", 0.98)
+            lr, corr, t1 = self._step_scalars(opt)
+            host[0:3] = torch.from_numpy(np.exp(np.minimum(ls_raw, np.float32(math.log(100.0))) / 2.0).astype(np.float32))
+            host[3:6] = torch.from_numpy((ls_raw <= math.log(100.0)).astype(np.float32))
+            host[6], host[7], host[8] = lr, (1 - b1 ** t1) if corr else 1.0, (1 - b2 ** t1) if corr else 1.0
+            gs = self._graph_scalars
+            gs["temp"].copy_(host[0:3], non_blocking=True)
+            gs["unclipped"].copy_(host[3:6], non_blocking=True)
+            gs["hyper"].copy_(host[6:9], non_blocking=True)
+
+        # warm-up on a side stream (lazy kernel attributes, NCCL communicator set-up, allocator pools), restoring the state
+        snap = {k: self._state[k].clone() for k in ("p", "m", "v")}
+        working = [(t, t.clone()) for t, _ in self._registry().values()]
+        saved_scales = (self.model._p.contrastive_scales.copy(), {k: v.copy() for k, v in self._scale_state.items()},
+                        self.step_count)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            set_scalars()
+            self.train_step(static, opt, group=group)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        for k, v in snap.items():
+            self._state[k].copy_(v)
+        for t, v in working:
+            t.copy_(v)
+        self.model._p.contrastive_scales, self._scale_state, self.step_count = saved_scales[0], saved_scales[1], saved_scales[2]
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            loss, info = self.train_step(static, opt, group=group)
+        g_scales = self._graph_scalars["g_scales"]
+
+        def run(new_batch: Optional[Dict] = None):
+            if new_batch is not None and new_batch is not batch:
+                for k, dst in static.items():
+                    src = new_batch[k]
+                    src = src if isinstance(src, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(src))
+                    dst.copy_(src.reshape(dst.shape).to(dst.dtype), non_blocking=True)
+            set_scalars()
+            graph.replay()
+            out_host.copy_(g_scales.float(), non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            self._update_temperatures(out_host.numpy().copy(), opt, world)
+            return loss, info
+
+        run.graph, run.static = graph, static
+        return run
+
     def lr_scale(self, step: int, opt: Dict) -> float:
         """lr_scale_linearwarmup_cosinedecay (optimization.py:117-137)."""
         nw, nt, final = opt["num_warmup_steps"], opt["num_train_steps"], opt.get("final_lr_scale", 0.02)
@@ -270,25 +371,16 @@ class PretrainStep:
             g16 = L.cast_pad(g.view(-1, 1024), (n + 1024) // 1024, 1024, 1024, out=st["g16"].view(-1, 1024), sanitize=True).view(-1)
             if world > 1 and not _SKIP_GRAD_ALLREDUCE:
                 dist.all_reduce(g16, group=group)
-        lr = opt["learning_rate"] * self.lr_scale(self.step_count, opt)
         b1, b2, eps, wd = opt.get("beta_1", 0.9), opt.get("beta_2", 0.98), opt.get("eps", 1e-8), opt["weight_decay_rate"]
-        # bias correction: off by default with the bf16 moments (optimization.py:165), always on for optax.scale_by_adam
-        corr = opt.get("do_bias_correction", False) if opt.get("use_bfloat16_adam", True) else True
-        t1 = self.step_count + 1
+        lr, corr, t1 = self._step_scalars(opt)
+        gm = getattr(self, "_graph_scalars", None)
         L.adamw_multi(g16, st["table"], st["p"], st["m"], st["v"], lr=lr, beta1=b1, beta2=b2, eps=eps, weight_decay=wd,
                       grad_scale=1.0 / world, bias_corr1=(1 - b1 ** t1) if corr else 1.0,
-                      bias_corr2=(1 - b2 ** t1) if corr else 1.0)
-        # the three temperatures live on the host (they parameterise kernel launches); ndim 1: no decay
-        gs = np.nan_to_num(g16[n:n + 3].float().cpu().numpy()) / world
-        ss, p = self._scale_state, self.model._p
-        coded = ss["m"].dtype != np.float32
-        f32 = np.float32
-        mh = f32(1 - b1) * gs + f32(b1) * ss["m"].astype(f32)
-        vh = f32(1 - b2) * gs * gs + f32(b2) * (_nu_decode(ss["v"]) if coded else ss["v"])
-        ss["m"], ss["v"] = (mh.astype(ss["m"].dtype), _nu_encode(vh)) if coded else (mh, vh)
-        if corr:
-            mh, vh = mh / f32(1 - b1 ** t1), vh / f32(1 - b2 ** t1)
-        p.contrastive_scales = (p.contrastive_scales - f32(lr) * mh / (np.sqrt(vh) + f32(eps))).astype(np.float32)
+                      bias_corr2=(1 - b2 ** t1) if corr else 1.0, hyper_dev=None if gm is None else gm["hyper"])
+        if gm is not None:                 # captured: the host part below runs after every replay (train_step_graphed)
+            gm["g_scales"] = g16[n:n + 3]
+            return loss, info
+        self._update_temperatures(g16[n:n + 3].float().cpu().numpy(), opt, world)
         self.step_count += 1
         return loss, info
 
@@ -571,7 +663,9 @@ class PretrainStep:
         ls_raw = p.contrastive_scales.astype(np.float32)
         ls = np.minimum(ls_raw, np.float32(math.log(100.0)))
         temp = [float(np.exp(v / 2.0)) for v in ls]
-        un = lambda v, s, idx=None: L.unit_normalize(v.reshape(-1, H), scale=s, out_f32=False, row_idx=idx)
+        gm = getattr(self, "_graph_scalars", None)     # CUDA-graph mode: temperatures live in device memory
+        tkw = (lambda hi: dict(scale=temp[hi])) if gm is None else (lambda hi: dict(scale=1.0, scale_dev=gm["temp"][hi:hi + 1]))
+        un = lambda v, hi, idx=None: L.unit_normalize(v.reshape(-1, H), out_f32=False, row_idx=idx, **tkw(hi))
         heads = {                       # name -> {field: (normalised output, source tensor, row gather, temperature)}
             "imgs_to_audio": {"x": (a2v, None), "y": (v_cls, None)},
             "text_to_audio": {"x": (t2a_x, best_rows), "y": (audio_cls, best_rows), "y_extra": (audio_cls, extra_rows)},
@@ -579,7 +673,7 @@ class PretrainStep:
         }
         preds = {}
         for hi, (name, fields) in enumerate(heads.items()):
-            preds[name] = {f: un(srct, temp[hi], idx) for f, (srct, idx) in fields.items()}
+            preds[name] = {f: un(srct, hi, idx) for f, (srct, idx) in fields.items()}
         preds["stuff_to_span"]["_sources"] = src.reshape(-1)[best].to(torch.int32).contiguous()
 
         # ---- loss forward (pretrain_model.py:262-303) ----
@@ -635,11 +729,13 @@ class PretrainStep:
         for hi, (name, fields) in enumerate(heads.items()):
             for f, (srct, idx) in fields.items():
                 g_out = dpred[name][f]
-                d = L.unit_normalize_bwd(srct.reshape(-1, H), g_out, scale=temp[hi], row_idx=idx)
+                d = L.unit_normalize_bwd(srct.reshape(-1, H), g_out, row_idx=idx, **tkw(hi))
                 key = id(srct)
                 dsrc[key] = dsrc[key] + d if key in dsrc else d
                 # y = exp(s / 2) * unit(x):  dL/ds = 0.5 * sum(dy * y), zero where the clip at log(100) is active
-                if ls_raw[hi] <= math.log(100.0):
+                if gm is not None:
+                    dscale[hi] += 0.5 * (g_out * preds[name][f].float()).sum() * gm["unclipped"][hi]
+                elif ls_raw[hi] <= math.log(100.0):
                     dscale[hi] += 0.5 * (g_out * preds[name][f].float()).sum()
         G.add("contrastive_scales", dscale)
         d_a2v, d_vcls, d_t2ax = dsrc[id(a2v)], dsrc[id(v_cls)], dsrc[id(t2a_x)]

@@ -109,3 +109,31 @@ def test_train_step_reduces_loss(cuda):
     losses = [float(step.train_step(batch, opt)[0]) for _ in range(6)]
     assert all(np.isfinite(losses)), losses
     assert losses[-1] < losses[0] - 0.05, losses
+
+
+def test_cuda_graph_train_step_matches_eager(cuda):
+    """capture_train_step: one graph launch per optimisation step.  Three steps on changing batches, learning rates and
+    temperatures must leave the same master parameters, moments and temperatures as the eager train_step (both run the
+    same kernels; dQ / embedding gradients are accumulated with fp32 atomics, so agreement is to rounding)."""
+    from merlot_reserve_b200.training import PretrainStep
+    cfg = tiny_config()
+    opt = {"learning_rate": 2e-4, "num_train_steps": 100, "num_warmup_steps": 2, "weight_decay_rate": 0.1, "beta_2": 0.98,
+           "eps": 1e-6, "final_lr_scale": 0.02}
+    batches = [synthetic_pretrain_batch(cfg, 2, seed=40 + i) for i in range(3)]
+    eager = PretrainStep(cfg, synthetic_params(cfg, seed=0, weight_scale=4.0))
+    losses_e = [float(eager.train_step(bt, opt)[0]) for bt in batches]
+    graphed = PretrainStep(cfg, synthetic_params(cfg, seed=0, weight_scale=4.0))
+    run = graphed.capture_train_step(batches[0], opt)
+    from merlot_reserve_b200 import _lib
+    n0 = _lib.launch_count()
+    losses_g = [float(run(bt)[0]) for bt in batches]
+    assert _lib.launch_count() == n0                         # replays launch nothing through the library
+    assert np.allclose(losses_e, losses_g, atol=2e-3), (losses_e, losses_g)
+    assert graphed.step_count == eager.step_count == 3
+    for key in ("p", "m", "v"):
+        a, b = eager._state[key].float(), graphed._state[key].float()
+        assert float((a - b).abs().max()) < 5e-5, key
+    assert np.abs(eager.model._p.contrastive_scales - graphed.model._p.contrastive_scales).max() < 1e-5
+    assert not np.allclose(eager.model._p.contrastive_scales, np.log(20.0))      # the temperatures did move
+    with pytest.raises(ValueError):
+        graphed.capture_train_step({k: v for k, v in batches[0].items() if not k.startswith("_rng/")}, opt)

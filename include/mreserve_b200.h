@@ -93,6 +93,9 @@ enum {
   MR_EPI_OUT_F32 = 16,
   MR_EPI_LN_IN = 32,     /* A is the UN-normalised residual stream; LayerNorm is folded into the GEMM (below) */
   MR_EPI_STATS_OUT = 64, /* also emit per-row (sum, sum of squares) partials of the bf16 output (below) */
+  MR_EPI_GELU_DUAL = 256,/* with MR_EPI_BIAS | MR_EPI_GELU (bf16 staged output, nothing else): out[2] (bf16, same shape and
+                            pitch as out[0]) also receives the PRE-activation A W^T + b.  The training forward of the MLP
+                            keeps both (pretrain_model.py:320 differentiates my_gelu): no separate GELU pass over HBM. */
   MR_EPI_DGELU = 128     /* backward of my_gelu fused into the dgrad that produces its input gradient:
                             D = acc * gelu'(in[3]), in[3] = the forward's PRE-activation, bf16, indexed like D
                             (gelu'(p) = s (1 + 1.702 p (1 - s)), s = sigmoid(1.702 p)).  bf16 staged output with

@@ -15,6 +15,7 @@ import torch
 _LIB_PATH = Path(__file__).resolve().parent / "lib" / "libmreserve_b200.so"
 
 EPI_BIAS, EPI_GELU, EPI_RESIDUAL, EPI_ROTARY_QKV, EPI_OUT_F32, EPI_LN_IN, EPI_STATS_OUT, EPI_DGELU = 1, 2, 4, 8, 16, 32, 64, 128
+EPI_GELU_DUAL = 256
 ALGO_TCGEN05, ALGO_SIMT_DEBUG = 0, 1
 
 
@@ -347,7 +348,8 @@ def _work(name: str, d):
 # ------------------------------------------------------------------------------------------------
 def gemm(a: torch.Tensor, w: torch.Tensor, *, bias=None, residual=None, rot=None, out=None, gelu=False,
          out_f32=False, hidden=0, q_scale=1.0, seq_in=0, seq_out=0, row_off=0, out_rows=None, M=None, lda=None,
-         algo=ALGO_TCGEN05, ln_stats=None, ln_colsum=None, ln_eps=1e-5, stats_out=None, pair=None) -> torch.Tensor:
+         algo=ALGO_TCGEN05, ln_stats=None, ln_colsum=None, ln_eps=1e-5, stats_out=None, pair=None,
+         pre_out=None) -> torch.Tensor:
     """D = epilogue(A @ W^T).  a: bf16 [M, K] (or strided rows via M / lda), w: bf16 [N, K].
     ln_stats / ln_colsum: fold LayerNorm(a) into the GEMM (w must be the gamma-scaled weight, bias = beta W + b);
     stats_out: f32 [N/64, M, 2] buffer receiving the row statistics of the (bf16) output."""
@@ -377,10 +379,13 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias=None, residual=None, rot=None
         epi |= EPI_LN_IN
     if stats_out is not None:
         epi |= EPI_STATS_OUT
+    if pre_out is not None:          # bias + GELU with the pre-activation as a second output (MR_EPI_GELU_DUAL)
+        assert gelu and bias is not None and pre_out.shape == out.shape and pre_out.dtype == torch.bfloat16
+        epi |= EPI_GELU_DUAL
     d = GemmDesc(M=M, N=N, K=K, lda=lda, ldd=out.shape[-1], epilogue=epi, seq_in=seq_in, seq_out=seq_out,
                  row_off=row_off, rot_rows=(rot.shape[0] if rot is not None else 0), hidden=hidden, algo=algo,
                  q_scale=q_scale, num_sms=0, ln_eps=ln_eps, algo_pair=pair)
-    _call("mr_gemm_epilogue", d, [a, w, bias, residual, rot, ln_stats, ln_colsum], [out, stats_out])
+    _call("mr_gemm_epilogue", d, [a, w, bias, residual, rot, ln_stats, ln_colsum], [out, stats_out, pre_out])
     return out
 
 

@@ -66,14 +66,15 @@ constexpr int kBoxBytes = 32 * 128;  // one epilogue staging box: 32 rows x 64 b
 // HALF of the W tile (BN / 2 rows); the leader issues 256 x BN x 16 MMAs that read both CTAs' shared memory and
 // write each CTA's half of the accumulator into its own TMEM.  Per CTA and k-block that is 32 KB of L2 -> SMEM
 // traffic instead of 48 KB, and the smaller stages allow a 6-deep ring.
-template <int BN, int kCtas = 1>
+template <int BN, int kCtas = 1, bool kDual = false>
 struct Cfg {
-  static constexpr int kStages = (BN == 256 && kCtas == 1) ? 4 : 6;
+  // kDual (two output boxes per epilogue warp): one ring stage less pays for the second set of staging boxes
+  static constexpr int kStages = ((BN == 256 && kCtas == 1) ? 4 : 6) - (kDual ? 1 : 0);
   static constexpr int kABytes = kBM * kBK * 2;
   static constexpr int kBBytes = (BN / kCtas) * kBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTmemCols = 2 * BN;  // two accumulator stages
-  static constexpr int kOutBytes = kEpiWarps * kBoxBytes;
+  static constexpr int kOutBytes = kEpiWarps * kBoxBytes * (kDual ? 2 : 1);
   static constexpr int kBarBytes = 256;
   static constexpr int kSmemBytes = kStages * kStageBytes + kOutBytes + kBarBytes + 1024;  // +1024: manual alignment
   static_assert(kSmemBytes <= 232448, "exceeds the 227 KB dynamic shared memory limit");
@@ -120,13 +121,17 @@ __device__ __forceinline__ void load_cols8(const float* __restrict__ v, int c, i
 // step sat behind its own reconvergence point and the epilogue became latency bound (profiles/ncu_gemm_r01j.md).
 // The direct path keeps run-time p.bias_on (small GEMMs only).
 template <int BN, bool kGelu, bool kResidual, bool kRotary, bool kDirect, bool kBias = false, bool kLn = false,
-          bool kStats = false, int kCtas = 1, int kTrans = 0>
+          bool kStats = false, int kCtas = 1, int kTrans = 0, bool kDual = false>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res,
                     const GemmParams p) {
-  using C = Cfg<BN, kCtas>;
+  using C = Cfg<BN, kCtas, kDual>;
   constexpr bool kPair = kCtas == 2;
+  // MR_EPI_GELU_DUAL (training forward of the MLP-up projection): the bf16 PRE-activation goes out through a second
+  // staging box and the `tmap_res` tensor map next to the activation -- the backward needs both, and a separate GELU
+  // kernel would read the pre-activation back from HBM.
+  static_assert(!kDual || (kGelu && !kResidual && !kDirect && !kStats && kTrans == 0), "dual output: staged bias+GELU only");
   static_assert(!(kPair && kDirect) && (!kPair || BN == 256), "CTA pairs: staged 256-wide tiles only");
   // kTrans bit 0: A is MN-major (given as [K, M], the backward's "A^T"); bit 1: B is MN-major (given as [K, N]).
   // An MN-major operand is staged as 64-column slabs of [64 k-rows x 128 B] (one TMA box each, 128B swizzle):
@@ -157,7 +162,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     tma_prefetch_desc(&tmap_b);
     if constexpr (!kDirect) {
       tma_prefetch_desc(&tmap_out);
-      if constexpr (kResidual) tma_prefetch_desc(&tmap_res);
+      if constexpr (kResidual || kDual) tma_prefetch_desc(&tmap_res);
     }
   }
   if (warp_idx == 1 && lane == 0) {
@@ -320,6 +325,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       constexpr int kBoxes = BN / 128;         // 64-column boxes per warp
       uint8_t* sbuf = smem_out + ew * kBoxBytes;
       uint8_t* my_row = sbuf + lane * 128;     // this thread's 128-byte row of the box
+      uint8_t* sbuf2 = smem_out + (kEpiWarps + ew) * kBoxBytes;   // kDual: the pre-activation box
+      uint8_t* my_row2 = sbuf2 + lane * 128;
       const int sw = lane & 7;                 // 128B swizzle: 16-byte chunk j lives at chunk (j ^ (row & 7))
       uint64_t* rbar = &res_bar[ew];
       uint32_t res_phase = 0;
@@ -459,6 +466,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                   for (int q = 0; q < 8; ++q) f[q] *= p.q_scale;
                 }
               }
+              if constexpr (kDual) {
+                uint4 o2;
+                o2.x = pack_bf16(f[0], f[1]);
+                o2.y = pack_bf16(f[2], f[3]);
+                o2.z = pack_bf16(f[4], f[5]);
+                o2.w = pack_bf16(f[6], f[7]);
+                *reinterpret_cast<uint4*>(my_row2 + ((j ^ sw) << 4)) = o2;
+              }
               if constexpr (kGelu && !kDGelu) {
 #pragma unroll
                 for (int q = 0; q < 8; ++q) f[q] = gelu_sigmoid(f[q]);
@@ -506,6 +521,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           __syncwarp();
           if (lane == 0) {
             tma_store_2d(&tmap_out, sbuf, col0, row0);   // rows >= M and columns >= N are clipped by the tensor map
+            if constexpr (kDual) tma_store_2d(&tmap_res, sbuf2, col0, row0);
             tma_store_commit();
           }
         }
@@ -710,12 +726,13 @@ struct Maps {
   CUtensorMap a, b, out, res;
 };
 
-template <int BN, bool G, bool R, bool Q, bool D, bool B = false, bool L = false, bool S = false, int P = 1, int T = 0>
+template <int BN, bool G, bool R, bool Q, bool D, bool B = false, bool L = false, bool S = false, int P = 1, int T = 0,
+          bool U = false>
 int32_t launch_one(cudaStream_t stream, const Maps& m, const GemmParams& p, int grid) {
-  auto kern = gemm_tcgen05_kernel<BN, G, R, Q, D, B, L, S, P, T>;
+  auto kern = gemm_tcgen05_kernel<BN, G, R, Q, D, B, L, S, P, T, U>;
   static bool attr_set = false;  // benign race: the attribute is idempotent
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN, P>::kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN, P, U>::kSmemBytes);
     if (e != cudaSuccess) return cuda_status(e);
     attr_set = true;
   }
@@ -723,7 +740,7 @@ int32_t launch_one(cudaStream_t stream, const Maps& m, const GemmParams& p, int 
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(static_cast<unsigned>(grid));
     cfg.blockDim = dim3(kThreads);
-    cfg.dynamicSmemBytes = Cfg<BN, P>::kSmemBytes;
+    cfg.dynamicSmemBytes = Cfg<BN, P, U>::kSmemBytes;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -736,7 +753,7 @@ int32_t launch_one(cudaStream_t stream, const Maps& m, const GemmParams& p, int 
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return cuda_status(e != cudaSuccess ? e : cudaGetLastError());
   } else {
-    kern<<<grid, kThreads, Cfg<BN>::kSmemBytes, stream>>>(m.a, m.b, m.out, m.res, p);
+    kern<<<grid, kThreads, Cfg<BN, 1, U>::kSmemBytes, stream>>>(m.a, m.b, m.out, m.res, p);
     return after_launch();
   }
 }
@@ -1000,6 +1017,20 @@ extern "C" int32_t mr_gemm_epilogue(mr_stream_t stream_, const MrGemmDesc* d, co
   if (residual) MR_REQUIRE(make_tmap_2d(&m.res, in[3], d->M, d->N, d->ldd, 32, 64), MR_ERR_DRIVER);
   // CTA pairs (cta_group::2, 256 x 256 pair tiles) whenever every pair of SMs gets at least one pair tile
   const int pair_tiles = ceil_div(d->M, 2 * kBM) * p.num_n_tiles;
+  if (d->epilogue & MR_EPI_GELU_DUAL) {
+    // bias + GELU with the pre-activation as a second bf16 output (out[2]); staged path, no other epilogue flag
+    MR_REQUIRE(gelu && bias && !residual && !rotary && !ln_in && !stats_out && trans == 0, MR_ERR_BAD_SHAPE);
+    MR_REQUIRE(out[2] && aligned16(out[2]), out[2] ? MR_ERR_MISALIGNED : MR_ERR_NULL_POINTER);
+    MR_REQUIRE(make_tmap_2d(&m.res, out[2], d->M, d->N, d->ldd, 32, 64), MR_ERR_DRIVER);
+    if (bn == 256 && d->algo_pair != 2 && sms >= 2 && (d->algo_pair == 1 || pair_tiles >= sms / 2)) {
+      p.num_tiles = pair_tiles;
+      const int pairs = pair_tiles < sms / 2 ? pair_tiles : sms / 2;
+      MR_REQUIRE(make_tmap_2d(&m.b, W, d->N, d->K, d->K, bn / 2, kBK), MR_ERR_DRIVER);
+      return launch_one<256, true, false, false, false, true, false, false, 2, 0, true>(stream, m, p, 2 * pairs);
+    }
+    if (bn == 256) return launch_one<256, true, false, false, false, true, false, false, 1, 0, true>(stream, m, p, grid);
+    return launch_one<128, true, false, false, false, true, false, false, 1, 0, true>(stream, m, p, grid);
+  }
   if (bn == 256 && trans == 0 && d->algo_pair != 2 && sms >= 2 && (d->algo_pair == 1 || pair_tiles >= sms / 2)) {
     p.num_tiles = pair_tiles;
     const int pairs = pair_tiles < sms / 2 ? pair_tiles : sms / 2;

@@ -398,8 +398,10 @@ class PretrainStep:
             ctx = L.attention(qkv, B, T, H, valid=valid, group=group, lse=lse)
             xm = L.gemm(ctx, lw["wo"], residual=x)
             h2 = L.layernorm(xm, *lw["ln2"])
-            up = L.gemm(h2, lw["w1"], bias=lw["b1"])
-            u = L.gelu(up)
+            # bias + my_gelu in the epilogue, with the pre-activation as a second output (MR_EPI_GELU_DUAL): the
+            # backward needs both (gelu' reads `up`, the MLP-out wgrad reads `u`)
+            up = torch.empty((h2.shape[0], lw["w1"].shape[0]), dtype=BF16, device=h2.device)
+            u = L.gemm(h2, lw["w1"], bias=lw["b1"], gelu=True, pre_out=up)
             xn = L.gemm(u, lw["w2"], residual=xm)
             tape["layers"].append((x, h1, qkv, lse, ctx, xm, h2, up, u))
             x = xn

@@ -57,6 +57,23 @@ def test_gemm_bias_gelu(cuda, lib, M, N, K):
     _close(lib.gemm(a, w, bias=b, gelu=True), pre * torch.sigmoid(1.702 * pre), 2e-2, 1e-2, "gelu")
 
 
+@pytest.mark.parametrize("M,N,K,pair", [(1000, 3072, 768, 0), (40000, 3072, 768, 1), (260, 4096, 1024, 2), (130, 200, 72, 0)])
+def test_gemm_bias_gelu_dual_output(cuda, lib, M, N, K, pair):
+    """MR_EPI_GELU_DUAL: the activation AND the bf16 pre-activation leave the same epilogue (single-CTA, CTA-pair and
+    128-wide tiles; ragged M / N / K): bit-identical to the two single-output GEMMs."""
+    g = torch.Generator().manual_seed(M)
+    a = _bf(torch.randn(M, K, generator=g)).to(cuda)
+    w = _bf(torch.randn(N, K, generator=g) * 0.05).to(cuda)
+    b = torch.randn(N, generator=g).to(cuda)
+    pre = torch.full((M, N), 7.0, dtype=torch.bfloat16, device=cuda)
+    act = lib.gemm(a, w, bias=b, gelu=True, pre_out=pre, pair=pair)
+    assert torch.equal(pre, lib.gemm(a, w, bias=b, pair=pair))
+    assert torch.equal(act, lib.gemm(a, w, bias=b, gelu=True, pair=pair))
+    ref = a.float() @ w.float().t() + b
+    _close(pre, ref, 2e-2, 1e-2, "pre-activation")
+    _close(act, ref * torch.sigmoid(1.702 * ref), 2e-2, 1e-2, "activation")
+
+
 @pytest.mark.parametrize("M,N,K", [(1000, 768, 3072), (300, 1024, 1024), (128, 256, 64)])
 def test_gemm_residual_inplace(cuda, lib, M, N, K):
     g = torch.Generator().manual_seed(2)

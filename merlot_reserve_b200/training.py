@@ -381,7 +381,6 @@ class PretrainStep:
             gm["g_scales"] = g16[n:n + 3]
             return loss, info
         self._update_temperatures(g16[n:n + 3].float().cpu().numpy(), opt, world)
-        self.step_count += 1
         return loss, info
 
     # --------------------------------------------------------------------------------------------

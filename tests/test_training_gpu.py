@@ -1,9 +1,16 @@
 """Parity of the full pretraining forward + BACKWARD (merlot_reserve_b200.training.PretrainStep) against torch
 autograd over the CPU oracle's restatement of pretrain/pretrain_model.py (the reference differentiates the same
-forward with jax.value_and_grad, pretrain_model.py:306-321).  Tolerance: every parameter gradient (flax layout) has
-cosine >= 0.99 with the fp32 autograd gradient (>= 0.95 for the three `cls` vectors and their cls_proj, whose
-gradients are sums over all sequences of strongly cancelling bf16 rows) -- the kernels run in bf16 with fp32
-accumulation, the oracle in fp32.
+forward with jax.value_and_grad, pretrain_model.py:306-321; the oracle's forward is pinned to the reference-executed
+fixtures in tests/test_reference_goldens.py).
+
+Tolerance, PER TENSOR, measured instead of guessed: the oracle is differentiated twice, in fp32 and with its
+bf16_graph() emulation of the reference's own bf16 module dtype (pretrain_model.py:323-324 casts the parameters to
+bf16 before value_and_grad).  floor_k = cosine(grad_bf16graph_k, grad_fp32_k) is how far the REFERENCE'S OWN bf16
+execution moves gradient k; the kernels (bf16 storage, fp32 accumulation) must stay within twice that distance:
+    1 - cosine(kernel_k, fp32_k)  <=  max(2 (1 - floor_k), 0.005).
+On this configuration the floors are >= 0.995 for 121 of 129 tensors, 0.96-0.99 for the `cls` vectors and cls_proj
+(sums over all sequences of strongly cancelling rows), and ~0 for the two attention-pool key biases, whose true
+gradient is zero (softmax is shift invariant): those are checked by magnitude, not direction.
 
 The gradient comparison uses the weight_scale = 4 parameters.  With the init-scale synthetic weights the model's
 outputs are almost identical for every sample (pairwise cosine > 0.9999), so the contrastive gradient is a
@@ -43,16 +50,23 @@ def test_pretrain_step_gradients_match_oracle_autograd(cuda, scale):
     params = synthetic_params(cfg, seed=0, weight_scale=scale)
     batch = synthetic_pretrain_batch(cfg, 2, seed=3)
 
-    tparams = _torch_tree(params)
-    preds = OracleMerlotReserve(cfg, tparams).pretrain_forward(batch)
-    ref_loss, _ = contrastive_loss(preds)
-    ref_loss.backward()
-    ref = {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in _flatten(tparams).items()}
+    def oracle_grads(bf16):
+        from oracle.reserve_oracle import bf16_graph
+        import contextlib
+        tparams = _torch_tree(params)
+        with (bf16_graph() if bf16 else contextlib.nullcontext()):
+            preds = OracleMerlotReserve(cfg, tparams).pretrain_forward(batch)
+            loss_, _ = contrastive_loss(preds)
+            loss_.backward()
+        return loss_.detach(), {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in _flatten(tparams).items()}
+
+    ref_loss, ref = oracle_grads(False)
+    _, ref16 = oracle_grads(True)
 
     step = PretrainStep(cfg, params)
     loss, info, grads = step.loss_and_grads(batch)
     got = step.grads_to_flax(grads)
-    assert abs(float(loss) - float(ref_loss.detach())) <= 0.1
+    assert abs(float(loss) - float(ref_loss)) <= 0.1
     assert set(got) == set(ref), sorted(set(ref) ^ set(got))
     worst = []
     for name, r in ref.items():
@@ -63,16 +77,25 @@ def test_pretrain_step_gradients_match_oracle_autograd(cuda, scale):
         if mag < 1e-7:
             assert g.abs().max().item() < 1e-4, name
             continue
-        cos = torch.nn.functional.cosine_similarity(g.flatten(), r.flatten(), dim=0).item()
-        err = (g - r).abs().max().item() / mag
-        worst.append((cos, err, name))
+        cosf = lambda a, b: torch.nn.functional.cosine_similarity(a.flatten().double(), b.flatten().double(), dim=0).item()
+        cos, floor = cosf(g, r), cosf(ref16[name].float(), r)
+        worst.append((cos, floor, name, g.abs().max().item(), mag))
     worst.sort()
     if scale == 1.0:
         assert all(np.isfinite(v).all() for v in got.values())
         return
-    loose = lambda n: n.endswith("transformer/cls") or "/cls_proj/" in n
-    bad = [(c, e, n) for c, e, n in worst if c < (0.95 if loose(n) else 0.99)]
-    assert not bad, f"{len(bad)} of {len(worst)} gradients off; worst: {bad[:8]}"
+    bad = []
+    for cos, floor, name, gmag, mag in worst:
+        if floor < 0.9:
+            # the reference's own bf16 execution returns noise here (true gradient ~ 0): bound the magnitude instead,
+            # by the noise the bf16 oracle itself shows
+            noise = ref16[name].float().abs().max().item()
+            if gmag > 4.0 * max(noise, mag) + 1e-6:
+                bad.append((cos, floor, name, "magnitude", gmag, noise))
+        elif 1.0 - cos > max(2.0 * (1.0 - floor), 0.005):
+            bad.append((cos, floor, name))
+    assert not bad, f"{len(bad)} of {len(worst)} gradients outside twice the bf16 noise floor: {bad[:8]}"
+    assert sum(1 for c, f, *_ in worst if c >= 0.995) >= 110, "most gradients are expected at cosine >= 0.995"
 
 
 def test_adamw_kernel(cuda, lib):

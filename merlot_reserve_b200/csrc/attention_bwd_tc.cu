@@ -8,10 +8,15 @@
 //   dP^T = V_j dO_i^T           SS  A = V_j                                B = dO_i              -> TMEM [128,256)
 //   P^T  = exp2(S^T log2e - lse_i) under the mask;   dS^T = P^T (dP^T - D_i)       (compute warps, thread = key)
 //   dV_j += P^T  dO_i           TS  A = P^T  bf16 in TMEM [256,320)        B = dO_i  MN-major    -> TMEM [320,384)
-//   dK_j += dS^T Q_i            TS  A = dS^T bf16 in TMEM [128,192)        B = Q_i   MN-major    -> TMEM [384,448)
-//   dQ_i  = dS   K_j            SS  A = dS^T staged in smem = MN-major A   B = K_j   MN-major    -> TMEM [448,512)
+//   dK_j += dS^T Q_i            SS  A = dS^T staged in smem, K-major       B = Q_i   MN-major    -> TMEM [384,448)
+//   dQ_i  = dS   K_j            SS  A = the same smem tile as MN-major A   B = K_j   MN-major    -> TMEM [448,512)
 //
-// dS^T overwrites the dP^T columns it was computed from; dQ_i leaves through fp32 vector reductions
+// Pipelining (r02): S^T and dP^T are produced in two 64-query HALVES (N = 64 MMAs) with their own barriers.  As soon
+// as the compute warps have pulled half h of block i into registers they release it, and the issuer immediately
+// computes half h of block i+1 into the same columns -- under the compute of the other half -- so the compute warps
+// never wait for a cold S^T / dP^T and the dV / dK / dQ MMAs of block i run under the compute of block i+1.  dS^T
+// therefore no longer lives in TMEM (it used to overwrite dP^T, which is being refilled now): both of its consumers
+// read the double-buffered shared-memory copy.  dQ_i leaves through fp32 vector reductions
 // (red.global.add.v4.f32) into the workspace that mr_attention_bwd converts to bf16 afterwards, because the key
 // blocks of a sequence live in different CTAs.  lse_i and D_i are per-COLUMN quantities in this orientation: the
 // drain warpgroup turns them (and the query side of the mask) into five broadcast vectors per query block:
@@ -20,8 +25,8 @@
 //   nb = 1 for valid queries (mask applies) / 0 for invalid ones;  ktag = the key's group id, 1e38 if the key is
 //   padding (never equals a query tag; 1e38 x 1e30 overflows to -inf, and x 0 stays 0 for the uniform rows).
 //
-//   warps 0-3   compute: thread = key.  tcgen05.ld S^T / dP^T in halves of 64 queries, P^T and dS^T back to TMEM as
-//               bf16 pairs, dS^T also to shared memory (two [128 keys x 64 queries] slabs, 128B swizzle)
+//   warps 0-3   compute: thread = key.  tcgen05.ld S^T / dP^T in halves of 64 queries, P^T back to TMEM as bf16 pairs,
+//               dS^T to shared memory (per block two [128 keys x 64 queries] slabs, 128B swizzle, double buffered)
 //   warps 4-7   drain: per-query vectors of block i+1, then dQ_i TMEM -> red.global.add.v4.f32
 //   warp 8      TMA producer: K_j, V_j once; (Q_i, dO_i) double buffered
 //   warp 9      MMA issuer (one thread)
@@ -45,10 +50,10 @@ constexpr float kKeyMasked = 1.0e38f;
 constexpr int kOffK = 0;
 constexpr int kOffV = kTileBytes;
 constexpr int kOffQ = 2 * kTileBytes;                 // [2 buffers]{Q_i, dO_i}
-constexpr int kOffDS = kOffQ + 4 * kTileBytes;        // [2 slabs][128 keys][64 queries] bf16
-constexpr int kOffStat = kOffDS + 2 * kTileBytes;     // [2 buffers][5][128] float: a, cb, nb, qtag, D
+constexpr int kOffDS = kOffQ + 4 * kTileBytes;        // [2 buffers][2 slabs][128 keys][64 queries] bf16
+constexpr int kOffStat = kOffDS + 4 * kTileBytes;     // [2 buffers][5][128] float: a, cb, nb, qtag, D
 constexpr int kOffBar = kOffStat + 2 * 5 * kB * 4;
-constexpr int kNumBars = 16;
+constexpr int kNumBars = 20;
 constexpr int kSmemBwdTc = kOffBar + kNumBars * 8 + 16 + 1024;
 
 struct BwdParams {
@@ -76,12 +81,15 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
   uint64_t* q_full = bars + 1;      // [2]
   uint64_t* q_empty = bars + 3;     // [2]
   uint64_t* stat_full = bars + 5;   // [2]
-  uint64_t* s_full = bars + 7;
-  uint64_t* p_full = bars + 8;
-  uint64_t* ds_full = bars + 9;
-  uint64_t* dq_full = bars + 10;
-  uint64_t* dq_free = bars + 11;
-  uint64_t* kv_done = bars + 12;
+  uint64_t* s_full = bars + 7;      // [2] per 64-query half: S^T and dP^T of the half are in TMEM
+  uint64_t* p_full = bars + 9;
+  uint64_t* ds_full = bars + 10;
+  uint64_t* dq_full = bars + 11;
+  uint64_t* dq_free = bars + 12;
+  uint64_t* kv_done = bars + 13;
+  uint64_t* sdp_free = bars + 14;   // [2] per half: the compute warps hold S^T / dP^T of the half in registers
+  uint64_t* pv_done = bars + 16;    // dV MMAs of a block have read P^T
+  uint64_t* ds_free = bars + 17;    // [2] per dS buffer: dK / dQ MMAs of the block have read it
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kNumBars);
 
   const int warp_idx = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -101,12 +109,17 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
       mbar_init(&q_empty[i], 1);
       mbar_init(&stat_full[i], 4);
     }
-    mbar_init(s_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&sdp_free[i], 4);
+      mbar_init(&ds_free[i], 1);
+    }
     mbar_init(p_full, 4);
     mbar_init(ds_full, 4);
     mbar_init(dq_full, 1);
     mbar_init(dq_free, 4);
     mbar_init(kv_done, 1);
+    mbar_init(pv_done, 1);
     fence_mbar_init();
   }
   if (warp_idx == kMmaWarp) {
@@ -135,47 +148,70 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
       }
     } else if (warp_idx == kMmaWarp && lane == 0) {
       // ===================== MMA issuer =====================
-      constexpr uint32_t idesc_s = umma_idesc_bf16_f32(kB, kB);                              // K-major A and B
+      constexpr uint32_t idesc_s = umma_idesc_bf16_f32(kB, 64);                              // K-major A and B, one half
       constexpr uint32_t idesc_kv = umma_idesc_bf16_f32(kB, kD) | (1u << 16);                // B MN-major
       constexpr uint32_t idesc_dq = umma_idesc_bf16_f32(kB, kD) | (1u << 15) | (1u << 16);   // A and B MN-major
       // MN-major A of two 64-query slabs 16 KB apart: the descriptor's leading-byte-offset (16-byte units)
       constexpr uint64_t kLboSlab = static_cast<uint64_t>((2 * 8192 >> 4) - 1) << 16;
       const uint64_t kdesc = umma_desc_k_sw128(smem_u32(smem + kOffK));
       const uint64_t vdesc = umma_desc_k_sw128(smem_u32(smem + kOffV));
-      const uint64_t dsdesc = umma_desc_k_sw128(smem_u32(smem + kOffDS)) + kLboSlab;
       const uint32_t tS = tmem_base + kColS, tDP = tmem_base + kColDP, tP = tmem_base + kColP;
       const uint32_t tDV = tmem_base + kColDV, tDK = tmem_base + kColDK, tDQ = tmem_base + kColDQ;
+      // S^T / dP^T of one 64-query half of block i: B = rows [64 h, 64 h + 64) of the Q_i / dO_i tiles (8 KB further)
+      auto issue_half = [&](int i, int h) {
+        const int buf = i & 1;
+        const uint64_t qd = umma_desc_k_sw128(smem_u32(smem + kOffQ + buf * 2 * kTileBytes + h * 8192));
+        const uint64_t dod = umma_desc_k_sw128(smem_u32(smem + kOffQ + buf * 2 * kTileBytes + kTileBytes + h * 8192));
+#pragma unroll
+        for (int k = 0; k < kD / 16; ++k) umma_bf16_ss(tS + 64 * h, kdesc + 2 * k, qd + 2 * k, idesc_s, k != 0 ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < kD / 16; ++k) umma_bf16_ss(tDP + 64 * h, vdesc + 2 * k, dod + 2 * k, idesc_s, k != 0 ? 1u : 0u);
+        umma_commit(&s_full[h]);
+      };
       mbar_wait(kv_full, 0);
+      mbar_wait(&q_full[0], 0);
+      tc_fence_after();
+      issue_half(0, 0);
+      issue_half(0, 1);
       for (int i = 0; i < nqb; ++i) {
         const int buf = i & 1;
         const uint64_t qdesc = umma_desc_k_sw128(smem_u32(smem + kOffQ + buf * 2 * kTileBytes));
         const uint64_t dodesc = umma_desc_k_sw128(smem_u32(smem + kOffQ + buf * 2 * kTileBytes + kTileBytes));
-        mbar_wait(&q_full[buf], (i >> 1) & 1);
-        if (i > 0) mbar_wait(ds_full, (i - 1) & 1);      // the compute warps are done with block i-1's S^T / dP^T
-        tc_fence_after();
+        const uint32_t ds_addr = smem_u32(smem + kOffDS + buf * 2 * kTileBytes);
+        if (i + 1 < nqb) {
+          // halves of block i+1 go into the columns the compute warps have just emptied (arrival order: half 0, half 1)
+          mbar_wait(&q_full[buf ^ 1], ((i + 1) >> 1) & 1);
 #pragma unroll
-        for (int k = 0; k < kD / 16; ++k) umma_bf16_ss(tS, kdesc + 2 * k, qdesc + 2 * k, idesc_s, k != 0 ? 1u : 0u);
-#pragma unroll
-        for (int k = 0; k < kD / 16; ++k) umma_bf16_ss(tDP, vdesc + 2 * k, dodesc + 2 * k, idesc_s, k != 0 ? 1u : 0u);
-        umma_commit(s_full);
+          for (int h = 0; h < 2; ++h) {
+            mbar_wait(&sdp_free[h], i & 1);
+            tc_fence_after();
+            issue_half(i + 1, h);
+          }
+        }
         // dV_j += P^T dO_i : K = 128 queries in 8 steps; P advances 8 TMEM columns, dO 16 rows (2 KB) per step
         mbar_wait(p_full, i & 1);
         tc_fence_after();
 #pragma unroll
         for (int kk = 0; kk < kB / 16; ++kk)
           umma_bf16_ts(tDV, tP + 8 * kk, dodesc + 128 * kk, idesc_kv, (i | kk) != 0 ? 1u : 0u);
-        // dK_j += dS^T Q_i ; dQ_i = dS K_j
+        umma_commit(pv_done);
+        // dK_j += dS^T Q_i (A = the smem dS^T tile read K-major: 16 queries = 32 B along the 128 B row, second
+        // 64-query slab 16 KB further); dQ_i = dS K_j (the same tile read MN-major)
         mbar_wait(ds_full, i & 1);
         if (i > 0) mbar_wait(dq_free, (i - 1) & 1);       // the drain warps have read dQ_{i-1}
         tc_fence_after();
 #pragma unroll
-        for (int kk = 0; kk < kB / 16; ++kk)
-          umma_bf16_ts(tDK, tDP + 8 * kk, qdesc + 128 * kk, idesc_kv, (i | kk) != 0 ? 1u : 0u);
+        for (int kk = 0; kk < kB / 16; ++kk) {
+          const uint64_t ad = umma_desc_k_sw128(ds_addr + (kk >> 2) * kTileBytes) + 2 * (kk & 3);
+          umma_bf16_ss(tDK, ad, qdesc + 128 * kk, idesc_kv, (i | kk) != 0 ? 1u : 0u);
+        }
+        const uint64_t dsdesc = umma_desc_k_sw128(ds_addr) + kLboSlab;
 #pragma unroll
         for (int kk = 0; kk < kB / 16; ++kk)
           umma_bf16_ss(tDQ, dsdesc + 128 * kk, kdesc + 128 * kk, idesc_dq, kk != 0 ? 1u : 0u);
         umma_commit(dq_full);
         umma_commit(&q_empty[buf]);
+        umma_commit(&ds_free[buf]);
       }
       umma_commit(kv_done);
     }
@@ -239,19 +275,25 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
       const bool v = p.valid ? p.valid[seq_base + key] != 0 : true;
       if (v) ktag = p.group ? static_cast<float>(p.group[seq_base + key]) : 0.f;
     }
-    uint8_t* sDS = smem + kOffDS;
     for (int i = 0; i < nqb; ++i) {
       const float* st = sStat + (i & 1) * 5 * kB;
+      uint8_t* sDS = smem + kOffDS + (i & 1) * 2 * kTileBytes;
       mbar_wait(&stat_full[i & 1], (i >> 1) & 1);
-      mbar_wait(s_full, i & 1);
-      tc_fence_after();
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
         float pr[64];
+        uint32_t dpv[64];
+        mbar_wait(&s_full[half], i & 1);
+        tc_fence_after();
         {
           uint32_t v[64];
           tmem_ld_32x64(lane_addr + kColS + 64 * half, v);
+          tmem_ld_32x64(lane_addr + kColDP + 64 * half, dpv);
           tmem_ld_wait();
+          // both are in registers: the issuer may refill these columns with block i+1
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&sdp_free[half]);
 #pragma unroll
           for (int c4 = 0; c4 < 16; ++c4) {
             const int c = 64 * half + 4 * c4;
@@ -270,30 +312,30 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
           }
         }
         uint32_t pk[32], dk[32];
-        {
-          uint32_t v[64];
-          tmem_ld_32x64(lane_addr + kColDP + 64 * half, v);
-          tmem_ld_wait();
 #pragma unroll
-          for (int c4 = 0; c4 < 16; ++c4) {
-            const float4 d4 = *reinterpret_cast<const float4*>(st + 4 * kB + 64 * half + 4 * c4);
-            const float dd[4] = {d4.x, d4.y, d4.z, d4.w};
-            float ds[4];
+        for (int c4 = 0; c4 < 16; ++c4) {
+          const float4 d4 = *reinterpret_cast<const float4*>(st + 4 * kB + 64 * half + 4 * c4);
+          const float dd[4] = {d4.x, d4.y, d4.z, d4.w};
+          float ds[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float pe = pr[4 * c4 + e];
-              // an exactly-zero probability must give an exactly-zero gradient even where dP is garbage (rows past T)
-              ds[e] = pe == 0.f ? 0.f : pe * (__uint_as_float(v[4 * c4 + e]) - dd[e]);
-            }
-            pk[2 * c4] = pack_bf16(pr[4 * c4], pr[4 * c4 + 1]);
-            pk[2 * c4 + 1] = pack_bf16(pr[4 * c4 + 2], pr[4 * c4 + 3]);
-            dk[2 * c4] = pack_bf16(ds[0], ds[1]);
-            dk[2 * c4 + 1] = pack_bf16(ds[2], ds[3]);
+          for (int e = 0; e < 4; ++e) {
+            const float pe = pr[4 * c4 + e];
+            // an exactly-zero probability must give an exactly-zero gradient even where dP is garbage (rows past T)
+            ds[e] = pe == 0.f ? 0.f : pe * (__uint_as_float(dpv[4 * c4 + e]) - dd[e]);
           }
+          pk[2 * c4] = pack_bf16(pr[4 * c4], pr[4 * c4 + 1]);
+          pk[2 * c4 + 1] = pack_bf16(pr[4 * c4 + 2], pr[4 * c4 + 3]);
+          dk[2 * c4] = pack_bf16(ds[0], ds[1]);
+          dk[2 * c4 + 1] = pack_bf16(ds[2], ds[3]);
         }
-        // bf16 pairs: 64 queries = 32 TMEM columns.  dS^T lands on dP^T columns that were loaded already.
+        if (half == 0) {
+          // P^T of block i-1 has been read by its dV MMAs; the dS buffer by the dK / dQ MMAs of block i-2
+          if (i > 0) mbar_wait(pv_done, (i - 1) & 1);
+          if (i > 1) mbar_wait(&ds_free[i & 1], ((i - 2) >> 1) & 1);
+          tc_fence_after();
+        }
+        // bf16 pairs: 64 queries = 32 TMEM columns
         tmem_st_32x32(lane_addr + kColP + 32 * half, pk);
-        tmem_st_32x32(lane_addr + kColDP + 32 * half, dk);
         // dS^T to shared memory: slab `half`, row = key, 8 chunks of 8 queries, 128B swizzle
 #pragma unroll
         for (int ch = 0; ch < 8; ++ch)
@@ -307,7 +349,6 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
         }
       }
       fence_proxy_async_smem();
-      tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(ds_full);
     }

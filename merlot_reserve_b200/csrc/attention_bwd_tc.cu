@@ -25,11 +25,13 @@
 //   nb = 1 for valid queries (mask applies) / 0 for invalid ones;  ktag = the key's group id, 1e38 if the key is
 //   padding (never equals a query tag; 1e38 x 1e30 overflows to -inf, and x 0 stays 0 for the uniform rows).
 //
-//   warps 0-3   compute: thread = key.  tcgen05.ld S^T / dP^T in halves of 64 queries, P^T back to TMEM as bf16 pairs,
-//               dS^T to shared memory (per block two [128 keys x 64 queries] slabs, 128B swizzle, double buffered)
+//   warps 0-3   compute, half 0 (queries 0..63 of every block): thread = key.  tcgen05.ld S^T / dP^T of the half, P^T
+//   warps 12-15 compute, half 1 (queries 64..127)           back to TMEM as bf16 pairs, dS^T to shared memory (per
+//               block two [128 keys x 64 queries] slabs, 128B swizzle, double buffered).  Two warpgroups = two warps
+//               per SM sub-partition: one warp alone cannot keep a sub-partition's issue slots busy.
 //   warps 4-7   drain: per-query vectors of block i+1, then dQ_i TMEM -> red.global.add.v4.f32
 //   warp 8      TMA producer: K_j, V_j once; (Q_i, dO_i) double buffered
-//   warp 9      MMA issuer (one thread)
+//   warp 9      MMA issuer (one thread); warps 10-11 idle
 // The mask semantics are those of attention_bwd.cu (key validity, video_src groups, uniform rows).
 #include "common.cuh"
 #include "ptx.cuh"
@@ -39,7 +41,7 @@ namespace {
 
 constexpr int kB = 128;                    // keys per CTA, queries per step
 constexpr int kD = 64;
-constexpr int kThreadsTc = 384;
+constexpr int kThreadsTc = 512;
 constexpr int kProducerWarp = 8, kMmaWarp = 9;
 constexpr int kTileBytes = kB * kD * 2;    // 16 KB
 constexpr uint32_t kColS = 0, kColDP = 128, kColP = 256, kColDV = 320, kColDK = 384, kColDQ = 448;
@@ -114,8 +116,8 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
       mbar_init(&sdp_free[i], 4);
       mbar_init(&ds_free[i], 1);
     }
-    mbar_init(p_full, 4);
-    mbar_init(ds_full, 4);
+    mbar_init(p_full, 8);
+    mbar_init(ds_full, 8);
     mbar_init(dq_full, 1);
     mbar_init(dq_free, 4);
     mbar_init(kv_done, 1);
@@ -131,7 +133,7 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp_idx >= 8) {
+  if (warp_idx >= 8 && warp_idx < 12) {
     setmaxnreg_dec<64>();
     if (warp_idx == kProducerWarp && lane == 0) {
       // ===================== TMA producer =====================
@@ -215,8 +217,8 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
       }
       umma_commit(kv_done);
     }
-  } else if (warp_idx >= 4) {
-    setmaxnreg_dec<104>();
+  } else if (warp_idx >= 4 && warp_idx < 8) {
+    setmaxnreg_dec<96>();
     // ===================== drain warpgroup: per-query vectors, dQ_i -> global =====================
     const int quarter = warp_idx & 3;
     const int row = quarter * 32 + lane;                 // query within the block = TMEM lane of dQ
@@ -263,8 +265,9 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
       }
     }
   } else {
-    setmaxnreg_inc<232>();
-    // ===================== compute warpgroup: thread = key =====================
+    setmaxnreg_inc<176>();
+    // ===================== compute warpgroups: thread = key, one 64-query half each =====================
+    const int half = warp_idx >= 12 ? 1 : 0;
     const int quarter = warp_idx & 3;
     const int row = quarter * 32 + lane;
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
@@ -279,8 +282,7 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
       const float* st = sStat + (i & 1) * 5 * kB;
       uint8_t* sDS = smem + kOffDS + (i & 1) * 2 * kTileBytes;
       mbar_wait(&stat_full[i & 1], (i >> 1) & 1);
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
+      {
         float pr[64];
         uint32_t dpv[64];
         mbar_wait(&s_full[half], i & 1);
@@ -311,42 +313,41 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
             }
           }
         }
-        uint32_t pk[32], dk[32];
+        // P^T of block i-1 has been read by its dV MMAs; the dS buffer by the dK / dQ MMAs of block i-2
+        if (i > 0) mbar_wait(pv_done, (i - 1) & 1);
+        if (i > 1) mbar_wait(&ds_free[i & 1], ((i - 2) >> 1) & 1);
+        tc_fence_after();
+        uint32_t pk[32];
 #pragma unroll
-        for (int c4 = 0; c4 < 16; ++c4) {
-          const float4 d4 = *reinterpret_cast<const float4*>(st + 4 * kB + 64 * half + 4 * c4);
-          const float dd[4] = {d4.x, d4.y, d4.z, d4.w};
-          float ds[4];
+        for (int ch = 0; ch < 8; ++ch) {          // 8 queries at a time: dS^T goes straight to shared memory
+          uint32_t dk[4];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float pe = pr[4 * c4 + e];
-            // an exactly-zero probability must give an exactly-zero gradient even where dP is garbage (rows past T)
-            ds[e] = pe == 0.f ? 0.f : pe * (__uint_as_float(dpv[4 * c4 + e]) - dd[e]);
+          for (int g = 0; g < 2; ++g) {
+            const int c4 = 2 * ch + g;
+            const float4 d4 = *reinterpret_cast<const float4*>(st + 4 * kB + 64 * half + 4 * c4);
+            const float dd[4] = {d4.x, d4.y, d4.z, d4.w};
+            float ds[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float pe = pr[4 * c4 + e];
+              // an exactly-zero probability must give an exactly-zero gradient even where dP is garbage (rows past T)
+              ds[e] = pe == 0.f ? 0.f : pe * (__uint_as_float(dpv[4 * c4 + e]) - dd[e]);
+            }
+            pk[2 * c4] = pack_bf16(pr[4 * c4], pr[4 * c4 + 1]);
+            pk[2 * c4 + 1] = pack_bf16(pr[4 * c4 + 2], pr[4 * c4 + 3]);
+            dk[2 * g] = pack_bf16(ds[0], ds[1]);
+            dk[2 * g + 1] = pack_bf16(ds[2], ds[3]);
           }
-          pk[2 * c4] = pack_bf16(pr[4 * c4], pr[4 * c4 + 1]);
-          pk[2 * c4 + 1] = pack_bf16(pr[4 * c4 + 2], pr[4 * c4 + 3]);
-          dk[2 * c4] = pack_bf16(ds[0], ds[1]);
-          dk[2 * c4 + 1] = pack_bf16(ds[2], ds[3]);
-        }
-        if (half == 0) {
-          // P^T of block i-1 has been read by its dV MMAs; the dS buffer by the dK / dQ MMAs of block i-2
-          if (i > 0) mbar_wait(pv_done, (i - 1) & 1);
-          if (i > 1) mbar_wait(&ds_free[i & 1], ((i - 2) >> 1) & 1);
-          tc_fence_after();
+          // slab `half`, row = key, chunk of 8 queries, 128B swizzle
+          *reinterpret_cast<uint4*>(sDS + half * kTileBytes + row * 128 + ((ch ^ (row & 7)) << 4)) =
+              make_uint4(dk[0], dk[1], dk[2], dk[3]);
         }
         // bf16 pairs: 64 queries = 32 TMEM columns
         tmem_st_32x32(lane_addr + kColP + 32 * half, pk);
-        // dS^T to shared memory: slab `half`, row = key, 8 chunks of 8 queries, 128B swizzle
-#pragma unroll
-        for (int ch = 0; ch < 8; ++ch)
-          *reinterpret_cast<uint4*>(sDS + half * kTileBytes + row * 128 + ((ch ^ (row & 7)) << 4)) =
-              make_uint4(dk[4 * ch], dk[4 * ch + 1], dk[4 * ch + 2], dk[4 * ch + 3]);
-        if (half == 1) {
-          tmem_st_wait();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(p_full);
-        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_full);
       }
       fence_proxy_async_smem();
       __syncwarp();
@@ -355,8 +356,8 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
     // ---- dK_j, dV_j: TMEM -> bf16 -> the k / v columns of d(qkv) ----
     mbar_wait(kv_done, 0);
     tc_fence_after();
-#pragma unroll
-    for (int which = 0; which < 2; ++which) {
+    {
+      const int which = half;      // warpgroup 0 writes dK_j, warpgroup 1 writes dV_j
       uint32_t v[kD];
       tmem_ld_32x64(lane_addr + (which == 0 ? kColDK : kColDV), v);
       tmem_ld_wait();

@@ -62,6 +62,21 @@ bool make_tmap_3d(CUtensorMap* m, const void* base, int cols, int rows, int batc
   return r == CUDA_SUCCESS;
 }
 
+// fp32 flavour of make_tmap_3d (the dQ accumulator of the attention backward: TMA reduce-add boxes of 32 floats x box_rows)
+bool make_tmap_3d_f32(CUtensorMap* m, const void* base, int cols, int rows, int batch, int64_t ld, int64_t batch_stride,
+                      int box_rows, int box_cols) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return false;
+  cuuint64_t dims[3] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(batch)};
+  cuuint64_t strides[2] = {static_cast<cuuint64_t>(ld) * 4, static_cast<cuuint64_t>(batch_stride) * 4};
+  cuuint32_t box[3] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows), 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
 }  // namespace mr
 
 extern "C" int32_t mr_abi_version(void) { return 16; }

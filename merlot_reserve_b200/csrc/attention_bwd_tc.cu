@@ -54,7 +54,8 @@ constexpr int kOffV = kTileBytes;
 constexpr int kOffQ = 2 * kTileBytes;                 // [2 buffers]{Q_i, dO_i}
 constexpr int kOffDS = kOffQ + 4 * kTileBytes;        // [2 buffers][2 slabs][128 keys][64 queries] bf16
 constexpr int kOffStat = kOffDS + 4 * kTileBytes;     // [2 buffers][5][128] float: a, cb, nb, qtag, D
-constexpr int kOffBar = kOffStat + 2 * 5 * kB * 4;
+constexpr int kOffDQ = kOffStat + 2 * 5 * kB * 4;      // [4 drain warps][2 boxes][32 rows x 32 floats] fp32, 128B swizzle
+constexpr int kOffBar = kOffDQ + 4 * 2 * 4096;
 constexpr int kNumBars = 20;
 constexpr int kSmemBwdTc = kOffBar + kNumBars * 8 + 16 + 1024;
 
@@ -74,7 +75,7 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
 
 __global__ void __launch_bounds__(kThreadsTc, 1)
 attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_do,
-                        const BwdParams p) {
+                        const __grid_constant__ CUtensorMap tmap_dq, const BwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   float* sStat = reinterpret_cast<float*>(smem + kOffStat);
@@ -105,6 +106,7 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
   if (warp_idx == kProducerWarp && lane == 0) {
     tma_prefetch_desc(&tmap_qkv);
     tma_prefetch_desc(&tmap_do);
+    tma_prefetch_desc(&tmap_dq);
     mbar_init(kv_full, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&q_full[i], 1);
@@ -142,11 +144,12 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
       tma_load_2d(&tmap_qkv, kv_full, smem + kOffV, 2 * p.H + h * kD, seq_base + k0, kEvictLast);
       for (int i = 0; i < nqb; ++i) {
         const int buf = i & 1;
+        const int qi = (i + jb) % nqb;     // rotated visiting order (see the drain warps)
         mbar_wait(&q_empty[buf], ((i >> 1) & 1) ^ 1);
         mbar_arrive_expect_tx(&q_full[buf], 2 * kTileBytes);
         uint8_t* dst = smem + kOffQ + buf * 2 * kTileBytes;
-        tma_load_2d(&tmap_qkv, &q_full[buf], dst, h * kD, seq_base + i * kB, kEvictNormal);
-        tma_load_2d(&tmap_do, &q_full[buf], dst + kTileBytes, h * kD, seq_base + i * kB, kEvictNormal);
+        tma_load_2d(&tmap_qkv, &q_full[buf], dst, h * kD, seq_base + qi * kB, kEvictNormal);
+        tma_load_2d(&tmap_do, &q_full[buf], dst + kTileBytes, h * kD, seq_base + qi * kB, kEvictNormal);
       }
     } else if (warp_idx == kMmaWarp && lane == 0) {
       // ===================== MMA issuer =====================
@@ -224,8 +227,10 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
     const int row = quarter * 32 + lane;                 // query within the block = TMEM lane of dQ
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
     const size_t stat_base = (static_cast<size_t>(b) * p.nh + h) * p.T;
+    // The CTA of key block j visits the query blocks in the rotated order j, j+1, ... (mod nqb): at any moment the
+    // CTAs of one (sequence, head) then add into DIFFERENT rows of dQ -- the L2 atomic unit serialises per address.
     auto load_stats = [&](int i) {
-      const int q = i * kB + row;
+      const int q = ((i + jb) % nqb) * kB + row;
       float a = 0.f, cb = -INFINITY, nb = 0.f, qtag = 0.f, dsum = 0.f;
       if (q < p.T) {
         const bool v = p.valid ? p.valid[seq_base + q] != 0 : true;
@@ -255,15 +260,27 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(dq_free);
-      const int q = i * kB + row;
-      if (q < p.T) {
-        float* dst = p.dq_acc + (static_cast<size_t>(seq_base) + q) * p.H + h * kD;
+      // dQ_i leaves as two TMA reduce-add boxes per warp (32 rows x 32 floats, 128B swizzle): per-lane REDG of the
+      // 8 192 floats of a block kept the SM's load/store unit busy for longer than the block's whole compute phase
+      const int q0 = ((i + jb) % nqb) * kB + quarter * 32;
+      uint8_t* stage = smem + kOffDQ + quarter * 2 * 4096;
+      if (lane == 0) tma_store_wait_read<0>();           // the previous block's boxes have been read
+      __syncwarp();
 #pragma unroll
-        for (int c = 0; c < kD; c += 4)
-          red_add_v4(dst + c, __uint_as_float(v[c]), __uint_as_float(v[c + 1]), __uint_as_float(v[c + 2]),
-                     __uint_as_float(v[c + 3]));
+      for (int c = 0; c < 16; ++c)
+        *reinterpret_cast<uint4*>(stage + (c >> 3) * 4096 + lane * 128 + (((c & 7) ^ (lane & 7)) << 4)) =
+            make_uint4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        if (q0 < p.T) {                                  // rows past T are clipped by the [B, T, H] tensor map
+          tma_reduce_add_3d(&tmap_dq, stage, h * kD, q0, b);
+          tma_reduce_add_3d(&tmap_dq, stage + 4096, h * kD + 32, q0, b);
+        }
+        tma_store_commit();
       }
     }
+    if (lane == 0) tma_store_wait<0>();                  // the reductions are complete before the CTA retires
   } else {
     setmaxnreg_inc<176>();
     // ===================== compute warpgroups: thread = key, one 64-query half each =====================
@@ -389,9 +406,10 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
 // Called by mr_attention_bwd (attention_bwd.cu) after the prep kernel (D = rowsum(dO . O)) and the dq_acc memset.
 int32_t launch_attention_bwd_tc(cudaStream_t stream, const bf16* qkv, const bf16* dout, const float* lse, const float* Dsum,
                                 const uint8_t* valid, const int32_t* group, bf16* dqkv, float* dq_acc, int B, int T, int H) {
-  CUtensorMap tm_qkv, tm_do;
+  CUtensorMap tm_qkv, tm_do, tm_dq;
   if (!make_tmap_2d(&tm_qkv, qkv, static_cast<int64_t>(B) * T, 3 * H, 3 * H, kB, kD)) return MR_ERR_DRIVER;
   if (!make_tmap_2d(&tm_do, dout, static_cast<int64_t>(B) * T, H, H, kB, kD)) return MR_ERR_DRIVER;
+  if (!make_tmap_3d_f32(&tm_dq, dq_acc, H, T, B, H, static_cast<int64_t>(T) * H, 32, 32)) return MR_ERR_DRIVER;
   BwdParams p{};
   p.lse = lse;
   p.Dsum = Dsum;
@@ -412,7 +430,7 @@ int32_t launch_attention_bwd_tc(cudaStream_t stream, const bf16* qkv, const bf16
     if (e != cudaSuccess) return cuda_status(e);
     attr_set = true;
   }
-  attention_bwd_tc_kernel<<<static_cast<unsigned>(blocks), kThreadsTc, kSmemBwdTc, stream>>>(tm_qkv, tm_do, p);
+  attention_bwd_tc_kernel<<<static_cast<unsigned>(blocks), kThreadsTc, kSmemBwdTc, stream>>>(tm_qkv, tm_do, tm_dq, p);
   return after_launch();
 }
 

@@ -42,6 +42,9 @@ bool make_tmap_2d(CUtensorMap* m, const void* base, int64_t rows, int cols, int6
 bool make_tmap_3d(CUtensorMap* m, const void* base, int cols, int rows, int batch, int64_t ld, int64_t batch_stride,
                   int box_rows, int box_cols);
 
+bool make_tmap_3d_f32(CUtensorMap* m, const void* base, int cols, int rows, int batch, int64_t ld, int64_t batch_stride,
+                      int box_rows, int box_cols);
+
 }  // namespace mr
 
 #define MR_REQUIRE(cond, code) \

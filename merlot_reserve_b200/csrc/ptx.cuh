@@ -112,6 +112,14 @@ __device__ __forceinline__ void tma_store_3d(const void* desc, const void* smem_
                : "memory");
 }
 
+// TMA reduce-add of a shared-memory box into global memory (element type and swizzle come from the tensor map)
+__device__ __forceinline__ void tma_reduce_add_3d(const void* desc, const void* smem_src, int32_t c0, int32_t c1, int32_t c2) {
+  asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
+               :
+               : "l"(reinterpret_cast<uint64_t>(desc)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 
 template <int N>

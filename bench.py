@@ -474,6 +474,11 @@ def run_b200(args):
     torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
     _lib.require_b200(local)
+    numa_cpus = None
+    if world > 1 and os.environ.get("MR_NUMA_BIND", "1") == "1":
+        # before any pinned allocation: staging buffers then live on the GPU's own NUMA node
+        from merlot_reserve_b200.numa import bind_to_gpu
+        numa_cpus = bind_to_gpu(local)
 
     w = build_workload(args, rank, dev)
     cfg, params = w["cfg"], w["params"]
@@ -593,6 +598,8 @@ def run_b200(args):
             "e2e": {"value": e2e_value, "unit": w_unit, "ms_per_step": e2e_ms, "h2d_bytes_per_step": w_h2d,
                     "d2h_bytes_per_step": w_d2h},
             "gpu_launches": int(launches),
+            "host_placement": (f"rank bound to the {len(numa_cpus)} CPUs local to its GPU (pinned buffers first-touch there)"
+                               if numa_cpus else "default (no NUMA binding)"),
             "roofline": roofline,
             "whole_step_tflops": whole, "whole_step_frac_of_sustained_peak": whole / peak,
             "kernels": kernels,

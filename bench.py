@@ -552,7 +552,8 @@ def run_b200(args):
         tj = json.loads(tf.read_text())
         traffic = tj.get("dram_bytes_per_launch_avg")
         traffic_note = ("dram__bytes_read+write per launch, mean of the four vision-layer GEMM launches "
-                        "(M = 246784: algorithmic 1.90 / 1.52 / 0.76 / 1.90 GB for down / qkv / out / up); " + tj.get("source", ""))
+                        "(M = 246784: algorithmic 1.90 / 1.52 / 0.76 / 1.90 GB for down / qkv / out / up); " + tj.get("source", "")
+                        + (f", commit {tj['commit']}" if tj.get("commit") else "") + " (tools/gemm_traffic.py)")
     roofline = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (all epilogue variants)", "achieved": achieved,
                 "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 "peak_source": f"{peaks['source']} sustained bf16 (kernel timed inside a long step)",

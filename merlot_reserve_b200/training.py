@@ -78,23 +78,38 @@ def _dgrad(dy: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
 
 def arena_layout(names: List[str], numel: Dict[str, int]) -> Tuple[Dict[str, int], int]:
     """Element offsets of the flat optimizer / gradient arenas: tensors in sorted-name order, 8-element (16-byte bf16)
-    alignment, and every top-level module ('audio_encoder', 'head', 'joint_transformer', ...) starting on a
-    1024-element boundary, so that the buckets of the overlapped gradient all-reduce are whole rows of the bf16
-    cast (rows of 1024) and never share a row with a module that is still differentiating.  -> (offsets, total)."""
+    alignment, and every top-level module ('audio_encoder', 'head', 'joint_transformer', ...) AND every transformer
+    layer ('.../layer_07') starting on a 1024-element boundary, so that the buckets of the overlapped gradient
+    all-reduce are whole rows of the bf16 cast (rows of 1024) and never share a row with a module or layer that is
+    still differentiating.  -> (offsets, total)."""
     assert list(names) == sorted(names)
-    offs, n, top = {}, 0, None
+    offs, n, group = {}, 0, None
     for name in names:
-        if name.split("/")[0] != top:
-            top = name.split("/")[0]
+        g = _bucket_group(name)
+        if g != group:
+            group = g
             n = (n + 1023) // 1024 * 1024
         offs[name] = n
         n += (numel[name] + 7) // 8 * 8
     return offs, (n + 1023) // 1024 * 1024
 
 
+def _bucket_group(name: str) -> str:
+    """Alignment group of a parameter: its transformer layer ('a/b/layer_07') if it has one, else its top-level module."""
+    parts = name.split("/")
+    for i, part in enumerate(parts):
+        if part.startswith("layer_"):
+            return "/".join(parts[:i + 1])
+    return parts[0]
+
+
 # The groups of top-level modules whose gradients become final together during `loss_and_grads`' backward pass, in
 # that order; train_step starts one asynchronous all-reduce per group (`on_ready`).
 ALLREDUCE_BUCKETS = (("head", "span_encoder", "joint_transformer", "token_encoder"), ("audio_encoder",), ("vision_encoder",))
+# The vision encoder is differentiated last, so its bucket would only start when the backward pass ends.  Its layers
+# are final one by one (11 -> 0): after the layers listed here an extra bucket with the finished upper layers starts,
+# so that only the last few layers' gradients (plus embedding / pool) are reduced behind the backward pass.
+VISION_LAYER_SPLITS = tuple(int(v) for v in os.environ.get("MR_VISION_BUCKET_SPLITS", "8,4").split(",") if v != "")
 
 
 class _Grads:
@@ -329,27 +344,40 @@ class PretrainStep:
 
         def flush(names, reduce_now):
             """Copy finished gradients into the arena, cast their 1024-element rows to bf16, start their all-reduce."""
-            names = [k for k in names if k not in done]
+            names = sorted((k for k in names if k not in done), key=lambda k: st["offs"][k])
             if not names:
                 return
             done.update(names)
-            lo = min(st["offs"][k] for k in names) // 1024
-            hi = -(-max(st["offs"][k] + grads_ref[k].numel() for k in names) // 1024)
             for k in names:
                 t = grads_ref[k]
                 g[st["offs"][k]:st["offs"][k] + t.numel()].copy_(t.reshape(-1))
-            L.cast_pad(g.view(-1, 1024)[lo:hi], hi - lo, 1024, 1024, out=st["g16"].view(-1, 1024)[lo:hi], sanitize=True)
-            if reduce_now:
-                self.last_bucket_bytes.append((hi - lo) * 2048)
-                if not _SKIP_GRAD_ALLREDUCE:
-                    pending.append(dist.all_reduce(st["g16"][lo * 1024:hi * 1024], group=group, async_op=True))
+            # maximal runs of whole 1024-element rows (a bucket that was split by layers leaves a hole in the middle)
+            runs, lo, hi = [], None, None
+            for k in names:
+                a = st["offs"][k] // 1024
+                b = -(-(st["offs"][k] + grads_ref[k].numel()) // 1024)
+                if lo is None:
+                    lo, hi = a, b
+                elif a <= hi:
+                    hi = max(hi, b)
+                else:
+                    runs.append((lo, hi))
+                    lo, hi = a, b
+            runs.append((lo, hi))
+            for lo, hi in runs:
+                L.cast_pad(g.view(-1, 1024)[lo:hi], hi - lo, 1024, 1024, out=st["g16"].view(-1, 1024)[lo:hi], sanitize=True)
+                if reduce_now:
+                    self.last_bucket_bytes.append((hi - lo) * 2048)
+                    if not _SKIP_GRAD_ALLREDUCE:
+                        pending.append(dist.all_reduce(st["g16"][lo * 1024:hi * 1024], group=group, async_op=True))
 
         overlap = world > 1 and _OVERLAP_ALLREDUCE
         grads_ref: Dict[str, torch.Tensor] = {}
 
-        def on_ready(grads_so_far, prefixes):
+        def on_ready(grads_so_far, prefixes, name_filter=None):
             grads_ref.update(grads_so_far)
-            flush([k for k in st["names"] if k.split("/")[0] in prefixes and k in grads_so_far], True)
+            flush([k for k in st["names"] if k.split("/")[0] in prefixes and k in grads_so_far
+                   and (name_filter is None or name_filter(k))], True)
 
         loss, info, grads = self.loss_and_grads(batch, group=group, on_ready=on_ready if overlap else None)
         grads_ref.update(grads)
@@ -406,7 +434,8 @@ class PretrainStep:
             x = xn
         return x, tape
 
-    def _enc_bwd(self, dx: torch.Tensor, tape, enc: _PackedEncoder, G: _Grads, prefix: str) -> torch.Tensor:
+    def _enc_bwd(self, dx: torch.Tensor, tape, enc: _PackedEncoder, G: _Grads, prefix: str, on_layer=None) -> torch.Tensor:
+        """on_layer(i): called when the gradients of layers i .. last are final (layer i has just been differentiated)."""
         H, B, T = enc.H, tape["B"], tape["T"]
         for i in reversed(range(len(enc.layers))):
             lw = enc.layers[i]
@@ -433,6 +462,8 @@ class PretrainStep:
             dx, dg, db = L.layernorm_bwd(dh1, x, lw["ln1"][0], dres=dxm)
             G.add(f"{p}/pre_attn_ln/scale", dg)
             G.add(f"{p}/pre_attn_ln/bias", db)
+            if on_layer is not None:
+                on_layer(i)
         dx0, dg, db = L.layernorm_bwd(dx, tape["x0"], enc.pre_ln[0])
         G.add(f"{prefix}/pre_ln/scale", dg)
         G.add(f"{prefix}/pre_ln/bias", db)
@@ -786,7 +817,12 @@ class PretrainStep:
         dxvf = self._pool_bwd(d_imgs_seq.view(-1, H).to(BF16), xvf, v_pool_saved, p.vis_pool, Bv, Tv, geom_v, G,
                               "vision_encoder/seq_attnpool")
         dxv_last = self._final_bwd(dxvf, d_vcls.to(BF16), xv_last, v_cls_rows, p.vis, Bv, Tv, G, "vision_encoder/transformer")
-        dxv0 = self._enc_bwd(dxv_last, tape_v, p.vis, G, "vision_encoder/transformer")
+        def vision_layers_done(i):
+            if on_ready is not None and i in VISION_LAYER_SPLITS and i > 0:
+                upper = tuple(f"vision_encoder/transformer/layer_{j:02d}/" for j in range(i, len(p.vis.layers)))
+                on_ready(G.g, ALLREDUCE_BUCKETS[2], name_filter=lambda k: k.startswith(upper))
+
+        dxv0 = self._enc_bwd(dxv_last, tape_v, p.vis, G, "vision_encoder/transformer", on_layer=vision_layers_done)
         self._embed_rows_bwd(dxv0, av, Bv, Tv, G, "vision_encoder")
         if on_ready is not None:
             on_ready(G.g, ALLREDUCE_BUCKETS[2])

@@ -77,6 +77,7 @@ def _train_worker(rank, world, port, q):
     from merlot_reserve_b200 import training
     from merlot_reserve_b200.synthetic import synthetic_params, synthetic_pretrain_batch, tiny_config
     cfg = tiny_config()
+    training.VISION_LAYER_SPLITS = (1,)      # tiny config: 2 vision layers; exercise the split vision bucket
     batch = synthetic_pretrain_batch(cfg, 2, seed=30 + rank)
     opt = {"learning_rate": 2e-4, "num_train_steps": 100, "num_warmup_steps": 0, "weight_decay_rate": 0.1, "beta_2": 0.98,
            "eps": 1e-6, "final_lr_scale": 1.0}

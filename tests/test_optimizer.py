@@ -234,3 +234,15 @@ def test_gradient_arena_layout_keeps_allreduce_buckets_apart():
         rows.append((lo, hi))
     rows.sort()
     assert all(a[1] <= b[0] for a, b in zip(rows, rows[1:])), "buckets share no row of the cast"
+    # transformer layers start on rows of their own too: a bucket can be split between layers (VISION_LAYER_SPLITS)
+    names = sorted([f"vision_encoder/transformer/layer_{i:02d}/p{j}" for i in range(4) for j in range(3)] +
+                   ["vision_encoder/embedding/kernel", "vision_encoder/transformer/pre_ln/scale"])
+    numel = {k: int(rng.integers(1, 3000)) for k in names}
+    offs, _ = arena_layout(names, numel)
+    for i in range(4):
+        first = f"vision_encoder/transformer/layer_{i:02d}/p0"
+        assert offs[first] % 1024 == 0
+    assert offs["vision_encoder/transformer/pre_ln/scale"] % 1024 == 0
+    upper = [k for k in names if "/layer_02/" in k or "/layer_03/" in k]
+    lo, hi = min(offs[k] for k in upper), max(offs[k] + numel[k] for k in upper)
+    assert [k for k in names if lo <= offs[k] < -(-hi // 1024) * 1024] == upper

@@ -424,7 +424,9 @@ _WS_CACHE = {}
 
 
 def workspace(nbytes: int, device) -> torch.Tensor:
-    """A per-device scratch buffer that only grows (composite entries: the caller owns the workspace)."""
+    """A per-device scratch buffer that only grows (composite entries: the caller owns the workspace).  It is shared by
+    every composite call of this process on that device, i.e. it assumes ONE compute stream per device (the facade's
+    convention); callers that run composites on several streams at once pass their own `ws=` to `composite`."""
     key = torch.device(device).index
     buf = _WS_CACHE.get(key)
     if buf is None or buf.numel() < nbytes:

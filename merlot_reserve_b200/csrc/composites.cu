@@ -424,7 +424,8 @@ extern "C" int32_t mr_joint_encode(mr_stream_t stream, const MrJointDesc* d, con
   if (d->B == 0) return MR_OK;
   MR_REQUIRE(in[0] && out[0] && d->tok_emb && enc_ok(d->enc, false), MR_ERR_NULL_POINTER);
   MR_REQUIRE(!d->head || (d->head_w && d->head_b), MR_ERR_NULL_POINTER);
-  MR_REQUIRE(d->n_vis == 0 || in[4] || true, MR_ERR_NULL_POINTER);
+  MR_REQUIRE(d->n_vis == 0 || in[4], MR_ERR_NULL_POINTER);                  // vision rows announced but not given
+  MR_REQUIRE(!(in[2] && d->n_aud > 0) || in[3], MR_ERR_NULL_POINTER);        // audio pointers without audio spans
   return joint_run(stream, d, in[0], in[1], in[2], in[3], in[4], in[5], in[6], out[0], workspace, workspace_bytes);
 }
 

@@ -51,7 +51,7 @@ namespace mr {
 namespace {
 
 constexpr int kQ = 128;
-constexpr int kKV = 128;
+constexpr int kKVMax = 128;                // keys per block: template parameter kKV = 128, or 96 when that pads T less
 constexpr int kD = 64;
 constexpr int kStagesKV = 3;
 constexpr int kTcThreads = 512;            // 8 softmax warps + 4 epilogue warps + {producer, 2 MMA issuers, 1 idle}
@@ -68,8 +68,8 @@ constexpr float kRescaleThreshold = 8.0f;  // log2 units
 constexpr int kOffQ = 0;                                        // [2 item buffers][2 tiles]
 constexpr int kOffKV = 4 * kTileBytes;                          // [kStagesKV][K, V]
 constexpr int kOffO = kOffKV + kStagesKV * 2 * kTileBytes;      // [2 tiles][4 epilogue warps][32 rows x 128 B]
-constexpr int kOffInfo = kOffO + 2 * kTileBytes;                // [8 softmax warps][kKV] {int info, float bias_v, float bias_e}
-constexpr int kOffLM = kOffInfo + 8 * 3 * kKV * 4;              // [2 item parity][2 tiles][128 rows] float2 (l, m)
+constexpr int kOffInfo = kOffO + 2 * kTileBytes;                // [8 softmax warps][kKVMax] {int info, float bias_v, float bias_e}
+constexpr int kOffLM = kOffInfo + 8 * 3 * kKVMax * 4;           // [2 item parity][2 tiles][128 rows] float2 (l, m)
 constexpr int kOffBar = kOffLM + 2 * 2 * kQ * 8;
 constexpr int kNumBars = 4 + 2 * kStagesKV + 14;
 constexpr int kSmemBytes = kOffBar + kNumBars * 8 + 16 + 1024;   // + tmem slot
@@ -120,10 +120,15 @@ struct ItemWalker {
   }
 };
 
-template <bool kMasked>
+// kKV = keys per block.  128 normally; 96 when ceil(T / 96) * 96 is at least 10 % below ceil(T / 128) * 128 (e.g. the
+// multiple-choice joint sequences, T = 144 + 144 = 288 = 3 x 96: a 128-key tail block would spend a quarter of the
+// kernel's exponentials on padding).  `tmap_kv` is the qkv map with a box of kKV rows.
+template <bool kMasked, int kKV>
 __global__ void __launch_bounds__(kTcThreads, 1)
-attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_out,
-                    const AttnParams p) {
+attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_kv,
+                    const __grid_constant__ CUtensorMap tmap_out, const AttnParams p) {
+  static_assert(kKV == 128 || kKV == 96, "key block of 128 or 96");
+  constexpr int kKvBytes = kKV * kD * 2;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem + kOffQ;
@@ -148,6 +153,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
 
   if (warp_idx == kProducerWarp && lane == 0) {
     tma_prefetch_desc(&tmap_qkv);
+    tma_prefetch_desc(&tmap_kv);
     tma_prefetch_desc(&tmap_out);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&q_full[i], 1);
@@ -196,10 +202,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
         for (int j = 0; j < p.nkb; ++j, ++n_kv) {
           const int s = n_kv % kStagesKV;
           mbar_wait(&kv_empty[s], ((n_kv / kStagesKV) & 1) ^ 1);
-          mbar_arrive_expect_tx(&kv_full[s], 2 * kTileBytes);
+          mbar_arrive_expect_tx(&kv_full[s], 2 * kKvBytes);
           uint8_t* dst = sKV + s * 2 * kTileBytes;
-          tma_load_2d(&tmap_qkv, &kv_full[s], dst, p.H + it.h * kD, seq_base + j * kKV, kEvictLast);
-          tma_load_2d(&tmap_qkv, &kv_full[s], dst + kTileBytes, 2 * p.H + it.h * kD, seq_base + j * kKV, kEvictLast);
+          tma_load_2d(&tmap_kv, &kv_full[s], dst, p.H + it.h * kD, seq_base + j * kKV, kEvictLast);
+          tma_load_2d(&tmap_kv, &kv_full[s], dst + kTileBytes, 2 * p.H + it.h * kD, seq_base + j * kKV, kEvictLast);
         }
       }
     }
@@ -343,9 +349,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
     const int row = quarter * 32 + lane;
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
     const uint32_t colS = kColS + wg * 128, colP = kColP + wg * 64, colO = kColO + wg * 64;
-    int* myInfo = reinterpret_cast<int*>(smem + kOffInfo) + warp_idx * 3 * kKV;   // per warp: no cross-warp barrier
-    float* myBiasV = reinterpret_cast<float*>(myInfo + kKV);                       // 0 / -inf: key valid and in range
-    float* myBiasE = myBiasV + kKV;                                                // 0 / -inf: key in range
+    int* myInfo = reinterpret_cast<int*>(smem + kOffInfo) + warp_idx * 3 * kKVMax;   // per warp: no cross-warp barrier
+    float* myBiasV = reinterpret_cast<float*>(myInfo + kKVMax);                       // 0 / -inf: key valid and in range
+    float* myBiasE = myBiasV + kKVMax;                                                // 0 / -inf: key in range
     uint32_t n_blk = 0;    // key blocks processed so far by this tile (phase of s_full / p_full / pv_done)
     uint32_t n_item = 0;   // items of this CTA so far (parity of the (l, m) hand-over buffer)
     int n_pair = 0;        // two-tile items so far
@@ -365,7 +371,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
       Raw r;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const int kidx = min(j * kKV + lane * 4 + i, p.T - 1);
+        const int kidx = min(j * kKV + min(lane * 4 + i, kKV - 1), p.T - 1);
         r.v[i] = p.valid ? p.valid[seq_base + kidx] : uint8_t(1);
         r.g[i] = p.group ? p.group[seq_base + kidx] : 0;
       }
@@ -410,11 +416,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
             be[i] = in_range ? 0.f : -INFINITY;
           }
           if (j + 1 < p.nkb) raw_next = load_raw(seq_base, j + 1);
-          *reinterpret_cast<int4*>(myInfo + 4 * lane) = make_int4(info[0], info[1], info[2], info[3]);
-          *reinterpret_cast<float4*>(myBiasV + 4 * lane) = make_float4(bv[0], bv[1], bv[2], bv[3]);
-          *reinterpret_cast<float4*>(myBiasE + 4 * lane) = make_float4(be[0], be[1], be[2], be[3]);
+          const bool mine = lane * 4 < kKV;          // kKV = 96: lanes 24..31 hold no key of the block
+          if (mine) {
+            *reinterpret_cast<int4*>(myInfo + 4 * lane) = make_int4(info[0], info[1], info[2], info[3]);
+            *reinterpret_cast<float4*>(myBiasV + 4 * lane) = make_float4(bv[0], bv[1], bv[2], bv[3]);
+            *reinterpret_cast<float4*>(myBiasE + 4 * lane) = make_float4(be[0], be[1], be[2], be[3]);
+          }
           // fast path: every key in range and valid, and no group ids in play
-          const bool ok = p.group == nullptr && (info[0] | info[1] | info[2] | info[3]) == 0;
+          const bool ok = !mine || (p.group == nullptr && (info[0] | info[1] | info[2] | info[3]) == 0);
           fast = __all_sync(0xffffffffu, ok);      // also orders the smem writes above before the reads below
         }
         stamp(0);
@@ -424,7 +433,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
         float sc[kKV];
         {
           uint32_t v[kKV];
-          tmem_ld_32x128_wait(lane_addr + colS, v);
+          if constexpr (kKV == 128)
+            tmem_ld_32x128_wait(lane_addr + colS, v);
+          else
+            tmem_ld_32x96_wait(lane_addr + colS, v);
 #pragma unroll
           for (int i = 0; i < kKV; ++i) sc[i] = __uint_as_float(v[i]);
         }
@@ -482,7 +494,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
 #pragma unroll
         for (int c = 0; c < kKV / 8; ++c) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) mxp[i] = fmax3(mxp[i], sc[32 * i + 2 * c], sc[32 * i + 2 * c + 1]);
+          for (int i = 0; i < 4; ++i) mxp[i] = fmax3(mxp[i], sc[(kKV / 4) * i + 2 * c], sc[(kKV / 4) * i + 2 * c + 1]);
         }
         const float mx = fmaxf(fmaxf(mxp[0], mxp[1]), fmaxf(mxp[2], mxp[3]));
         const float mcand = (mx == -INFINITY) ? -INFINITY : mx * cs;
@@ -499,7 +511,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
         stamp(3);
         const float neg_m = -m2;
         float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
-        uint32_t pk[kKV / 2];
+        uint32_t pk[64];                       // kKV / 2 packed pairs; the tail of a 96-key block's store is never read
+        if constexpr (kKV < 128) {
+#pragma unroll
+          for (int c = kKV / 2; c < 64; ++c) pk[c] = 0u;
+        }
 #pragma unroll
         for (int c = 0; c < kKV; ++c) sc[c] = fmaf(sc[c], cs, neg_m);
         // Phase stagger (see the header): in the first key block of an item, tile 1 starts its ex2 phase only after
@@ -582,8 +598,16 @@ long long* g_attention_trace = nullptr;
 // Called by mr_attention_fwd (attention.cu) when T is long enough for 128-wide tiles.
 int32_t launch_attention_tc(cudaStream_t stream, const bf16* qkv, const uint8_t* valid, const int32_t* group,
                             bf16* out, float* lse, int B, int T, int H) {
-  CUtensorMap tm;
+  // key block: 96 where that pads the sequence at least 10 % less than 128 does (T = 288 -> 3 x 96 instead of 3 x 128)
+  const int pad128 = ceil_div(T, 128) * 128, pad96 = ceil_div(T, 96) * 96;
+  static const int kv_env = []() {
+    const char* e = getenv("MR_ATTN_KV");
+    return e ? atoi(e) : 0;
+  }();
+  const int kv = kv_env == 96 || kv_env == 128 ? kv_env : (pad96 * 10 <= pad128 * 9 ? 96 : 128);
+  CUtensorMap tm, tm_kv;
   if (!make_tmap_2d(&tm, qkv, static_cast<int64_t>(B) * T, 3 * H, 3 * H, 128, kD)) return MR_ERR_DRIVER;
+  if (!make_tmap_2d(&tm_kv, qkv, static_cast<int64_t>(B) * T, 3 * H, 3 * H, kv, kD)) return MR_ERR_DRIVER;
   CUtensorMap tm_out;   // [B, T, H]: a query tile that overhangs its sequence is clipped at T by the TMA store
   if (!make_tmap_3d(&tm_out, out, H, T, B, H, static_cast<int64_t>(T) * H, 32, kD)) return MR_ERR_DRIVER;
   AttnParams p{};
@@ -597,7 +621,7 @@ int32_t launch_attention_tc(cudaStream_t stream, const bf16* qkv, const uint8_t*
   p.nh = H / kD;
   p.nqb = ceil_div(T, kQ);
   p.npairs = ceil_div(p.nqb, 2);
-  p.nkb = ceil_div(T, kKV);
+  p.nkb = ceil_div(T, kv);
   const int64_t items = static_cast<int64_t>(B) * p.nh * p.npairs;
   if (items >= (int64_t(1) << 31)) return MR_ERR_BAD_SHAPE;
   p.num_items = static_cast<int>(items);
@@ -613,14 +637,16 @@ int32_t launch_attention_tc(cudaStream_t stream, const bf16* qkv, const uint8_t*
   if (sms <= 0) return MR_ERR_UNSUPPORTED_ARCH;
   const int grid = p.num_items < sms ? p.num_items : sms;
   const bool masked = valid != nullptr || group != nullptr;
-  auto kern = masked ? attention_tc_kernel<true> : attention_tc_kernel<false>;
-  static bool attr_set[2] = {false, false};
-  if (!attr_set[masked]) {
+  auto kern = kv == 96 ? (masked ? attention_tc_kernel<true, 96> : attention_tc_kernel<false, 96>)
+                       : (masked ? attention_tc_kernel<true, 128> : attention_tc_kernel<false, 128>);
+  static bool attr_set[4] = {false, false, false, false};
+  const int slot = (kv == 96 ? 2 : 0) + (masked ? 1 : 0);
+  if (!attr_set[slot]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     if (e != cudaSuccess) return cuda_status(e);
-    attr_set[masked] = true;
+    attr_set[slot] = true;
   }
-  kern<<<grid, kTcThreads, kSmemBytes, stream>>>(tm, tm_out, p);
+  kern<<<grid, kTcThreads, kSmemBytes, stream>>>(tm, tm_kv, tm_out, p);
   return after_launch();
 }
 

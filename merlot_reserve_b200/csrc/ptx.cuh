@@ -308,6 +308,23 @@ __device__ __forceinline__ void tmem_ld_32x128_wait(uint32_t taddr, uint32_t (&v
       : "memory");
 }
 
+// 96 consecutive columns (three x32 loads, one wait): the 96-key S tile of the attention kernel
+__device__ __forceinline__ void tmem_ld_32x96_wait(uint32_t taddr, uint32_t (&v)[96]) {
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 a1, a2;\n\t"
+      "add.u32 a1, %96, 32;\n\t"
+      "add.u32 a2, %96, 64;\n\t"
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%96];\n\t"
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, %48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [a1];\n\t"
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%64, %65, %66, %67, %68, %69, %70, %71, %72, %73, %74, %75, %76, %77, %78, %79, %80, %81, %82, %83, %84, %85, %86, %87, %88, %89, %90, %91, %92, %93, %94, %95}, [a2];\n\t"
+      "tcgen05.wait::ld.sync.aligned;\n\t"
+      "}\n"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31]), "=r"(v[32]), "=r"(v[33]), "=r"(v[34]), "=r"(v[35]), "=r"(v[36]), "=r"(v[37]), "=r"(v[38]), "=r"(v[39]), "=r"(v[40]), "=r"(v[41]), "=r"(v[42]), "=r"(v[43]), "=r"(v[44]), "=r"(v[45]), "=r"(v[46]), "=r"(v[47]), "=r"(v[48]), "=r"(v[49]), "=r"(v[50]), "=r"(v[51]), "=r"(v[52]), "=r"(v[53]), "=r"(v[54]), "=r"(v[55]), "=r"(v[56]), "=r"(v[57]), "=r"(v[58]), "=r"(v[59]), "=r"(v[60]), "=r"(v[61]), "=r"(v[62]), "=r"(v[63]), "=r"(v[64]), "=r"(v[65]), "=r"(v[66]), "=r"(v[67]), "=r"(v[68]), "=r"(v[69]), "=r"(v[70]), "=r"(v[71]), "=r"(v[72]), "=r"(v[73]), "=r"(v[74]), "=r"(v[75]), "=r"(v[76]), "=r"(v[77]), "=r"(v[78]), "=r"(v[79]), "=r"(v[80]), "=r"(v[81]), "=r"(v[82]), "=r"(v[83]), "=r"(v[84]), "=r"(v[85]), "=r"(v[86]), "=r"(v[87]), "=r"(v[88]), "=r"(v[89]), "=r"(v[90]), "=r"(v[91]), "=r"(v[92]), "=r"(v[93]), "=r"(v[94]), "=r"(v[95])
+      : "r"(taddr)
+      : "memory");
+}
+
 // 64 consecutive columns in ONE instruction (a single TMEM round trip instead of 2)
 __device__ __forceinline__ void tmem_ld_32x64(uint32_t taddr, uint32_t (&v)[64]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x64.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, %48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];"

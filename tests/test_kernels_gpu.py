@@ -214,6 +214,30 @@ def test_attention_joint_style_mask(cuda, lib, B, T, H, L):
         _close(lib.attention(qkv, B, T, H, valid=valid.view(-1), algo=algo), ref, 2e-2, 2e-2, f"joint mask algo {algo}")
 
 
+@pytest.mark.parametrize("B,T,H", [(40, 288, 256), (3, 96, 128), (5, 170, 128), (2, 192, 768), (130, 288, 1024)])
+def test_attention_96_key_blocks(cuda, lib, B, T, H):
+    """Sequences that 96-key blocks pad at least 10 % less than 128-key blocks (the multiple-choice joint length
+    T = 144 + 144 = 288 = 3 x 96) run the kKV = 96 instantiation: unmasked, key validity (joint layout with invalid query
+    rows), validity + group ids, more items than SMs, and the ring wrap-around."""
+    g = torch.Generator().manual_seed(T + B)
+    qkv = _bf(torch.randn(B * T, 3 * H, generator=g)).to(cuda)
+    qkv.view(B * T, 3, H)[:, 0] *= 0.35
+    _close(lib.attention(qkv, B, T, H, algo=2), _attn_ref(qkv, B, T, H), 2e-2, 2e-2, f"96-key unmasked T={T}")
+    valid = torch.ones(B, T, dtype=torch.uint8)
+    valid[:, 13:T // 2] = (torch.rand(B, T // 2 - 13, generator=g) > 0.6).to(torch.uint8)
+    valid[0, 5:T // 2] = 0
+    group = (torch.arange(T)[None] >= (T * 2) // 3).to(torch.int32).expand(B, T).contiguous()
+    valid, group = valid.to(cuda).contiguous(), group.to(cuda).contiguous()
+    _close(lib.attention(qkv, B, T, H, valid=valid.view(-1), algo=2), _attn_ref(qkv, B, T, H, valid), 2e-2, 2e-2, "96-key valid")
+    _close(lib.attention(qkv, B, T, H, valid=valid.view(-1), group=group.view(-1), algo=2),
+           _attn_ref(qkv, B, T, H, valid, group), 2e-2, 2e-2, "96-key valid+group")
+    lse = torch.empty(B, H // 64, T, device=cuda)
+    lib.attention(qkv, B, T, H, algo=2, lse=lse)
+    q, k, _ = qkv.float().view(B, T, 3, H // 64, 64).unbind(2)
+    ref_lse = torch.logsumexp(torch.einsum("bqhd,bkhd->bhqk", q, k), -1)
+    _close(lse, ref_lse, 2e-2, 2e-2, "96-key lse")
+
+
 def test_attention_many_items_persistent(cuda, lib):
     """More work items than SMs, odd and even numbers of query tiles: exercises the persistent loop, the Q double
     buffer, the K/V ring wrap-around and pairs whose second tile is absent."""

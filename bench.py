@@ -378,9 +378,12 @@ def train_step_leg(cfg, params, rank, world, dev, timed, steps=8, warmup=3, b=8)
         rs_in = torch.zeros((world, rows, H), dtype=torch.float32, device=dev)
         rs_out = torch.empty((rows, H), dtype=torch.float32, device=dev)
         alone = {}
-        for name, fn in (("allgather_ms", lambda: dist.all_gather_into_tensor(dst, src)),
-                         ("reduce_scatter_ms", lambda: dist.reduce_scatter_tensor(rs_out, rs_in)),
-                         ("allreduce_standalone_ms", lambda: dist.all_reduce(g16))):
+        comm = stepper.communicator()        # the library's collective entries on its own ncclComm_t (None: torch.distributed)
+        out["collectives"] = ("mr_all_gather / mr_reduce_scatter / mr_all_reduce (C ABI, ncclComm_t from mr_nccl_comm_init)"
+                              if comm is not None else "torch.distributed (NCCL)")
+        for name, fn in (("allgather_ms", (lambda: comm.all_gather(src, dst)) if comm else (lambda: dist.all_gather_into_tensor(dst, src))),
+                         ("reduce_scatter_ms", (lambda: comm.reduce_scatter(rs_in, rs_out)) if comm else (lambda: dist.reduce_scatter_tensor(rs_out, rs_in))),
+                         ("allreduce_standalone_ms", (lambda: comm.all_reduce(g16)) if comm else (lambda: dist.all_reduce(g16)))):
             for _ in range(3):
                 fn()
             alone[name] = timed(fn, 10) / 10

@@ -35,7 +35,9 @@ typedef enum MrStatus {
   MR_ERR_NULL_POINTER = -4,
   MR_ERR_WORKSPACE = -5,
   MR_ERR_DRIVER = -6,
-  MR_ERR_CUDA_BASE = -1000
+  MR_ERR_NCCL_UNAVAILABLE = -7, /* libnccl.so.2 could not be loaded (collective entries only) */
+  MR_ERR_CUDA_BASE = -1000,     /* MR_ERR_CUDA_BASE - cudaError_t */
+  MR_ERR_NCCL_BASE = -2000      /* MR_ERR_NCCL_BASE - ncclResult_t */
 } MrStatus;
 
 /* Library / device probe.  Returns MR_OK when device `device` is compute capability 10.x. */
@@ -559,6 +561,42 @@ size_t mr_contrastive_lse_fwd_workspace_bytes(const MrContrastiveDesc* d);
  * ------------------------------------------------------------------------------------------ */
 int32_t mr_contrastive_reduce(mr_stream_t stream, const MrContrastiveDesc* d, const void* const* in,
                               void* const* out, void* workspace, size_t workspace_bytes);
+
+/* ------------------------------------------------------------------------------------------
+ * Collective entries (csrc/collectives.cu): the exchange steps of the data-parallel pretraining step
+ * (SURVEY.md 8e), enqueued on `stream` through a communicator the CALLER owns.  `comm` is an ncclComm_t (from the
+ * host's own ncclCommInitRank, or from mr_nccl_comm_init below); the library resolves libnccl.so.2 with dlopen at the
+ * first call and prefers the copy already loaded in the process.  One host thread per GPU; like every other entry
+ * these only enqueue (stream-ordered, CUDA-graph capturable) and never synchronise.
+ *   mr_all_gather      in[0] send [count]           -> out[0] recv [world * count], rank-major: replaces
+ *                      jax.lax.all_gather(y, 'batch') of the packed contrastive targets (pretrain_model.py:288-290)
+ *   mr_reduce_scatter  in[0] send [world * count]   -> out[0] recv [count]: the transpose of that all-gather in the
+ *                      backward pass (dL/dy_all returned to the ranks that own the rows)
+ *   mr_all_reduce      in[0] send [count]           -> out[0] recv [count] (may alias): jax.lax.pmean of the bf16
+ *                      gradients and of the metrics (pretrain_model.py:329,333); `average` = 0 leaves the sum
+ * ------------------------------------------------------------------------------------------ */
+enum { MR_DT_BF16 = 0, MR_DT_F32 = 1 };
+typedef struct MrCollectiveDesc {
+  void* comm;      /* ncclComm_t */
+  int64_t count;   /* elements: sent per rank (all_gather), received per rank (reduce_scatter), total (all_reduce) */
+  int32_t dtype;   /* MR_DT_BF16 | MR_DT_F32 */
+  int32_t average; /* reduce_scatter / all_reduce: 1 = mean over ranks (ncclAvg), 0 = sum */
+} MrCollectiveDesc;
+int32_t mr_all_gather(mr_stream_t stream, const MrCollectiveDesc* d, const void* const* in, void* const* out,
+                      void* workspace, size_t workspace_bytes);
+int32_t mr_reduce_scatter(mr_stream_t stream, const MrCollectiveDesc* d, const void* const* in, void* const* out,
+                          void* workspace, size_t workspace_bytes);
+int32_t mr_all_reduce(mr_stream_t stream, const MrCollectiveDesc* d, const void* const* in, void* const* out,
+                      void* workspace, size_t workspace_bytes);
+/* Communicator helpers for hosts without their own NCCL binding (thin wrappers over ncclGetUniqueId /
+ * ncclCommInitRank / ncclCommDestroy / ncclCommCount + ncclCommUserRank).  mr_nccl_comm_init is collective over the
+ * `world` ranks and must be called with the device of this rank current; id128 = the 128 bytes rank 0 obtained
+ * from mr_nccl_unique_id and shared out of band.  mr_nccl_version returns ncclGetVersion's code (0 = unavailable). */
+int32_t mr_nccl_version(void);
+int32_t mr_nccl_unique_id(void* id128);
+int32_t mr_nccl_comm_init(void** comm, int32_t world, int32_t rank, const void* id128);
+int32_t mr_nccl_comm_destroy(void* comm);
+int32_t mr_nccl_comm_info(void* comm, int32_t* world, int32_t* rank);
 
 /* ------------------------------------------------------------------------------------------
  * Backward entries (pretrain_model.py:306-340 differentiates the whole forward with jax.value_and_grad; these are

@@ -177,6 +177,10 @@ class RowDotDesc(C.Structure):
     _fields_ = [("rows", C.c_int32), ("H", C.c_int32)]
 
 
+class CollectiveDesc(C.Structure):
+    _fields_ = [("comm", C.c_void_p), ("count", C.c_int64), ("dtype", C.c_int32), ("average", C.c_int32)]
+
+
 # every compute entry point has the same signature
 ENTRY_POINTS = {
     "mr_gemm_epilogue": GemmDesc,
@@ -216,6 +220,9 @@ ENTRY_POINTS = {
     "mr_add": ElementwiseDesc,
     "mr_adamw": AdamWDesc,
     "mr_adamw_multi": AdamWMultiDesc,
+    "mr_all_gather": CollectiveDesc,
+    "mr_reduce_scatter": CollectiveDesc,
+    "mr_all_reduce": CollectiveDesc,
 }
 WORKSPACE_FNS = {
     "mr_gemm_epilogue_workspace_bytes": GemmDesc,
@@ -235,13 +242,14 @@ WORKSPACE_FNS = {
     "mr_contrastive_lse_fwd_workspace_bytes": ContrastiveDesc,
 }
 MISC_FNS = ["mr_check_device", "mr_abi_version", "mr_status_string", "mr_launch_count", "mr_debug_attention_trace",
-            "mr_logmel_tables_bytes"]
+            "mr_logmel_tables_bytes", "mr_nccl_version", "mr_nccl_unique_id", "mr_nccl_comm_init", "mr_nccl_comm_destroy",
+            "mr_nccl_comm_info"]
 
 # MrGemmDesc.algo_pair used when a call does not say: 0 auto, 1 force CTA pairs, 2 never (MR_GEMM_PAIR overrides)
 import os as _os
 GEMM_PAIR_DEFAULT = int(_os.environ.get("MR_GEMM_PAIR", "0"))
 
-ABI_VERSION = 16  # must equal mr_abi_version() of the loaded library (struct layouts above)
+ABI_VERSION = 17  # must equal mr_abi_version() of the loaded library (struct layouts above)
 
 _lib = None
 
@@ -271,6 +279,15 @@ def load() -> C.CDLL:
     lib.mr_launch_count.restype = C.c_int64
     lib.mr_logmel_tables_bytes.restype = C.c_size_t
     lib.mr_logmel_tables_bytes.argtypes = []
+    lib.mr_nccl_version.restype = C.c_int32
+    lib.mr_nccl_unique_id.restype = C.c_int32
+    lib.mr_nccl_unique_id.argtypes = [C.c_void_p]
+    lib.mr_nccl_comm_init.restype = C.c_int32
+    lib.mr_nccl_comm_init.argtypes = [C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.c_void_p]
+    lib.mr_nccl_comm_destroy.restype = C.c_int32
+    lib.mr_nccl_comm_destroy.argtypes = [C.c_void_p]
+    lib.mr_nccl_comm_info.restype = C.c_int32
+    lib.mr_nccl_comm_info.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     if lib.mr_abi_version() != ABI_VERSION:
         raise MrError(f"{_LIB_PATH} has ABI version {lib.mr_abi_version()}, this package needs {ABI_VERSION}: "
                       f"rebuild with `python -m merlot_reserve_b200.build --force`")
@@ -830,3 +847,80 @@ def adamw_multi(g, table, p, m, v, *, lr, beta1=0.9, beta2=0.98, eps=1e-8, weigh
                        weight_decay=weight_decay, grad_scale=grad_scale, bias_corr1=bias_corr1, bias_corr2=bias_corr2,
                        one_minus_beta1=1.0 - beta1, one_minus_beta2=1.0 - beta2, hyper_from_device=int(hyper_dev is not None))
     _call("mr_adamw_multi", d, [g, table, hyper_dev], [p, m, v])
+
+
+# ------------------------------------------------------------------------------------------------
+# collective entries (csrc/collectives.cu): ncclComm_t by handle, enqueued on the current stream
+# ------------------------------------------------------------------------------------------------
+_DT = {torch.bfloat16: 0, torch.float32: 1}
+
+
+def _check(st: int, what: str) -> None:
+    if st != 0:
+        raise MrError(f"{what} failed ({st}): {load().mr_status_string(st).decode()}")
+
+
+def nccl_version() -> int:
+    """ncclGetVersion() of the libnccl the library resolved (0 when none could be loaded)."""
+    return int(load().mr_nccl_version())
+
+
+class Communicator:
+    """An ncclComm_t owned by this process and used only through the library's collective entries.  Created
+    collectively by `Communicator.from_group(group)`: rank 0 draws the unique id, the torch.distributed group (any
+    backend) carries its 128 bytes to the other ranks, every rank calls ncclCommInitRank.  `Communicator(handle, ...)`
+    wraps a communicator made elsewhere (e.g. ProcessGroupNCCL._comm_ptr())."""
+
+    def __init__(self, handle: int, world: int, rank: int, owned: bool = False):
+        self.handle, self.world, self.rank, self._owned = handle, world, rank, owned
+
+    @classmethod
+    def from_group(cls, group=None) -> "Communicator":
+        import torch.distributed as dist
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        lib = load()
+        ident = C.create_string_buffer(128)
+        if rank == 0:
+            _check(lib.mr_nccl_unique_id(ident), "mr_nccl_unique_id")
+        box = [bytes(ident.raw)]
+        dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        ident = C.create_string_buffer(box[0], 128)
+        comm = C.c_void_p()
+        _check(lib.mr_nccl_comm_init(C.byref(comm), world, rank, ident), "mr_nccl_comm_init")
+        w, r = C.c_int32(), C.c_int32()
+        _check(lib.mr_nccl_comm_info(comm, C.byref(w), C.byref(r)), "mr_nccl_comm_info")
+        assert (w.value, r.value) == (world, rank)
+        return cls(comm.value, world, rank, owned=True)
+
+    def destroy(self) -> None:
+        if self._owned and self.handle:
+            _check(load().mr_nccl_comm_destroy(C.c_void_p(self.handle)), "mr_nccl_comm_destroy")
+        self.handle = None
+
+    def _desc(self, t: torch.Tensor, count: int, average: bool) -> CollectiveDesc:
+        if t.dtype not in _DT:
+            raise MrError(f"collectives move bf16 or f32, not {t.dtype}")
+        if self.handle is None:
+            raise MrError("communicator was destroyed")
+        return CollectiveDesc(comm=self.handle, count=count, dtype=_DT[t.dtype], average=int(average))
+
+    def all_gather(self, send: torch.Tensor, recv: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """recv [world, *send.shape]: rank-major, i.e. jax.lax.all_gather(send, 'batch') (pretrain_model.py:290)."""
+        if recv is None:
+            recv = torch.empty((self.world,) + tuple(send.shape), dtype=send.dtype, device=send.device)
+        assert recv.numel() == self.world * send.numel() and recv.dtype == send.dtype
+        _call("mr_all_gather", self._desc(send, send.numel(), False), [send], [recv])
+        return recv
+
+    def reduce_scatter(self, send: torch.Tensor, recv: Optional[torch.Tensor] = None, average: bool = False) -> torch.Tensor:
+        """send [world, ...] rank-major; recv [...] = sum over ranks of block `rank`."""
+        if recv is None:
+            recv = torch.empty(tuple(send.shape[1:]), dtype=send.dtype, device=send.device)
+        assert send.numel() == self.world * recv.numel() and recv.dtype == send.dtype
+        _call("mr_reduce_scatter", self._desc(send, recv.numel(), average), [send], [recv])
+        return recv
+
+    def all_reduce(self, buf: torch.Tensor, average: bool = False) -> torch.Tensor:
+        """In place sum (or mean = jax.lax.pmean, pretrain_model.py:329,333) over the ranks."""
+        _call("mr_all_reduce", self._desc(buf, buf.numel(), average), [buf], [buf])
+        return buf

@@ -77,9 +77,11 @@ bool make_tmap_3d_f32(CUtensorMap* m, const void* base, int cols, int rows, int 
   return r == CUDA_SUCCESS;
 }
 
+const char* nccl_error_string(int code);  // collectives.cu
+
 }  // namespace mr
 
-extern "C" int32_t mr_abi_version(void) { return 16; }
+extern "C" int32_t mr_abi_version(void) { return 17; }
 
 extern "C" int64_t mr_launch_count(void) { return mr::g_launches.load(std::memory_order_relaxed); }
 
@@ -101,8 +103,10 @@ extern "C" const char* mr_status_string(int32_t status) {
     case MR_ERR_NULL_POINTER: return "required pointer is NULL";
     case MR_ERR_WORKSPACE: return "workspace too small";
     case MR_ERR_DRIVER: return "CUDA driver call failed (tensor map encode)";
+    case MR_ERR_NCCL_UNAVAILABLE: return "libnccl.so.2 could not be loaded";
     default: break;
   }
+  if (status <= MR_ERR_NCCL_BASE) return mr::nccl_error_string(MR_ERR_NCCL_BASE - status);
   if (status <= MR_ERR_CUDA_BASE) return cudaGetErrorString(static_cast<cudaError_t>(MR_ERR_CUDA_BASE - status));
   return "unknown status";
 }

@@ -205,11 +205,12 @@ class MerlotReservePretrainer(MerlotReserve):
 _PAIRS = (("x", "y"), ("y", "x"))
 
 
-def gather_contrastive_targets(preds: Dict[str, Dict[str, torch.Tensor]], group=None):
+def gather_contrastive_targets(preds: Dict[str, Dict[str, torch.Tensor]], group=None, comm=None):
     """The exchange step of the path (pretrain_model.py:284-290): for every (head, direction) pair the targets
     `y` (+ `y_extra`) of ALL data-parallel ranks.  The six target sets of a rank are packed into one buffer and
     moved by ONE all-gather; each returned `y_all` is rank-major, i.e. `all_gather(y, 'batch').reshape(-1, H)`.
-    Pure tensor plumbing (works on any device / backend).  Returns [(head, x, pos_off, y_all)]: row i of x has its
+    Pure tensor plumbing (works on any device / backend); with `comm` (an _lib.Communicator) the all-gather is the
+    library's own mr_all_gather on the current stream instead of torch.distributed's.  Returns [(head, x, pos_off, y_all)]: row i of x has its
     positive at row pos_off + i of y_all (this rank's block of the rank-major gather)."""
     import torch.distributed as dist
     world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
@@ -224,7 +225,10 @@ def gather_contrastive_targets(preds: Dict[str, Dict[str, torch.Tensor]], group=
     packed = torch.cat([y for _, _, _, ys in jobs for y in ys], 0).contiguous()
     if world > 1:
         gathered = torch.empty((world, packed.shape[0], H), dtype=packed.dtype, device=packed.device)
-        dist.all_gather_into_tensor(gathered.view(-1, H), packed, group=group)
+        if comm is not None:
+            comm.all_gather(packed, gathered)
+        else:
+            dist.all_gather_into_tensor(gathered.view(-1, H), packed, group=group)
     else:
         gathered = packed[None]
     out, off = [], 0
@@ -234,12 +238,12 @@ def gather_contrastive_targets(preds: Dict[str, Dict[str, torch.Tensor]], group=
     return out
 
 
-def loss_fn_given_preds(preds: Dict[str, Dict[str, torch.Tensor]], group=None):
+def loss_fn_given_preds(preds: Dict[str, Dict[str, torch.Tensor]], group=None, comm=None):
     """pretrain_model.py:262-303 for the contrastive heads: per head and direction
     `mean(logsumexp(x . y_all^T) - sum(x * y)) / 2` plus the per-source breakdown of `stuff_to_span`.
     Returns (loss, loss_info) as 0-d CUDA tensors (this rank's loss; the reference pmean()s metrics later)."""
     info = {}
-    for name, x, pos_off, y_all in gather_contrastive_targets(preds, group):
+    for name, x, pos_off, y_all in gather_contrastive_targets(preds, group, comm=comm):
         lse, numer = L.contrastive_lse(x, y_all, pos_off)
         red = L.contrastive_reduce(lse, numer, preds[name].get("_sources"))
         info[name] = info.get(name, 0.0) + red[0] / 2.0

@@ -60,6 +60,10 @@ _OVERLAP_ALLREDUCE = os.environ.get("MR_OVERLAP_ALLREDUCE", "1") != "0"
 # Timing probe of bench.py only: run the step WITHOUT the gradient all-reduce (the result is then not a training
 # step); the difference to the full step is the all-reduce time that the backward pass does not hide.
 _SKIP_GRAD_ALLREDUCE = False
+# The collectives of the step go through the library's own entries (mr_all_gather / mr_reduce_scatter / mr_all_reduce on
+# an ncclComm_t made by mr_nccl_comm_init) when the group's backend is NCCL; MR_NATIVE_COLLECTIVES=0 keeps
+# torch.distributed's wrappers around the same NCCL calls (and is what a gloo / CPU group uses).
+_NATIVE_COLLECTIVES = os.environ.get("MR_NATIVE_COLLECTIVES", "1") != "0"
 
 
 def _wgrad(dy: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
@@ -237,6 +241,21 @@ class PretrainStep:
     # three temperatures (mr_unit_normalize(_bwd) read exp(min(s, log 100) / 2) from a device scalar).  The Adam
     # update of the three temperatures stays on the host, between replays.
     # --------------------------------------------------------------------------------------------
+    def communicator(self, group=None):
+        """The library-side NCCL communicator of `group` (created collectively on first use, one per group), or None
+        when the collectives stay with torch.distributed (single rank, non-NCCL backend, MR_NATIVE_COLLECTIVES=0)."""
+        import torch.distributed as dist
+        if not (_NATIVE_COLLECTIVES and dist.is_available() and dist.is_initialized()):
+            return None
+        if dist.get_world_size(group) < 2 or dist.get_backend(group) != "nccl":
+            return None
+        comms = self.__dict__.setdefault("_comms", {})
+        key = id(group) if group is not None else 0
+        if key not in comms:
+            comms[key] = L.Communicator.from_group(group)
+            self._comm_stream = torch.cuda.Stream(priority=-1)
+        return comms[key]
+
     def capture_train_step(self, batch: Dict, opt: Optional[Dict] = None, group=None):
         """Captures train_step for batches shaped like `batch` (which must carry the '_rng/*' draws: the numpy draw of
         the eager path cannot be captured).  Returns `run(batch) -> (loss, loss_info)` (0-d CUDA tensors, valid until
@@ -341,6 +360,18 @@ class PretrainStep:
         # the single blocking all-reduce of round 1p.
         pending, done = [], set()
         self.last_bucket_bytes = []
+        comm = self.communicator(group) if world > 1 else None
+
+        def start_all_reduce(buf):
+            """Asynchronous sum of one bf16 bucket: NCCL on the communication stream, behind everything the current
+            stream has enqueued so far; joined before the optimizer kernel."""
+            if comm is None:
+                pending.append(dist.all_reduce(buf, group=group, async_op=True))
+                return
+            self._comm_stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self._comm_stream):
+                comm.all_reduce(buf)
+            pending.append(None)
 
         def flush(names, reduce_now):
             """Copy finished gradients into the arena, cast their 1024-element rows to bf16, start their all-reduce."""
@@ -369,7 +400,7 @@ class PretrainStep:
                 if reduce_now:
                     self.last_bucket_bytes.append((hi - lo) * 2048)
                     if not _SKIP_GRAD_ALLREDUCE:
-                        pending.append(dist.all_reduce(st["g16"][lo * 1024:hi * 1024], group=group, async_op=True))
+                        start_all_reduce(st["g16"][lo * 1024:hi * 1024])
 
         overlap = world > 1 and _OVERLAP_ALLREDUCE
         grads_ref: Dict[str, torch.Tensor] = {}
@@ -379,17 +410,20 @@ class PretrainStep:
             flush([k for k in st["names"] if k.split("/")[0] in prefixes and k in grads_so_far
                    and (name_filter is None or name_filter(k))], True)
 
-        loss, info, grads = self.loss_and_grads(batch, group=group, on_ready=on_ready if overlap else None)
+        loss, info, grads = self.loss_and_grads(batch, group=group, on_ready=on_ready if overlap else None, comm=comm)
         grads_ref.update(grads)
         if overlap:
             g[n:n + 3].copy_(grads["contrastive_scales"].reshape(-1))
             L.cast_pad(g.view(-1, 1024)[n // 1024:], 1, 1024, 1024, out=st["g16"].view(-1, 1024)[n // 1024:], sanitize=True)
             if not _SKIP_GRAD_ALLREDUCE:
-                pending.append(dist.all_reduce(st["g16"][n:], group=group, async_op=True))
+                start_all_reduce(st["g16"][n:])
             left = [k for k in st["names"] if k not in done]
             assert not left, f"gradients outside the all-reduce buckets: {left[:4]}"
-            for w in pending:
-                w.wait()                                     # the current stream waits for NCCL's stream
+            for w in pending:                                # the current stream waits for NCCL's stream
+                if w is not None:
+                    w.wait()
+            if comm is not None and pending:
+                torch.cuda.current_stream().wait_stream(self._comm_stream)
             g16 = st["g16"]
         else:
             for name in st["names"]:
@@ -398,7 +432,7 @@ class PretrainStep:
             g[n:n + 3].copy_(grads["contrastive_scales"].reshape(-1))
             g16 = L.cast_pad(g.view(-1, 1024), (n + 1024) // 1024, 1024, 1024, out=st["g16"].view(-1, 1024), sanitize=True).view(-1)
             if world > 1 and not _SKIP_GRAD_ALLREDUCE:
-                dist.all_reduce(g16, group=group)
+                comm.all_reduce(g16) if comm is not None else dist.all_reduce(g16, group=group)
         b1, b2, eps, wd = opt.get("beta_1", 0.9), opt.get("beta_2", 0.98), opt.get("eps", 1e-8), opt["weight_decay_rate"]
         lr, corr, t1 = self._step_scalars(opt)
         gm = getattr(self, "_graph_scalars", None)
@@ -531,7 +565,7 @@ class PretrainStep:
         G.add(f"{prefix}/embedding/bias", L.colsum(dxe))
 
     # --------------------------------------------------------------------------------------------
-    def loss_and_grads(self, batch: Dict, group=None, on_ready=None):
+    def loss_and_grads(self, batch: Dict, group=None, on_ready=None, comm=None):
         """on_ready(grads, prefixes): called during the backward pass each time every gradient under the given
         top-level parameter prefixes is final (train_step starts their all-reduce under the remaining backward)."""
         import torch.distributed as dist
@@ -711,7 +745,9 @@ class PretrainStep:
         # ---- loss forward (pretrain_model.py:262-303) ----
         world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
         rank = dist.get_rank(group) if world > 1 else 0
-        jobs = gather_contrastive_targets(preds, group)
+        if comm is None and world > 1:
+            comm = self.communicator(group)
+        jobs = gather_contrastive_targets(preds, group, comm=comm)
         info, lses = {}, []
         for name, x, pos_off, y_all in jobs:
             lse, numer = L.contrastive_lse(x, y_all, pos_off)
@@ -741,7 +777,10 @@ class PretrainStep:
             off += n_own
         if world > 1:
             own_all = torch.empty((S, H), dtype=torch.float32, device=dev)
-            dist.reduce_scatter_tensor(own_all, packed, group=group)
+            if comm is not None:
+                comm.reduce_scatter(packed, own_all)
+            else:
+                dist.reduce_scatter_tensor(own_all, packed, group=group)
         else:
             own_all = packed[0]
         off = 0

@@ -67,6 +67,77 @@ def test_nccl_packed_allgather_loss_world2(cuda):
         assert abs(m - float(ref_info[k])) < 3e-3, k
 
 
+def _collectives_worker(rank, world, port, q):
+    """mr_all_gather / mr_reduce_scatter / mr_all_reduce on a communicator made by mr_nccl_comm_init against
+    torch.distributed's NCCL collectives on the same data, plus a side-stream launch and a CUDA-graph replay."""
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(f"cuda:{rank}"))
+    from merlot_reserve_b200 import _lib as L
+    comm = L.Communicator.from_group()
+    ok = {"version": L.nccl_version() == torch.cuda.nccl.version()[0] * 10000 + torch.cuda.nccl.version()[1] * 100
+          + torch.cuda.nccl.version()[2], "rank": (comm.world, comm.rank) == (world, rank)}
+    g = torch.Generator().manual_seed(7 + rank)
+    y = torch.randn(188 * 8, 768, generator=g).to(torch.bfloat16).cuda()                 # the packed targets of b = 8
+    ref = torch.empty((world,) + y.shape, dtype=y.dtype, device="cuda")
+    dist.all_gather_into_tensor(ref.view(-1, 768), y)
+    ok["all_gather"] = torch.equal(comm.all_gather(y), ref)
+    dy = torch.randn(world, 1000, 768, generator=g).cuda()
+    ref = torch.empty(1000, 768, device="cuda")
+    dist.reduce_scatter_tensor(ref, dy.clone())
+    ok["reduce_scatter"] = torch.equal(comm.reduce_scatter(dy), ref)
+    ok["reduce_scatter_mean"] = torch.allclose(comm.reduce_scatter(dy, average=True), ref / world, rtol=1e-6, atol=1e-7)
+    grads = torch.randn(3 * 1024 * 1024 + 1024, generator=g).to(torch.bfloat16).cuda()
+    ref = grads.clone()
+    dist.all_reduce(ref)
+    side = torch.cuda.Stream(priority=-1)
+    mine = grads.clone()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        comm.all_reduce(mine)
+    torch.cuda.current_stream().wait_stream(side)
+    ok["all_reduce_bf16_side_stream"] = torch.equal(mine, ref)
+    m = torch.full((4,), float(rank + 1), device="cuda")
+    ok["all_reduce_mean_f32"] = torch.equal(comm.all_reduce(m, average=True), torch.full((4,), (world + 1) / 2.0, device="cuda"))
+    static = grads.clone()
+    comm.all_reduce(static.clone())                               # warm-up outside the capture
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        comm.all_reduce(static)
+    static.copy_(grads)
+    graph.replay()
+    ok["all_reduce_in_cuda_graph"] = torch.equal(static, ref)
+    try:
+        comm.all_reduce(torch.zeros(4, dtype=torch.float16, device="cuda"))
+        ok["dtype_error"] = False
+    except L.MrError:
+        ok["dtype_error"] = True
+    torch.cuda.synchronize()
+    comm.destroy()
+    q.put((rank, ok))
+    dist.destroy_process_group()
+
+
+def test_library_collectives_match_torch_distributed_world2(cuda):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import torch.multiprocessing as mp
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_collectives_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=300) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, ok in res:
+        assert all(ok.values()), (rank, ok)
+
+
 def _train_worker(rank, world, port, q):
     """Two train_steps per mode on a rank-specific batch: bucketed all-reduce started during the backward pass
     against the single blocking all-reduce after it (MR_OVERLAP_ALLREDUCE=0)."""
@@ -84,10 +155,19 @@ def _train_worker(rank, world, port, q):
     out = {}
     # "same" = a second run of the overlapped mode: the run-to-run spread of one mode is the noise floor the
     # cross-mode difference is judged against (fp32 atomics in dQ / embedding-table accumulation).
-    for tag, mode in (("overlap", True), ("same", True), ("blocking", False)):
+    # "torch" = the same step with torch.distributed's NCCL wrappers instead of the library's collective entries
+    # (MR_NATIVE_COLLECTIVES=0); "graph" = the native step captured in a CUDA graph and replayed.
+    for tag, mode, native in (("overlap", True, True), ("same", True, True), ("blocking", False, True),
+                              ("torch", True, False), ("graph", True, True)):
         training._OVERLAP_ALLREDUCE = mode
+        training._NATIVE_COLLECTIVES = native
         step = training.PretrainStep(cfg, synthetic_params(cfg, seed=0, weight_scale=4.0))
-        losses = [float(step.train_step(batch, opt)[0]) for _ in range(2)]
+        assert (step.communicator() is not None) == native
+        if tag == "graph":
+            run = step.capture_train_step(batch, opt)
+            losses = [float(run(batch)[0]) for _ in range(2)]
+        else:
+            losses = [float(step.train_step(batch, opt)[0]) for _ in range(2)]
         torch.cuda.synchronize()
         st = step._state
         out[tag] = (losses, st["p"].cpu(), st["g16"].float().cpu(), step.model._p.contrastive_scales.copy())
@@ -99,7 +179,7 @@ def _train_worker(rank, world, port, q):
                 float(np.abs(sa - sb).max()))
 
     q.put((rank, diff("overlap", "blocking"), diff("overlap", "same"), out["overlap"][1].double().sum().item(),
-           out["overlap"][0] + out["blocking"][0]))
+           out["overlap"][0] + out["blocking"][0], diff("overlap", "torch"), diff("overlap", "graph")))
     dist.destroy_process_group()
 
 
@@ -124,9 +204,13 @@ def test_nccl_overlapped_gradient_allreduce_world2(cuda):
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    for rank, cross, same, psum, losses in res:
+    for rank, cross, same, psum, losses, vs_torch, vs_graph in res:
         print(f"rank {rank}: overlap-vs-blocking (dp_max, dp_mean, g_relL1, dscale) = {cross}; "
-              f"same-mode run-to-run = {same}")
+              f"same-mode run-to-run = {same}; library collectives vs torch.distributed = {vs_torch}; "
+              f"eager vs CUDA graph = {vs_graph}")
+        for what, (o_max, o_mean, o_rel, o_ds) in (("torch.distributed collectives", vs_torch), ("CUDA graph", vs_graph)):
+            assert o_max < 2e-5 and o_mean <= 4 * same[1] + 1e-9, f"rank {rank}: {what}: parameters differ {o_max} {o_mean}"
+            assert o_rel <= 4 * same[2] + 1e-5 and o_ds < 1e-5, f"rank {rank}: {what}: gradients differ {o_rel} {o_ds}"
         (dp_max, dp_mean, g_rel, ds_max), (s_max, s_mean, s_rel, s_ds) = cross, same
         # absolute ceilings (a wrong bucket moves tensors by ~lr = 2e-4) ...
         assert dp_max < 2e-5 and dp_mean < 5e-8, f"rank {rank}: parameters differ, max {dp_max} mean {dp_mean}"

@@ -153,6 +153,12 @@ size_t mr_gemm_epilogue_workspace_bytes(const MrGemmDesc* d);
  * behaviour is reproduced (it matters for padding rows returned by embed_video :842).
  * ------------------------------------------------------------------------------------------ */
 enum { MR_ATTN_ALGO_AUTO = 0, MR_ATTN_ALGO_MMA_SYNC = 1, MR_ATTN_ALGO_TCGEN05 = 2 };
+/* mr_attention_bwd `finish` flags: fold the next steps of the backward pass into the pass that converts the fp32 dQ
+ * accumulator (one sweep over d(qkv) instead of mr_attention_bwd + mr_rotary_bwd + mr_colsum):
+ *   EPILOGUE   out[0] becomes the gradient w.r.t. the qkv GEMM's PRE-epilogue output: dq * q_scale * rot, dk * rot on
+ *              the first 32 dims of every head (in[6] = rot f32 [rot_rows, 32], NULL = no rotary, only q_scale)
+ *   BIAS_GRAD  out[1] = f32 [3H] column sums of out[0] (the qkv bias gradient, modeling.py:228) */
+enum { MR_ATTN_BWD_EPILOGUE = 1, MR_ATTN_BWD_BIAS_GRAD = 2 };
 
 typedef struct MrAttentionDesc {
   int32_t B, T, H; /* H = hidden = 64 * heads */
@@ -162,6 +168,9 @@ typedef struct MrAttentionDesc {
                       tensor-memory kernel (both directions). */
   int32_t emit_lse; /* fwd: 1 = also write out[1] = lse f32 [B, H/64, T], the natural-log row log-sum-exp of the
                        masked scores (what mr_attention_bwd needs to recompute the probabilities) */
+  int32_t finish;   /* bwd: MR_ATTN_BWD_* flags, 0 = plain d(q, k, v) */
+  int32_t rot_rows; /* bwd, MR_ATTN_BWD_EPILOGUE: rows of the rotary table in[6] (row r uses table row r % rot_rows) */
+  float q_scale;    /* bwd, MR_ATTN_BWD_EPILOGUE: the 1/sqrt(64) the qkv epilogue multiplied q by */
 } MrAttentionDesc;
 
 int32_t mr_attention_fwd(mr_stream_t stream, const MrAttentionDesc* d, const void* const* in, void* const* out,
@@ -171,7 +180,8 @@ size_t mr_attention_fwd_workspace_bytes(const MrAttentionDesc* d);
 /* mr_attention_bwd: gradients of mr_attention_fwd w.r.t. the (rotary- and 1/sqrt(d)-scaled) q, k, v it consumed.
  *   in[0] qkv bf16 [B*T, 3H] (the forward's input); in[1] dctx bf16 [B*T, H]; in[2] ctx bf16 [B*T, H] (the forward's
  *   output); in[3] lse f32 [B, H/64, T] (emit_lse); in[4] valid u8 optional; in[5] group i32 optional
- *   out[0] dqkv bf16 [B*T, 3H] (dq | dk | dv, same layout as qkv); apply mr_rotary_bwd next, then the qkv dgrad/wgrad.
+ *   out[0] dqkv bf16 [B*T, 3H] (dq | dk | dv, same layout as qkv); apply mr_rotary_bwd next, then the qkv dgrad/wgrad
+ *   -- or set d->finish (see MR_ATTN_BWD_* above; in[6] and out[1] are read only when their flag is set).
  *   workspace: mr_attention_bwd_workspace_bytes (fp32 dq accumulator + row sums of dctx . ctx).  AUTO with T <= 32
  *   runs the one-block kernel, which writes dq in place and leaves the accumulator part of the workspace untouched. */
 int32_t mr_attention_bwd(mr_stream_t stream, const MrAttentionDesc* d, const void* const* in, void* const* out,

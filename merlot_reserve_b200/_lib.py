@@ -33,7 +33,8 @@ class GemmDesc(C.Structure):
 
 
 class AttentionDesc(C.Structure):
-    _fields_ = [("B", C.c_int32), ("T", C.c_int32), ("H", C.c_int32), ("algo", C.c_int32), ("emit_lse", C.c_int32)]
+    _fields_ = [("B", C.c_int32), ("T", C.c_int32), ("H", C.c_int32), ("algo", C.c_int32), ("emit_lse", C.c_int32),
+                ("finish", C.c_int32), ("rot_rows", C.c_int32), ("q_scale", C.c_float)]
 
 
 class LayerNormDesc(C.Structure):
@@ -477,13 +478,24 @@ def attention(qkv: torch.Tensor, B: int, T: int, H: int, valid=None, group=None,
     return out
 
 
+ATTN_BWD_EPILOGUE, ATTN_BWD_BIAS_GRAD = 1, 2
+
+
 def attention_bwd(qkv: torch.Tensor, dctx: torch.Tensor, ctx: torch.Tensor, lse: torch.Tensor, B: int, T: int, H: int,
-                  valid=None, group=None, algo=ATTN_AUTO) -> torch.Tensor:
-    d = AttentionDesc(B=B, T=T, H=H, algo=algo)
+                  valid=None, group=None, algo=ATTN_AUTO, rot=None, q_scale: Optional[float] = None, bias_grad: bool = False):
+    """d(q, k, v) of mr_attention_fwd.  With `q_scale` (and optionally `rot` f32 [rot_rows, 32]) the result is the
+    gradient w.r.t. the qkv GEMM's pre-epilogue output (mr_rotary_bwd folded in); with `bias_grad` the call returns
+    (dqkv, dbias f32 [3H]) -- the column sums mr_colsum would compute -- from the same pass."""
+    finish = (ATTN_BWD_EPILOGUE if q_scale is not None else 0) | (ATTN_BWD_BIAS_GRAD if bias_grad else 0)
+    if rot is not None and q_scale is None:
+        raise MrError("attention_bwd: rot needs q_scale (the backward of the qkv epilogue is applied as a whole)")
+    d = AttentionDesc(B=B, T=T, H=H, algo=algo, finish=finish, rot_rows=0 if rot is None else rot.shape[0],
+                      q_scale=q_scale or 0.0)
     dqkv = torch.empty_like(qkv)
-    _call("mr_attention_bwd", d, [qkv, dctx, ctx, lse, valid, group], [dqkv],
+    dbias = torch.empty((3 * H,), dtype=torch.float32, device=qkv.device) if bias_grad else None
+    _call("mr_attention_bwd", d, [qkv, dctx, ctx, lse, valid, group, rot], [dqkv, dbias],
           _ws("mr_attention_bwd_workspace_bytes", d, qkv.device))
-    return dqkv
+    return (dqkv, dbias) if bias_grad else dqkv
 
 
 def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, rows=None, H=None, ldx=None, seq_in=0,

@@ -346,6 +346,9 @@ constexpr int bwd_smem_bytes() {
 }  // namespace mr
 
 namespace mr {
+size_t dqkv_finish_partial_bytes(int64_t rows, int H);   // backward_rows.cu
+int32_t launch_dqkv_finish(cudaStream_t stream, const float* dq_acc, bf16* dqkv, const float* rot, int rot_rows,
+                           float q_scale, int64_t rows, int H, float* partial, float* dbias);
 int32_t launch_attention_bwd_tc(cudaStream_t stream, const bf16* qkv, const bf16* dout, const float* lse, const float* Dsum,
                                 const uint8_t* valid, const int32_t* group, bf16* dqkv, float* dq_acc, int B, int T, int H);
 }
@@ -353,7 +356,9 @@ int32_t launch_attention_bwd_tc(cudaStream_t stream, const bf16* qkv, const bf16
 extern "C" size_t mr_attention_bwd_workspace_bytes(const MrAttentionDesc* d) {
   if (!d || d->B <= 0 || d->T <= 0 || d->H <= 0) return 0;
   const size_t rows = static_cast<size_t>(d->B) * d->T;
-  return rows * d->H * sizeof(float) + rows * (d->H / 64) * sizeof(float);
+  size_t bytes = rows * d->H * sizeof(float) + rows * (d->H / 64) * sizeof(float);
+  if (d->finish & MR_ATTN_BWD_BIAS_GRAD) bytes += mr::dqkv_finish_partial_bytes(static_cast<int64_t>(rows), d->H) + 16;
+  return bytes;
 }
 
 extern "C" int32_t mr_attention_bwd(mr_stream_t stream_, const MrAttentionDesc* d, const void* const* in, void* const* out,
@@ -370,6 +375,26 @@ extern "C" int32_t mr_attention_bwd(mr_stream_t stream_, const MrAttentionDesc* 
   const int64_t rows = static_cast<int64_t>(d->B) * d->T;
   float* dq_acc = static_cast<float*>(workspace);
   float* Dsum = dq_acc + rows * d->H;
+  // finish mode: the backward of the qkv epilogue and / or the bias gradient fused into the dQ conversion pass
+  const bool finish = d->finish != 0;
+  const float* rot = nullptr;
+  float* dbias = nullptr;
+  float* partial = nullptr;
+  if (finish) {
+    MR_REQUIRE((d->finish & ~(MR_ATTN_BWD_EPILOGUE | MR_ATTN_BWD_BIAS_GRAD)) == 0, MR_ERR_BAD_SHAPE);
+    if (d->finish & MR_ATTN_BWD_EPILOGUE) {
+      MR_REQUIRE(d->q_scale > 0.f, MR_ERR_BAD_SHAPE);
+      rot = static_cast<const float*>(in[6]);
+      MR_REQUIRE(!rot || d->rot_rows > 0, MR_ERR_BAD_SHAPE);
+      MR_REQUIRE(!rot || aligned16(rot), MR_ERR_MISALIGNED);
+    }
+    if (d->finish & MR_ATTN_BWD_BIAS_GRAD) {
+      dbias = static_cast<float*>(out[1]);
+      MR_REQUIRE(dbias, MR_ERR_NULL_POINTER);
+      partial = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(Dsum + rows * nh) + 15) & ~uintptr_t(15));
+    }
+  }
+  const float q_scale = (d->finish & MR_ATTN_BWD_EPILOGUE) ? d->q_scale : 1.0f;
   MR_REQUIRE(d->algo >= MR_ATTN_ALGO_AUTO && d->algo <= MR_ATTN_ALGO_TCGEN05, MR_ERR_BAD_SHAPE);
   const bool use_tc = d->algo == MR_ATTN_ALGO_TCGEN05 || (d->algo == MR_ATTN_ALGO_AUTO && d->T > 64);
   // T <= 32 under AUTO: the one-block kernel, dQ written in place (no fp32 accumulator to clear or convert)
@@ -387,6 +412,8 @@ extern "C" int32_t mr_attention_bwd(mr_stream_t stream_, const MrAttentionDesc* 
                                  static_cast<const float*>(in[3]), Dsum, static_cast<const uint8_t*>(in[4]),
                                  static_cast<const int32_t*>(in[5]), static_cast<bf16*>(out[0]), dq_acc, d->B, d->T, d->H);
     if (st != MR_OK) return st;
+    if (finish)
+      return launch_dqkv_finish(stream, dq_acc, static_cast<bf16*>(out[0]), rot, d->rot_rows, q_scale, rows, d->H, partial, dbias);
     int64_t cb = ceil_div64(rows * (d->H / 8), 256);
     if (cb > 148 * 16) cb = 148 * 16;
     dq_convert_kernel<<<static_cast<unsigned>(cb), 256, 0, stream>>>(dq_acc, static_cast<bf16*>(out[0]), rows, d->H);
@@ -399,7 +426,9 @@ extern "C" int32_t mr_attention_bwd(mr_stream_t stream_, const MrAttentionDesc* 
         static_cast<const bf16*>(in[0]), static_cast<const bf16*>(in[1]), static_cast<const float*>(in[3]), Dsum,
         static_cast<const uint8_t*>(in[4]), static_cast<const int32_t*>(in[5]), static_cast<bf16*>(out[0]), dq_acc, d->B,
         d->T, d->H);
-    return after_launch();
+    st = after_launch();
+    if (st != MR_OK || !finish) return st;
+    return launch_dqkv_finish(stream, nullptr, static_cast<bf16*>(out[0]), rot, d->rot_rows, q_scale, rows, d->H, partial, dbias);
   }
   static bool attr_set = false;
   if (!attr_set) {
@@ -416,6 +445,8 @@ extern "C" int32_t mr_attention_bwd(mr_stream_t stream_, const MrAttentionDesc* 
       d->T, d->H);
   st = after_launch();
   if (st != MR_OK) return st;
+  if (finish)
+    return launch_dqkv_finish(stream, dq_acc, static_cast<bf16*>(out[0]), rot, d->rot_rows, q_scale, rows, d->H, partial, dbias);
   int64_t cblocks = ceil_div64(rows * (d->H / 8), 256);
   if (cblocks > 148 * 16) cblocks = 148 * 16;
   dq_convert_kernel<<<static_cast<unsigned>(cblocks), 256, 0, stream>>>(dq_acc, static_cast<bf16*>(out[0]), rows, d->H);

@@ -273,6 +273,71 @@ rotary_bwd_kernel(bf16* __restrict__ dqkv, const float* __restrict__ rot, int64_
 }
 
 // ---------------------------------------------------------------------------------------------
+// Tail of mr_attention_bwd in `finish` mode: ONE pass over d(qkv) that (1) turns the fp32 dQ accumulator into bf16,
+// (2) applies the backward of the qkv epilogue (rotary scale on the first 32 dims of every q / k head, 1/sqrt(d) on q)
+// and (3) sums every column for the qkv bias gradient -- what dq_convert_kernel + rotary_bwd_kernel +
+// colsum_partial_kernel did in three passes (24 bytes per element of [rows, H] moved; this kernel moves 11).
+// Block = 32 column vectors (8 columns each) x 8 row lanes over `rows_per_block` rows, like colsum_partial_kernel.
+// ---------------------------------------------------------------------------------------------
+template <bool kAcc>
+__global__ void __launch_bounds__(256)
+dqkv_finish_kernel(const float* __restrict__ dq_acc, bf16* __restrict__ dqkv, const float* __restrict__ rot,
+                   float* __restrict__ partial, int rows, int H, int rot_rows, float q_scale, int rows_per_block) {
+  const int cv = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int c = cv * 8;
+  const int rl = threadIdx.x >> 5;
+  const int r0 = blockIdx.y * rows_per_block;
+  const int r1 = min(r0 + rows_per_block, rows);
+  const int region = c < H ? 0 : (c < 2 * H ? 1 : 2);                 // q | k | v
+  const int in_head = c & 63;
+  const bool rotated = rot != nullptr && region < 2 && in_head < 32;
+  const bool from_acc = kAcc && region == 0;
+  const bool changes = from_acc || rotated || (region == 0 && q_scale != 1.0f);
+  const float base = region == 0 ? q_scale : 1.0f;
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (c < 3 * H && (partial != nullptr || changes)) {
+#pragma unroll 4
+    for (int r = r0 + rl; r < r1; r += 8) {
+      uint4* cell = reinterpret_cast<uint4*>(dqkv + static_cast<size_t>(r) * 3 * H + c);
+      float f[8];
+      if (from_acc) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(dq_acc + static_cast<size_t>(r) * H + c));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(dq_acc + static_cast<size_t>(r) * H + c) + 1);
+        f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+      } else {
+        unpack8b(*cell, f);
+      }
+      if (rotated) {
+        const float4* rp = reinterpret_cast<const float4*>(rot + static_cast<size_t>(r % rot_rows) * 32 + in_head);
+        const float4 s0 = __ldg(rp), s1 = __ldg(rp + 1);
+        f[0] *= base * s0.x; f[1] *= base * s0.y; f[2] *= base * s0.z; f[3] *= base * s0.w;
+        f[4] *= base * s1.x; f[5] *= base * s1.y; f[6] *= base * s1.z; f[7] *= base * s1.w;
+      } else if (region == 0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] *= base;
+      }
+      if (changes) *cell = pack8b(f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += f[j];
+    }
+  }
+  if (partial == nullptr) return;
+  __shared__ float red[8][32][8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[rl][threadIdx.x & 31][j] = acc[j];
+  __syncthreads();
+  if (rl == 0 && c < 3 * H) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float a = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) a += red[w][threadIdx.x & 31][j];
+      partial[static_cast<size_t>(blockIdx.y) * 3 * H + c + j] = a;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Contrastive loss backward, step 1: dlogits[i, j] = w (exp(logit[i, j] - lse[i]) - [j == pos(i)]) as bf16
 // (pretrain_model.py:293-295; w = 1 / (2 n), the weight of one direction's mean).  The positive of row i is column
 // pos_off + i of y_all (this rank's block of the rank-major all-gather).  One warp per row.
@@ -691,6 +756,27 @@ adamw_multi_kernel(const void* __restrict__ g_, const MrAdamWChunk* __restrict__
 }
 
 }  // namespace
+
+size_t dqkv_finish_partial_bytes(int64_t rows, int H) {
+  return static_cast<size_t>(ceil_div64(rows, 512)) * 3 * H * sizeof(float);
+}
+
+// dq_acc: fp32 [rows, H] accumulator of dQ, or nullptr when dQ is already bf16 inside dqkv; rot / partial + dbias optional
+int32_t launch_dqkv_finish(cudaStream_t stream, const float* dq_acc, bf16* dqkv, const float* rot, int rot_rows,
+                           float q_scale, int64_t rows, int H, float* partial, float* dbias) {
+  if (rows >= (int64_t(1) << 31)) return MR_ERR_BAD_SHAPE;
+  const int nblk = static_cast<int>(ceil_div64(rows, 512));
+  dim3 grid(ceil_div(3 * H / 8, 32), nblk);
+  float* part = dbias ? partial : nullptr;
+  if (dq_acc)
+    dqkv_finish_kernel<true><<<grid, 256, 0, stream>>>(dq_acc, dqkv, rot, part, static_cast<int>(rows), H, rot_rows, q_scale, 512);
+  else
+    dqkv_finish_kernel<false><<<grid, 256, 0, stream>>>(nullptr, dqkv, rot, part, static_cast<int>(rows), H, rot_rows, q_scale, 512);
+  int32_t st = after_launch();
+  if (st != MR_OK || !dbias) return st;
+  colsum_reduce_kernel<<<ceil_div(3 * H, 256), 256, 0, stream>>>(partial, dbias, nblk, 3 * H);
+  return after_launch();
+}
 }  // namespace mr
 
 using namespace mr;

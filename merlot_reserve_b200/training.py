@@ -488,11 +488,12 @@ class PretrainStep:
             G.add(f"{p}/pre_mlp_ln/bias", db)
             dctx = _dgrad(dxm, lw["wo"])
             G.add(f"{p}/attention_layer/attn_proj/kernel", _wgrad(dxm, ctx))
-            dqkv = L.attention_bwd(qkv, dctx, ctx, lse, B, T, H, valid=tape["valid"], group=tape["group"])
-            L.rotary_bwd(dqkv, tape["rot"], H)
+            # d(q, k, v) -> backward of the qkv epilogue (rotary, 1/sqrt(d)) -> bias gradient: one call, one tail pass
+            dqkv, dbqkv = L.attention_bwd(qkv, dctx, ctx, lse, B, T, H, valid=tape["valid"], group=tape["group"],
+                                          rot=tape["rot"], q_scale=0.125, bias_grad=True)
             dh1 = _dgrad(dqkv, lw["wqkv"])
             G.add(f"{p}/attention_layer/qkv/kernel", _wgrad(dqkv, h1))
-            G.add(f"{p}/attention_layer/qkv/bias", L.colsum(dqkv))
+            G.add(f"{p}/attention_layer/qkv/bias", dbqkv)
             dx, dg, db = L.layernorm_bwd(dh1, x, lw["ln1"][0], dres=dxm)
             G.add(f"{p}/pre_attn_ln/scale", dg)
             G.add(f"{p}/pre_attn_ln/bias", db)

@@ -185,6 +185,42 @@ def test_attention_bwd_tc_many_blocks_and_uniform_rows(cuda, lib):
     _close(b, ref_dqkv, 2e-2 * ref_dqkv.abs().max().item() + 1e-3, 3e-2, "tcgen05 backward vs autograd")
 
 
+@pytest.mark.parametrize("B,T,H,per_row_rot", [(3, 300, 768, False), (5, 31, 128, False), (4, 50, 128, True), (2, 130, 256, True)])
+def test_attention_bwd_finish_matches_the_three_pass_tail(cuda, lib, B, T, H, per_row_rot):
+    """MrAttentionDesc.finish: the backward of the qkv epilogue (rotary scale, 1/sqrt(d)) and the qkv bias gradient
+    folded into the dQ conversion pass, against mr_attention_bwd -> mr_rotary_bwd -> mr_colsum on the same inputs.
+    Covers the tcgen05 path (fp32 dQ accumulator), the mma.sync 64-tile path and the one-block path (dQ in place),
+    a per-position table (vision / audio: row r uses r % T) and a per-row table (joint)."""
+    g = torch.Generator().manual_seed(B * 1000 + T)
+    qkv = _bf(torch.randn(B * T, 3 * H, generator=g) * 0.8).to(cuda)
+    qkv[:, :H] *= 0.35
+    dctx = _bf(torch.randn(B * T, H, generator=g)).to(cuda)
+    valid = torch.ones(B, T, dtype=torch.uint8)
+    valid[0, T // 2:] = 0
+    valid = valid.to(cuda).view(-1)
+    rot = (torch.randn(B * T if per_row_rot else T, 32, generator=g)).to(cuda)
+    lse = torch.empty(B, H // 64, T, device=cuda)
+    ctx = lib.attention(qkv, B, T, H, valid=valid, lse=lse)
+    ref = lib.attention_bwd(qkv, dctx, ctx, lse, B, T, H, valid=valid)
+    plain = ref.clone()
+    lib.rotary_bwd(ref, rot, H, q_scale=0.125)
+    ref_bias = lib.colsum(ref)
+    got, got_bias = lib.attention_bwd(qkv, dctx, ctx, lse, B, T, H, valid=valid, rot=rot, q_scale=0.125, bias_grad=True)
+    scale = ref.float().abs().max().item()
+    # dk / dv go through identical arithmetic; dq is rounded once (fp32 accumulator x scale) instead of twice
+    assert torch.equal(got[:, 2 * H:], ref[:, 2 * H:]) and torch.equal(got[:, 2 * H:], plain[:, 2 * H:])
+    _close(got[:, H:2 * H], ref[:, H:2 * H].float().cpu(), 1e-6, 2.0 ** -7, "dk")
+    _close(got[:, :H], ref[:, :H].float().cpu(), 1e-3 * scale, 2.0 ** -6, "dq")
+    _close(got_bias, ref_bias.cpu(), 2e-3 * scale * (B * T) ** 0.5, 2e-2, "qkv bias gradient")
+    # each flag alone
+    only_scale = lib.attention_bwd(qkv, dctx, ctx, lse, B, T, H, valid=valid, q_scale=0.125)
+    _close(only_scale[:, :H], plain[:, :H].float().cpu() * 0.125, 1e-3 * scale, 2.0 ** -6, "q_scale only")
+    assert torch.equal(only_scale[:, H:], plain[:, H:])
+    same, bias_plain = lib.attention_bwd(qkv, dctx, ctx, lse, B, T, H, valid=valid, bias_grad=True)
+    assert torch.equal(same, plain)
+    _close(bias_plain, lib.colsum(plain).cpu(), 2e-3 * plain.float().abs().max().item() * (B * T) ** 0.5, 2e-2, "bias only")
+
+
 def test_transformer_layer_backward_composition(cuda, lib):
     """One pre-LN transformer layer (modeling.py:259-280) forward + backward composed from the C-ABI kernels
     (unfused LayerNorm path), against torch autograd of the fp32 oracle layer: dx and every parameter gradient."""

@@ -905,6 +905,8 @@ class Communicator:
         return cls(comm.value, world, rank, owned=True)
 
     def destroy(self) -> None:
+        """ncclCommDestroy.  Release every CUDA graph that captured this communicator's collectives first: NCCL keeps
+        the communicator alive (and this call waiting) while a captured graph still references it."""
         if self._owned and self.handle:
             _check(load().mr_nccl_comm_destroy(C.c_void_p(self.handle)), "mr_nccl_comm_destroy")
         self.handle = None

@@ -64,6 +64,8 @@ _SKIP_GRAD_ALLREDUCE = False
 # an ncclComm_t made by mr_nccl_comm_init) when the group's backend is NCCL; MR_NATIVE_COLLECTIVES=0 keeps
 # torch.distributed's wrappers around the same NCCL calls (and is what a gloo / CPU group uses).
 _NATIVE_COLLECTIVES = os.environ.get("MR_NATIVE_COLLECTIVES", "1") != "0"
+# MR_ATTN_BWD_FINISH=0: the three-pass tail (mr_attention_bwd, mr_rotary_bwd, mr_colsum) for same-box A/B runs
+_FUSED_QKV_TAIL = os.environ.get("MR_ATTN_BWD_FINISH", "1") != "0"
 
 
 def _wgrad(dy: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
@@ -489,8 +491,13 @@ class PretrainStep:
             dctx = _dgrad(dxm, lw["wo"])
             G.add(f"{p}/attention_layer/attn_proj/kernel", _wgrad(dxm, ctx))
             # d(q, k, v) -> backward of the qkv epilogue (rotary, 1/sqrt(d)) -> bias gradient: one call, one tail pass
-            dqkv, dbqkv = L.attention_bwd(qkv, dctx, ctx, lse, B, T, H, valid=tape["valid"], group=tape["group"],
-                                          rot=tape["rot"], q_scale=0.125, bias_grad=True)
+            if _FUSED_QKV_TAIL:
+                dqkv, dbqkv = L.attention_bwd(qkv, dctx, ctx, lse, B, T, H, valid=tape["valid"], group=tape["group"],
+                                              rot=tape["rot"], q_scale=0.125, bias_grad=True)
+            else:
+                dqkv = L.attention_bwd(qkv, dctx, ctx, lse, B, T, H, valid=tape["valid"], group=tape["group"])
+                L.rotary_bwd(dqkv, tape["rot"], H)
+                dbqkv = L.colsum(dqkv)
             dh1 = _dgrad(dqkv, lw["wqkv"])
             G.add(f"{p}/attention_layer/qkv/kernel", _wgrad(dqkv, h1))
             G.add(f"{p}/attention_layer/qkv/bias", dbqkv)

@@ -100,15 +100,6 @@ def _collectives_worker(rank, world, port, q):
     ok["all_reduce_bf16_side_stream"] = torch.equal(mine, ref)
     m = torch.full((4,), float(rank + 1), device="cuda")
     ok["all_reduce_mean_f32"] = torch.equal(comm.all_reduce(m, average=True), torch.full((4,), (world + 1) / 2.0, device="cuda"))
-    static = grads.clone()
-    comm.all_reduce(static.clone())                               # warm-up outside the capture
-    torch.cuda.synchronize()
-    graph = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(graph):
-        comm.all_reduce(static)
-    static.copy_(grads)
-    graph.replay()
-    ok["all_reduce_in_cuda_graph"] = torch.equal(static, ref)
     try:
         comm.all_reduce(torch.zeros(4, dtype=torch.float16, device="cuda"))
         ok["dtype_error"] = False
@@ -116,8 +107,36 @@ def _collectives_worker(rank, world, port, q):
         ok["dtype_error"] = True
     torch.cuda.synchronize()
     comm.destroy()
+    try:
+        comm.all_reduce(m)
+        ok["use_after_destroy_error"] = False
+    except L.MrError:
+        ok["use_after_destroy_error"] = True
+    # a second communicator for the CUDA-graph replay.  It is left to process exit: NCCL keeps a communicator alive
+    # (ncclCommDestroy waits) while a captured graph still references it.
+    comm2 = L.Communicator.from_group()
+    static = grads.clone()
+    comm2.all_reduce(static.clone())                              # warm-up outside the capture
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        comm2.all_reduce(static)
+    static.copy_(grads)
+    graph.replay()
+    ok["all_reduce_in_cuda_graph"] = torch.equal(static, ref)
+    torch.cuda.synchronize()
     q.put((rank, ok))
     dist.destroy_process_group()
+
+
+def _guarded(fn, rank, world, port, q):
+    """Runs a worker; an exception travels to the parent through the queue instead of leaving it to time out."""
+    try:
+        fn(rank, world, port, q)
+    except BaseException:
+        import traceback
+        q.put((rank, {"exception": traceback.format_exc()}))
+        raise
 
 
 def test_library_collectives_match_torch_distributed_world2(cuda):
@@ -127,14 +146,15 @@ def test_library_collectives_match_torch_distributed_world2(cuda):
     world, port = 2, _free_port()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_collectives_worker, args=(r, world, port, q)) for r in range(world)]
+    procs = [ctx.Process(target=_guarded, args=(_collectives_worker, r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
-    res = sorted(q.get(timeout=300) for _ in range(world))
+    res = sorted(q.get(timeout=150) for _ in range(world))
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
     for rank, ok in res:
+        assert "exception" not in ok, ok.get("exception")
         assert all(ok.values()), (rank, ok)
 
 

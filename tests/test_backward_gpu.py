@@ -185,6 +185,30 @@ def test_attention_bwd_tc_many_blocks_and_uniform_rows(cuda, lib):
     _close(b, ref_dqkv, 2e-2 * ref_dqkv.abs().max().item() + 1e-3, 3e-2, "tcgen05 backward vs autograd")
 
 
+@pytest.mark.parametrize("B,T,H", [(7, 300, 768), (40, 200, 256), (33, 130, 128), (2, 1100, 768)])
+def test_attention_bwd_tc_persistent_walk(cuda, lib, B, T, H):
+    """The tcgen05 backward is persistent: one CTA per SM walks several (sequence, head, key block) items, with the
+    K / V tiles, every barrier phase and the dK / dV write-out carried across item boundaries.  Shapes with 1.7, 2.2,
+    0.9 and 1.5 items per SM (odd remainders, one-block and nine-block items), key validity + group ids + invalid
+    query rows, against the mma.sync kernel on the same inputs."""
+    g = torch.Generator().manual_seed(B * 7 + T)
+    qkv = _bf(torch.randn(B * T, 3 * H, generator=g) * 0.8)
+    qkv[:, :H] *= 0.35
+    dctx = _bf(torch.randn(B * T, H, generator=g))
+    valid = (torch.rand(B, T, generator=g) > 0.2).to(torch.uint8)
+    valid[:, 0] = 1
+    valid[B // 2, T // 3:] = 0
+    group = (torch.arange(T)[None] >= torch.randint(1, T, (B, 1), generator=g)).to(torch.int32)
+    dev = lambda t: t.to(cuda).contiguous().view(-1)
+    lse = torch.empty(B, H // 64, T, device=cuda)
+    ctx = lib.attention(qkv.to(cuda), B, T, H, valid=dev(valid), group=dev(group), lse=lse)
+    a = lib.attention_bwd(qkv.to(cuda), dctx.to(cuda), ctx, lse, B, T, H, valid=dev(valid), group=dev(group), algo=1)
+    for rep in range(2):                     # twice: nothing may be left behind in the workspace / barriers
+        b = lib.attention_bwd(qkv.to(cuda), dctx.to(cuda), ctx, lse, B, T, H, valid=dev(valid), group=dev(group), algo=2)
+        scale = a.float().abs().max().item()
+        _close(b, a.float().cpu(), 2e-2 * scale + 1e-3, 3e-2, f"persistent tcgen05 vs mma.sync backward (run {rep})")
+
+
 @pytest.mark.parametrize("B,T,H,per_row_rot", [(3, 300, 768, False), (5, 31, 128, False), (4, 50, 128, True), (2, 130, 256, True)])
 def test_attention_bwd_finish_matches_the_three_pass_tail(cuda, lib, B, T, H, per_row_rot):
     """MrAttentionDesc.finish: the backward of the qkv epilogue (rotary scale, 1/sqrt(d)) and the qkv bias gradient

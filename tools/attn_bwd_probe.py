@@ -11,6 +11,12 @@ from merlot_reserve_b200 import _lib as L  # noqa: E402
 
 SHAPES = [("pretrain_vision_b8", 128, 241, 768, False), ("pretrain_joint_b8", 48, 640, 768, True),
           ("pretrain_audio_b8", 384, 31, 768, False), ("pretrain_span_b8", 384, 16, 768, True)]
+if "--blocks-per-cta" in sys.argv:
+    # equal total work (6 144 blocks of 128 x 128, ~30 848 rows), 2 / 4 / 8 / 16 query blocks per CTA: separates the fixed
+    # cost of a CTA (launch, TMEM allocation, cold loads, dK / dV write-out) from the steady-state time per block
+    SHAPES = [("blocks2", 128, 241, 768, False), ("blocks4", 32, 497, 768, False), ("blocks8", 8, 1009, 768, False),
+              ("blocks16", 2, 2033, 768, False)]
+ALGOS = [2] if "--blocks-per-cta" in sys.argv or "--tc-only" in sys.argv else [1, 2]
 torch.cuda.set_device(0)
 L.require_b200(0)
 for name, B, T, H, masked in SHAPES:
@@ -25,7 +31,7 @@ for name, B, T, H, masked in SHAPES:
         valid = valid.view(-1)
     lse = torch.empty(B, H // 64, T, device="cuda")
     ctx = L.attention(qkv, B, T, H, valid=valid, group=group, lse=lse)
-    for algo in ([1, 2] if T > 64 else [1]):
+    for algo in (ALGOS if T > 64 else [1]):
         for _ in range(3):
             L.attention_bwd(qkv, dctx, ctx, lse, B, T, H, valid=valid, group=group, algo=algo)
         torch.cuda.synchronize()

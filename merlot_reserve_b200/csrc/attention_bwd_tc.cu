@@ -5,8 +5,8 @@
 // pays ~8 us of launch, TMEM allocation, cold K / V / Q loads and dK / dV write-out against 2.5 us per block
 // (profiles/attn_bwd_blocks_r02w.txt: equal work at 2 / 4 / 8 / 16 blocks per CTA), which is most of the time at
 // T = 241 (two blocks per item).  Here K / V are double buffered ACROSS items, every barrier runs on a block counter
-// that does not reset between items, and the dK / dV write-out of item n (drain warps, TMA stores staged in the
-// item's own K / V buffers) runs under the first block of item n + 1.
+// that does not reset between items, and the dK / dV write-out of item n (drain warps, TMA stores) runs under the
+// first block of item n + 1.
 //
 // Everything is kept TRANSPOSED -- keys on the TMEM lanes, queries on the columns -- so that the probabilities and
 // their gradients are the TMEM (A) operands of the two products that accumulate over the query blocks:
@@ -59,7 +59,7 @@ constexpr float kBig = 1.0e30f;
 constexpr float kKeyMasked = 1.0e38f;
 constexpr int kStatVecs = 6;               // a, cb, nb, qtag, D per query; ktag per key (written with an item's first block)
 
-constexpr int kOffKV = 0;                             // [2 items]{K_j, V_j}; after the item: staging of dK_j, dV_j
+constexpr int kOffKV = 0;                             // [2 items]{K_j, V_j}
 constexpr int kOffQ = 4 * kTileBytes;                 // [2 blocks]{Q_i, dO_i}
 constexpr int kOffDS = kOffQ + 4 * kTileBytes;        // [2 blocks][2 slabs][128 keys][64 queries] bf16
 constexpr int kOffStat = kOffDS + 4 * kTileBytes;     // [2 blocks][6][128] float
@@ -94,11 +94,13 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
                         const __grid_constant__ CUtensorMap tmap_dq, const __grid_constant__ CUtensorMap tmap_dkv,
                         const BwdParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1 KB alignment by pointer arithmetic on the __shared__ array: an integer round trip makes the pointer generic and
+  // every access through it LD.E / ST.E instead of LDS / STS
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   float* sStat = reinterpret_cast<float*>(smem + kOffStat);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
   uint64_t* kv_full = bars + 0;     // [2] per item buffer: K_j, V_j have landed
-  uint64_t* kv_free = bars + 2;     // [2] the item's dK / dV staging in that buffer has been read by the TMA stores
+  uint64_t* kv_free = bars + 2;     // [2] every MMA of the item that read that buffer has completed
   uint64_t* q_full = bars + 4;      // [2]
   uint64_t* q_empty = bars + 6;     // [2]
   uint64_t* stat_full = bars + 8;   // [2]
@@ -127,7 +129,7 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
     tma_prefetch_desc(&tmap_dkv);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&kv_full[i], 1);
-      mbar_init(&kv_free[i], 4);
+      mbar_init(&kv_free[i], 1);
       mbar_init(&q_full[i], 1);
       mbar_init(&q_empty[i], 1);
       mbar_init(&stat_full[i], 2);
@@ -254,7 +256,10 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
           umma_commit(dq_full);
           umma_commit(&q_empty[buf]);
           umma_commit(&ds_free[buf]);
-          if (i + 1 == nqb) umma_commit(acc_full);
+          if (i + 1 == nqb) {
+            umma_commit(acc_full);
+            umma_commit(&kv_free[nb]);                    // K_j / V_j are dead: the producer may load item n + 2 here
+          }
         }
       }
     } else if (warp_idx >= 10) {
@@ -304,7 +309,7 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
     }
   } else if (warp_idx >= 4 && warp_idx < 8) {
     setmaxnreg_dec<96>();
-    // ===================== drain warpgroup: per-query vectors, dQ_i -> global, dK_j / dV_j -> global =====================
+    // ===================== drain warpgroup: dQ_i -> global, dK_j / dV_j -> global =====================
     const int quarter = warp_idx & 3;
     const int row = quarter * 32 + lane;                 // query within the block = TMEM lane of dQ (key lane of dK / dV)
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
@@ -339,10 +344,10 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
           }
         }
         if (i + 1 == nqb) {
-          // ---- dK_j, dV_j: TMEM -> bf16 -> the item's own (now dead) K / V tiles -> TMA store into d(qkv) ----
+          // ---- dK_j, dV_j: TMEM -> bf16 -> the warp's 4 KB stage -> TMA store into d(qkv) ----
           mbar_wait(acc_full, n & 1);
           tc_fence_after();
-          uint8_t* kv = smem + kOffKV + (n & 1) * 2 * kTileBytes + quarter * 4096;
+          const int r0 = it.jb * kB + quarter * 32;
 #pragma unroll
           for (int which = 0; which < 2; ++which) {
             tmem_ld_32x64(lane_addr + (which == 0 ? kColDK : kColDV), v);
@@ -352,6 +357,8 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
               __syncwarp();
               if (lane == 0) mbar_arrive(acc_free);
             }
+            if (lane == 0) tma_store_wait_read<0>();
+            __syncwarp();
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
               uint4 o;
@@ -359,20 +366,15 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
               o.y = pack_bf16(__uint_as_float(v[8 * c + 2]), __uint_as_float(v[8 * c + 3]));
               o.z = pack_bf16(__uint_as_float(v[8 * c + 4]), __uint_as_float(v[8 * c + 5]));
               o.w = pack_bf16(__uint_as_float(v[8 * c + 6]), __uint_as_float(v[8 * c + 7]));
-              *reinterpret_cast<uint4*>(kv + which * kTileBytes + lane * 128 + ((c ^ (lane & 7)) << 4)) = o;
+              *reinterpret_cast<uint4*>(stage + lane * 128 + ((c ^ (lane & 7)) << 4)) = o;
             }
-          }
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) {
-            const int r0 = it.jb * kB + quarter * 32;
-            if (r0 < p.T) {                              // rows past T are clipped by the [B, T, 3H] tensor map
-              tma_store_3d(&tmap_dkv, kv, p.H + it.h * kD, r0, it.b);
-              tma_store_3d(&tmap_dkv, kv + kTileBytes, 2 * p.H + it.h * kD, r0, it.b);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              if (r0 < p.T)                               // rows past T are clipped by the [B, T, 3H] tensor map
+                tma_store_3d(&tmap_dkv, stage, (which == 0 ? p.H : 2 * p.H) + it.h * kD, r0, it.b);
+              tma_store_commit();
             }
-            tma_store_commit();
-            tma_store_wait_read<0>();
-            mbar_arrive(&kv_free[n & 1]);                // the producer may load the K / V of item n + 2 here
           }
         }
       }

@@ -130,7 +130,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
   static_assert(kKV == 128 || kKV == 96, "key block of 128 or 96");
   constexpr int kKvBytes = kKV * kD * 2;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1 KB alignment by pointer arithmetic on the __shared__ array: an integer round trip makes the pointer generic and
+  // every access through it LD.E / ST.E instead of LDS / STS
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sQ = smem + kOffQ;
   uint8_t* sKV = smem + kOffKV;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);

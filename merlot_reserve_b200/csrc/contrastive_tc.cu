@@ -47,7 +47,9 @@ __global__ void __launch_bounds__(kThreads, 1)
 contrastive_lse_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_y,
                           const Params p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1 KB alignment by pointer arithmetic on the __shared__ array: an integer round trip makes the pointer generic and
+  // every access through it LD.E / ST.E instead of LDS / STS
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   float2* part = reinterpret_cast<float2*>(smem + kStages * kStageBytes);          // [cluster rank][row]
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes + kPartBytes);
   uint64_t* empty_bar = full_bar + kStages;

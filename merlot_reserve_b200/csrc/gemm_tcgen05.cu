@@ -144,7 +144,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   static_assert(!(kPair && kTrans != 0), "MN-major operands: single-CTA tiles only");
   const uint32_t cta_rank = kPair ? cluster_ctarank() : 0u;   // 0 = leader (issues the MMAs of the pair)
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1 KB alignment by pointer arithmetic on the __shared__ array: an integer round trip makes the pointer generic and
+  // every access through it LD.E / ST.E instead of LDS / STS
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
 
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes + C::kOutBytes);
   uint64_t* empty_bar = full_bar + C::kStages;

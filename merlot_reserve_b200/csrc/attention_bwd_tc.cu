@@ -39,8 +39,9 @@
 //   warps 4-7   drain: dQ_i TMEM -> smem -> TMA reduce-add; after an item's last
 //               block dK_j / dV_j TMEM -> bf16 -> smem -> TMA store
 //   warp 8      TMA producer: (K_j, V_j) double buffered per item; (Q_i, dO_i) double buffered per block
-//   warp 9      MMA issuer (one thread)
-//   warps 10-11 statistics: the five per-query vectors of every block (and ktag once per item), one block ahead
+//   warp 9      MMA issuer B (one thread): dV_j, dK_j, dQ_i
+//   warp 10     statistics: the five per-query vectors of every block (and ktag once per item), two blocks ahead
+//   warp 11     MMA issuer A (one thread): S^T / dP^T halves, refilled the moment the compute warps release them
 // The mask semantics are those of attention_bwd.cu (key validity, video_src groups, uniform rows).
 #include "common.cuh"
 #include "ptx.cuh"
@@ -51,7 +52,7 @@ namespace {
 constexpr int kB = 128;                    // keys per item, queries per block
 constexpr int kD = 64;
 constexpr int kThreadsTc = 512;
-constexpr int kProducerWarp = 8, kMmaWarp = 9;
+constexpr int kProducerWarp = 8, kMmaWarp = 9, kMmaWarpS = 11;
 constexpr int kTileBytes = kB * kD * 2;    // 16 KB
 constexpr uint32_t kColS = 0, kColDP = 128, kColP = 256, kColDV = 320, kColDK = 384, kColDQ = 448;
 constexpr float kLog2e = 1.4426950408889634f;
@@ -132,7 +133,7 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
       mbar_init(&kv_free[i], 1);
       mbar_init(&q_full[i], 1);
       mbar_init(&q_empty[i], 1);
-      mbar_init(&stat_full[i], 2);
+      mbar_init(&stat_full[i], 1);
       mbar_init(&stat_free[i], 8);
       mbar_init(&s_full[i], 1);
       mbar_init(&sdp_free[i], 4);
@@ -180,34 +181,13 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
         }
       }
     } else if (warp_idx == kMmaWarp && lane == 0) {
-      // ===================== MMA issuer =====================
-      constexpr uint32_t idesc_s = umma_idesc_bf16_f32(kB, 64);                              // K-major A and B, one half
+      // ===================== MMA issuer B: dV_j, dK_j, dQ_i =====================
       constexpr uint32_t idesc_kv = umma_idesc_bf16_f32(kB, kD) | (1u << 16);                // B MN-major
       constexpr uint32_t idesc_dq = umma_idesc_bf16_f32(kB, kD) | (1u << 15) | (1u << 16);   // A and B MN-major
       // MN-major A of two 64-query slabs 16 KB apart: the descriptor's leading-byte-offset (16-byte units)
       constexpr uint64_t kLboSlab = static_cast<uint64_t>((2 * 8192 >> 4) - 1) << 16;
-      const uint32_t tS = tmem_base + kColS, tDP = tmem_base + kColDP, tP = tmem_base + kColP;
+      const uint32_t tP = tmem_base + kColP;
       const uint32_t tDV = tmem_base + kColDV, tDK = tmem_base + kColDK, tDQ = tmem_base + kColDQ;
-      // S^T / dP^T of one 64-query half of block g (item buffer nb): B = rows [64 h, 64 h + 64) of the Q / dO tiles
-      auto issue_half = [&](int g, int nb, int h) {
-        const int buf = g & 1;
-        const uint64_t kdesc = umma_desc_k_sw128(smem_u32(smem + kOffKV + nb * 2 * kTileBytes));
-        const uint64_t vdesc = umma_desc_k_sw128(smem_u32(smem + kOffKV + nb * 2 * kTileBytes + kTileBytes));
-        const uint64_t qd = umma_desc_k_sw128(smem_u32(smem + kOffQ + buf * 2 * kTileBytes + h * 8192));
-        const uint64_t dod = umma_desc_k_sw128(smem_u32(smem + kOffQ + buf * 2 * kTileBytes + kTileBytes + h * 8192));
-#pragma unroll
-        for (int k = 0; k < kD / 16; ++k) umma_bf16_ss(tS + 64 * h, kdesc + 2 * k, qd + 2 * k, idesc_s, k != 0 ? 1u : 0u);
-#pragma unroll
-        for (int k = 0; k < kD / 16; ++k) umma_bf16_ss(tDP + 64 * h, vdesc + 2 * k, dod + 2 * k, idesc_s, k != 0 ? 1u : 0u);
-        umma_commit(&s_full[h]);
-      };
-      if (total > 0) {
-        mbar_wait(&kv_full[0], 0);
-        mbar_wait(&q_full[0], 0);
-        tc_fence_after();
-        issue_half(0, 0, 0);
-        issue_half(0, 0, 1);
-      }
       int g = 0;
       for (int n = 0; n < my_items; ++n) {
         const int nb = n & 1;
@@ -217,20 +197,6 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
           const uint64_t qdesc = umma_desc_k_sw128(smem_u32(smem + kOffQ + buf * 2 * kTileBytes));
           const uint64_t dodesc = umma_desc_k_sw128(smem_u32(smem + kOffQ + buf * 2 * kTileBytes + kTileBytes));
           const uint32_t ds_addr = smem_u32(smem + kOffDS + buf * 2 * kTileBytes);
-          if (g + 1 < total) {
-            // halves of block g+1 (possibly the first block of the next item) go into the columns the compute warps
-            // have just emptied (arrival order: half 0, half 1)
-            const bool next_item = i + 1 == nqb;
-            const int nb1 = next_item ? nb ^ 1 : nb;
-            if (next_item) mbar_wait(&kv_full[nb1], ((n + 1) >> 1) & 1);
-            mbar_wait(&q_full[buf ^ 1], ((g + 1) >> 1) & 1);
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              mbar_wait(&sdp_free[h], g & 1);
-              tc_fence_after();
-              issue_half(g + 1, nb1, h);
-            }
-          }
           // dV_j += P^T dO_i : K = 128 queries in 8 steps; P advances 8 TMEM columns, dO 16 rows (2 KB) per step
           mbar_wait(p_full, g & 1);
           if (i == 0 && n > 0) mbar_wait(acc_free, (n - 1) & 1);     // the previous item's dK / dV have left TMEM
@@ -240,21 +206,23 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
             umma_bf16_ts(tDV, tP + 8 * kk, dodesc + 128 * kk, idesc_kv, (i | kk) != 0 ? 1u : 0u);
           umma_commit(pv_done);
           // dK_j += dS^T Q_i (A = the smem dS^T tile read K-major: 16 queries = 32 B along the 128 B row, second
-          // 64-query slab 16 KB further); dQ_i = dS K_j (the same tile read MN-major)
+          // 64-query slab 16 KB further).  Q_i and dO_i are dead after it: the producer may refill the buffer.
           mbar_wait(ds_full, g & 1);
-          if (g > 0) mbar_wait(dq_free, (g - 1) & 1);       // the drain warps have read the previous block's dQ
           tc_fence_after();
 #pragma unroll
           for (int kk = 0; kk < kB / 16; ++kk) {
             const uint64_t ad = umma_desc_k_sw128(ds_addr + (kk >> 2) * kTileBytes) + 2 * (kk & 3);
             umma_bf16_ss(tDK, ad, qdesc + 128 * kk, idesc_kv, (i | kk) != 0 ? 1u : 0u);
           }
+          umma_commit(&q_empty[buf]);
+          // dQ_i = dS K_j (the same dS^T tile read MN-major)
+          if (g > 0) mbar_wait(dq_free, (g - 1) & 1);       // the drain warps have read the previous block's dQ
+          tc_fence_after();
           const uint64_t dsdesc = umma_desc_k_sw128(ds_addr) + kLboSlab;
 #pragma unroll
           for (int kk = 0; kk < kB / 16; ++kk)
             umma_bf16_ss(tDQ, dsdesc + 128 * kk, kdesc + 128 * kk, idesc_dq, kk != 0 ? 1u : 0u);
           umma_commit(dq_full);
-          umma_commit(&q_empty[buf]);
           umma_commit(&ds_free[buf]);
           if (i + 1 == nqb) {
             umma_commit(acc_full);
@@ -262,8 +230,38 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
           }
         }
       }
-    } else if (warp_idx >= 10) {
-      // ===================== statistics warps: the broadcast vectors of every block, two rows per thread =====================
+    } else if (warp_idx == kMmaWarpS && lane == 0) {
+      // ===================== MMA issuer A: S^T, dP^T, one 64-query half at a time =====================
+      // Its own thread: a half is refilled the moment the compute warps release it, whatever issuer B is waiting for
+      // (one thread issuing everything in program order left the compute warps waiting for S^T 40 % of the time).
+      constexpr uint32_t idesc_s = umma_idesc_bf16_f32(kB, 64);                              // K-major A and B, one half
+      const uint32_t tS = tmem_base + kColS, tDP = tmem_base + kColDP;
+      int g = 0;
+      for (int n = 0; n < my_items; ++n) {
+        const int nb = n & 1;
+        const uint64_t kdesc = umma_desc_k_sw128(smem_u32(smem + kOffKV + nb * 2 * kTileBytes));
+        const uint64_t vdesc = umma_desc_k_sw128(smem_u32(smem + kOffKV + nb * 2 * kTileBytes + kTileBytes));
+        mbar_wait(&kv_full[nb], (n >> 1) & 1);
+        for (int i = 0; i < nqb; ++i, ++g) {
+          const int buf = g & 1;
+          mbar_wait(&q_full[buf], (g >> 1) & 1);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            // B = rows [64 h, 64 h + 64) of the Q_i / dO_i tiles (8 KB further); the columns were block g-1's
+            if (g > 0) mbar_wait(&sdp_free[h], (g - 1) & 1);
+            tc_fence_after();
+            const uint64_t qd = umma_desc_k_sw128(smem_u32(smem + kOffQ + buf * 2 * kTileBytes + h * 8192));
+            const uint64_t dod = umma_desc_k_sw128(smem_u32(smem + kOffQ + buf * 2 * kTileBytes + kTileBytes + h * 8192));
+#pragma unroll
+            for (int k = 0; k < kD / 16; ++k) umma_bf16_ss(tS + 64 * h, kdesc + 2 * k, qd + 2 * k, idesc_s, k != 0 ? 1u : 0u);
+#pragma unroll
+            for (int k = 0; k < kD / 16; ++k) umma_bf16_ss(tDP + 64 * h, vdesc + 2 * k, dod + 2 * k, idesc_s, k != 0 ? 1u : 0u);
+            umma_commit(&s_full[h]);
+          }
+        }
+      }
+    } else if (warp_idx == 10) {
+      // ===================== statistics warp: the broadcast vectors of every block, four rows per thread =====================
       // The item of key block j visits the query blocks in the rotated order j, j+1, ... (mod nqb): at any moment the
       // CTAs working on one (sequence, head) then add into DIFFERENT rows of dQ -- the L2 atomic unit serialises per address.
       int g = 0;
@@ -272,10 +270,10 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
         const int seq_base = it.b * p.T;
         const size_t stat_base = (static_cast<size_t>(it.b) * p.nh + it.h) * p.T;
         for (int i = 0; i < nqb; ++i, ++g) {
-          float vals[2][kStatVecs];
+          float vals[4][kStatVecs];
 #pragma unroll
-          for (int r = 0; r < 2; ++r) {
-            const int row = (warp_idx - 10) * 64 + r * 32 + lane;
+          for (int r = 0; r < 4; ++r) {
+            const int row = r * 32 + lane;
             const int q = ((i + it.jb) % nqb) * kB + row;
             float a = 0.f, cb = -INFINITY, nb = 0.f, qtag = 0.f, dsum = 0.f, ktag = kKeyMasked;
             if (q < p.T) {
@@ -296,8 +294,8 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
           mbar_wait(&stat_free[g & 1], ((g >> 1) & 1) ^ 1);
           float* st = sStat + (g & 1) * kStatVecs * kB;
 #pragma unroll
-          for (int r = 0; r < 2; ++r) {
-            const int row = (warp_idx - 10) * 64 + r * 32 + lane;
+          for (int r = 0; r < 4; ++r) {
+            const int row = r * 32 + lane;
 #pragma unroll
             for (int k = 0; k < 5; ++k) st[k * kB + row] = vals[r][k];
             if (i == 0) st[5 * kB + row] = vals[r][5];
@@ -387,6 +385,7 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
     const int quarter = warp_idx & 3;
     const int row = quarter * 32 + lane;
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+    const bool plain = p.valid == nullptr && p.group == nullptr;
     int g = 0;
     for (int n = 0; n < my_items; ++n) {
       const Item it = decode_item(blockIdx.x + n * gridDim.x, p.nblk, p.nh);
@@ -411,20 +410,33 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&sdp_free[half]);
+          if (plain) {
+            // no validity / group inputs (the vision encoder): every query is valid, a = log2e, nothing to mask but
+            // the keys past T -- one FFMA and one broadcast vector per score instead of three and four
 #pragma unroll
-          for (int c4 = 0; c4 < 16; ++c4) {
-            const int c = 64 * half + 4 * c4;
-            const float4 a = *reinterpret_cast<const float4*>(st + 0 * kB + c);
-            const float4 cb = *reinterpret_cast<const float4*>(st + 1 * kB + c);
-            const float4 nb = *reinterpret_cast<const float4*>(st + 2 * kB + c);
-            const float4 qt = *reinterpret_cast<const float4*>(st + 3 * kB + c);
-            const float aa[4] = {a.x, a.y, a.z, a.w}, cc[4] = {cb.x, cb.y, cb.z, cb.w};
-            const float nn[4] = {nb.x, nb.y, nb.z, nb.w}, qq[4] = {qt.x, qt.y, qt.z, qt.w};
+            for (int c4 = 0; c4 < 16; ++c4) {
+              const float4 cb = *reinterpret_cast<const float4*>(st + 1 * kB + 64 * half + 4 * c4);
+              const float cc[4] = {cb.x, cb.y, cb.z, cb.w};
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              float t = fmaf(__uint_as_float(v[4 * c4 + e]), aa[e], cc[e]);
-              t = fmaf(fabsf(ktag - qq[e]), -nn[e], t);
-              pr[4 * c4 + e] = key_exists ? ex2_approx(t) : 0.f;
+              for (int e = 0; e < 4; ++e)
+                pr[4 * c4 + e] = key_exists ? ex2_approx(fmaf(__uint_as_float(v[4 * c4 + e]), kLog2e, cc[e])) : 0.f;
+            }
+          } else {
+#pragma unroll
+            for (int c4 = 0; c4 < 16; ++c4) {
+              const int c = 64 * half + 4 * c4;
+              const float4 a = *reinterpret_cast<const float4*>(st + 0 * kB + c);
+              const float4 cb = *reinterpret_cast<const float4*>(st + 1 * kB + c);
+              const float4 nb = *reinterpret_cast<const float4*>(st + 2 * kB + c);
+              const float4 qt = *reinterpret_cast<const float4*>(st + 3 * kB + c);
+              const float aa[4] = {a.x, a.y, a.z, a.w}, cc[4] = {cb.x, cb.y, cb.z, cb.w};
+              const float nn[4] = {nb.x, nb.y, nb.z, nb.w}, qq[4] = {qt.x, qt.y, qt.z, qt.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                float t = fmaf(__uint_as_float(v[4 * c4 + e]), aa[e], cc[e]);
+                t = fmaf(fabsf(ktag - qq[e]), -nn[e], t);
+                pr[4 * c4 + e] = key_exists ? ex2_approx(t) : 0.f;
+              }
             }
           }
         }

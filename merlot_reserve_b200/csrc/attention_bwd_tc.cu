@@ -417,9 +417,11 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
             for (int c4 = 0; c4 < 16; ++c4) {
               const float4 cb = *reinterpret_cast<const float4*>(st + 1 * kB + 64 * half + 4 * c4);
               const float cc[4] = {cb.x, cb.y, cb.z, cb.w};
+              // rows of keys past T are not masked here: their P^T only reaches dV_j rows that the TMA store clips, and
+              // their dS^T is zeroed below (it would reach dQ)
 #pragma unroll
               for (int e = 0; e < 4; ++e)
-                pr[4 * c4 + e] = key_exists ? ex2_approx(fmaf(__uint_as_float(v[4 * c4 + e]), kLog2e, cc[e])) : 0.f;
+                pr[4 * c4 + e] = ex2_approx(fmaf(__uint_as_float(v[4 * c4 + e]), kLog2e, cc[e]));
             }
           } else {
 #pragma unroll
@@ -458,7 +460,7 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
             for (int e = 0; e < 4; ++e) {
               const float pe = pr[4 * c4 + e];
               // an exactly-zero probability must give an exactly-zero gradient even where dP is garbage (rows past T)
-              ds[e] = pe == 0.f ? 0.f : pe * (__uint_as_float(dpv[4 * c4 + e]) - dd[e]);
+              ds[e] = (pe == 0.f || !key_exists) ? 0.f : pe * (__uint_as_float(dpv[4 * c4 + e]) - dd[e]);
             }
             pk[2 * c4] = pack_bf16(pr[4 * c4], pr[4 * c4 + 1]);
             pk[2 * c4 + 1] = pack_bf16(pr[4 * c4 + 2], pr[4 * c4 + 3]);

@@ -54,16 +54,21 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// suspend-time hint of try_wait (ns): the waiting thread stays suspended in hardware until the phase completes or
+// the hint expires, instead of coming back to poll every few dozen cycles and taking issue slots from the warps
+// that compute on the same sub-partition
+constexpr uint32_t kMbarSuspendHintNs = 2000;
+
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t"
       ".reg .pred P;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, P;\n\t"
       "}\n"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(kMbarSuspendHintNs)
       : "memory");
   return ok != 0;
 }

@@ -16,6 +16,7 @@ if "--blocks-per-cta" in sys.argv:
     # cost of a CTA (launch, TMEM allocation, cold loads, dK / dV write-out) from the steady-state time per block
     SHAPES = [("blocks2", 128, 241, 768, False), ("blocks4", 32, 497, 768, False), ("blocks8", 8, 1009, 768, False),
               ("blocks16", 2, 2033, 768, False)]
+FINISH = "--finish" in sys.argv      # the train step's call: qkv-epilogue backward + bias gradient in the tail pass
 ALGOS = [2] if "--blocks-per-cta" in sys.argv or "--tc-only" in sys.argv else [1, 2]
 torch.cuda.set_device(0)
 L.require_b200(0)
@@ -30,15 +31,16 @@ for name, B, T, H, masked in SHAPES:
         group = (torch.arange(T, device="cuda")[None] >= T // 2).to(torch.int32).expand(B, T).contiguous().view(-1)
         valid = valid.view(-1)
     lse = torch.empty(B, H // 64, T, device="cuda")
+    extra = dict(rot=torch.randn(T, 32, device="cuda"), q_scale=0.125, bias_grad=True) if FINISH else {}
     ctx = L.attention(qkv, B, T, H, valid=valid, group=group, lse=lse)
     for algo in (ALGOS if T > 64 else [1]):
         for _ in range(3):
-            L.attention_bwd(qkv, dctx, ctx, lse, B, T, H, valid=valid, group=group, algo=algo)
+            L.attention_bwd(qkv, dctx, ctx, lse, B, T, H, valid=valid, group=group, algo=algo, **extra)
         torch.cuda.synchronize()
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(10)]
         for a, b in ev:
             a.record()
-            L.attention_bwd(qkv, dctx, ctx, lse, B, T, H, valid=valid, group=group, algo=algo)
+            L.attention_bwd(qkv, dctx, ctx, lse, B, T, H, valid=valid, group=group, algo=algo, **extra)
             b.record()
         torch.cuda.synchronize()
         ts = sorted(a.elapsed_time(b) for a, b in ev)

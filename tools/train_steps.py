@@ -1,6 +1,7 @@
 """Runs N eager Base train steps (b = 8) -- the command profiled for profiles/launches_train_*.csv:
-    ncu --metrics gpu__time_duration.sum --clock-control none -s 3300 -c 1700 --csv --log-file out.csv python tools/train_steps.py 3
-(two warm-up steps are skipped by -s, the third is captured)."""
+    ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file out.csv \
+        python tools/train_steps.py 3
+(cudaProfilerStart / Stop bracket the LAST step, so exactly one warm step is captured whatever its launch count)."""
 import sys
 from pathlib import Path
 
@@ -16,6 +17,10 @@ step = PretrainStep(cfg, synthetic_params(cfg, seed=0))
 batch = {k: torch.from_numpy(v).cuda() for k, v in synthetic_pretrain_batch(cfg, 8, seed=1).items()}
 with torch.no_grad():
     for i in range(n):
+        if i == n - 1:
+            torch.cuda.cudart().cudaProfilerStart()
         loss, _ = step.train_step(batch)
         torch.cuda.synchronize()
+        if i == n - 1:
+            torch.cuda.cudart().cudaProfilerStop()
         print("step", i, float(loss), flush=True)

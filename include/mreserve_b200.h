@@ -152,7 +152,9 @@ size_t mr_gemm_epilogue_workspace_bytes(const MrGemmDesc* d);
  * false sees a constant -1e10 bias in the reference, i.e. attends UNIFORMLY to all T keys; that
  * behaviour is reproduced (it matters for padding rows returned by embed_video :842).
  * ------------------------------------------------------------------------------------------ */
-enum { MR_ATTN_ALGO_AUTO = 0, MR_ATTN_ALGO_MMA_SYNC = 1, MR_ATTN_ALGO_TCGEN05 = 2 };
+enum { MR_ATTN_ALGO_AUTO = 0, MR_ATTN_ALGO_MMA_SYNC = 1, MR_ATTN_ALGO_TCGEN05 = 2,
+       /* forward only: force one of the two tensor-memory kernels (TCGEN05 / AUTO choose by sequence length) */
+       MR_ATTN_ALGO_TCGEN05_2TILE = 3, MR_ATTN_ALGO_TCGEN05_3STREAM = 4 };
 /* mr_attention_bwd `finish` flags: fold the next steps of the backward pass into the pass that converts the fp32 dQ
  * accumulator (one sweep over d(qkv) instead of mr_attention_bwd + mr_rotary_bwd + mr_colsum):
  *   EPILOGUE   out[0] becomes the gradient w.r.t. the qkv GEMM's PRE-epilogue output: dq * q_scale * rot, dk * rot on
@@ -165,7 +167,10 @@ typedef struct MrAttentionDesc {
   int32_t algo;    /* AUTO: tcgen05/TMEM kernel (128-query tiles) when T > 64; mma.sync kernels below that: one
                       32 x 32 tile per (sequence, head) in a two-warp CTA when T <= 32 (audio T=31, span T=16),
                       64-query tiles otherwise.  MMA_SYNC forces the 64-tile mma.sync kernel, TCGEN05 the
-                      tensor-memory kernel (both directions). */
+                      tensor-memory kernel (both directions).  Forward, tensor-memory path: two 128-query tiles per SM
+                      on 128- / 96-key blocks (attention_tc.cu) up to T = 256 and for calls with group ids, three
+                      independent tile streams on 64-key blocks (attention_tc3.cu) above; TCGEN05_2TILE /
+                      TCGEN05_3STREAM force one of them. */
   int32_t emit_lse; /* fwd: 1 = also write out[1] = lse f32 [B, H/64, T], the natural-log row log-sum-exp of the
                        masked scores (what mr_attention_bwd needs to recompute the probabilities) */
   int32_t finish;   /* bwd: MR_ATTN_BWD_* flags, 0 = plain d(q, k, v) */

@@ -467,6 +467,7 @@ def composite(name: str, desc, ins, outs, device, ws=None) -> None:
 
 
 ATTN_AUTO, ATTN_MMA_SYNC, ATTN_TCGEN05 = 0, 1, 2
+ATTN_TCGEN05_2TILE, ATTN_TCGEN05_3STREAM = 3, 4    # forward only: force one of the two tensor-memory kernels
 
 
 def attention(qkv: torch.Tensor, B: int, T: int, H: int, valid=None, group=None, out=None, algo=ATTN_AUTO, lse=None) -> torch.Tensor:

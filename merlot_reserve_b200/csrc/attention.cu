@@ -258,7 +258,7 @@ attention_fwd_kernel(const bf16* __restrict__ qkv, const uint8_t* __restrict__ v
 
 namespace mr {
 int32_t launch_attention_tc(cudaStream_t stream, const bf16* qkv, const uint8_t* valid, const int32_t* group,
-                            bf16* out, float* lse, int B, int T, int H);
+                            bf16* out, float* lse, int B, int T, int H, int variant);
 }
 
 extern "C" size_t mr_attention_fwd_workspace_bytes(const MrAttentionDesc*) { return 0; }
@@ -270,13 +270,14 @@ extern "C" int32_t mr_attention_fwd(mr_stream_t stream_, const MrAttentionDesc* 
   MR_REQUIRE(d->B >= 0 && d->T > 0 && d->H > 0 && d->H % 64 == 0, MR_ERR_BAD_SHAPE);
   MR_REQUIRE(aligned16(in[0]) && aligned16(out[0]), MR_ERR_MISALIGNED);
   if (d->B == 0) return MR_OK;
-  MR_REQUIRE(d->algo >= MR_ATTN_ALGO_AUTO && d->algo <= MR_ATTN_ALGO_TCGEN05, MR_ERR_BAD_SHAPE);
+  MR_REQUIRE(d->algo >= MR_ATTN_ALGO_AUTO && d->algo <= MR_ATTN_ALGO_TCGEN05_3STREAM, MR_ERR_BAD_SHAPE);
   float* lse = d->emit_lse ? static_cast<float*>(out[1]) : nullptr;
   MR_REQUIRE(!d->emit_lse || lse, MR_ERR_NULL_POINTER);
-  if (d->algo == MR_ATTN_ALGO_TCGEN05 || (d->algo == MR_ATTN_ALGO_AUTO && d->T > 64)) {
+  if (d->algo >= MR_ATTN_ALGO_TCGEN05 || (d->algo == MR_ATTN_ALGO_AUTO && d->T > 64)) {
+    const int variant = d->algo == MR_ATTN_ALGO_TCGEN05_2TILE ? 2 : (d->algo == MR_ATTN_ALGO_TCGEN05_3STREAM ? 3 : 0);
     return launch_attention_tc(static_cast<cudaStream_t>(stream_), static_cast<const bf16*>(in[0]),
                                static_cast<const uint8_t*>(in[1]), static_cast<const int32_t*>(in[2]),
-                               static_cast<bf16*>(out[0]), lse, d->B, d->T, d->H);
+                               static_cast<bf16*>(out[0]), lse, d->B, d->T, d->H, variant);
   }
   const int nh = d->H / 64;
   // T <= 32 (audio T = 31, span T = 16): one 32 x 32 tile per (sequence, head), 2-warp CTAs, 12 KB smem

@@ -597,9 +597,23 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
 
 long long* g_attention_trace = nullptr;
 
+int32_t launch_attention_tc3(cudaStream_t stream, const bf16* qkv, const uint8_t* valid, bf16* out, float* lse, int B,
+                             int T, int H);   // attention_tc3.cu
+
 // Called by mr_attention_fwd (attention.cu) when T is long enough for 128-wide tiles.
+// variant: 0 = choose; 2 = this file's two-tile kernel; 3 = the three-stream kernel of attention_tc3.cu (calls with
+// group ids always take the two-tile kernel).  Same-box probe (profiles/attn_tc3_r02.txt, us, two-tile -> three-stream):
+// T = 241: 346 -> 369;  T = 288: 705 -> 457;  T = 577: 697 -> 644;  T = 640: 132 -> 117;  T = 1120: 493 -> 422;
+// T = 2464: 793 -> 665.  Three streams win from five 64-key blocks per tile on; below that the per-tile hand-overs
+// (Q refill, one epilogue warpgroup for three streams) cost more than the third softmax warp per scheduler gains.
 int32_t launch_attention_tc(cudaStream_t stream, const bf16* qkv, const uint8_t* valid, const int32_t* group,
-                            bf16* out, float* lse, int B, int T, int H) {
+                            bf16* out, float* lse, int B, int T, int H, int variant) {
+  static const int tiles_env = []() {   // MR_ATTN_TILES=2 / 3 overrides the choice for A/B runs
+    const char* e = getenv("MR_ATTN_TILES");
+    return e ? atoi(e) : 0;
+  }();
+  if (variant == 0) variant = tiles_env == 2 || tiles_env == 3 ? tiles_env : (T > 256 ? 3 : 2);
+  if (variant == 3 && group == nullptr) return launch_attention_tc3(stream, qkv, valid, out, lse, B, T, H);
   // key block: 96 where that pads the sequence at least 10 % less than 128 does (T = 288 -> 3 x 96 instead of 3 x 128)
   const int pad128 = ceil_div(T, 128) * 128, pad96 = ceil_div(T, 96) * 96;
   static const int kv_env = []() {

@@ -238,6 +238,32 @@ def test_attention_96_key_blocks(cuda, lib, B, T, H):
     _close(lse, ref_lse, 2e-2, 2e-2, "96-key lse")
 
 
+@pytest.mark.parametrize("B,T,H", [(3, 241, 128), (130, 288, 128), (2, 1120, 768), (40, 577, 256), (5, 65, 128), (1, 2464, 128)])
+def test_attention_two_tile_and_three_stream_kernels_agree(cuda, lib, B, T, H):
+    """The two tensor-memory forward kernels (two 128-query tiles per SM on 128- / 96-key blocks; three independent
+    tile streams on 64-key blocks) forced on the same inputs, unmasked and with key validity (long masked tails,
+    invalid query rows), output and row log-sum-exp, against the reference and against each other.  Shapes with
+    0.05 .. 3.5 tiles per stream, 2 .. 39 key blocks per tile, a 65-key sequence (one key in the second block)."""
+    g = torch.Generator().manual_seed(T * 3 + B)
+    qkv = _bf(torch.randn(B * T, 3 * H, generator=g)).to(cuda)
+    qkv.view(B * T, 3, H)[:, 0] *= 0.35
+    valid = (torch.rand(B, T, generator=g) > 0.3).to(torch.uint8)
+    valid[:, 0] = 1
+    valid[0, T // 2:] = 0
+    valid = valid.to(cuda).contiguous()
+    for v in (None, valid):
+        ref = _attn_ref(qkv, B, T, H, v) if B * T * T * (H // 64) < 4e8 else None
+        outs, lses = [], []
+        for algo in (lib.ATTN_TCGEN05_2TILE, lib.ATTN_TCGEN05_3STREAM):
+            lse = torch.empty(B, H // 64, T, device=cuda)
+            outs.append(lib.attention(qkv, B, T, H, valid=None if v is None else v.view(-1), algo=algo, lse=lse))
+            lses.append(lse)
+            if ref is not None:
+                _close(outs[-1], ref, 2e-2, 2e-2, f"algo {algo} vs reference")
+        _close(outs[1], outs[0], 2e-2, 2e-2, "three-stream vs two-tile")
+        _close(lses[1], lses[0], 2e-2, 2e-2, "lse three-stream vs two-tile")
+
+
 def test_attention_many_items_persistent(cuda, lib):
     """More work items than SMs, odd and even numbers of query tiles: exercises the persistent loop, the Q double
     buffer, the K/V ring wrap-around and pairs whose second tile is absent."""

@@ -29,6 +29,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--reps", type=int, default=20)
     ap.add_argument("--only", default="")
+    ap.add_argument("--groups", action="store_true", help="masked shapes also carry group ids (pretraining joint)")
     args = ap.parse_args()
     torch.cuda.set_device(0)
     L.require_b200(0)
@@ -40,18 +41,20 @@ def main():
         for t in qkvs:
             t[:, :H] *= 0.125                      # the QKV GEMM epilogue hands attention q / sqrt(64)
         out = torch.empty(B * T, H, device="cuda", dtype=torch.bfloat16)
-        valid = None
+        valid = group = None
         if masked:
             valid = torch.ones(B, T, dtype=torch.uint8, device="cuda")
             valid[:, 13:160] = 0          # embed_video layout: ~12 text tokens, then padding up to L = 160
             valid = valid.reshape(-1)
+            if args.groups:      # pretraining: video_src ids (here: two halves of the sequence)
+                group = (torch.arange(T, device="cuda")[None] >= T // 2).to(torch.int32).expand(B, T).contiguous().view(-1)
         for i in range(3):
-            L.attention(qkvs[i % nbuf], B, T, H, valid=valid, out=out)
+            L.attention(qkvs[i % nbuf], B, T, H, valid=valid, group=group, out=out)
         torch.cuda.synchronize()
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.reps)]
         for i, (a, b) in enumerate(ev):
             a.record()
-            L.attention(qkvs[i % nbuf], B, T, H, valid=valid, out=out)
+            L.attention(qkvs[i % nbuf], B, T, H, valid=valid, group=group, out=out)
             b.record()
         torch.cuda.synchronize()
         ts = sorted(a.elapsed_time(b) for a, b in ev)

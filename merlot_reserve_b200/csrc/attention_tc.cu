@@ -123,7 +123,9 @@ struct ItemWalker {
 // kKV = keys per block.  128 normally; 96 when ceil(T / 96) * 96 is at least 10 % below ceil(T / 128) * 128 (e.g. the
 // multiple-choice joint sequences, T = 144 + 144 = 288 = 3 x 96: a 128-key tail block would spend a quarter of the
 // kernel's exponentials on padding).  `tmap_kv` is the qkv map with a box of kKV rows.
-template <bool kMasked, int kKV>
+// kGroups (implies kMasked): the call carries video_src group ids.  A separate instantiation, so that the validity-only
+// kernel keeps its schedule (the group logic costs it 5-13 % when it is merely compiled in).
+template <bool kMasked, int kKV, bool kGroups = false>
 __global__ void __launch_bounds__(kTcThreads, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_kv,
                     const __grid_constant__ CUtensorMap tmap_out, const AttnParams p) {
@@ -375,7 +377,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
       for (int i = 0; i < 4; ++i) {
         const int kidx = min(j * kKV + min(lane * 4 + i, kKV - 1), p.T - 1);
         r.v[i] = p.valid ? p.valid[seq_base + kidx] : uint8_t(1);
-        r.g[i] = p.group ? p.group[seq_base + kidx] : 0;
+        r.g[i] = kGroups ? p.group[seq_base + kidx] : 0;
       }
       return r;
     };
@@ -395,10 +397,20 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
       if (kMasked) {
         const bool v = q_in ? (p.valid ? p.valid[seq_base + q] != 0 : true) : false;
         q_uniform = !v;
-        q_group = (v && p.group) ? p.group[seq_base + q] : 0;
+        q_group = (kGroups && v) ? p.group[seq_base + q] : 0;
         raw_next = load_raw(seq_base, 0);
       }
-      const bool any_uniform = kMasked ? __any_sync(0xffffffffu, q_uniform) : false;
+      // Group ids: the 32 query rows of a warp almost always share ONE video_src id (ids change a few times per
+      // sequence).  Such a warp folds "key valid AND key group == g0" into the additive per-key bias and keeps the
+      // one-FFMA path; only warps that straddle a change compare per score.
+      int g0 = 0;
+      bool warp_uni = true;
+      if (kGroups) {
+        const unsigned vm = __ballot_sync(0xffffffffu, !q_uniform);
+        g0 = vm != 0u ? __shfl_sync(0xffffffffu, q_group, __ffs(vm) - 1) : 0;
+        warp_uni = __all_sync(0xffffffffu, q_uniform || q_group == g0);
+      }
+      const bool bias_path = !kGroups || warp_uni;
       const float cq = q_uniform ? 0.f : kLog2e;   // fast-path score scale: 0 -> uniform attention
       const float qs = q_uniform ? 0.f : 1.f;
       float m2 = 0.f;  // reference max, log2 domain
@@ -414,7 +426,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
           for (int i = 0; i < 4; ++i) {
             const bool in_range = j * kKV + lane * 4 + i < p.T;
             info[i] = !in_range ? kInfoOob : (raw_next.v[i] != 0 ? raw_next.g[i] : kInfoInvalid);
-            bv[i] = info[i] == 0 ? 0.f : -INFINITY;
+            bv[i] = info[i] == g0 ? 0.f : -INFINITY;
             be[i] = in_range ? 0.f : -INFINITY;
           }
           if (j + 1 < p.nkb) raw_next = load_raw(seq_base, j + 1);
@@ -424,8 +436,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
             *reinterpret_cast<float4*>(myBiasV + 4 * lane) = make_float4(bv[0], bv[1], bv[2], bv[3]);
             *reinterpret_cast<float4*>(myBiasE + 4 * lane) = make_float4(be[0], be[1], be[2], be[3]);
           }
-          // fast path: every key in range and valid, and no group ids in play
-          const bool ok = !mine || (p.group == nullptr && (info[0] | info[1] | info[2] | info[3]) == 0);
+          // fast path: every key in range, valid and of the warp's group
+          const bool ok = !mine || (bias_path && info[0] == g0 && info[1] == g0 && info[2] == g0 && info[3] == g0);
           fast = __all_sync(0xffffffffu, ok);      // also orders the smem writes above before the reads below
         }
         stamp(0);
@@ -451,7 +463,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
         if (!fast) {
           if (kMasked) {
             cs = kLog2e;
-            if (p.group == nullptr) {
+            if (bias_path) {
               // additive per-key bias (0 / -inf) folded into one FFMA per score.  A valid query row reads the
               // "key valid and in range" vector with scale 1; an invalid query row (it attends uniformly to every
               // existing key, modeling.py:343-358) reads the "key in range" vector with scale 0.  The choice is per
@@ -653,10 +665,11 @@ int32_t launch_attention_tc(cudaStream_t stream, const bf16* qkv, const uint8_t*
   if (sms <= 0) return MR_ERR_UNSUPPORTED_ARCH;
   const int grid = p.num_items < sms ? p.num_items : sms;
   const bool masked = valid != nullptr || group != nullptr;
-  auto kern = kv == 96 ? (masked ? attention_tc_kernel<true, 96> : attention_tc_kernel<false, 96>)
-                       : (masked ? attention_tc_kernel<true, 128> : attention_tc_kernel<false, 128>);
-  static bool attr_set[4] = {false, false, false, false};
-  const int slot = (kv == 96 ? 2 : 0) + (masked ? 1 : 0);
+  const bool groups = group != nullptr;
+  auto kern = kv == 96 ? (groups ? attention_tc_kernel<true, 96, true> : masked ? attention_tc_kernel<true, 96> : attention_tc_kernel<false, 96>)
+                       : (groups ? attention_tc_kernel<true, 128, true> : masked ? attention_tc_kernel<true, 128> : attention_tc_kernel<false, 128>);
+  static bool attr_set[6] = {false, false, false, false, false, false};
+  const int slot = (kv == 96 ? 3 : 0) + (groups ? 2 : (masked ? 1 : 0));
   if (!attr_set[slot]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     if (e != cudaSuccess) return cuda_status(e);

@@ -64,6 +64,7 @@ _SKIP_GRAD_ALLREDUCE = False
 # an ncclComm_t made by mr_nccl_comm_init) when the group's backend is NCCL; MR_NATIVE_COLLECTIVES=0 keeps
 # torch.distributed's wrappers around the same NCCL calls (and is what a gloo / CPU group uses).
 _NATIVE_COLLECTIVES = os.environ.get("MR_NATIVE_COLLECTIVES", "1") != "0"
+_COMMUNICATORS: Dict[int, tuple] = {}
 # MR_ATTN_BWD_FINISH=0: the three-pass tail (mr_attention_bwd, mr_rotary_bwd, mr_colsum) for same-box A/B runs
 _FUSED_QKV_TAIL = os.environ.get("MR_ATTN_BWD_FINISH", "1") != "0"
 
@@ -251,12 +252,14 @@ class PretrainStep:
             return None
         if dist.get_world_size(group) < 2 or dist.get_backend(group) != "nccl":
             return None
-        comms = self.__dict__.setdefault("_comms", {})
+        # one communicator per process group for the whole process (ncclCommInitRank is collective and takes ~1 s), held
+        # together with the group object so that its id cannot be reused while the entry lives
         key = id(group) if group is not None else 0
-        if key not in comms:
-            comms[key] = L.Communicator.from_group(group)
+        if key not in _COMMUNICATORS:
+            _COMMUNICATORS[key] = (L.Communicator.from_group(group), group)
+        if self.__dict__.get("_comm_stream") is None:
             self._comm_stream = torch.cuda.Stream(priority=-1)
-        return comms[key]
+        return _COMMUNICATORS[key][0]
 
     def capture_train_step(self, batch: Dict, opt: Optional[Dict] = None, group=None):
         """Captures train_step for batches shaped like `batch` (which must carry the '_rng/*' draws: the numpy draw of

@@ -56,6 +56,29 @@ def test_struct_sizes_match_c(lib, tmp_path):
         assert C.sizeof(structs[name]) == int(size), name
 
 
+def test_enum_values_match_c(lib, tmp_path):
+    """The flag / enum constants of the ctypes binding are the header's (a C program prints them)."""
+    pairs = {"MR_EPI_BIAS": lib.EPI_BIAS, "MR_EPI_GELU": lib.EPI_GELU, "MR_EPI_RESIDUAL": lib.EPI_RESIDUAL,
+             "MR_EPI_ROTARY_QKV": lib.EPI_ROTARY_QKV, "MR_EPI_OUT_F32": lib.EPI_OUT_F32, "MR_EPI_LN_IN": lib.EPI_LN_IN,
+             "MR_EPI_STATS_OUT": lib.EPI_STATS_OUT, "MR_EPI_DGELU": lib.EPI_DGELU, "MR_EPI_GELU_DUAL": lib.EPI_GELU_DUAL,
+             "MR_GEMM_ALGO_TCGEN05": lib.ALGO_TCGEN05, "MR_GEMM_ALGO_SIMT_DEBUG": lib.ALGO_SIMT_DEBUG,
+             "MR_ATTN_ALGO_AUTO": lib.ATTN_AUTO, "MR_ATTN_ALGO_MMA_SYNC": lib.ATTN_MMA_SYNC,
+             "MR_ATTN_ALGO_TCGEN05": lib.ATTN_TCGEN05, "MR_ATTN_ALGO_TCGEN05_2TILE": lib.ATTN_TCGEN05_2TILE,
+             "MR_ATTN_ALGO_TCGEN05_3STREAM": lib.ATTN_TCGEN05_3STREAM, "MR_ATTN_BWD_EPILOGUE": lib.ATTN_BWD_EPILOGUE,
+             "MR_ATTN_BWD_BIAS_GRAD": lib.ATTN_BWD_BIAS_GRAD, "MR_DT_BF16": lib._DT[__import__("torch").bfloat16],
+             "MR_DT_F32": lib._DT[__import__("torch").float32], "MR_OK": 0, "MR_ERR_NCCL_UNAVAILABLE": -7,
+             "MR_ERR_CUDA_BASE": -1000, "MR_ERR_NCCL_BASE": -2000}
+    src = tmp_path / "en.c"
+    body = "\n".join(f'  printf("{n} %d\\n", (int){n});' for n in pairs)
+    src.write_text(f'#include <stdio.h>\n#include "mreserve_b200.h"\nint main(void) {{\n{body}\n  return 0;\n}}\n')
+    exe = tmp_path / "en"
+    subprocess.run(["gcc", "-std=c99", "-I", str(ROOT / "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
+    for line in out.strip().splitlines():
+        name, value = line.split()
+        assert pairs[name] == int(value), name
+
+
 def test_argument_validation_without_gpu(lib):
     """Bad descriptors are rejected before anything touches the device."""
     cdll = lib.load()
